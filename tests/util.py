@@ -1,0 +1,67 @@
+"""Shared helpers for tests (synthetic data, toy parameters)."""
+import numpy as np
+
+
+def is_prime(n: int) -> bool:
+    if n < 2:
+        return False
+    for p in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37):
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def ntt_primes(n: int, bits: int, count: int):
+    """`count` largest `bits`-bit primes = 1 mod 2n"""
+    out, p = [], ((1 << bits) - 1) // (2 * n) * (2 * n) + 1
+    while len(out) < count:
+        if p < (1 << bits) and is_prime(p):
+            out.append(p)
+        p -= 2 * n
+    return out
+
+
+def toy_params(n: int = 1024, bits: int = 40, k: int = 4, tbits: int = 20):
+    primes = ntt_primes(n, bits, k - 1) + ntt_primes(n, bits + 1, 1)
+    t = ntt_primes(n, tbits, 1)[0]
+    return n, primes, t
+
+
+def sift_like(rng: np.random.Generator, nb: int, d: int, nlist: int, nq: int):
+    """SIFT-shaped synthetic data: uint8-valued float vectors from a Gaussian mixture."""
+    centres = rng.uniform(0, 160, size=(nlist, d))
+    assign = rng.integers(0, nlist, size=nb)
+    base = np.clip(np.rint(centres[assign] + rng.normal(0, 24, size=(nb, d))), 0, 255).astype(np.float32)
+    qa = rng.integers(0, nlist, size=nq)
+    query = np.clip(np.rint(centres[qa] + rng.normal(0, 24, size=(nq, d))), 0, 255).astype(np.float32)
+    return base, query, centres.astype(np.float32)
+
+
+def build_ivf(base: np.ndarray, centroids: np.ndarray):
+    """Assign every base vector to its nearest centroid; returns (list_offsets, ids, vectors in list order)."""
+    d2 = ((base[:, None, :].astype(np.float64) - centroids[None, :, :].astype(np.float64)) ** 2).sum(-1) \
+        if base.shape[0] * centroids.shape[0] <= 4_000_000 else None
+    if d2 is None:
+        b2 = (base.astype(np.float64) ** 2).sum(1)[:, None]
+        c2 = (centroids.astype(np.float64) ** 2).sum(1)[None, :]
+        d2 = b2 + c2 - 2.0 * base.astype(np.float64) @ centroids.astype(np.float64).T
+    assign = d2.argmin(1)
+    order = np.argsort(assign, kind="stable")
+    counts = np.bincount(assign, minlength=centroids.shape[0])
+    offsets = np.zeros(centroids.shape[0] + 1, dtype=np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return offsets, order.astype(np.int64), np.ascontiguousarray(base[order])
