@@ -1,0 +1,182 @@
+/*
+ * prefhetch_b200.h — C ABI of the B200-native engine for PreFHEtch's server-side search hot path.
+ *
+ * The reference has no plugin/FFI layer: its seam is the `Server` member-function surface
+ * (ref: include/server/server_lib.h:25-49) called from the Drogon handlers
+ * (ref: src/server/controllers/Query.cc:18,49,87).  Each entry point below names the reference
+ * interface it replaces.  All pointers are HOST pointers unless the name says `_device`; shapes
+ * are run-time values (the reference's are compile-time constants,
+ * ref: include/common/client_server_utils.h:10-20).  No exceptions cross this boundary: every
+ * call returns a status code and pf_last_error() gives the message
+ * (the reference throws std::runtime_error, ref: src/server/server_lib.cpp:66,94).
+ * Calls on one engine are serialised internally (the reference `Server` is a non-re-entrant
+ * singleton, ref: include/server/server_lib.h:20-23, src/server/server_lib.cpp:121).
+ *
+ * Ciphertext word layout everywhere: uint64 [poly 2][limb L][coeff N] (SEAL Ciphertext::data()).
+ * "coefficient form" / "NTT form" are SEAL's (bit-reversed NTT output, smallest primitive root).
+ */
+#ifndef PREFHETCH_B200_H
+#define PREFHETCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+#define PF_MAX_PRIMES 16
+
+enum {
+    PF_OK = 0,
+    PF_ERR_INVALID = 1,  /* bad argument / unsupported parameter set */
+    PF_ERR_CUDA = 2,     /* CUDA runtime failure (no CPU fallback exists) */
+    PF_ERR_CAPACITY = 3, /* caller buffer too small; required size reported where documented */
+    PF_ERR_STATE = 4,    /* call out of order (no index / no Galois key loaded) */
+    PF_ERR_FORMAT = 5    /* malformed serialized ciphertext / key */
+};
+
+typedef struct pf_engine pf_engine;
+
+typedef struct {
+    uint32_t struct_size;   /* sizeof(pf_params) */
+    int32_t device;         /* CUDA device ordinal */
+    uint64_t poly_degree;   /* N: power of two in [1024, 16384] */
+    uint32_t num_primes;    /* k = data primes + 1 special prime (SEAL key-level chain) */
+    uint32_t dim;           /* vector dimension d (ref: PRECISE_VECTOR_DIMENSIONS) */
+    uint64_t primes[PF_MAX_PRIMES];
+    uint64_t plain_modulus; /* t, batching prime */
+    uint32_t query_cts;     /* m: ciphertexts per query (dimension chunks), power of two */
+    uint32_t partial_g;     /* g: partial sums per candidate, power of two dividing d_pad/m */
+    uint32_t rank;          /* this engine keeps the IVF lists l with l % world == rank */
+    uint32_t world;
+} pf_params;
+
+typedef struct {
+    uint64_t nlist, ntotal, nblocks, nblocks_local;
+    uint64_t db_bytes;      /* NTT-domain plaintext bytes resident in HBM (this shard) */
+    uint32_t K, C, R, d_pad; /* diagonals per block, candidates per block, rotations per chunk */
+    uint32_t L, k;
+} pf_index_info;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int pf_abi_version(void);
+/* replaces: Server::Server (ref: src/server/server_lib.cpp:32-46).  Fails with PF_ERR_CUDA when no
+ * CUDA device is usable: there is deliberately no CPU path. */
+int pf_engine_create(const pf_params *params, pf_engine **out);
+void pf_engine_destroy(pf_engine *e);
+/* last error message of this engine (or of the calling thread when e == NULL) */
+const char *pf_last_error(const pf_engine *e);
+/* stream all engine work is launched on (a cudaStream_t); set to run on the caller's stream */
+void *pf_engine_stream(pf_engine *e);
+int pf_engine_set_stream(pf_engine *e, void *cuda_stream);
+int pf_engine_synchronize(pf_engine *e);
+
+/* ---- index ------------------------------------------------------------------------------ */
+/* replaces: Server::init_index's hand-over of the trained IVF index to the searcher
+ * (ref: src/server/server_lib.cpp:55-99): centroids [nlist][d] as `quantizer->reconstruct` returns
+ * them (:107), inverted lists CSR style (list_offsets[nlist+1]; ids / vectors in list order, i.e.
+ * FAISS invlists order).  Vectors must be integer valued in [0,255] for the encrypted path
+ * (SIFT is; ref data set dataset.sh).  Encodes every block of this rank's lists into NTT-domain
+ * plaintext diagonals in HBM (kernels, not host code). */
+int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const int64_t *list_offsets,
+                  const int64_t *ids, const float *vectors);
+int pf_get_index_info(pf_engine *e, pf_index_info *out);
+/* replaces: Server::retrieve_centroids (ref: src/server/server_lib.cpp:101-109) */
+int pf_retrieve_centroids(pf_engine *e, float *out, uint64_t cap_floats);
+
+/* ---- stage 1: coarse quantization ------------------------------------------------------- */
+/* replaces: sort_nearest_centroids + the first-NPROBE slice (ref: src/client/client_lib.cpp:50-81,
+ * :93-103).  Same arithmetic (float difference, double square, float running sum), ascending,
+ * ties by lower index.  out_idx [nq][nprobe]; out_dist optional. */
+int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprobe, int64_t *out_idx,
+                       float *out_dist);
+
+/* ---- stage 2, plaintext ------------------------------------------------------------------ */
+/* replaces: the m_Index->search_encrypted call in Server::coarseSearch
+ * (ref: src/server/server_lib.cpp:111-138): for every query, for each given list in order, one
+ * (distance, id) per stored vector, packed back to back; list_sizes[i] = candidates of query i.
+ * Distances are the exact squared L2 of Server::preciseSearch (ref: :140-167).  If *total > cap
+ * nothing past cap is written and PF_ERR_CAPACITY is returned with *total = required entries. */
+int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64_t *idx, uint32_t nprobe,
+                          float *dist, int64_t *labels, uint64_t cap, uint64_t *list_sizes, uint64_t *total);
+/* replaces: Server::preciseSearch (ref: src/server/server_lib.cpp:140-167): ids [nq][nids] are
+ * base-file row numbers, out [nq][nids]. */
+int pf_precise_search(pf_engine *e, uint64_t nq, const float *x, const int64_t *ids, uint32_t nids, float *out);
+
+/* ---- stage 2, encrypted ------------------------------------------------------------------ */
+/* Galois key for element `galois_elt`, words [L][2][k][N] in NTT form (SEAL KSwitchKeys data of
+ * that element, GaloisKeys::key(galois_elt)). */
+int pf_set_galois_key(pf_engine *e, uint32_t galois_elt, const uint64_t *key_words);
+/* SEAL-serialized GaloisKeys (compr_mode none), all elements it holds */
+int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len);
+uint32_t pf_galois_elt_from_step(pf_engine *e, int step);
+
+typedef struct {
+    uint64_t nresults;        /* result ciphertexts written (sum over queries) */
+    uint64_t out_bytes;       /* bytes written to out_cts */
+    uint64_t useful_distances; /* real candidates covered */
+    uint64_t slot_distances;   /* candidates incl. padding = nresults * C */
+} pf_search_stats;
+
+/* The encrypted variant of Server::coarseSearch (additive to ref: src/server/controllers/Query.cc:29-63):
+ * query_cts holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level) back to back,
+ * ct_offsets[nq*m+1] their byte offsets.  For query i and each of its lists idx[i][p] (in order, lists
+ * not owned by this rank are skipped) one result ciphertext per block of the list is written to
+ * out_cts in SEAL format (coefficient form), result_offsets[nresults+1].  results_per_query[nq].
+ * labels / list_sizes as in pf_search_lists_plain (ids of the owned probed lists, packed);
+ * probed_sizes[nq][nprobe] = length of each probed list (0 when not owned) so the client can map
+ * candidate j of a list to (result j / C, candidate j % C). */
+int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
+                              const int64_t *idx, uint32_t nprobe, uint8_t *out_cts, uint64_t out_cap,
+                              uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
+                              int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
+                              pf_search_stats *stats);
+
+/* Device-resident form of the same step (what `value` in bench.py times): d_query_cts is a DEVICE
+ * pointer to raw words [nq][m][2][L][N] (coefficient form); d_out a DEVICE buffer of
+ * cap_results*2*L*N words receiving coefficient-form results in the order above.  idx is a host
+ * array.  Asynchronous on the engine stream. */
+int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, const int64_t *idx, uint32_t nprobe,
+                     uint64_t *d_out, uint64_t cap_results, uint64_t *results_per_query, pf_search_stats *stats);
+
+/* per-phase device timers (CUDA events on the engine stream), accumulated since the last reset */
+enum { PF_T_COARSE = 0, PF_T_TONTT = 1, PF_T_ROTATE = 2, PF_T_MAC = 3, PF_T_INTT = 4, PF_T_COUNT = 8 };
+int pf_timing_enable(pf_engine *e, int on);
+int pf_timing_read(pf_engine *e, float *ms /*[PF_T_COUNT]*/, uint64_t *launches /*[PF_T_COUNT]*/, int reset);
+/* kernels launched by this engine since creation (all phases) */
+uint64_t pf_launch_count(pf_engine *e);
+
+/* ---- primitives (parity-test entry points; host buffers, results copied back) ------------ */
+/* in-place forward / inverse negacyclic NTT of npoly polynomials; limb[i] selects the modulus of
+ * polynomial i (0..k-1 coefficient primes, -1 = plain modulus t).  SEAL: util/ntt.cpp. */
+int pf_ntt_forward(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t *limb);
+int pf_ntt_inverse(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t *limb);
+/* out[2][L][N] = sum_{k<K} cts[k] (.) pts[k]  (+ addend[L][N] on polynomial 0 when non-NULL);
+ * SEAL: Evaluator::multiply_plain (NTT) + add_inplace chain. */
+int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_t K, const uint64_t *addend,
+                 uint64_t *out);
+/* SEAL: Evaluator::add */
+int pf_ct_add(pf_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *out);
+/* SEAL: Evaluator::transform_to_ntt_inplace / transform_from_ntt_inplace on ncts ciphertexts */
+int pf_ct_to_ntt(pf_engine *e, uint64_t *cts, uint64_t ncts);
+int pf_ct_from_ntt(pf_engine *e, uint64_t *cts, uint64_t ncts);
+/* SEAL: Evaluator::rotate_rows on a coefficient-form ciphertext (key for 3^step must be loaded) */
+int pf_rotate_rows(pf_engine *e, const uint64_t *ct, int step, uint64_t *out);
+/* rotated query set: cts[m][2][L][N] coefficient form -> rot[K][2][L][N] NTT form.  chain != 0 applies
+ * the step-1 key repeatedly, otherwise the key of every step 1..R-1 is used on the input. */
+int pf_rotate_query_set(pf_engine *e, const uint64_t *cts, int chain, uint64_t *rot);
+/* SEAL: BatchEncoder::encode of N slot values (mod t) */
+int pf_batch_encode(pf_engine *e, const uint64_t *values, uint64_t *plain);
+/* encode one block of nvec integer vectors xs[nvec][d]: diag[K][L][N], norm[L][N] (NTT form) */
+int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *diag, uint64_t *norm);
+/* SEAL wire format (compr_mode none) of a coefficient-form size-2 ciphertext */
+size_t pf_ct_serialized_size(pf_engine *e);
+int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written);
+int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, int *is_ntt, size_t *consumed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1476 @@
+// pf_engine.cu — engine and C ABI (include/prefhetch_b200.h) of the B200-native PreFHEtch search
+// hot path.  Host orchestration only: every arithmetic step runs in the sm_100a kernels of
+// pf_ntt.cuh / pf_mac.cuh / pf_keyswitch.cuh / pf_encode.cuh / pf_plain.cuh.  There is no CPU
+// fallback: without a CUDA device pf_engine_create fails with PF_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/prefhetch_b200.h"
+#include "pf_common.cuh"
+#include "pf_encode.cuh"
+#include "pf_host_math.h"
+#include "pf_keyswitch.cuh"
+#include "pf_mac.cuh"
+#include "pf_ntt.cuh"
+#include "pf_plain.cuh"
+
+namespace {
+
+thread_local std::string g_tls_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct GaloisKey {
+    DevBuf key;  // [L][2][k][N]
+    DevBuf perm; // u32[N]
+    u32 einv = 0;
+};
+
+struct BlockInfo {
+    long long vec_offset;
+    u32 nvec;
+    u32 list;
+};
+
+constexpr size_t SEAL_CT_HEADER = 16 + 32 + 1 + 8 * 5 + 16 + 8; // bytes before the data words
+
+} // namespace
+
+struct pf_engine {
+    pf_params prm{};
+    int N = 0, logn = 0, k = 0, L = 0;
+    u32 d = 0, d_pad = 0, m = 0, g = 0, dc = 0, R = 0, K = 0, C = 0;
+    u64 t = 0;
+    std::mutex mu;
+    mutable std::string err;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+
+    // device tables
+    DevBuf d_mods; // DevModulus[k+1] (index k = plain modulus)
+    DevBuf d_tw;   // Twiddle[k+1][2][N]
+    DevBuf d_inv_index_map;
+    std::vector<u64> h_q;
+    u64 q_mod_t = 0;
+    std::vector<u64> delta_mod_q, p_half_mod_q, p_inv_mod_q, p_inv_mod_q_sh;
+    u64 p_half = 0;
+    int max_prime_bits = 0;
+    bool mac_wide = false;
+
+    std::map<u32, GaloisKey> gkeys;
+
+    // index
+    bool has_index = false;
+    u64 nlist = 0, ntotal = 0;
+    std::vector<float> h_centroids;
+    std::vector<long long> h_list_offsets;
+    std::vector<long long> h_ids;
+    DevBuf d_centroids, d_ids, d_base_f32, d_base_u8, d_pos_of_id;
+    bool ids_are_rows = false;
+    std::vector<BlockInfo> blocks;            // local blocks
+    std::vector<long long> list_block_start;  // [nlist+1] into blocks (0 length for lists not owned)
+    DevBuf d_diag, d_norm;
+    size_t diag_block_words = 0, norm_block_words = 0;
+
+    // scratch
+    DevBuf s_x, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
+    DevBuf s_rot, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_qcts, s_out, s_tmp, s_plain,
+        s_encblocks;
+    PinBuf h_stage, h_stage2;
+
+    // timing
+    bool timing = false;
+    float t_ms[PF_T_COUNT] = {0};
+    uint64_t t_launch[PF_T_COUNT] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    std::vector<cudaEvent_t> event_pool;
+
+    int fail(int code, const char *fmt, ...) const {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        g_tls_error = buf;
+        return code;
+    }
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return e->fail(PF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                           __LINE__);                                                                    \
+    } while (0)
+
+// ---- timing -------------------------------------------------------------------------------
+struct PhaseTimer {
+    pf_engine *e;
+    int phase;
+    cudaEvent_t a = nullptr, b = nullptr;
+    uint64_t launches0;
+    PhaseTimer(pf_engine *e_, int phase_) : e(e_), phase(phase_), launches0(e_->launches) {
+        if (!e->timing) return;
+        auto get = [&]() {
+            cudaEvent_t ev;
+            if (!e->event_pool.empty()) {
+                ev = e->event_pool.back();
+                e->event_pool.pop_back();
+            } else {
+                cudaEventCreate(&ev);
+            }
+            return ev;
+        };
+        a = get();
+        b = get();
+        cudaEventRecord(a, e->stream);
+    }
+    ~PhaseTimer() {
+        e->t_launch[phase] += e->launches - launches0;
+        if (!e->timing) return;
+        cudaEventRecord(b, e->stream);
+        e->pending_events.push_back({phase, {a, b}});
+    }
+};
+
+void drain_events(pf_engine *e) {
+    for (auto &pe : e->pending_events) {
+        float ms = 0;
+        if (cudaEventSynchronize(pe.second.second) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess)
+            e->t_ms[pe.first] += ms;
+        e->event_pool.push_back(pe.second.first);
+        e->event_pool.push_back(pe.second.second);
+    }
+    e->pending_events.clear();
+}
+
+// ---- NTT launch helpers -------------------------------------------------------------------
+template <int LOGN>
+cudaError_t set_ntt_attrs() {
+    cudaError_t r;
+    const int smem = (int)NttCfg<LOGN>::SMEM;
+#define SETATTR(K)                                                                  \
+    r = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (r != cudaSuccess) return r;
+    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_PLAIN>));
+    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_LIFT>));
+    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
+    SETATTR((ntt_inv_kernel<LOGN>));
+#undef SETATTR
+    return cudaSuccess;
+}
+
+template <int LOGN>
+void launch_ntt_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
+    const size_t smem = NttCfg<LOGN>::SMEM;
+    const int nt = NttCfg<LOGN>::NT;
+    if (inverse)
+        ntt_inv_kernel<LOGN><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_PLAIN)
+        ntt_fwd_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_LIFT)
+        ntt_fwd_kernel<LOGN, NTT_IN_LIFT><<<grid, nt, smem, s>>>(p);
+    else
+        ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE><<<grid, nt, smem, s>>>(p);
+}
+
+void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) {
+    p.mods = e->d_mods.as<DevModulus>();
+    p.tw = e->d_tw.as<Twiddle>();
+    // gridDim.y/z limits: z <= 65535, y <= 65535
+    switch (e->logn) {
+    case 10: launch_ntt_t<10>(inmode, inverse, p, grid, e->stream); break;
+    case 11: launch_ntt_t<11>(inmode, inverse, p, grid, e->stream); break;
+    case 12: launch_ntt_t<12>(inmode, inverse, p, grid, e->stream); break;
+    case 13: launch_ntt_t<13>(inmode, inverse, p, grid, e->stream); break;
+    case 14: launch_ntt_t<14>(inmode, inverse, p, grid, e->stream); break;
+    }
+    e->launches++;
+}
+
+// transform `count` consecutive [L][N] polynomials (limb of polynomial y*L + x is x), in place or not
+void ntt_limbs(pf_engine *e, const u64 *in, u64 *out, size_t count, bool inverse) {
+    const size_t N = e->N;
+    size_t done = 0;
+    while (done < count) {
+        const size_t n = std::min<size_t>(count - done, 32768);
+        NttParams p{};
+        p.in = in + done * e->L * N;
+        p.out = out + done * e->L * N;
+        p.in_sx = p.out_sx = (long long)N;
+        p.in_sy = p.out_sy = (long long)(e->L * N);
+        for (int i = 0; i < e->L; i++) p.mod_map[i] = i;
+        launch_ntt(e, NTT_IN_PLAIN, inverse, p, dim3(e->L, (unsigned)n, 1));
+        done += n;
+    }
+}
+
+// ---- engine construction -------------------------------------------------------------------
+int build_tables(pf_engine *e) {
+    using pfh::minimal_primitive_root; using pfh::invmod; using pfh::shoup; using pfh::ratio128; using pfh::bitrev;
+    using pfh::big_mul_word; using pfh::big_div_word; using pfh::big_mod_word;
+    const int N = e->N, k = e->k, L = e->L, logn = e->logn;
+    std::vector<DevModulus> mods(k + 1);
+    std::vector<Twiddle> tw((size_t)(k + 1) * 2 * N);
+    for (int j = 0; j <= k; j++) {
+        const u64 q = (j == k) ? e->t : e->h_q[j];
+        const u64 psi = minimal_primitive_root(2ull * N, q);
+        if (!psi) return e->fail(PF_ERR_INVALID, "modulus %llu has no primitive 2N-th root", (unsigned long long)q);
+        const u64 psi_inv = invmod(psi, q), n_inv = invmod((u64)N % q, q);
+        DevModulus &m = mods[j];
+        m.q = q;
+        u64 r0, r1;
+        ratio128(q, r0, r1);
+        m.ratio0 = r0;
+        m.ratio1 = r1;
+        m.n_inv = n_inv;
+        m.n_inv_sh = shoup(n_inv, q);
+        Twiddle *f = tw.data() + (size_t)j * 2 * N, *inv = f + N;
+        u64 p = 1, ip = 1;
+        for (int i = 0; i < N; i++) {
+            const uint32_t r = bitrev((uint32_t)i, logn);
+            f[r].x = p;
+            f[r].y = shoup(p, q);
+            inv[r].x = ip;
+            inv[r].y = shoup(ip, q);
+            p = pfh::mulmod(p, psi, q);
+            ip = pfh::mulmod(ip, psi_inv, q);
+        }
+        m.inv_last_w = pfh::mulmod(inv[1].x, n_inv, q);
+        m.inv_last_w_sh = shoup(m.inv_last_w, q);
+        m.pad = 0;
+    }
+    CK(e->d_mods.ensure(mods.size() * sizeof(DevModulus)));
+    CK(cudaMemcpy(e->d_mods.p, mods.data(), mods.size() * sizeof(DevModulus), cudaMemcpyHostToDevice));
+    CK(e->d_tw.ensure(tw.size() * sizeof(Twiddle)));
+    CK(cudaMemcpy(e->d_tw.p, tw.data(), tw.size() * sizeof(Twiddle), cudaMemcpyHostToDevice));
+
+    // BatchEncoder index map (SEAL batchencoder.cpp) and its inverse
+    std::vector<u32> inv_map(N);
+    {
+        const u64 row = N >> 1, m2 = 2ull * N;
+        u64 pos = 1;
+        for (u64 i = 0; i < row; i++) {
+            const u64 i1 = (pos - 1) >> 1, i2 = (m2 - pos - 1) >> 1;
+            inv_map[bitrev((uint32_t)i1, logn)] = (u32)i;
+            inv_map[bitrev((uint32_t)i2, logn)] = (u32)(row | i);
+            pos = (pos * 3) & (m2 - 1);
+        }
+    }
+    CK(e->d_inv_index_map.ensure(N * sizeof(u32)));
+    CK(cudaMemcpy(e->d_inv_index_map.p, inv_map.data(), N * sizeof(u32), cudaMemcpyHostToDevice));
+
+    // BFV scaling constants: floor(Q/t) mod q_j, Q mod t
+    std::vector<u64> Q{1};
+    for (int j = 0; j < L; j++) big_mul_word(Q, e->h_q[j]);
+    std::vector<u64> quo = Q;
+    e->q_mod_t = big_div_word(quo, e->t);
+    e->delta_mod_q.resize(L);
+    for (int j = 0; j < L; j++) e->delta_mod_q[j] = big_mod_word(quo, e->h_q[j]);
+    // special prime constants
+    const u64 P = e->h_q[k - 1];
+    e->p_half = P >> 1;
+    e->p_half_mod_q.resize(L);
+    e->p_inv_mod_q.resize(L);
+    e->p_inv_mod_q_sh.resize(L);
+    for (int j = 0; j < L; j++) {
+        const u64 q = e->h_q[j];
+        e->p_half_mod_q[j] = e->p_half % q;
+        e->p_inv_mod_q[j] = invmod(P % q, q);
+        e->p_inv_mod_q_sh[j] = shoup(e->p_inv_mod_q[j], q);
+    }
+    return PF_OK;
+}
+
+u32 galois_elt_from_step(const pf_engine *e, int step) { // SEAL util/galois.cpp get_elt_from_step
+    const u32 n = (u32)e->N, m2 = 2 * n, row = n >> 1;
+    if (step == 0) return m2 - 1;
+    const u32 pos = (u32)(step < 0 ? -step : step);
+    if (pos >= row) return 0;
+    const u32 s = step < 0 ? row - pos : pos;
+    u64 x = 1;
+    for (u32 i = 0; i < s; i++) x = (x * 3) & (m2 - 1);
+    return (u32)x;
+}
+
+int set_galois_key_words(pf_engine *e, u32 elt, const u64 *words, bool device_src) {
+    const u32 N = (u32)e->N;
+    if (!(elt & 1) || elt >= 2 * N) return e->fail(PF_ERR_INVALID, "Galois element %u is not odd and < 2N", elt);
+    GaloisKey &gk = e->gkeys[elt];
+    const size_t words_n = (size_t)e->L * 2 * e->k * N;
+    CK(gk.key.ensure(words_n * 8));
+    CK(cudaMemcpyAsync(gk.key.p, words, words_n * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       e->stream));
+    std::vector<u32> perm(N); // SEAL GaloisTool::generate_table_ntt
+    for (u32 i = 0; i < N; i++) {
+        const u32 rev = pfh::bitrev(i, e->logn);
+        const u64 raw = ((u64)elt * (2ull * rev + 1)) >> 1;
+        perm[i] = pfh::bitrev((u32)(raw & (N - 1)), e->logn);
+    }
+    CK(gk.perm.ensure(N * sizeof(u32)));
+    CK(cudaMemcpyAsync(gk.perm.p, perm.data(), N * sizeof(u32), cudaMemcpyHostToDevice, e->stream));
+    // inverse of elt modulo 2N (elt is odd): Newton iteration on 2-adic inverse
+    u32 inv = elt;
+    for (int i = 0; i < 5; i++) inv *= 2 - elt * inv;
+    gk.einv = inv & (2 * N - 1);
+    CK(cudaStreamSynchronize(e->stream)); // perm is a stack vector
+    return PF_OK;
+}
+
+// ---- rotations ------------------------------------------------------------------------------
+// Run a batch of rotation jobs (already filled on the host) through the key-switch pipeline.
+int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs) {
+    const int L = e->L, N = e->N, k = e->k;
+    const size_t per_d = (size_t)L * (L + 1) * N, per_S = (size_t)2 * (L + 1) * N, per_W = (size_t)2 * L * N;
+    const size_t zmax = std::max<size_t>(1, std::min<size_t>(512, ((size_t)1 << 30) / ((per_d + per_S + per_W) * 8)));
+    CK(e->s_rotjobs.ensure(jobs.size() * sizeof(RotJob)));
+    CK(cudaMemcpyAsync(e->s_rotjobs.p, jobs.data(), jobs.size() * sizeof(RotJob), cudaMemcpyHostToDevice, e->stream));
+    const size_t zb = std::min(zmax, jobs.size());
+    CK(e->s_ks_d.ensure(zb * per_d * 8));
+    CK(e->s_ks_S.ensure(zb * per_S * 8));
+    CK(e->s_ks_W.ensure(zb * per_W * 8));
+    KsParams kp{};
+    kp.mods = e->d_mods.as<DevModulus>();
+    kp.d = e->s_ks_d.as<u64>();
+    kp.S = e->s_ks_S.as<u64>();
+    kp.W = e->s_ks_W.as<u64>();
+    kp.L = L;
+    kp.k = k;
+    kp.N = N;
+    kp.p_half = e->p_half;
+    for (int j = 0; j < L; j++) {
+        kp.p_half_mod_q[j] = e->p_half_mod_q[j];
+        kp.p_inv_mod_q[j] = e->p_inv_mod_q[j];
+        kp.p_inv_mod_q_sh[j] = e->p_inv_mod_q_sh[j];
+    }
+    for (size_t z0 = 0; z0 < jobs.size(); z0 += zb) {
+        const unsigned nz = (unsigned)std::min(zb, jobs.size() - z0);
+        const RotJob *dj = e->s_rotjobs.as<RotJob>() + z0;
+        kp.jobs = dj;
+        // 1. d[J][I] = NTT_I(sigma(c1)_J mod q_I): grid (I<L+1, J<L, z)
+        NttParams np{};
+        np.jobs = dj;
+        np.in_sy = N;
+        np.out = kp.d;
+        np.out_sx = N;
+        np.out_sy = (long long)(L + 1) * N;
+        np.out_sz = (long long)per_d;
+        for (int I = 0; I <= L; I++) np.mod_map[I] = (I == L) ? k - 1 : I;
+        for (int J = 0; J < L; J++) np.src_map[J] = J;
+        launch_ntt(e, NTT_IN_GALOIS_REDUCE, false, np, dim3(L + 1, L, nz));
+        // 2. S_c[I]
+        ks_accumulate_kernel<<<dim3(N / 512, L + 1, nz), 256, 0, e->stream>>>(kp);
+        e->launches++;
+        // 3. u_c = INTT_P(S_c[L]) in place: grid (1, 2, z)
+        NttParams ip{};
+        ip.in = kp.S + (size_t)L * N;
+        ip.out = kp.S + (size_t)L * N;
+        ip.in_sy = ip.out_sy = (long long)(L + 1) * N;
+        ip.in_sz = ip.out_sz = (long long)per_S;
+        ip.mod_map[0] = k - 1;
+        launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(1, 2, nz));
+        ks_moddown_prep_kernel<<<dim3(N / 256, 2, nz), 256, 0, e->stream>>>(kp);
+        e->launches++;
+        // NTT_j(W_c[j]) in place: grid (L, 2, z)
+        NttParams wp{};
+        wp.in = kp.W;
+        wp.out = kp.W;
+        wp.in_sx = wp.out_sx = N;
+        wp.in_sy = wp.out_sy = (long long)L * N;
+        wp.in_sz = wp.out_sz = (long long)per_W;
+        for (int j = 0; j < L; j++) wp.mod_map[j] = j;
+        launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
+        // 4. finish
+        ks_finish_kernel<<<dim3(N / 256, 2 * L, nz), 256, 0, e->stream>>>(kp);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+const GaloisKey *find_key(pf_engine *e, int step) {
+    auto it = e->gkeys.find(galois_elt_from_step(e, step));
+    return it == e->gkeys.end() ? nullptr : &it->second;
+}
+
+// rot[nq][K][2][L][N] (NTT form) from d_cts[nq][m][2][L][N] (coefficient form, device)
+int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int force_chain) {
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N, m = e->m, R = e->R, K = e->K;
+    {
+        PhaseTimer pt(e, PF_T_TONTT);
+        // r = 0 members: NTT of the input ciphertexts straight into rot[i][a*R]
+        for (size_t off = 0; off < nq * m; off += 16384) {
+            const size_t cnt = std::min<size_t>(16384, nq * m - off);
+            NttParams p{};
+            p.in = d_cts + off * ctw;
+            p.out = rot + (off / m) * K * ctw + (off % m) * R * ctw;
+            p.in_sx = p.out_sx = N;
+            p.in_sy = p.out_sy = (long long)L * N; // y = poly (0,1)
+            p.in_sz = (long long)ctw;
+            p.out_sz = (long long)(R * ctw);
+            for (int i = 0; i < L; i++) p.mod_map[i] = i;
+            // out stride per ciphertext is R*ctw only while (i, a) advance uniformly: a*R + i*K = (i*m+a)*R
+            launch_ntt(e, NTT_IN_PLAIN, false, p, dim3(L, 2, (unsigned)cnt));
+        }
+    }
+    if (R == 1) return PF_OK;
+    PhaseTimer pt(e, PF_T_ROTATE);
+    bool direct = !force_chain;
+    for (size_t r = 1; r < R && direct; r++) direct = find_key(e, (int)r) != nullptr;
+    if (!direct && !find_key(e, 1))
+        return e->fail(PF_ERR_STATE, "no usable Galois keys: need steps 1..%u or step 1", (unsigned)(R - 1));
+    std::vector<RotJob> jobs;
+    if (direct) {
+        jobs.reserve(nq * m * (R - 1));
+        for (size_t i = 0; i < nq; i++)
+            for (size_t a = 0; a < m; a++)
+                for (size_t r = 1; r < R; r++) {
+                    const GaloisKey *gk = find_key(e, (int)r);
+                    RotJob j{};
+                    j.c1_coef = d_cts + (i * m + a) * ctw + (size_t)L * N;
+                    j.c0_ntt = rot + (i * K + a * R) * ctw;
+                    j.key = gk->key.as<u64>();
+                    j.perm = gk->perm.as<u32>();
+                    j.out = rot + (i * K + a * R + r) * ctw;
+                    j.einv = gk->einv;
+                    jobs.push_back(j);
+                }
+        return run_rot_jobs(e, jobs);
+    }
+    // chain: rot_r = rotate(rot_{r-1}, 1); needs c1 of the previous member in coefficient form
+    const GaloisKey *gk = find_key(e, 1);
+    CK(e->s_c1coef.ensure(nq * m * (size_t)L * N * 8));
+    u64 *c1c = e->s_c1coef.as<u64>();
+    for (size_t r = 1; r < R; r++) {
+        jobs.clear();
+        for (size_t i = 0; i < nq; i++)
+            for (size_t a = 0; a < m; a++) {
+                RotJob j{};
+                const u64 *prev = rot + (i * K + a * R + r - 1) * ctw;
+                if (r == 1) {
+                    j.c1_coef = d_cts + (i * m + a) * ctw + (size_t)L * N;
+                } else {
+                    u64 *dst = c1c + (i * m + a) * (size_t)L * N;
+                    ntt_limbs(e, prev + (size_t)L * N, dst, 1, true);
+                    j.c1_coef = dst;
+                }
+                j.c0_ntt = prev;
+                j.key = gk->key.as<u64>();
+                j.perm = gk->perm.as<u32>();
+                j.out = rot + (i * K + a * R + r) * ctw;
+                j.einv = gk->einv;
+                jobs.push_back(j);
+            }
+        int rc = run_rot_jobs(e, jobs);
+        if (rc) return rc;
+    }
+    return PF_OK;
+}
+
+// ---- MAC launch -----------------------------------------------------------------------------
+template <int T, bool WIDE>
+void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    const size_t smem = (size_t)p.K * 2 * T * 8;
+    auto kern = mac_kernel<T, 2, 4, WIDE>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
+    e->launches++;
+}
+
+int mac_tile(const pf_engine *e) { return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64); }
+
+void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    const int T = mac_tile(e);
+    if (e->mac_wide) {
+        if (T == 256) launch_mac_t<256, true>(e, p, nchunks);
+        else if (T == 128) launch_mac_t<128, true>(e, p, nchunks);
+        else launch_mac_t<64, true>(e, p, nchunks);
+    } else {
+        if (T == 256) launch_mac_t<256, false>(e, p, nchunks);
+        else if (T == 128) launch_mac_t<128, false>(e, p, nchunks);
+        else launch_mac_t<64, false>(e, p, nchunks);
+    }
+}
+
+// Build the (query, block) pair list for this rank and the chunk table.  Returns PF_OK.
+struct PairPlan {
+    std::vector<long long> pair_block;
+    std::vector<MacChunk> chunks;
+    std::vector<uint64_t> results_per_query;
+    uint64_t useful = 0;
+};
+
+int plan_pairs(pf_engine *e, uint64_t nq, const int64_t *idx, uint32_t nprobe, PairPlan &pl) {
+    pl.results_per_query.assign(nq, 0);
+    std::vector<int> pair_query;
+    for (uint64_t i = 0; i < nq; i++)
+        for (uint32_t p = 0; p < nprobe; p++) {
+            const int64_t l = idx[i * nprobe + p];
+            if (l < 0 || (uint64_t)l >= e->nlist)
+                return e->fail(PF_ERR_INVALID, "list id %lld of query %llu out of range [0,%llu)", (long long)l,
+                               (unsigned long long)i, (unsigned long long)e->nlist);
+            for (long long b = e->list_block_start[l]; b < e->list_block_start[l + 1]; b++) {
+                pl.pair_block.push_back(b);
+                pair_query.push_back((int)i);
+                pl.results_per_query[i]++;
+                pl.useful += e->blocks[b].nvec;
+            }
+        }
+    const size_t P = pl.pair_block.size();
+    const int T = mac_tile(e);
+    const size_t ctas_per_chunk = (size_t)e->L * (e->N / T);
+    const size_t want_chunks = (4 * 148 + ctas_per_chunk - 1) / ctas_per_chunk;
+    size_t CH = std::max<size_t>(4, std::min<size_t>(64, P / std::max<size_t>(1, want_chunks)));
+    size_t s = 0;
+    while (s < P) {
+        size_t epos = s;
+        while (epos < P && pair_query[epos] == pair_query[s] && epos - s < CH) epos++;
+        pl.chunks.push_back(MacChunk{pair_query[s], (int)s, (int)(epos - s), 0});
+        s = epos;
+    }
+    return PF_OK;
+}
+
+// The device-resident step: rotations, MAC, inverse NTT.  d_out must hold P ciphertexts.
+int search_core(pf_engine *e, uint64_t nq, const u64 *d_cts, const PairPlan &pl, u64 *d_out) {
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N, P = pl.pair_block.size();
+    CK(e->s_rot.ensure(nq * e->K * ctw * 8));
+    u64 *rot = e->s_rot.as<u64>();
+    int rc = build_rotated_sets(e, d_cts, nq, rot, 0);
+    if (rc) return rc;
+    if (!P) return PF_OK;
+    CK(e->s_chunks.ensure(pl.chunks.size() * sizeof(MacChunk)));
+    CK(e->s_pairblock.ensure(P * sizeof(long long)));
+    CK(cudaMemcpyAsync(e->s_chunks.p, pl.chunks.data(), pl.chunks.size() * sizeof(MacChunk), cudaMemcpyHostToDevice,
+                       e->stream));
+    CK(cudaMemcpyAsync(e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long), cudaMemcpyHostToDevice,
+                       e->stream));
+    {
+        PhaseTimer pt(e, PF_T_MAC);
+        MacParams mp{};
+        mp.rot = rot;
+        mp.diag = e->d_diag.as<u64>();
+        mp.norm = e->d_norm.as<u64>();
+        mp.diag_sb = (long long)e->diag_block_words;
+        mp.diag_sk = (long long)L * N;
+        mp.norm_sb = (long long)e->norm_block_words;
+        mp.chunks = e->s_chunks.as<MacChunk>();
+        mp.pair_block = e->s_pairblock.as<long long>();
+        mp.out = d_out;
+        mp.mods = e->d_mods.as<DevModulus>();
+        mp.K = e->K;
+        mp.L = L;
+        mp.N = N;
+        launch_mac(e, mp, (unsigned)pl.chunks.size());
+    }
+    {
+        PhaseTimer pt(e, PF_T_INTT);
+        ntt_limbs(e, d_out, d_out, 2 * P, true);
+    }
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+void write_seal_header(uint8_t *p, uint64_t total) {
+    p[0] = 0x5E;
+    p[1] = 0xA1;
+    p[2] = 0x10;
+    p[3] = 4;
+    p[4] = 1;
+    p[5] = 0;
+    p[6] = p[7] = 0;
+    memcpy(p + 8, &total, 8);
+}
+
+// SEAL Ciphertext::save_members, compr_mode none (ciphertext.cpp, dynarray.h)
+void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t parms_id[4]) {
+    const uint64_t words = (uint64_t)2 * e->L * e->N, total = SEAL_CT_HEADER + words * 8;
+    write_seal_header(p, total);
+    p += 16;
+    memcpy(p, parms_id, 32);
+    p += 32;
+    *p++ = (uint8_t)(is_ntt ? 1 : 0);
+    uint64_t v = 2;
+    memcpy(p, &v, 8);
+    p += 8;
+    v = (uint64_t)e->N;
+    memcpy(p, &v, 8);
+    p += 8;
+    v = (uint64_t)e->L;
+    memcpy(p, &v, 8);
+    p += 8;
+    const double scale = 1.0;
+    memcpy(p, &scale, 8);
+    p += 8;
+    v = 1;
+    memcpy(p, &v, 8);
+    p += 8;
+    write_seal_header(p, 16 + 8 + words * 8);
+    p += 16;
+    memcpy(p, &words, 8);
+}
+
+// returns 0 on success; data_off = offset of the words, nlimbs = coeff_modulus_size
+int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_ntt, uint64_t parms_id[4],
+                    uint64_t *nlimbs, size_t *total_out) {
+    if (len < SEAL_CT_HEADER) return -1;
+    if (p[0] != 0x5E || p[1] != 0xA1 || p[2] != 0x10 || p[3] != 4) return -2;
+    if (p[5] != 0) return -3; // compressed streams are not accepted (zstd absent)
+    uint64_t total, size, n, cms, words;
+    memcpy(&total, p + 8, 8);
+    if (total > len) return -1;
+    memcpy(parms_id, p + 16, 32);
+    *is_ntt = p[48] ? 1 : 0;
+    memcpy(&size, p + 49, 8);
+    memcpy(&n, p + 57, 8);
+    memcpy(&cms, p + 65, 8);
+    const uint8_t *in = p + 89;
+    if (in[0] != 0x5E || in[1] != 0xA1 || in[5] != 0) return -2;
+    memcpy(&words, in + 16, 8);
+    if (size != 2 || n != (uint64_t)e->N || words != size * n * cms) return -4;
+    if (SEAL_CT_HEADER + words * 8 != total) return -4;
+    *nlimbs = cms;
+    *total_out = (size_t)total;
+    return 0;
+}
+
+} // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+const char *pf_last_error(const pf_engine *e) { return e ? e->err.c_str() : g_tls_error.c_str(); }
+
+int pf_engine_create(const pf_params *prm, pf_engine **out) {
+    if (!out) return PF_ERR_INVALID;
+    *out = nullptr;
+    auto tls_fail = [](int code, const std::string &msg) {
+        g_tls_error = msg;
+        return code;
+    };
+    if (!prm || prm->struct_size != sizeof(pf_params)) return tls_fail(PF_ERR_INVALID, "pf_params.struct_size mismatch");
+    const uint64_t N = prm->poly_degree;
+    if (N < 1024 || N > 16384 || (N & (N - 1))) return tls_fail(PF_ERR_INVALID, "poly_degree must be a power of two in [1024,16384]");
+    if (prm->num_primes < 2 || prm->num_primes > PF_MAX_PRIMES) return tls_fail(PF_ERR_INVALID, "num_primes must be in [2,16]");
+    if (!prm->world || prm->rank >= prm->world) return tls_fail(PF_ERR_INVALID, "rank/world invalid");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0 || prm->device < 0 || prm->device >= ndev)
+        return tls_fail(PF_ERR_CUDA, std::string("no usable CUDA device (this engine has no CPU path): ") +
+                                         (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range"));
+    pf_engine *e = new pf_engine();
+    e->prm = *prm;
+    e->N = (int)N;
+    e->logn = __builtin_ctzll(N);
+    e->k = (int)prm->num_primes;
+    e->L = e->k - 1;
+    e->t = prm->plain_modulus;
+    auto bail = [&](int code) {
+        g_tls_error = e->err;
+        delete e;
+        return code;
+    };
+    for (int j = 0; j < e->k; j++) {
+        const u64 q = prm->primes[j];
+        if (q >> 61 || q < 2 || (q - 1) % (2 * N) || !pfh::is_prime(q))
+            return bail(e->fail(PF_ERR_INVALID, "prime %d (%llu) must be a prime = 1 mod 2N below 2^61", j, (unsigned long long)q));
+        for (int i = 0; i < j; i++)
+            if (prm->primes[i] == q) return bail(e->fail(PF_ERR_INVALID, "primes must be distinct"));
+        e->h_q.push_back(q);
+        e->max_prime_bits = std::max(e->max_prime_bits, 64 - __builtin_clzll(q));
+    }
+    if (e->t < 2 || e->t >> 32 || (e->t - 1) % (2 * N) || !pfh::is_prime(e->t))
+        return bail(e->fail(PF_ERR_INVALID, "plain_modulus must be a prime = 1 mod 2N below 2^32"));
+    // layout
+    e->d = prm->dim;
+    u32 dp = 1;
+    while (dp < e->d) dp <<= 1;
+    e->d_pad = dp;
+    e->m = prm->query_cts ? prm->query_cts : 1;
+    e->g = prm->partial_g ? prm->partial_g : 1;
+    if (!e->d || (e->m & (e->m - 1)) || (e->g & (e->g - 1)) || dp % e->m || (dp / e->m) % e->g || dp / e->m > N / 2)
+        return bail(e->fail(PF_ERR_INVALID, "layout invalid: need m | d_pad, g | d_pad/m, d_pad/m <= N/2 (powers of two)"));
+    e->dc = dp / e->m;
+    e->R = e->dc / e->g;
+    e->K = e->m * e->R;
+    e->C = (u32)(N / e->g);
+    if (e->K > 128) return bail(e->fail(PF_ERR_INVALID, "K = m*d_pad/(m*g) = %u diagonals per block exceeds 128; raise g", e->K));
+    int logk = 0;
+    while ((1u << logk) < std::max<u32>(e->K, 2 * (u32)e->L)) logk++;
+    e->mac_wide = e->max_prime_bits + 1 + logk > 64;
+    if (e->max_prime_bits + 1 + 4 > 64)
+        return bail(e->fail(PF_ERR_INVALID, "coefficient primes above 59 bits are not supported by the key-switch accumulator"));
+    if (cudaSetDevice(prm->device) != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaSetDevice(%d) failed", prm->device));
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(e->fail(PF_ERR_CUDA, "cudaStreamCreate failed"));
+    e->own_stream = true;
+    cudaError_t ar = cudaSuccess;
+    switch (e->logn) {
+    case 10: ar = set_ntt_attrs<10>(); break;
+    case 11: ar = set_ntt_attrs<11>(); break;
+    case 12: ar = set_ntt_attrs<12>(); break;
+    case 13: ar = set_ntt_attrs<13>(); break;
+    case 14: ar = set_ntt_attrs<14>(); break;
+    }
+    if (ar != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ar)));
+    int rc = build_tables(e);
+    if (rc) return bail(rc);
+    *out = e;
+    return PF_OK;
+}
+
+void pf_engine_destroy(pf_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->prm.device);
+    cudaStreamSynchronize(e->stream);
+    drain_events(e);
+    for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+void *pf_engine_stream(pf_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int pf_engine_set_stream(pf_engine *e, void *s) {
+    if (!e) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    cudaStreamSynchronize(e->stream);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    e->stream = (cudaStream_t)s;
+    e->own_stream = false;
+    return PF_OK;
+}
+
+int pf_engine_synchronize(pf_engine *e) {
+    if (!e) return PF_ERR_INVALID;
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+int pf_timing_enable(pf_engine *e, int on) {
+    if (!e) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->timing = on != 0;
+    return PF_OK;
+}
+
+int pf_timing_read(pf_engine *e, float *ms, uint64_t *launches, int reset) {
+    if (!e) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaStreamSynchronize(e->stream));
+    drain_events(e);
+    for (int i = 0; i < PF_T_COUNT; i++) {
+        if (ms) ms[i] = e->t_ms[i];
+        if (launches) launches[i] = e->t_launch[i];
+        if (reset) {
+            e->t_ms[i] = 0;
+            e->t_launch[i] = 0;
+        }
+    }
+    return PF_OK;
+}
+
+uint64_t pf_launch_count(pf_engine *e) { return e ? e->launches : 0; }
+
+uint32_t pf_galois_elt_from_step(pf_engine *e, int step) { return e ? galois_elt_from_step(e, step) : 0; }
+
+// ---- index ------------------------------------------------------------------------------------
+int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const int64_t *list_offsets,
+                  const int64_t *ids, const float *vectors) {
+    if (!e || !nlist || !centroids || !list_offsets || !ids || !vectors) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const u32 d = e->d;
+    const int N = e->N, L = e->L;
+    const uint64_t ntotal = (uint64_t)list_offsets[nlist];
+    for (uint64_t l = 0; l < nlist; l++)
+        if (list_offsets[l + 1] < list_offsets[l] || list_offsets[0] != 0)
+            return e->fail(PF_ERR_INVALID, "list_offsets must start at 0 and be non-decreasing");
+    e->has_index = false;
+    e->nlist = nlist;
+    e->ntotal = ntotal;
+    e->h_centroids.assign(centroids, centroids + nlist * d);
+    e->h_list_offsets.assign(list_offsets, list_offsets + nlist + 1);
+    e->h_ids.assign(ids, ids + ntotal);
+    CK(e->d_centroids.ensure(nlist * d * sizeof(float)));
+    CK(cudaMemcpyAsync(e->d_centroids.p, centroids, nlist * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(e->d_ids.ensure(std::max<size_t>(8, ntotal * 8)));
+    CK(cudaMemcpyAsync(e->d_ids.p, ids, ntotal * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(e->d_base_f32.ensure(std::max<size_t>(4, ntotal * d * sizeof(float))));
+    CK(cudaMemcpyAsync(e->d_base_f32.p, vectors, ntotal * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    // id -> list-ordered position, when ids are exactly the base row numbers (ref: server_lib.cpp:154-156)
+    e->ids_are_rows = true;
+    {
+        std::vector<long long> pos(ntotal, -1);
+        for (uint64_t i = 0; i < ntotal && e->ids_are_rows; i++) {
+            const int64_t id = ids[i];
+            if (id < 0 || (uint64_t)id >= ntotal || pos[id] != -1) e->ids_are_rows = false;
+            else pos[id] = (long long)i;
+        }
+        if (e->ids_are_rows) {
+            CK(e->d_pos_of_id.ensure(std::max<size_t>(8, ntotal * 8)));
+            CK(cudaMemcpy(e->d_pos_of_id.p, pos.data(), ntotal * 8, cudaMemcpyHostToDevice));
+        }
+    }
+    // uint8 copy for the encoder; rejects non-integer / out-of-range values
+    CK(e->d_base_u8.ensure(std::max<size_t>(4, ntotal * d)));
+    CK(e->s_tmp.ensure(sizeof(int)));
+    CK(cudaMemsetAsync(e->s_tmp.p, 0, sizeof(int), e->stream));
+    if (ntotal) {
+        const size_t n = ntotal * d;
+        quantize_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_base_f32.as<float>(),
+                                                                            e->d_base_u8.as<unsigned char>(), n,
+                                                                            e->s_tmp.as<int>());
+        e->launches++;
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, e->s_tmp.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    const bool encodable = !bad;
+
+    // blocks of the lists this rank owns
+    e->blocks.clear();
+    e->list_block_start.assign(nlist + 1, 0);
+    for (uint64_t l = 0; l < nlist; l++) {
+        e->list_block_start[l] = (long long)e->blocks.size();
+        if (l % e->prm.world != e->prm.rank) continue;
+        const long long n = list_offsets[l + 1] - list_offsets[l];
+        for (long long o = 0; o < n; o += e->C)
+            e->blocks.push_back(BlockInfo{list_offsets[l] + o, (u32)std::min<long long>(e->C, n - o), (u32)l});
+    }
+    e->list_block_start[nlist] = (long long)e->blocks.size();
+    const size_t nb = e->blocks.size();
+    e->diag_block_words = (size_t)e->K * L * N;
+    e->norm_block_words = (size_t)L * N;
+    if (!encodable) {
+        // plaintext stages remain usable; the encrypted path needs integer data
+        e->blocks.clear();
+        e->list_block_start.assign(nlist + 1, 0);
+        e->d_diag.release();
+        e->d_norm.release();
+        e->has_index = true;
+        return e->fail(PF_ERR_INVALID, "base vectors are not integers in [0,255]: encrypted search disabled, plaintext stages loaded"), PF_OK;
+    }
+    CK(e->d_diag.ensure(std::max<size_t>(8, nb * e->diag_block_words * 8)));
+    CK(e->d_norm.ensure(std::max<size_t>(8, nb * e->norm_block_words * 8)));
+
+    // encode in batches of zb blocks
+    const size_t plain_words = (size_t)(e->K + 1) * N;
+    const size_t zb = std::max<size_t>(1, std::min<size_t>(nb ? nb : 1, ((size_t)256 << 20) / (plain_words * 8)));
+    CK(e->s_plain.ensure(zb * plain_words * 8));
+    CK(e->s_encblocks.ensure(std::max<size_t>(1, nb) * sizeof(EncodeBlock)));
+    {
+        std::vector<EncodeBlock> eb(nb);
+        for (size_t b = 0; b < nb; b++) eb[b] = EncodeBlock{e->blocks[b].vec_offset, e->blocks[b].nvec, 0};
+        if (nb) CK(cudaMemcpy(e->s_encblocks.p, eb.data(), nb * sizeof(EncodeBlock), cudaMemcpyHostToDevice));
+    }
+    for (size_t b0 = 0; b0 < nb; b0 += zb) {
+        const unsigned nz = (unsigned)std::min(zb, nb - b0);
+        EncodeParams ep{};
+        ep.base = e->d_base_u8.as<unsigned char>();
+        ep.blocks = e->s_encblocks.as<EncodeBlock>() + b0;
+        ep.inv_index_map = e->d_inv_index_map.as<u32>();
+        ep.plain = e->s_plain.as<u64>();
+        ep.t = e->t;
+        ep.N = N;
+        ep.d = (int)d;
+        ep.dc = (int)e->dc;
+        ep.R = (int)e->R;
+        ep.K = (int)e->K;
+        ep.g = (int)e->g;
+        encode_slots_kernel<<<dim3(N / 256, e->K + 1, nz), 256, 0, e->stream>>>(ep);
+        e->launches++;
+        // BatchEncoder::encode: inverse NTT mod t, in place, all K+1 plaintexts of every block
+        NttParams ip{};
+        ip.in = ip.out = e->s_plain.as<u64>();
+        ip.in_sy = ip.out_sy = N;
+        ip.in_sz = ip.out_sz = (long long)plain_words;
+        ip.mod_map[0] = e->k;
+        launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(1, e->K + 1, nz));
+        // diagonals: centred lift + forward NTT per limb
+        NttParams fp{};
+        fp.in = e->s_plain.as<u64>();
+        fp.in_sx = 0;
+        fp.in_sy = N;
+        fp.in_sz = (long long)plain_words;
+        fp.out = e->d_diag.as<u64>() + b0 * e->diag_block_words;
+        fp.out_sx = N;
+        fp.out_sy = (long long)L * N;
+        fp.out_sz = (long long)e->diag_block_words;
+        fp.lift_t = e->t;
+        fp.lift_thr = (e->t + 1) >> 1;
+        for (int i = 0; i < L; i++) fp.mod_map[i] = i;
+        launch_ntt(e, NTT_IN_LIFT, false, fp, dim3(L, e->K, nz));
+        // norms: BFV scaling variant, then forward NTT
+        ScaleParams sp{};
+        sp.plain = e->s_plain.as<u64>();
+        sp.plain_sz = (long long)plain_words;
+        sp.plain_off = (long long)e->K * N;
+        sp.out = e->d_norm.as<u64>() + b0 * e->norm_block_words;
+        sp.mods = e->d_mods.as<DevModulus>();
+        sp.t = e->t;
+        sp.q_mod_t = e->q_mod_t;
+        sp.half_t = (e->t + 1) >> 1;
+        for (int i = 0; i < L; i++) sp.delta_mod_q[i] = e->delta_mod_q[i];
+        sp.N = N;
+        sp.L = L;
+        scale_plain_kernel<<<dim3(N / 256, 1, nz), 256, 0, e->stream>>>(sp);
+        e->launches++;
+        ntt_limbs(e, sp.out, sp.out, nz, false);
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e->stream));
+    e->has_index = true;
+    return PF_OK;
+}
+
+int pf_get_index_info(pf_engine *e, pf_index_info *o) {
+    if (!e || !o) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    memset(o, 0, sizeof(*o));
+    o->nlist = e->nlist;
+    o->ntotal = e->ntotal;
+    o->nblocks_local = e->blocks.size();
+    uint64_t nb = 0;
+    if (e->has_index)
+        for (uint64_t l = 0; l < e->nlist; l++) {
+            const uint64_t n = (uint64_t)(e->h_list_offsets[l + 1] - e->h_list_offsets[l]);
+            nb += (n + e->C - 1) / e->C;
+        }
+    o->nblocks = nb;
+    o->db_bytes = e->blocks.size() * (e->diag_block_words + e->norm_block_words) * 8;
+    o->K = e->K;
+    o->C = e->C;
+    o->R = e->R;
+    o->d_pad = e->d_pad;
+    o->L = (uint32_t)e->L;
+    o->k = (uint32_t)e->k;
+    return PF_OK;
+}
+
+int pf_retrieve_centroids(pf_engine *e, float *out, uint64_t cap) {
+    if (!e || !out) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    if (cap < e->h_centroids.size()) return e->fail(PF_ERR_CAPACITY, "need %zu floats", e->h_centroids.size());
+    memcpy(out, e->h_centroids.data(), e->h_centroids.size() * sizeof(float));
+    return PF_OK;
+}
+
+// ---- stage 1 ------------------------------------------------------------------------------------
+int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprobe, int64_t *out_idx, float *out_dist) {
+    if (!e || !x || !out_idx) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    // ref: src/client/client_lib.cpp:96-99 throws when NPROBE exceeds the centroid count
+    if (!nprobe || nprobe > e->nlist) return e->fail(PF_ERR_INVALID, "Centroids count is not equal to NPROBE (nprobe %u, nlist %llu)", nprobe, (unsigned long long)e->nlist);
+    if (!nq) return PF_OK;
+    CK(cudaSetDevice(e->prm.device));
+    const u32 d = e->d;
+    const int nlist = (int)e->nlist;
+    PhaseTimer pt(e, PF_T_COARSE);
+    CK(e->s_x.ensure(nq * d * sizeof(float)));
+    CK(e->s_dist.ensure(nq * (size_t)nlist * sizeof(float)));
+    CK(e->s_keys.ensure(nq * (size_t)nlist * sizeof(u64)));
+    CK(e->s_idx.ensure(nq * nprobe * sizeof(long long)));
+    CK(e->s_outdist.ensure(nq * nprobe * sizeof(float)));
+    CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
+        const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
+        coarse_dist_kernel<<<dim3((nlist + 127) / 128, nqb), 128, d * sizeof(float), e->stream>>>(
+            e->s_x.as<float>() + q0 * d, e->d_centroids.as<float>(), e->s_dist.as<float>() + q0 * nlist, nlist, (int)d);
+        topk_select_kernel<<<nqb, 256, 0, e->stream>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
+                                                       e->s_idx.as<long long>() + q0 * nprobe,
+                                                       e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
+        e->launches += 2;
+    }
+    CK(cudaMemcpyAsync(out_idx, e->s_idx.p, nq * nprobe * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, e->s_outdist.p, nq * nprobe * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+// ---- stage 2, plaintext ---------------------------------------------------------------------------
+int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64_t *idx, uint32_t nprobe, float *dist,
+                          int64_t *labels, uint64_t cap, uint64_t *list_sizes, uint64_t *total) {
+    if (!e || !x || !idx || !list_sizes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    CK(cudaSetDevice(e->prm.device));
+    std::vector<ListJob> jobs;
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < nq; i++) {
+        uint64_t cnt = 0;
+        for (uint32_t p = 0; p < nprobe; p++) {
+            const int64_t l = idx[i * nprobe + p];
+            if (l < 0 || (uint64_t)l >= e->nlist)
+                return e->fail(PF_ERR_INVALID, "list id %lld out of range", (long long)l);
+            const long long n = e->h_list_offsets[l + 1] - e->h_list_offsets[l];
+            if (n > 0) jobs.push_back(ListJob{e->h_list_offsets[l], (long long)w, (int)n, (int)i});
+            w += (uint64_t)n;
+            cnt += (uint64_t)n;
+        }
+        list_sizes[i] = cnt;
+    }
+    if (total) *total = w;
+    if (w > cap || (w && (!dist || !labels))) return e->fail(PF_ERR_CAPACITY, "output needs %llu entries, capacity %llu", (unsigned long long)w, (unsigned long long)cap);
+    if (!w) return PF_OK;
+    const u32 d = e->d;
+    CK(e->s_x.ensure(nq * d * sizeof(float)));
+    CK(e->s_jobs.ensure(jobs.size() * sizeof(ListJob)));
+    CK(e->s_pl_dist.ensure(w * sizeof(float)));
+    CK(e->s_pl_labels.ensure(w * sizeof(long long)));
+    CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->s_jobs.p, jobs.data(), jobs.size() * sizeof(ListJob), cudaMemcpyHostToDevice, e->stream));
+    list_l2_kernel<<<(unsigned)jobs.size(), 128, d * sizeof(float), e->stream>>>(
+        e->s_x.as<float>(), e->d_base_f32.as<float>(), e->d_ids.as<long long>(), e->s_jobs.as<ListJob>(),
+        e->s_pl_dist.as<float>(), e->s_pl_labels.as<long long>(), (int)d, w);
+    e->launches++;
+    CK(cudaMemcpyAsync(dist, e->s_pl_dist.p, w * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(labels, e->s_pl_labels.p, w * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+int pf_precise_search(pf_engine *e, uint64_t nq, const float *x, const int64_t *ids, uint32_t nids, float *out) {
+    if (!e || !x || !ids || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    if (!e->ids_are_rows) return e->fail(PF_ERR_STATE, "index ids are not base row numbers 0..ntotal-1");
+    if (!nq || !nids) return PF_OK;
+    CK(cudaSetDevice(e->prm.device));
+    const u32 d = e->d;
+    CK(e->s_x.ensure(nq * d * sizeof(float)));
+    CK(e->s_ids.ensure(nq * nids * sizeof(long long)));
+    CK(e->s_pl_dist.ensure(nq * nids * sizeof(float)));
+    CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->s_ids.p, ids, nq * nids * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    precise_l2_kernel<<<dim3((nids + 127) / 128, (unsigned)nq), 128, d * sizeof(float), e->stream>>>(
+        e->s_x.as<float>(), e->d_base_f32.as<float>(), e->d_pos_of_id.as<long long>(), e->s_ids.as<long long>(),
+        e->s_pl_dist.as<float>(), (int)d, (int)nids, (long long)e->ntotal);
+    e->launches++;
+    CK(cudaMemcpyAsync(out, e->s_pl_dist.p, nq * nids * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+// ---- Galois keys ------------------------------------------------------------------------------------
+int pf_set_galois_key(pf_engine *e, uint32_t elt, const uint64_t *words) {
+    if (!e || !words) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    return set_galois_key_words(e, elt, (const u64 *)words, false);
+}
+
+// SEAL KSwitchKeys::save_members inside a Serialization::Save envelope (kswitchkeys.h), compr none
+int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
+    if (!e || !bytes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    if (len < 16 + 32 + 8 || bytes[0] != 0x5E || bytes[1] != 0xA1 || bytes[5] != 0)
+        return e->fail(PF_ERR_FORMAT, "not an uncompressed SEAL stream");
+    uint64_t total;
+    memcpy(&total, bytes + 8, 8);
+    if (total > len) return e->fail(PF_ERR_FORMAT, "truncated GaloisKeys stream");
+    size_t off = 16 + 32;
+    uint64_t dim1;
+    memcpy(&dim1, bytes + off, 8);
+    off += 8;
+    const size_t key_ct_words = (size_t)2 * e->k * e->N;
+    std::vector<u64> words((size_t)e->L * key_ct_words);
+    for (uint64_t index = 0; index < dim1; index++) {
+        if (off + 8 > total) return e->fail(PF_ERR_FORMAT, "truncated GaloisKeys stream");
+        uint64_t dim2;
+        memcpy(&dim2, bytes + off, 8);
+        off += 8;
+        if (!dim2) continue;
+        if (dim2 != (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "key %llu has %llu parts, expected %d", (unsigned long long)index, (unsigned long long)dim2, e->L);
+        for (uint64_t j = 0; j < dim2; j++) {
+            int is_ntt;
+            uint64_t pid[4], cms;
+            size_t ctotal;
+            if (parse_ct_prefix(e, bytes + off, total - off, &is_ntt, pid, &cms, &ctotal) || cms != (uint64_t)e->k || !is_ntt)
+                return e->fail(PF_ERR_FORMAT, "malformed key ciphertext (index %llu part %llu)", (unsigned long long)index, (unsigned long long)j);
+            memcpy(words.data() + j * key_ct_words, bytes + off + SEAL_CT_HEADER, key_ct_words * 8);
+            off += ctotal;
+        }
+        int rc = set_galois_key_words(e, (u32)(2 * index + 1), words.data(), false);
+        if (rc) return rc;
+    }
+    return PF_OK;
+}
+
+// ---- stage 2, encrypted -------------------------------------------------------------------------------
+int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, const int64_t *idx, uint32_t nprobe,
+                     uint64_t *d_out, uint64_t cap_results, uint64_t *results_per_query, pf_search_stats *stats) {
+    if (!e || !d_query_cts || !idx) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index || (!e->d_diag.p && e->ntotal)) return e->fail(PF_ERR_STATE, "no encodable index loaded");
+    CK(cudaSetDevice(e->prm.device));
+    PairPlan pl;
+    int rc = plan_pairs(e, nq, idx, nprobe, pl);
+    if (rc) return rc;
+    const uint64_t P = pl.pair_block.size();
+    if (stats) {
+        stats->nresults = P;
+        stats->out_bytes = P * 2ull * e->L * e->N * 8;
+        stats->useful_distances = pl.useful;
+        stats->slot_distances = P * e->C;
+    }
+    if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
+    if (P > cap_results || (P && !d_out)) return e->fail(PF_ERR_CAPACITY, "need room for %llu result ciphertexts, capacity %llu", (unsigned long long)P, (unsigned long long)cap_results);
+    return search_core(e, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out);
+}
+
+int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
+                              const int64_t *idx, uint32_t nprobe, uint8_t *out_cts, uint64_t out_cap,
+                              uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
+                              int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
+                              pf_search_stats *stats) {
+    if (!e || !query_cts || !ct_offsets || !idx) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index || (!e->d_diag.p && e->ntotal)) return e->fail(PF_ERR_STATE, "no encodable index loaded");
+    CK(cudaSetDevice(e->prm.device));
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N, ncts = nq * e->m;
+    PairPlan pl;
+    int rc = plan_pairs(e, nq, idx, nprobe, pl);
+    if (rc) return rc;
+    const uint64_t P = pl.pair_block.size();
+    const size_t ct_bytes = SEAL_CT_HEADER + ctw * 8;
+    // labels / sizes of the owned probed lists (same packing as pf_search_lists_plain)
+    uint64_t nlabels = 0;
+    for (uint64_t i = 0; i < nq; i++) {
+        uint64_t cnt = 0;
+        for (uint32_t p = 0; p < nprobe; p++) {
+            const int64_t l = idx[i * nprobe + p];
+            const bool owned = (uint64_t)l % e->prm.world == e->prm.rank;
+            const uint64_t n = owned ? (uint64_t)(e->h_list_offsets[l + 1] - e->h_list_offsets[l]) : 0;
+            if (probed_sizes) probed_sizes[i * nprobe + p] = n;
+            if (labels && nlabels + n <= label_cap)
+                memcpy(labels + nlabels, e->h_ids.data() + e->h_list_offsets[l], n * sizeof(int64_t));
+            nlabels += n;
+            cnt += n;
+        }
+        if (list_sizes) list_sizes[i] = cnt;
+    }
+    if (stats) {
+        stats->nresults = P;
+        stats->out_bytes = P * ct_bytes;
+        stats->useful_distances = pl.useful;
+        stats->slot_distances = P * e->C;
+    }
+    if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
+    if (P > max_results || P * ct_bytes > out_cap || (labels && nlabels > label_cap))
+        return e->fail(PF_ERR_CAPACITY, "need %llu results / %llu bytes / %llu labels", (unsigned long long)P, (unsigned long long)(P * ct_bytes), (unsigned long long)nlabels);
+    // parse + upload the query ciphertexts
+    CK(e->s_qcts.ensure(std::max<size_t>(8, ncts * ctw * 8)));
+    uint64_t parms_id[4] = {0, 0, 0, 0};
+    for (size_t c = 0; c < ncts; c++) {
+        const uint8_t *src = query_cts + ct_offsets[c];
+        const size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
+        int is_ntt;
+        uint64_t cms;
+        size_t total;
+        const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
+        if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is compressed; save with compr_mode_type::none", c);
+        if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
+        if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
+        CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, src + SEAL_CT_HEADER, ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    CK(e->s_out.ensure(std::max<size_t>(8, P * ctw * 8)));
+    rc = search_core(e, nq, e->s_qcts.as<u64>(), pl, e->s_out.as<u64>());
+    if (rc) return rc;
+    // serialize: header per result, words straight from the device into the stream
+    for (uint64_t r = 0; r < P; r++) {
+        uint8_t *dst = out_cts + r * ct_bytes;
+        write_ct_prefix(e, dst, 0, parms_id);
+        CK(cudaMemcpyAsync(dst + SEAL_CT_HEADER, e->s_out.as<u64>() + r * ctw, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+        if (result_offsets) result_offsets[r] = r * ct_bytes;
+    }
+    if (result_offsets) result_offsets[P] = P * ct_bytes;
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+// ---- primitives -----------------------------------------------------------------------------------------
+static int ntt_host(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t *limb, bool inverse) {
+    if (!e || !polys || !limb) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t N = e->N;
+    CK(e->s_tmp.ensure(std::max<size_t>(8, npoly * N * 8)));
+    CK(cudaMemcpyAsync(e->s_tmp.p, polys, npoly * N * 8, cudaMemcpyHostToDevice, e->stream));
+    for (uint64_t i = 0; i < npoly; i++) {
+        const int li = limb[i] < 0 ? e->k : limb[i];
+        if (li > e->k) return e->fail(PF_ERR_INVALID, "limb index %d out of range", limb[i]);
+        NttParams p{};
+        p.in = p.out = e->s_tmp.as<u64>() + i * N;
+        p.mod_map[0] = li;
+        launch_ntt(e, NTT_IN_PLAIN, inverse, p, dim3(1, 1, 1));
+    }
+    CK(cudaMemcpyAsync(polys, e->s_tmp.p, npoly * N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_ntt_forward(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t *limb) { return ntt_host(e, polys, npoly, limb, false); }
+int pf_ntt_inverse(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t *limb) { return ntt_host(e, polys, npoly, limb, true); }
+
+static int ct_ntt_host(pf_engine *e, uint64_t *cts, uint64_t ncts, bool inverse) {
+    if (!e || !cts) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t ctw = (size_t)2 * e->L * e->N;
+    CK(e->s_tmp.ensure(std::max<size_t>(8, ncts * ctw * 8)));
+    CK(cudaMemcpyAsync(e->s_tmp.p, cts, ncts * ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    ntt_limbs(e, e->s_tmp.as<u64>(), e->s_tmp.as<u64>(), 2 * ncts, inverse);
+    CK(cudaMemcpyAsync(cts, e->s_tmp.p, ncts * ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+int pf_ct_to_ntt(pf_engine *e, uint64_t *cts, uint64_t ncts) { return ct_ntt_host(e, cts, ncts, false); }
+int pf_ct_from_ntt(pf_engine *e, uint64_t *cts, uint64_t ncts) { return ct_ntt_host(e, cts, ncts, true); }
+
+int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_t K, const uint64_t *addend, uint64_t *out) {
+    if (!e || !cts || !pts || !out || !K) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (K != e->K) return e->fail(PF_ERR_INVALID, "K must equal the engine layout's K = %u", e->K);
+    CK(cudaSetDevice(e->prm.device));
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N, ptw = (size_t)L * N;
+    DevBuf dc, dp, dn, dout, dch, dpb;
+    CK(dc.ensure(K * ctw * 8));
+    CK(dp.ensure(K * ptw * 8));
+    CK(dn.ensure(ptw * 8));
+    CK(dout.ensure(ctw * 8));
+    CK(dch.ensure(sizeof(MacChunk)));
+    CK(dpb.ensure(8));
+    CK(cudaMemcpyAsync(dc.p, cts, K * ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(dp.p, pts, K * ptw * 8, cudaMemcpyHostToDevice, e->stream));
+    if (addend) CK(cudaMemcpyAsync(dn.p, addend, ptw * 8, cudaMemcpyHostToDevice, e->stream));
+    const MacChunk ch{0, 0, 1, 0};
+    const long long pb = 0;
+    CK(cudaMemcpyAsync(dch.p, &ch, sizeof(ch), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(dpb.p, &pb, 8, cudaMemcpyHostToDevice, e->stream));
+    MacParams mp{};
+    mp.rot = dc.as<u64>();
+    mp.diag = dp.as<u64>();
+    mp.norm = addend ? dn.as<u64>() : nullptr;
+    mp.diag_sb = (long long)(K * ptw);
+    mp.diag_sk = (long long)ptw;
+    mp.norm_sb = (long long)ptw;
+    mp.chunks = dch.as<MacChunk>();
+    mp.pair_block = dpb.as<long long>();
+    mp.out = dout.as<u64>();
+    mp.mods = e->d_mods.as<DevModulus>();
+    mp.K = (int)K;
+    mp.L = L;
+    mp.N = N;
+    launch_mac(e, mp, 1);
+    CK(cudaMemcpyAsync(out, dout.p, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_ct_add(pf_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    if (!e || !a || !b || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t ctw = (size_t)2 * e->L * e->N;
+    CK(e->s_tmp.ensure(3 * ctw * 8));
+    u64 *da = e->s_tmp.as<u64>(), *db = da + ctw, *dc = db + ctw;
+    CK(cudaMemcpyAsync(da, a, ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(db, b, ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    ct_add_kernel<<<dim3(e->N / 256, 2 * e->L), 256, 0, e->stream>>>(da, db, dc, e->d_mods.as<DevModulus>(), e->L, e->N);
+    e->launches++;
+    CK(cudaMemcpyAsync(out, dc, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_rotate_rows(pf_engine *e, const uint64_t *ct, int step, uint64_t *out) {
+    if (!e || !ct || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const GaloisKey *gk = find_key(e, step);
+    if (!gk) return e->fail(PF_ERR_STATE, "no Galois key for step %d", step);
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N;
+    CK(e->s_tmp.ensure(3 * ctw * 8));
+    u64 *din = e->s_tmp.as<u64>(), *dntt = din + ctw, *dout = dntt + ctw;
+    CK(cudaMemcpyAsync(din, ct, ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    ntt_limbs(e, din, dntt, 2, false);
+    std::vector<RotJob> jobs(1);
+    jobs[0].c1_coef = din + (size_t)L * N;
+    jobs[0].c0_ntt = dntt;
+    jobs[0].key = gk->key.as<u64>();
+    jobs[0].perm = gk->perm.as<u32>();
+    jobs[0].out = dout;
+    jobs[0].einv = gk->einv;
+    int rc = run_rot_jobs(e, jobs);
+    if (rc) return rc;
+    ntt_limbs(e, dout, dout, 2, true); // SEAL returns BFV ciphertexts in coefficient form
+    CK(cudaMemcpyAsync(out, dout, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_rotate_query_set(pf_engine *e, const uint64_t *cts, int chain, uint64_t *rot) {
+    if (!e || !cts || !rot) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t ctw = (size_t)2 * e->L * e->N;
+    CK(e->s_qcts.ensure(e->m * ctw * 8));
+    CK(e->s_rot.ensure(e->K * ctw * 8));
+    CK(cudaMemcpyAsync(e->s_qcts.p, cts, e->m * ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    int rc = build_rotated_sets(e, e->s_qcts.as<u64>(), 1, e->s_rot.as<u64>(), chain);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(rot, e->s_rot.p, e->K * ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_batch_encode(pf_engine *e, const uint64_t *values, uint64_t *plain) {
+    if (!e || !values || !plain) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t N = e->N;
+    CK(e->s_tmp.ensure(2 * N * 8));
+    u64 *dv = e->s_tmp.as<u64>(), *dp = dv + N;
+    CK(cudaMemcpyAsync(dv, values, N * 8, cudaMemcpyHostToDevice, e->stream));
+    slot_scatter_kernel<<<(unsigned)(N / 256), 256, 0, e->stream>>>(dv, e->d_inv_index_map.as<u32>(), dp);
+    e->launches++;
+    NttParams p{};
+    p.in = p.out = dp;
+    p.mod_map[0] = e->k;
+    launch_ntt(e, NTT_IN_PLAIN, true, p, dim3(1, 1, 1));
+    CK(cudaMemcpyAsync(plain, dp, N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
+int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *diag, uint64_t *norm) {
+    if (!e || !xs || !diag || !norm) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    if (nvec > e->C) return e->fail(PF_ERR_INVALID, "block holds at most %u vectors", e->C);
+    // a one-list, one-block index built through the same kernels as pf_load_index
+    const u32 d = e->d;
+    std::vector<float> v((size_t)std::max<u32>(nvec, 1) * d, 0.f), cent(d, 0.f);
+    for (size_t i = 0; i < (size_t)nvec * d; i++) v[i] = (float)xs[i];
+    std::vector<int64_t> ids(std::max<u32>(nvec, 1)), off{0, (int64_t)nvec};
+    for (u32 i = 0; i < nvec; i++) ids[i] = i;
+    pf_params p2 = e->prm;
+    p2.rank = 0;
+    p2.world = 1;
+    pf_engine *tmp = nullptr;
+    int rc = pf_engine_create(&p2, &tmp);
+    if (rc) return e->fail(rc, "%s", pf_last_error(nullptr));
+    rc = pf_load_index(tmp, 1, cent.data(), off.data(), ids.data(), v.data());
+    if (rc == PF_OK && !tmp->d_diag.p) rc = tmp->fail(PF_ERR_INVALID, "vectors must be integers in [0,255]");
+    if (rc == PF_OK && nvec) {
+        cudaMemcpy(diag, tmp->d_diag.p, tmp->diag_block_words * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(norm, tmp->d_norm.p, tmp->norm_block_words * 8, cudaMemcpyDeviceToHost);
+    } else if (rc == PF_OK) {
+        memset(diag, 0, tmp->diag_block_words * 8);
+        memset(norm, 0, tmp->norm_block_words * 8);
+    }
+    if (rc) e->fail(rc, "%s", pf_last_error(tmp));
+    pf_engine_destroy(tmp);
+    return rc;
+}
+
+size_t pf_ct_serialized_size(pf_engine *e) { return e ? SEAL_CT_HEADER + (size_t)2 * e->L * e->N * 8 : 0; }
+
+int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written) {
+    if (!e || !ct || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    const size_t need = pf_ct_serialized_size(e);
+    if (written) *written = need;
+    if (cap < need) return e->fail(PF_ERR_CAPACITY, "need %zu bytes", need);
+    const uint64_t pid[4] = {0, 0, 0, 0};
+    write_ct_prefix(e, out, is_ntt, pid);
+    memcpy(out + SEAL_CT_HEADER, ct, need - SEAL_CT_HEADER);
+    return PF_OK;
+}
+
+int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, int *is_ntt, size_t *consumed) {
+    if (!e || !in || !ct) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    int ntt;
+    uint64_t pid[4], cms;
+    size_t total;
+    const int pr = parse_ct_prefix(e, in, len, &ntt, pid, &cms, &total);
+    if (pr || cms != (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "malformed ciphertext (code %d)", pr);
+    memcpy(ct, in + SEAL_CT_HEADER, total - SEAL_CT_HEADER);
+    if (is_ntt) *is_ntt = ntt;
+    if (consumed) *consumed = total;
+    return PF_OK;
+}
+
+} // extern "C"

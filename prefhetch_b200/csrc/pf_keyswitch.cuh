@@ -1,0 +1,99 @@
+// pf_keyswitch.cuh — Galois automorphism + hybrid key switching with one special prime, restating
+// SEAL 4.1 Evaluator::apply_galois_inplace / switch_key_inplace (BFV branch) so that the rotated
+// ciphertext is bit-identical to SEAL's, delivered directly in NTT form for the MAC:
+//   1. d[J][I]   = NTT_I( sigma(c1)_J mod q_I )            (pf_ntt.cuh, NTT_IN_GALOIS_REDUCE)
+//   2. S_c[I]    = sum_J d[J][I] (.) key_J[c][I]            (ks_accumulate_kernel, lazy sums)
+//   3. u_c       = INTT_P(S_c[P]);  W_c[j] = ((u_c + P/2) mod P mod q_j) - (P/2 mod q_j)
+//   4. out_c[j]  = (S_c[j] - NTT_j(W_c[j])) * P^{-1}  (+ sigma_ntt(c0)[j] for c = 0)
+// SEAL performs step 4 in coefficient form; doing it in NTT form is the same value because the
+// NTT is linear and every operation is exact mod q_j.
+#pragma once
+#include "pf_common.cuh"
+#include "pf_mac.cuh"
+#include "pf_ntt.cuh"
+
+struct KsParams {
+    const RotJob *jobs;
+    const DevModulus *mods;
+    u64 *d;   // [z][L][L+1][N]
+    u64 *S;   // [z][2][L+1][N]
+    u64 *W;   // [z][2][L][N]
+    int L, k, N;
+    u64 p_half;
+    u64 p_half_mod_q[PF_NTT_MAXMAP];
+    u64 p_inv_mod_q[PF_NTT_MAXMAP], p_inv_mod_q_sh[PF_NTT_MAXMAP];
+};
+
+// grid (N/512, L+1, z); thread = 2 coefficients of output limb I, both key components
+__global__ void __launch_bounds__(256) ks_accumulate_kernel(const KsParams p) {
+    const int I = blockIdx.y, z = blockIdx.z, L = p.L, N = p.N;
+    const int ki = (I == L) ? p.k - 1 : I;
+    const DevModulus m = p.mods[ki];
+    const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
+    const RotJob job = p.jobs[z];
+    LazyAcc a00, a01, a10, a11;
+    lazy_zero(a00);
+    lazy_zero(a01);
+    lazy_zero(a10);
+    lazy_zero(a11);
+    const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
+    for (int J = 0; J < L; J++) {
+        const ulonglong2 dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
+        const u64 *kj = job.key + (size_t)J * 2 * p.k * N;
+        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
+        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(p.k + ki) * N) + c2);
+        lazy_mac(a00, dv.x, k0.x);
+        lazy_mac(a01, dv.y, k0.y);
+        lazy_mac(a10, dv.x, k1.x);
+        lazy_mac(a11, dv.y, k1.y);
+    }
+    u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
+    ulonglong2 r0, r1;
+    r0.x = lazy_reduce(a00, m);
+    r0.y = lazy_reduce(a01, m);
+    r1.x = lazy_reduce(a10, m);
+    r1.y = lazy_reduce(a11, m);
+    reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
+    reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
+}
+
+// after INTT_P of S_c[L] (in place): W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).  grid (N/256, 2, z)
+__global__ void __launch_bounds__(256) ks_moddown_prep_kernel(const KsParams p) {
+    const int c = blockIdx.y, z = blockIdx.z, L = p.L, N = p.N;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const DevModulus mp = p.mods[p.k - 1];
+    const u64 u = p.S[((size_t)z * 2 + c) * (L + 1) * N + (size_t)L * N + i];
+    const u64 v = barrett64(u + p.p_half, mp.q, mp.ratio1);
+    for (int j = 0; j < L; j++) {
+        const DevModulus mj = p.mods[j];
+        const u64 w = submod(barrett64(v, mj.q, mj.ratio1), p.p_half_mod_q[j], mj.q);
+        p.W[(((size_t)z * 2 + c) * L + j) * N + i] = w;
+    }
+}
+
+// out_c[j] = (S_c[j] - Wntt_c[j]) * P^{-1} (+ c0_ntt[j][perm] for c = 0).  grid (N/256, 2*L, z)
+__global__ void __launch_bounds__(256) ks_finish_kernel(const KsParams p) {
+    const int c = blockIdx.y / p.L, j = blockIdx.y % p.L, z = blockIdx.z, L = p.L, N = p.N;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const RotJob job = p.jobs[z];
+    const u64 q = p.mods[j].q;
+    const u64 s = p.S[((size_t)z * 2 + c) * (L + 1) * N + (size_t)j * N + i];
+    const u64 w = p.W[(((size_t)z * 2 + c) * L + j) * N + i];
+    u64 r = mul_shoup(submod(s, w, q), p.p_inv_mod_q[j], p.p_inv_mod_q_sh[j], q);
+    if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * N + job.perm[i]], q);
+    job.out[((size_t)c * L + j) * N + i] = r;
+}
+
+// NTT-domain Galois permutation of whole polynomials: out[y][i] = in[y][perm[i]].  grid (N/256, npoly)
+__global__ void __launch_bounds__(256) galois_ntt_perm_kernel(const u64 *in, const u32 *perm, u64 *out, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    out[(size_t)blockIdx.y * N + i] = in[(size_t)blockIdx.y * N + perm[i]];
+}
+
+// element-wise ciphertext add: limb of polynomial y is y % L.  grid (N/256, 2*L)
+__global__ void __launch_bounds__(256) ct_add_kernel(const u64 *a, const u64 *b, u64 *out, const DevModulus *mods,
+                                                     int L, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const size_t o = (size_t)blockIdx.y * N + i;
+    out[o] = addmod(a[o], b[o], mods[blockIdx.y % L].q);
+}

@@ -1,0 +1,52 @@
+"""CPU checks of the boundary: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/prefhetch_b200.h declares.  No compute calls (no GPU here)."""
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from prefhetch_b200 import _capi, build
+    build.build()
+    return _capi.load()
+
+
+def test_header_symbols_exported(lib):
+    from prefhetch_b200 import _capi
+    hdr = (ROOT / "include" / "prefhetch_b200.h").read_text()
+    declared = set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pf_abi_version() == 1
+
+
+def test_no_cpu_fallback(lib):
+    """without a CUDA device the engine refuses to exist (PF_ERR_CUDA), it never computes on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import prefhetch_b200 as pf
+    with pytest.raises(pf.PfError) as ei:
+        pf.Engine(128)
+    assert ei.value.code == 2 and "no CPU path" in str(ei.value)
+
+
+def test_product_does_not_touch_oracle():
+    """the product tree must not import, link or execute anything under oracle/"""
+    for p in (ROOT / "prefhetch_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".cpp"):
+            txt = p.read_text()
+            assert not re.search(r"pf_oracle|import\s+oracle|from\s+oracle|#include\s+\"[^\"]*oracle|libpf_oracle", txt), p
+
+
+def test_built_for_sm_100a():
+    import subprocess
+    so = ROOT / "prefhetch_b200" / "libprefhetch_b200.so"
+    out = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -65,3 +65,45 @@ def build_ivf(base: np.ndarray, centroids: np.ndarray):
     offsets = np.zeros(centroids.shape[0] + 1, dtype=np.int64)
     np.cumsum(counts, out=offsets[1:])
     return offsets, order.astype(np.int64), np.ascontiguousarray(base[order])
+
+
+class OracleClient:
+    """Client side of the protocol (keygen / encrypt / decrypt), played by the CPU oracle in tests.
+    A real deployment uses Microsoft SEAL here; the server never sees these secrets."""
+
+    def __init__(self, oracle, n, primes, t, d, m, g, seed=2025):
+        self.o = oracle
+        self.ctx = oracle.Context(n, primes, t)
+        self.lay = oracle.LayoutPlan(n, d, m, g)
+        self.sk = self.ctx.keygen(seed)
+        self.seed = seed
+        self.keys = {}
+
+    def galois_key(self, step):
+        if step not in self.keys:
+            self.keys[step] = self.ctx.galois_keygen(self.sk, self.ctx.galois_elt(step), self.seed + 1000 + step)
+        return self.keys[step]
+
+    def step_keys(self):
+        return [self.galois_key(r) for r in range(1, self.lay.R)]
+
+    def encrypt_query(self, q, seed):
+        """-> [m][2][L][n] coefficient form"""
+        qi = np.asarray(q).astype(np.int64)
+        return np.stack([self.ctx.encrypt(self.sk, self.ctx.encode(self.lay.query_slots(self.ctx.t, qi, a)), seed + a)
+                         for a in range(self.lay.m)])
+
+    def serialize_queries(self, cts):
+        """cts [nq][m][2][L][n] -> (blob uint8, offsets)"""
+        blobs = [self.ctx.ct_save(ct) for q in cts for ct in q]
+        offs = np.zeros(len(blobs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in blobs])
+        return np.frombuffer(b"".join(blobs), dtype=np.uint8).copy(), offs
+
+    def distances(self, result_ct, q, nvec):
+        plain, budget = self.ctx.decrypt(self.sk, result_ct)
+        slots = self.ctx.decode(plain).astype(np.int64)
+        tab = self.lay.slot_table()
+        qi = np.asarray(q).astype(np.int64)
+        d = (slots[tab].sum(axis=1) + int((qi * qi).sum())) % self.ctx.t
+        return d[:nvec], budget
