@@ -1,0 +1,486 @@
+#!/usr/bin/env python3
+"""bench.py — encrypted candidate distances/sec of the PreFHEtch server-side search hot path.
+
+One "step" = one batch of encrypted queries through the whole hot path on synthetic SIFT-shaped
+data: stage 1 (plaintext coarse quantization, top-nprobe) + stage 2 (rotated query sets, ct x pt
+multiply-accumulate over every candidate block of the probed lists, add of the norms, inverse NTT).
+  value : whole-job useful candidate distances/s with query ciphertexts already resident in HBM
+  e2e   : the same metric through the C-ABI call with HOST buffers (SEAL-serialized query
+          ciphertexts in pinned memory -> SEAL-serialized result ciphertexts in pinned memory)
+  roofline : the ct x pt MAC kernel against the measured HBM copy bandwidth
+  cpu_baseline : the CPU oracle (port of the same op sequence) on a bounded sample, all host cores
+`--impl reference` times that CPU path alone (the reference's own server cannot be built here:
+FAISS fork / SEAL / Drogon are network FetchContent dependencies).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the single-GPU configuration the metric is quoted on
+    "sift1m_nlist1024_nprobe16": dict(nb=1_000_000, d=128, nlist=1024, nprobe=16, n=8192, g=8, m=1, tbits=24, nq=64),
+    # BASELINE.json configs[2]: lists sharded across 2/4/8 GPUs
+    "sift1m_nlist4096_nprobe64": dict(nb=1_000_000, d=128, nlist=4096, nprobe=64, n=8192, g=32, m=1, tbits=24, nq=64),
+    # small smoke configuration (configs[0] shape)
+    "siftsmall_nlist100_nprobe8": dict(nb=10_000, d=128, nlist=100, nprobe=8, n=8192, g=8, m=1, tbits=24, nq=16),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic SIFT-shaped data: uint8-valued vectors from a Gaussian mixture
+# ----------------------------------------------------------------------------------------------
+def make_dataset(cfg, device, seed=1234):
+    """Index build (out of the timed path; the reference does it once in Server::init_index).
+    torch is used only as plumbing for the k-means-style assignment."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    nb, d, nlist = cfg["nb"], cfg["d"], cfg["nlist"]
+    centres = torch.rand((nlist, d), generator=g, device=device) * 160.0
+    assign = torch.randint(0, nlist, (nb,), generator=g, device=device)
+    base = torch.clamp(torch.round(centres[assign] + torch.randn((nb, d), generator=g, device=device) * 24.0), 0, 255)
+    # IVF centroids = mean of the assigned vectors of each true cluster (one Lloyd step from the truth)
+    cent = torch.zeros((nlist, d), device=device).index_add_(0, assign, base)
+    cnt = torch.bincount(assign, minlength=nlist).clamp(min=1).unsqueeze(1)
+    cent = cent / cnt
+    # assign every vector to its nearest centroid (what faiss::IndexIVF::add does)
+    lab = torch.empty(nb, dtype=torch.long, device=device)
+    c2 = (cent * cent).sum(1)
+    for s in range(0, nb, 65536):
+        x = base[s:s + 65536]
+        dist = c2[None, :] - 2.0 * x @ cent.T
+        lab[s:s + 65536] = dist.argmin(1)
+    order = torch.argsort(lab, stable=True)
+    counts = torch.bincount(lab, minlength=nlist)
+    offsets = torch.zeros(nlist + 1, dtype=torch.long, device=device)
+    offsets[1:] = torch.cumsum(counts, 0)
+    vecs = base[order].contiguous()
+    # query pool from the same mixture
+    npool = 4096
+    qa = torch.randint(0, nlist, (npool,), generator=g, device=device)
+    queries = torch.clamp(torch.round(centres[qa] + torch.randn((npool, d), generator=g, device=device) * 24.0), 0, 255)
+    return dict(centroids=cent.cpu().numpy().astype(np.float32), offsets=offsets.cpu().numpy().astype(np.int64),
+                ids=order.cpu().numpy().astype(np.int64), vectors=vecs.cpu().numpy().astype(np.float32),
+                queries=queries.cpu().numpy().astype(np.float32))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle's OpenMP whole-step driver on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_pipeline(cfg, data, nq_sample, nthreads, steps=1, warmup=0, seed=5):
+    """Runs the CPU port of the step on `nq_sample` queries of the workload.  Only this function and
+    --impl reference execute oracle/ (as the baseline, never as the product)."""
+    from oracle import pf_oracle as O
+    n, d, g, m, nprobe = cfg["n"], cfg["d"], cfg["g"], cfg["m"], cfg["nprobe"]
+    primes, t = O.BFV_DEFAULT_PRIMES[n], O.BATCHING_T[(n, cfg["tbits"])]
+    ctx = O.Context(n, primes, t)
+    lay = O.LayoutPlan(n, d, m, g)
+    rng = np.random.default_rng(seed)
+    q = data["queries"][:nq_sample]
+    idx, _ = O.coarse_quantize(q, data["centroids"], nprobe)
+    offsets = data["offsets"]
+    # blocks touched by the sample
+    block_of = {}
+    boff, bnv, pair_q, pair_b, useful = [], [], [], [], 0
+    for i in range(nq_sample):
+        for l in idx[i]:
+            n_l = int(offsets[l + 1] - offsets[l])
+            for b0 in range(0, n_l, lay.C):
+                key = (int(l), b0)
+                if key not in block_of:
+                    block_of[key] = len(boff)
+                    boff.append(int(offsets[l]) + b0)
+                    bnv.append(min(lay.C, n_l - b0))
+                pair_q.append(i)
+                pair_b.append(block_of[key])
+                useful += min(lay.C, n_l - b0)
+    xs = data["vectors"].astype(np.int32)
+    t0 = time.perf_counter()
+    diag, norm = O.encode_blocks(ctx, lay, xs, boff, bnv, nthreads)
+    enc_s = time.perf_counter() - t0
+    # ciphertext-shaped random residues (throughput does not depend on the values) and random keys
+    L, k = ctx.L, ctx.k
+    cts = np.stack([rng.integers(0, primes[l], size=(nq_sample, m, 2, n), dtype=np.uint64) for l in range(L)], axis=3)
+    cts = np.ascontiguousarray(cts)
+    keys = []
+    for r in range(1, lay.R):
+        keys.append(np.ascontiguousarray(
+            np.stack([rng.integers(0, primes[j], size=(L, 2, n), dtype=np.uint64) for j in range(k)], axis=2)))
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        idx2, _ = O.coarse_quantize(q, data["centroids"], nprobe)
+        out, (rot_s, mac_s) = O.search_pairs(ctx, lay, cts, keys, False, pair_q, pair_b, diag, norm, nthreads)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append((dt, rot_s, mac_s))
+    dt = float(np.mean([x[0] for x in times]))
+    return dict(useful=useful, slots=len(pair_q) * lay.C, seconds=dt, rot_s=float(np.mean([x[1] for x in times])),
+                mac_s=float(np.mean([x[2] for x in times])), encode_s=enc_s, pairs=len(pair_q), nq=nq_sample,
+                distinct_blocks=len(boff))
+
+
+def run_reference(args, cfg, cfg_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pf_oracle as O
+    O.build()
+    data = make_dataset(cfg, "cpu") if cfg["nb"] <= 200_000 else make_dataset_cpu_light(cfg)
+    nthreads = O.max_threads()
+    nq_sample = min(cfg["nq"], 8)
+    r = cpu_pipeline(cfg, data, nq_sample, nthreads, steps=args.steps, warmup=args.warmup)
+    val = r["useful"] / r["seconds"]
+    line = {
+        "metric": "encrypted candidate distances/sec", "value": val, "unit": "distances/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": cfg_name, **{k: cfg[k] for k in ("nb", "d", "nlist", "nprobe", "n", "g")},
+                   "queries_per_step": nq_sample},
+        "cpu_baseline": {"value": val, "unit": "distances/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{nq_sample} queries x {r['pairs']} (query,block) pairs per step, whole hot path "
+                                   f"(rotations {r['rot_s']:.2f}s + MAC/INTT {r['mac_s']:.2f}s)"},
+        "e2e": {"value": val, "unit": "distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "queries_per_s": nq_sample / r["seconds"],
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def make_dataset_cpu_light(cfg, seed=1234):
+    """CPU-only dataset for the reference arm when no GPU plumbing is wanted: same generator family, numpy."""
+    rng = np.random.default_rng(seed)
+    nb, d, nlist = cfg["nb"], cfg["d"], cfg["nlist"]
+    centres = rng.uniform(0, 160, size=(nlist, d)).astype(np.float32)
+    assign = rng.integers(0, nlist, size=nb)
+    base = np.clip(np.rint(centres[assign] + rng.normal(0, 24, size=(nb, d)).astype(np.float32)), 0, 255).astype(np.float32)
+    cent = np.zeros((nlist, d), dtype=np.float64)
+    np.add.at(cent, assign, base)
+    cent = (cent / np.maximum(np.bincount(assign, minlength=nlist), 1)[:, None]).astype(np.float32)
+    lab = np.empty(nb, dtype=np.int64)
+    c2 = (cent * cent).sum(1)
+    for s in range(0, nb, 65536):
+        x = base[s:s + 65536]
+        lab[s:s + 65536] = (c2[None, :] - 2.0 * x @ cent.T).argmin(1)
+    order = np.argsort(lab, kind="stable")
+    offsets = np.zeros(nlist + 1, dtype=np.int64)
+    np.cumsum(np.bincount(lab, minlength=nlist), out=offsets[1:])
+    qa = rng.integers(0, nlist, size=4096)
+    queries = np.clip(np.rint(centres[qa] + rng.normal(0, 24, size=(4096, d))), 0, 255).astype(np.float32)
+    return dict(centroids=cent, offsets=offsets, ids=order.astype(np.int64),
+                vectors=np.ascontiguousarray(base[order]), queries=queries)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=None, choices=list(CONFIGS))
+    ap.add_argument("--nq", type=int, default=None, help="queries per step")
+    ap.add_argument("--g", type=int, default=None, help="partial-sum factor of the layout")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name = args.config or ("sift1m_nlist1024_nprobe16" if max(args.gpus, world) == 1 else "sift1m_nlist4096_nprobe64")
+    cfg = dict(CONFIGS[cfg_name])
+    if args.nq:
+        cfg["nq"] = args.nq
+    if args.g:
+        cfg["g"] = args.g
+
+    if args.impl == "reference":
+        return run_reference(args, cfg, cfg_name)
+
+    import torch
+    import torch.distributed as dist
+    import prefhetch_b200 as pf
+    from prefhetch_b200.build import build as build_lib
+    if rank == 0:
+        build_lib()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    n, d, g, m, nprobe, nq = cfg["n"], cfg["d"], cfg["g"], cfg["m"], cfg["nprobe"], cfg["nq"]
+    t_setup = time.perf_counter()
+    data = make_dataset(cfg, dev)
+    eng = pf.Engine(d, n, pf.bfv_default_primes(n), pf.batching_plain_modulus(n, cfg["tbits"]), m, g,
+                    device=local_rank, rank=rank, world=world)
+    info = eng.load_index(data["centroids"], data["offsets"], data["ids"], data["vectors"])
+    eng.set_list_sizes(data["offsets"])
+    L, k, K, C_ = eng.L, eng.k, info["K"], info["C"]
+    ctw = eng.ctw
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    # synthetic Galois keys / query ciphertexts: uniform residues (timing does not depend on values;
+    # parity with real encryptions is what tests/ and smoke() check)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2025)
+    primes = eng.primes
+
+    def rand_residues(shape_prefix, limbs):
+        cols = [torch.randint(0, primes[j], shape_prefix + (n,), generator=gen, device=dev, dtype=torch.int64)
+                for j in limbs]
+        return torch.stack(cols, dim=len(shape_prefix)).contiguous()
+
+    for r in range(1, info["R"]):
+        key = rand_residues((L, 2), range(k))  # [L][2][k][n]
+        eng.set_galois_key(eng.galois_elt(r), key.cpu().numpy().view(np.uint64))
+    npool_steps = 4
+    ct_pool = [rand_residues((nq, m, 2), range(L)) for _ in range(npool_steps)]  # [nq][m][2][L][n]
+    queries = data["queries"]
+    nsteps_total = args.warmup + args.steps
+    qsets = [queries[(s * nq) % (len(queries) - nq):][:nq] for s in range(nsteps_total)]
+    max_res = int(eng._blocks_per_list.max()) * nprobe * nq
+    d_out = torch.empty((max_res, 2, L, n), dtype=torch.int64, device=dev)
+    log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f}s  index: {info}  max_res {max_res}")
+
+    def step(s):
+        x = qsets[s]
+        idx = eng.coarse_quantize(x, nprobe)
+        rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, d_out.data_ptr(), max_res)
+        return idx, st
+
+    def gather_results(st):
+        """result ciphertexts of every shard to rank 0 (the response is assembled there)"""
+        if world == 1:
+            return
+        cnt = torch.tensor([st["nresults"]], device=dev, dtype=torch.int64)
+        cnts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        if rank == 0:
+            for r in range(1, world):
+                c = int(cnts[r].item())
+                if c:
+                    dist.recv(gather_buf[:c], src=r)
+        else:
+            c = int(st["nresults"])
+            if c:
+                dist.send(d_out[:c], dst=0)
+
+    gather_buf = torch.empty_like(d_out) if (world > 1 and rank == 0) else None
+
+    # ---- value: device-resident timed region --------------------------------------------------
+    with torch.cuda.stream(stream):
+        for s in range(args.warmup):
+            _, st = step(s)
+            gather_results(st)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        eng.timing_enable(True)
+        eng.timing_read(reset=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches0 = eng.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        useful = slots = nres = 0
+        blocks_distinct = pairs = 0
+        ev0.record(stream)
+        for s in range(args.warmup, nsteps_total):
+            idx, st = step(s)
+            gather_results(st)
+            useful += st["useful_distances"]
+            slots += st["slot_distances"]
+            nres += st["nresults"]
+        ev1.record(stream)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clocks = sampler.stop()
+        launches = eng.launch_count() - launches0
+        phases = eng.timing_read(reset=True)
+        eng.timing_enable(False)
+
+    # distinct blocks per step for the algorithmic-bytes formula (host-side bookkeeping, untimed)
+    bpl = eng._blocks_per_list
+    for s in range(args.warmup, nsteps_total):
+        idx = eng.coarse_quantize(qsets[s], nprobe)
+        own = idx[(idx % world) == rank] if world > 1 else idx.reshape(-1)
+        pairs += int(bpl[own].sum())
+        blocks_distinct += int(bpl[np.unique(own)].sum())
+
+    t_max = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    tot = torch.tensor([useful, slots, nres, launches, pairs, blocks_distinct], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(t_max.item())
+    useful_all, slots_all, nres_all, launches_all = (float(x) for x in tot[:4].tolist())
+    ms_step = ms_total / args.steps
+    value = useful_all / (ms_total * 1e-3)
+
+    # ---- roofline of the MAC kernel (rank-local launch, measured with CUDA events on its stream) --
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    mac_ms = phases["mac"]["ms"] / max(1, phases["mac"]["launches"])
+    LN8 = 8.0 * L * n
+    alg_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * blocks_distinct + 2.0 * pairs) / args.steps  # rank-local
+    streamed_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * pairs + 2.0 * pairs) / args.steps
+    achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "mac_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes_per_launch": alg_bytes, "streamed_bytes_per_launch": streamed_bytes,
+                "streamed_gbs": streamed_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
+                "ms_per_launch": mac_ms}
+
+    # ---- e2e: host buffers through the public C-ABI call ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ctb = eng.ct_bytes
+        hdr = np.frombuffer(eng.ct_serialize(np.zeros((2, L, n), dtype=np.uint64)), dtype=np.uint8)[:ctb - ctw * 8]
+        qblob = torch.empty(nq * m * ctb, dtype=torch.uint8).pin_memory()
+        qnp = qblob.numpy()
+        host_ct = ct_pool[0].cpu().numpy().view(np.uint64).reshape(nq * m, -1)
+        for c in range(nq * m):
+            qnp[c * ctb: c * ctb + len(hdr)] = hdr
+            qnp[c * ctb + len(hdr): (c + 1) * ctb] = host_ct[c].view(np.uint8)
+        offs = (np.arange(nq * m + 1, dtype=np.uint64) * ctb)
+        out_host = torch.empty(max_res * ctb, dtype=torch.uint8).pin_memory()
+        out_np = out_host.numpy()
+        e_steps = max(2, min(args.steps, 5))
+        e_useful, h2d, d2h = 0, 0, 0
+        for s in range(2 + e_steps):
+            if s == 2:
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            x = qsets[s % nsteps_total]
+            idx = eng.coarse_quantize(x, nprobe)
+            res = eng.coarseSearchEncrypted(qnp, offs, idx, out=out_np)
+            if s >= 2:
+                e_useful += res.stats["useful_distances"]
+                h2d += nq * m * ctb + x.nbytes
+                d2h += res.stats["out_bytes"] + idx.nbytes
+        torch.cuda.synchronize()
+        e_dt = time.perf_counter() - t0
+        et = torch.tensor([e_dt], device=dev, dtype=torch.float64)
+        eu = torch.tensor([e_useful], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(eu, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(eu.item()) / float(et.item()), "unit": "distances/s",
+               "h2d_bytes_per_step": h2d // e_steps, "d2h_bytes_per_step": d2h // e_steps,
+               "ms_per_step": float(et.item()) / e_steps * 1e3, "steps": e_steps}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import pf_oracle as O
+            O.build()
+            nthreads = O.max_threads()
+            nq_s = min(nq, 8)
+            r = cpu_pipeline(cfg, data, nq_s, nthreads)
+            r1 = cpu_pipeline(cfg, data, 1, 1)
+            cpu = {"value": r["useful"] / r["seconds"], "unit": "distances/s", "cores": nthreads, "kind": "port",
+                   "sample": f"{nq_s} queries / {r['pairs']} (query,block) pairs of the same workload, whole hot path, "
+                             f"{nthreads} OpenMP threads ({r['seconds']:.2f}s: rotations {r['rot_s']:.2f}s, MAC+INTT "
+                             f"{r['mac_s']:.2f}s)",
+                   "single_thread_value": r1["useful"] / r1["seconds"], "queries_per_s": nq_s / r["seconds"]}
+        except Exception as ex:  # the baseline is a report, not the product
+            cpu = {"value": None, "error": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": "encrypted candidate distances/sec", "value": value, "unit": "distances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": cfg_name, "nb": cfg["nb"], "d": d, "nlist": cfg["nlist"], "nprobe": nprobe,
+                       "poly_degree": n, "limbs": L, "g": g, "query_cts": m, "queries_per_step": nq,
+                       "parallelism": f"lists%{world}" if world > 1 else "single",
+                       "l2_policy": f"inputs larger than L2: NTT-domain DB {info['db_bytes'] / 2**30:.1f} GiB/rank "
+                                    "streamed from HBM, query batches rotate through a pool"},
+            "queries_per_s": nq * args.steps / (ms_total * 1e-3),
+            "slot_distances_per_s": slots_all / (ms_total * 1e-3),
+            "result_cts_per_step": nres_all / args.steps,
+            "gpu_launches": int(launches_all),
+            "clocks": clocks, "roofline": roofline,
+            "phases_ms_per_step": {kk: v["ms"] / args.steps for kk, v in phases.items()},
+            "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
