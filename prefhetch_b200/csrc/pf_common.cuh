@@ -13,7 +13,7 @@ struct DevModulus {
     u64 ratio0, ratio1;  // floor(2^128/q) low / high words
     u64 n_inv, n_inv_sh; // N^{-1} mod q and its Shoup quotient
     u64 inv_last_w, inv_last_w_sh; // irp[1] * N^{-1} (last inverse stage with the scaling folded in)
-    u64 pad;
+    u64 split_shift; // s = ceil(bits(q)/2): operand split point of the MAC storage format (0 = canonical)
 };
 
 // twiddle tables per modulus: fwd[N] then inv[N], each entry {w, floor(w*2^64/q)}

@@ -72,6 +72,7 @@ struct PinBuf {
 struct GaloisKey {
     DevBuf key;  // [L][2][k][N]
     DevBuf perm; // u32[N]
+    DevBuf km;   // [2][L+1][N] hoisting correction term (pf_keyswitch.cuh)
     u32 einv = 0;
 };
 
@@ -124,7 +125,7 @@ struct pf_engine {
 
     // scratch
     DevBuf s_x, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
-    DevBuf s_rot, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_qcts, s_out, s_tmp, s_plain,
+    DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_qcts, s_out, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
 
@@ -209,6 +210,7 @@ cudaError_t set_ntt_attrs() {
     if (r != cudaSuccess) return r;
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_PLAIN>));
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_LIFT>));
+    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_REDUCE>));
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
     SETATTR((ntt_inv_kernel<LOGN>));
 #undef SETATTR
@@ -225,6 +227,8 @@ void launch_ntt_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaS
         ntt_fwd_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_LIFT)
         ntt_fwd_kernel<LOGN, NTT_IN_LIFT><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_REDUCE)
+        ntt_fwd_kernel<LOGN, NTT_IN_REDUCE><<<grid, nt, smem, s>>>(p);
     else
         ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE><<<grid, nt, smem, s>>>(p);
 }
@@ -293,7 +297,7 @@ int build_tables(pf_engine *e) {
         }
         m.inv_last_w = pfh::mulmod(inv[1].x, n_inv, q);
         m.inv_last_w_sh = shoup(m.inv_last_w, q);
-        m.pad = 0;
+        m.split_shift = (u64)((64 - __builtin_clzll(q) + 1) / 2);
     }
     CK(e->d_mods.ensure(mods.size() * sizeof(DevModulus)));
     CK(cudaMemcpy(e->d_mods.p, mods.data(), mods.size() * sizeof(DevModulus), cudaMemcpyHostToDevice));
@@ -368,13 +372,30 @@ int set_galois_key_words(pf_engine *e, u32 elt, const u64 *words, bool device_sr
     u32 inv = elt;
     for (int i = 0; i < 5; i++) inv *= 2 - elt * inv;
     gk.einv = inv & (2 * N - 1);
+    // hoisting term: M[I] = NTT_I(negation mask of sigma), KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I]
+    const int L = e->L, k = e->k;
+    CK(gk.km.ensure((size_t)2 * (L + 1) * N * 8));
+    CK(e->s_tmp.ensure((size_t)(L + 2) * N * 8));
+    u64 *mask = e->s_tmp.as<u64>(), *M = mask + N;
+    galois_negmask_kernel<<<N / 256, 256, 0, e->stream>>>(mask, gk.einv, (int)N);
+    e->launches++;
+    NttParams mp{};
+    mp.in = mask;
+    mp.out = M;
+    mp.out_sx = N;
+    for (int I = 0; I <= L; I++) mp.mod_map[I] = (I == L) ? k - 1 : I;
+    launch_ntt(e, NTT_IN_PLAIN, false, mp, dim3(L + 1, 1, 1));
+    galois_km_kernel<<<dim3(N / 256, L + 1, 2), 256, 0, e->stream>>>(M, gk.key.as<u64>(), gk.km.as<u64>(),
+                                                                    e->d_mods.as<DevModulus>(), L, k, (int)N);
+    e->launches++;
     CK(cudaStreamSynchronize(e->stream)); // perm is a stack vector
+    CK(cudaGetLastError());
     return PF_OK;
 }
 
 // ---- rotations ------------------------------------------------------------------------------
 // Run a batch of rotation jobs (already filled on the host) through the key-switch pipeline.
-int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs) {
+int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) {
     const int L = e->L, N = e->N, k = e->k;
     const size_t per_d = (size_t)L * (L + 1) * N, per_S = (size_t)2 * (L + 1) * N, per_W = (size_t)2 * L * N;
     const size_t zmax = std::max<size_t>(1, std::min<size_t>(512, ((size_t)1 << 30) / ((per_d + per_S + per_W) * 8)));
@@ -393,6 +414,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs) {
     kp.k = k;
     kp.N = N;
     kp.p_half = e->p_half;
+    kp.out_split = out_split ? 1 : 0;
     for (int j = 0; j < L; j++) {
         kp.p_half_mod_q[j] = e->p_half_mod_q[j];
         kp.p_inv_mod_q[j] = e->p_inv_mod_q[j];
@@ -443,40 +465,98 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs) {
     return PF_OK;
 }
 
+// D[c][J][I] = NTT_I(c1_J mod q_I) for `ncts` ciphertexts (c1 at d_cts + c*ct_stride + L*N), and the
+// zero-coefficient flags that select the exact path (pf_keyswitch.cuh).
+int hoist_digits(pf_engine *e, const u64 *d_cts, size_t ncts, size_t ct_stride) {
+    const int L = e->L, N = e->N, k = e->k;
+    const size_t per_d = (size_t)L * (L + 1) * N;
+    CK(e->s_hoistD.ensure(ncts * per_d * 8));
+    CK(e->s_flags.ensure(std::max<size_t>(4, ncts * sizeof(int))));
+    CK(cudaMemsetAsync(e->s_flags.p, 0, ncts * sizeof(int), e->stream));
+    for (size_t off = 0; off < ncts; off += 16384) {
+        const size_t cnt = std::min<size_t>(16384, ncts - off);
+        NttParams p{};
+        p.in = d_cts + off * ct_stride + (size_t)L * N;
+        p.in_sy = N;
+        p.in_sz = (long long)ct_stride;
+        p.out = e->s_hoistD.as<u64>() + off * per_d;
+        p.out_sx = N;
+        p.out_sy = (long long)(L + 1) * N;
+        p.out_sz = (long long)per_d;
+        p.zero_flags = e->s_flags.as<int>() + off;
+        for (int I = 0; I <= L; I++) p.mod_map[I] = (I == L) ? k - 1 : I;
+        launch_ntt(e, NTT_IN_REDUCE, false, p, dim3(L + 1, L, (unsigned)cnt));
+    }
+    return PF_OK;
+}
+
 const GaloisKey *find_key(pf_engine *e, int step) {
     auto it = e->gkeys.find(galois_elt_from_step(e, step));
     return it == e->gkeys.end() ? nullptr : &it->second;
 }
 
-// rot[nq][K][2][L][N] (NTT form) from d_cts[nq][m][2][L][N] (coefficient form, device)
-int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int force_chain) {
+void split_convert_chunks(pf_engine *e, const u64 *in, u64 *out, size_t chunk_words, size_t nchunks, size_t in_stride,
+                          size_t out_stride, bool to_split) {
+    for (size_t c0 = 0; c0 < nchunks; c0 += 32768) {
+        const unsigned ny = (unsigned)std::min<size_t>(32768, nchunks - c0);
+        split_convert_kernel<<<dim3((unsigned)((chunk_words + 255) / 256), ny), 256, 0, e->stream>>>(
+            in + c0 * in_stride, out + c0 * out_stride, chunk_words, in_stride, out_stride, e->d_mods.as<DevModulus>(),
+            e->L, e->N, to_split ? 1 : 0);
+        e->launches++;
+    }
+}
+
+void split_convert(pf_engine *e, const u64 *in, u64 *out, size_t nwords, bool to_split) {
+    // whole [..][L][N] arrays: chunk per polynomial group keeps blockIdx.x small
+    const size_t chunk = (size_t)e->L * e->N;
+    split_convert_chunks(e, in, out, chunk, nwords / chunk, chunk, chunk, to_split);
+}
+
+// rot[nq][K][2][L][N] (NTT form; split operand format unless the engine is in wide mode or
+// `canonical_out`) from d_cts[nq][m][2][L][N] (coefficient form, device)
+int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int force_chain, bool canonical_out) {
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N, m = e->m, R = e->R, K = e->K;
+    const bool want_split = !e->mac_wide && !canonical_out;
+    bool direct = !force_chain;
+    for (size_t r = 1; r < R && direct; r++) direct = find_key(e, (int)r) != nullptr;
+    if (R > 1 && !direct && !find_key(e, 1))
+        return e->fail(PF_ERR_STATE, "no usable Galois keys: need steps 1..%u or step 1", (unsigned)(R - 1));
+    // NTT of the input ciphertexts.  Direct mode with split output keeps a canonical copy (the rotation
+    // jobs read c0 from it) and writes the r = 0 members split; otherwise they go straight into rot.
+    const bool side_copy = want_split && (direct || R == 1);
+    u64 *ntt_dst = rot;
+    size_t dst_stride = R * ctw;
+    if (side_copy) {
+        CK(e->s_cqntt.ensure(nq * m * ctw * 8));
+        ntt_dst = e->s_cqntt.as<u64>();
+        dst_stride = ctw;
+    }
     {
         PhaseTimer pt(e, PF_T_TONTT);
-        // r = 0 members: NTT of the input ciphertexts straight into rot[i][a*R]
         for (size_t off = 0; off < nq * m; off += 16384) {
             const size_t cnt = std::min<size_t>(16384, nq * m - off);
             NttParams p{};
             p.in = d_cts + off * ctw;
-            p.out = rot + (off / m) * K * ctw + (off % m) * R * ctw;
+            p.out = ntt_dst + off * dst_stride; // ciphertext (i, a) -> rot member (i*K + a*R) = (i*m + a)*R
             p.in_sx = p.out_sx = N;
-            p.in_sy = p.out_sy = (long long)L * N; // y = poly (0,1)
+            p.in_sy = p.out_sy = (long long)L * N; // y = polynomial 0 / 1
             p.in_sz = (long long)ctw;
-            p.out_sz = (long long)(R * ctw);
+            p.out_sz = (long long)dst_stride;
             for (int i = 0; i < L; i++) p.mod_map[i] = i;
-            // out stride per ciphertext is R*ctw only while (i, a) advance uniformly: a*R + i*K = (i*m+a)*R
             launch_ntt(e, NTT_IN_PLAIN, false, p, dim3(L, 2, (unsigned)cnt));
+        }
+        if (side_copy) {
+            split_convert_chunks(e, ntt_dst, rot, ctw, nq * m, ctw, R * ctw, true);
         }
     }
     if (R == 1) return PF_OK;
     PhaseTimer pt(e, PF_T_ROTATE);
-    bool direct = !force_chain;
-    for (size_t r = 1; r < R && direct; r++) direct = find_key(e, (int)r) != nullptr;
-    if (!direct && !find_key(e, 1))
-        return e->fail(PF_ERR_STATE, "no usable Galois keys: need steps 1..%u or step 1", (unsigned)(R - 1));
     std::vector<RotJob> jobs;
     if (direct) {
+        int hrc = hoist_digits(e, d_cts, nq * m, ctw);
+        if (hrc) return hrc;
+        const size_t per_d = (size_t)L * (L + 1) * N;
         jobs.reserve(nq * m * (R - 1));
         for (size_t i = 0; i < nq; i++)
             for (size_t a = 0; a < m; a++)
@@ -484,14 +564,17 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
                     const GaloisKey *gk = find_key(e, (int)r);
                     RotJob j{};
                     j.c1_coef = d_cts + (i * m + a) * ctw + (size_t)L * N;
-                    j.c0_ntt = rot + (i * K + a * R) * ctw;
+                    j.c0_ntt = side_copy ? ntt_dst + (i * m + a) * ctw : rot + (i * K + a * R) * ctw;
                     j.key = gk->key.as<u64>();
                     j.perm = gk->perm.as<u32>();
                     j.out = rot + (i * K + a * R + r) * ctw;
                     j.einv = gk->einv;
+                    j.D = e->s_hoistD.as<u64>() + (i * m + a) * per_d;
+                    j.KM = gk->km.as<u64>();
+                    j.flag = e->s_flags.as<int>() + (i * m + a);
                     jobs.push_back(j);
                 }
-        return run_rot_jobs(e, jobs);
+        return run_rot_jobs(e, jobs, want_split);
     }
     // chain: rot_r = rotate(rot_{r-1}, 1); needs c1 of the previous member in coefficient form
     const GaloisKey *gk = find_key(e, 1);
@@ -517,17 +600,18 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
                 j.einv = gk->einv;
                 jobs.push_back(j);
             }
-        int rc = run_rot_jobs(e, jobs);
+        int rc = run_rot_jobs(e, jobs, false);
         if (rc) return rc;
     }
+    if (want_split) split_convert(e, rot, rot, nq * K * ctw, true);
     return PF_OK;
 }
 
 // ---- MAC launch -----------------------------------------------------------------------------
-template <int T, bool WIDE>
+template <int T, int UNROLL, bool WIDE>
 void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const size_t smem = (size_t)p.K * 2 * T * 8;
-    auto kern = mac_kernel<T, 2, 4, WIDE>;
+    auto kern = mac_kernel<T, UNROLL, WIDE>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
     e->launches++;
@@ -535,17 +619,19 @@ void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
 
 int mac_tile(const pf_engine *e) { return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64); }
 
+template <int T>
+void launch_mac_tile(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    if (e->mac_wide) launch_mac_t<T, 1, true>(e, p, nchunks);
+    else if (p.K >= 4) launch_mac_t<T, 2, false>(e, p, nchunks);
+    else if (p.K == 2) launch_mac_t<T, 1, false>(e, p, nchunks);
+    else launch_mac_t<T, 1, false>(e, p, nchunks);
+}
+
 void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const int T = mac_tile(e);
-    if (e->mac_wide) {
-        if (T == 256) launch_mac_t<256, true>(e, p, nchunks);
-        else if (T == 128) launch_mac_t<128, true>(e, p, nchunks);
-        else launch_mac_t<64, true>(e, p, nchunks);
-    } else {
-        if (T == 256) launch_mac_t<256, false>(e, p, nchunks);
-        else if (T == 128) launch_mac_t<128, false>(e, p, nchunks);
-        else launch_mac_t<64, false>(e, p, nchunks);
-    }
+    if (T == 256) launch_mac_tile<256>(e, p, nchunks);
+    else if (T == 128) launch_mac_tile<128>(e, p, nchunks);
+    else launch_mac_tile<64>(e, p, nchunks);
 }
 
 // Build the (query, block) pair list for this rank and the chunk table.  Returns PF_OK.
@@ -593,7 +679,7 @@ int search_core(pf_engine *e, uint64_t nq, const u64 *d_cts, const PairPlan &pl,
     const size_t ctw = (size_t)2 * L * N, P = pl.pair_block.size();
     CK(e->s_rot.ensure(nq * e->K * ctw * 8));
     u64 *rot = e->s_rot.as<u64>();
-    int rc = build_rotated_sets(e, d_cts, nq, rot, 0);
+    int rc = build_rotated_sets(e, d_cts, nq, rot, 0, false);
     if (rc) return rc;
     if (!P) return PF_OK;
     CK(e->s_chunks.ensure(pl.chunks.size() * sizeof(MacChunk)));
@@ -756,11 +842,14 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     e->K = e->m * e->R;
     e->C = (u32)(N / e->g);
     if (e->K > 128) return bail(e->fail(PF_ERR_INVALID, "K = m*d_pad/(m*g) = %u diagonals per block exceeds 128; raise g", e->K));
-    int logk = 0;
-    while ((1u << logk) < std::max<u32>(e->K, 2 * (u32)e->L)) logk++;
-    e->mac_wide = e->max_prime_bits + 1 + logk > 64;
-    if (e->max_prime_bits + 1 + 4 > 64)
-        return bail(e->fail(PF_ERR_INVALID, "coefficient primes above 59 bits are not supported by the key-switch accumulator"));
+    // split-operand lazy sums (pf_mac.cuh) need 2*ceil(bits/2) + 2 + log2(terms) <= 64
+    const int sbits = 2 * ((e->max_prime_bits + 1) / 2) + 2;
+    int logk = 0, logl = 0;
+    while ((1u << logk) < e->K) logk++;
+    while ((1 << logl) < e->L) logl++;
+    e->mac_wide = sbits + logk > 64;
+    if (sbits + logl > 64)
+        return bail(e->fail(PF_ERR_INVALID, "coefficient primes of %d bits with %d limbs overflow the key-switch accumulator", e->max_prime_bits, e->L));
     if (cudaSetDevice(prm->device) != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaSetDevice(%d) failed", prm->device));
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "cudaStreamCreate failed"));
@@ -960,6 +1049,7 @@ int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const in
         fp.out_sz = (long long)e->diag_block_words;
         fp.lift_t = e->t;
         fp.lift_thr = (e->t + 1) >> 1;
+        fp.out_split = e->mac_wide ? 0 : 1;
         for (int i = 0; i < L; i++) fp.mod_map[i] = i;
         launch_ntt(e, NTT_IN_LIFT, false, fp, dim3(L, e->K, nz));
         // norms: BFV scaling variant, then forward NTT
@@ -1312,6 +1402,10 @@ int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_
     CK(cudaMemcpyAsync(dc.p, cts, K * ctw * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(dp.p, pts, K * ptw * 8, cudaMemcpyHostToDevice, e->stream));
     if (addend) CK(cudaMemcpyAsync(dn.p, addend, ptw * 8, cudaMemcpyHostToDevice, e->stream));
+    if (!e->mac_wide) {
+        split_convert(e, dc.as<u64>(), dc.as<u64>(), K * ctw, true);
+        split_convert(e, dp.as<u64>(), dp.as<u64>(), K * ptw, true);
+    }
     const MacChunk ch{0, 0, 1, 0};
     const long long pb = 0;
     CK(cudaMemcpyAsync(dch.p, &ch, sizeof(ch), cudaMemcpyHostToDevice, e->stream));
@@ -1373,7 +1467,12 @@ int pf_rotate_rows(pf_engine *e, const uint64_t *ct, int step, uint64_t *out) {
     jobs[0].perm = gk->perm.as<u32>();
     jobs[0].out = dout;
     jobs[0].einv = gk->einv;
-    int rc = run_rot_jobs(e, jobs);
+    int rc = hoist_digits(e, din, 1, ctw);
+    if (rc) return rc;
+    jobs[0].D = e->s_hoistD.as<u64>();
+    jobs[0].KM = gk->km.as<u64>();
+    jobs[0].flag = e->s_flags.as<int>();
+    rc = run_rot_jobs(e, jobs, false);
     if (rc) return rc;
     ntt_limbs(e, dout, dout, 2, true); // SEAL returns BFV ciphertexts in coefficient form
     CK(cudaMemcpyAsync(out, dout, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -1390,7 +1489,7 @@ int pf_rotate_query_set(pf_engine *e, const uint64_t *cts, int chain, uint64_t *
     CK(e->s_qcts.ensure(e->m * ctw * 8));
     CK(e->s_rot.ensure(e->K * ctw * 8));
     CK(cudaMemcpyAsync(e->s_qcts.p, cts, e->m * ctw * 8, cudaMemcpyHostToDevice, e->stream));
-    int rc = build_rotated_sets(e, e->s_qcts.as<u64>(), 1, e->s_rot.as<u64>(), chain);
+    int rc = build_rotated_sets(e, e->s_qcts.as<u64>(), 1, e->s_rot.as<u64>(), chain, true);
     if (rc) return rc;
     CK(cudaMemcpyAsync(rot, e->s_rot.p, e->K * ctw * 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1436,6 +1535,8 @@ int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *di
     rc = pf_load_index(tmp, 1, cent.data(), off.data(), ids.data(), v.data());
     if (rc == PF_OK && !tmp->d_diag.p) rc = tmp->fail(PF_ERR_INVALID, "vectors must be integers in [0,255]");
     if (rc == PF_OK && nvec) {
+        if (!tmp->mac_wide) split_convert(tmp, tmp->d_diag.as<u64>(), tmp->d_diag.as<u64>(), tmp->diag_block_words, false);
+        cudaStreamSynchronize(tmp->stream);
         cudaMemcpy(diag, tmp->d_diag.p, tmp->diag_block_words * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(norm, tmp->d_norm.p, tmp->norm_block_words * 8, cudaMemcpyDeviceToHost);
     } else if (rc == PF_OK) {

@@ -3,6 +3,15 @@
 // ciphertext is bit-identical to SEAL's, delivered directly in NTT form for the MAC:
 //   1. d[J][I]   = NTT_I( sigma(c1)_J mod q_I )            (pf_ntt.cuh, NTT_IN_GALOIS_REDUCE)
 //   2. S_c[I]    = sum_J d[J][I] (.) key_J[c][I]            (ks_accumulate_kernel, lazy sums)
+//      HOISTED (exactly the same d, without the L(L+1) NTTs per rotation):  with
+//      D[J][I] = NTT_I(c1_J mod q_I) computed once per query ciphertext, neg = 0/1 polynomial of the
+//      positions sigma negates, M[I] = NTT_I(neg):
+//         d[J][I] = perm_sigma(D[J][I]) + (q_J mod q_I) * M[I]        whenever c1_J has no zero coefficient,
+//      because sigma(c1)_J takes the unsigned residue q_J - x at negated positions and
+//      (q_J - x) mod q_I = -(x mod q_I) + q_J (mod q_I).  Hence
+//         S_c[I] = sum_J perm_sigma(D[J][I]) (.) key_J[c][I] + KM_c[I],   KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I]
+//      with KM precomputed per key.  A ciphertext whose c1 has a zero coefficient (probability ~N*L/q)
+//      raises its flag and takes the exact path, so the result is SEAL's bit for bit in every case.
 //   3. u_c       = INTT_P(S_c[P]);  W_c[j] = ((u_c + P/2) mod P mod q_j) - (P/2 mod q_j)
 //   4. out_c[j]  = (S_c[j] - NTT_j(W_c[j])) * P^{-1}  (+ sigma_ntt(c0)[j] for c = 0)
 // SEAL performs step 4 in coefficient form; doing it in NTT form is the same value because the
@@ -22,6 +31,7 @@ struct KsParams {
     u64 p_half;
     u64 p_half_mod_q[PF_NTT_MAXMAP];
     u64 p_inv_mod_q[PF_NTT_MAXMAP], p_inv_mod_q_sh[PF_NTT_MAXMAP];
+    int out_split; // write the rotated ciphertext in the MAC's split operand format
 };
 
 // grid (N/512, L+1, z); thread = 2 coefficients of output limb I, both key components
@@ -31,30 +41,78 @@ __global__ void __launch_bounds__(256) ks_accumulate_kernel(const KsParams p) {
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
     const RotJob job = p.jobs[z];
+    const bool hoisted = job.D && !*job.flag;
     LazyAcc a00, a01, a10, a11;
     lazy_zero(a00);
     lazy_zero(a01);
     lazy_zero(a10);
     lazy_zero(a11);
+    const int sh = (int)m.split_shift;
     const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
+    u32 px = 0, py = 0;
+    if (hoisted) {
+        const uint2 pp = reinterpret_cast<const uint2 *>(job.perm)[c2];
+        px = pp.x;
+        py = pp.y;
+    }
     for (int J = 0; J < L; J++) {
-        const ulonglong2 dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
+        ulonglong2 dv;
+        if (hoisted) {
+            const u64 *dj = job.D + ((size_t)J * (L + 1) + I) * N;
+            dv.x = dj[px];
+            dv.y = dj[py];
+        } else {
+            dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
+        }
         const u64 *kj = job.key + (size_t)J * 2 * p.k * N;
         const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
         const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(p.k + ki) * N) + c2);
-        lazy_mac(a00, dv.x, k0.x);
-        lazy_mac(a01, dv.y, k0.y);
-        lazy_mac(a10, dv.x, k1.x);
-        lazy_mac(a11, dv.y, k1.y);
+        const SplitOp dx = make_op(split_word(dv.x, sh)), dy = make_op(split_word(dv.y, sh));
+        const SplitOp k0x = make_op(split_word(k0.x, sh)), k0y = make_op(split_word(k0.y, sh));
+        const SplitOp k1x = make_op(split_word(k1.x, sh)), k1y = make_op(split_word(k1.y, sh));
+        lazy_mac(a00, dx.x0, dx.x1, dx.xs, k0x.x0, k0x.x1, k0x.xs);
+        lazy_mac(a01, dy.x0, dy.x1, dy.xs, k0y.x0, k0y.x1, k0y.xs);
+        lazy_mac(a10, dx.x0, dx.x1, dx.xs, k1x.x0, k1x.x1, k1x.xs);
+        lazy_mac(a11, dy.x0, dy.x1, dy.xs, k1y.x0, k1y.x1, k1y.xs);
     }
     u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
     ulonglong2 r0, r1;
-    r0.x = lazy_reduce(a00, m);
-    r0.y = lazy_reduce(a01, m);
-    r1.x = lazy_reduce(a10, m);
-    r1.y = lazy_reduce(a11, m);
+    r0.x = lazy_reduce(a00, sh, m);
+    r0.y = lazy_reduce(a01, sh, m);
+    r1.x = lazy_reduce(a10, sh, m);
+    r1.y = lazy_reduce(a11, sh, m);
+    if (hoisted) {
+        const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
+        const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
+        r0.x = addmod(r0.x, m0.x, m.q);
+        r0.y = addmod(r0.y, m0.y, m.q);
+        r1.x = addmod(r1.x, m1.x, m.q);
+        r1.y = addmod(r1.y, m1.y, m.q);
+    }
     reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
     reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
+}
+
+// neg[i] = 1 where coefficient position i of sigma(a) holds a negated coefficient.  grid (N/256)
+__global__ void __launch_bounds__(256) galois_negmask_kernel(u64 *out, u32 einv, int N) {
+    const u32 idx = blockIdx.x * 256 + threadIdx.x;
+    const u32 i0 = (u32)(((u64)idx * einv) & (2u * N - 1));
+    out[idx] = i0 >= (u32)N ? 1ull : 0ull;
+}
+
+// KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I].  M[L+1][N] NTT form.  grid (N/256, L+1, 2)
+__global__ void __launch_bounds__(256) galois_km_kernel(const u64 *M, const u64 *key, u64 *KM, const DevModulus *mods,
+                                                        int L, int k, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, c = blockIdx.z;
+    const int ki = (I == L) ? k - 1 : I;
+    const DevModulus m = mods[ki];
+    u64 acc = 0;
+    for (int J = 0; J < L; J++) {
+        const u64 f = mods[J].q % m.q;
+        const u64 kv = key[(((size_t)J * 2 + c) * k + ki) * N + i];
+        acc = addmod(acc, mulmod(f, kv, m), m.q);
+    }
+    KM[((size_t)c * (L + 1) + I) * N + i] = mulmod(acc, M[(size_t)I * N + i], m);
 }
 
 // after INTT_P of S_c[L] (in place): W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).  grid (N/256, 2, z)
@@ -81,6 +139,7 @@ __global__ void __launch_bounds__(256) ks_finish_kernel(const KsParams p) {
     const u64 w = p.W[(((size_t)z * 2 + c) * L + j) * N + i];
     u64 r = mul_shoup(submod(s, w, q), p.p_inv_mod_q[j], p.p_inv_mod_q_sh[j], q);
     if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * N + job.perm[i]], q);
+    if (p.out_split) r = split_word(r, (int)p.mods[j].split_shift);
     job.out[((size_t)c * L + j) * N + i] = r;
 }
 

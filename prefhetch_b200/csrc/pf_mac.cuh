@@ -11,9 +11,7 @@
 //    128-bit L1-bypassing loads, a warp covering 512 contiguous bytes — are the only HBM stream.
 //  * each thread owns 2 adjacent coefficients and BT blocks at a time; accumulators stay in
 //    registers across the whole k loop.
-//  * integer work is trimmed for primes <= 2^50 (all SEAL BFVDefault primes up to N=16384): the four
-//    32x32 partial products are accumulated in three separate lazy sums (lo with carry count,
-//    mid 64-bit, hi 64-bit) — 4 IMAD(.WIDE) + 1 carry add per 64x64 MAC, no 128-bit carry chains.
+//  * integer work is trimmed by the split operand format below: 3 IMAD.WIDE.U32 per 64x64 MAC.
 #pragma once
 #include "pf_common.cuh"
 
@@ -36,37 +34,49 @@ struct MacParams {
     int K, L, N;
 };
 
+// ---- split-operand lazy accumulation -------------------------------------------------------------
+// Operands of the MAC (rotated query ciphertexts and plaintext diagonals) are stored in HBM in
+// "split" form  w = (x >> s) << 32 | (x & (2^s - 1)),  s = ceil(bits(q)/2)  (both halves < 2^25 for
+// every SEAL BFVDefault prime up to N = 16384).  A 64x64 product then needs three 32x32->64
+// multiply-adds (Karatsuba) into plain 64-bit sums that cannot overflow over K <= 128 terms:
+//   lo += x0*y0;  hi += x1*y1;  kz += (x0+x1)*(y0+y1);      x*y = lo + (kz-lo-hi)*2^s + hi*2^2s
+// = 3 IMAD.WIDE.U32 per MAC, no carries, accumulators in aligned register pairs.
 struct LazyAcc {
-    u32 l0, l1, c; // sum of lo*lo partial products, with carry count
-    u64 mid;       // sum of lo*hi + hi*lo
-    u64 hi;        // sum of hi*hi
+    u64 lo, kz, hi;
 };
 
-__device__ __forceinline__ void lazy_zero(LazyAcc &a) {
-    a.l0 = a.l1 = a.c = 0;
-    a.mid = a.hi = 0;
+__device__ __forceinline__ void lazy_zero(LazyAcc &a) { a.lo = a.kz = a.hi = 0; }
+
+__device__ __forceinline__ void mad_wide(u64 &acc, u32 a, u32 b) {
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b));
 }
 
-__device__ __forceinline__ void lazy_mac(LazyAcc &a, u64 x, u64 y) {
-    const u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
-    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-        "addc.u32 %2, %2, 0;"
-        : "+r"(a.l0), "+r"(a.l1), "+r"(a.c)
-        : "r"(x0), "r"(y0));
-    a.mid += (u64)x0 * y1;
-    a.mid += (u64)x1 * y0;
-    a.hi += (u64)x1 * y1;
+// xs / ys = x0 + x1, y0 + y1 precomputed by the caller (shared by several MACs)
+__device__ __forceinline__ void lazy_mac(LazyAcc &a, u32 x0, u32 x1, u32 xs, u32 y0, u32 y1, u32 ys) {
+    mad_wide(a.lo, x0, y0);
+    mad_wide(a.hi, x1, y1);
+    mad_wide(a.kz, xs, ys);
 }
 
-__device__ __forceinline__ u64 lazy_reduce(const LazyAcc &a, const DevModulus &m) {
-    const u64 lo64 = ((u64)a.l1 << 32) | a.l0;
-    const u64 vlo = lo64 + (a.mid << 32);
-    const u64 vhi = (u64)a.c + (a.mid >> 32) + a.hi + (vlo < lo64 ? 1ull : 0ull);
+__device__ __forceinline__ void add128(u64 &lo, u64 &hi, u64 alo, u64 ahi) {
+    lo += alo;
+    hi += ahi + (lo < alo ? 1ull : 0ull);
+}
+
+__device__ __forceinline__ u64 lazy_reduce(const LazyAcc &a, int s, const DevModulus &m) {
+    const u64 mid = a.kz - a.lo - a.hi; // exact: kz >= lo + hi term by term
+    u64 vlo = a.lo, vhi = 0;
+    add128(vlo, vhi, mid << s, mid >> (64 - s));
+    const int s2 = 2 * s;
+    if (s2 < 64) add128(vlo, vhi, a.hi << s2, a.hi >> (64 - s2));
+    else vhi += a.hi << (s2 - 64);
     return barrett128(vlo, vhi, m.q, m.ratio0, m.ratio1);
 }
 
-// generic accumulator for primes > 2^50: full 128-bit sum, reduced every `period` terms by the caller
+__device__ __forceinline__ u64 split_word(u64 x, int s) { return ((x >> s) << 32) | (x & ((1ull << s) - 1)); }
+__device__ __forceinline__ u64 unsplit_word(u64 w, int s) { return ((w >> 32) << s) | (w & 0xffffffffull); }
+
+// generic accumulator for primes whose split sums could overflow: canonical operands, full 128-bit sum
 struct WideAcc {
     u64 lo, hi;
 };
@@ -77,10 +87,136 @@ __device__ __forceinline__ void wide_mac(WideAcc &a, u64 x, u64 y) {
         : "l"(x), "l"(y));
 }
 
-template <int T, int BT, int UNROLL, bool WIDE>
-__global__ void __launch_bounds__(256) mac_kernel(const MacParams p) {
-    constexpr int TX = T / 2;      // threads along the slice (2 coefficients each)
-    constexpr int BY = 256 / TX;   // block lanes
+struct SplitOp {
+    u32 x0, x1, xs;
+};
+__device__ __forceinline__ SplitOp make_op(u64 w) {
+    SplitOp o;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(o.x0), "=r"(o.x1) : "l"(w));
+    o.xs = o.x0 + o.x1;
+    return o;
+}
+
+template <int BT, int UNROLL, int TX>
+__device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulonglong2 *sct, const DevModulus &m,
+                                                int split, size_t coef0, size_t LN, int tx, size_t pair0) {
+    const ulonglong2 *bp[BT];
+#pragma unroll
+    for (int j = 0; j < BT; j++) {
+        const long long b = p.pair_block[pair0 + j];
+        bp[j] = reinterpret_cast<const ulonglong2 *>(p.diag + (size_t)b * p.diag_sb + coef0) + tx;
+    }
+    LazyAcc acc[BT][2][2]; // [block][poly][coef]
+#pragma unroll
+    for (int j = 0; j < BT; j++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            lazy_zero(acc[j][c][0]);
+            lazy_zero(acc[j][c][1]);
+        }
+    const size_t sk2 = (size_t)p.diag_sk / 2;
+    // software pipeline over k in groups of UNROLL: the loads of group i+1 are issued before the MACs
+    // of group i, so every thread keeps UNROLL*BT..2*UNROLL*BT 128-bit loads in flight at all times.
+    ulonglong2 pa[UNROLL][BT], pb[UNROLL][BT];
+    auto load_group = [&](ulonglong2(&dst)[UNROLL][BT]) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++)
+#pragma unroll
+            for (int j = 0; j < BT; j++) {
+                dst[u][j] = ldg_stream(bp[j]);
+                bp[j] += sk2;
+            }
+    };
+    auto mac_group = [&](const ulonglong2(&pt)[UNROLL][BT], int k0) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const ulonglong2 c0 = sct[(size_t)((k0 + u) * 2 + 0) * TX];
+            const ulonglong2 c1 = sct[(size_t)((k0 + u) * 2 + 1) * TX];
+            const SplitOp a00 = make_op(c0.x), a01 = make_op(c0.y), a10 = make_op(c1.x), a11 = make_op(c1.y);
+#pragma unroll
+            for (int j = 0; j < BT; j++) {
+                const SplitOp b0 = make_op(pt[u][j].x), b1 = make_op(pt[u][j].y);
+                lazy_mac(acc[j][0][0], a00.x0, a00.x1, a00.xs, b0.x0, b0.x1, b0.xs);
+                lazy_mac(acc[j][0][1], a01.x0, a01.x1, a01.xs, b1.x0, b1.x1, b1.xs);
+                lazy_mac(acc[j][1][0], a10.x0, a10.x1, a10.xs, b0.x0, b0.x1, b0.xs);
+                lazy_mac(acc[j][1][1], a11.x0, a11.x1, a11.xs, b1.x0, b1.x1, b1.xs);
+            }
+        }
+    };
+    load_group(pa);
+    int k0 = 0;
+    for (; k0 + 2 * UNROLL <= p.K; k0 += 2 * UNROLL) {
+        load_group(pb);
+        mac_group(pa, k0);
+        if (k0 + 2 * UNROLL < p.K) load_group(pa);
+        mac_group(pb, k0 + UNROLL);
+    }
+    if (k0 < p.K) mac_group(pa, k0); // K == UNROLL (odd number of groups only happens for one group)
+#pragma unroll
+    for (int j = 0; j < BT; j++) {
+        const size_t pair = pair0 + j;
+        ulonglong2 r0, r1;
+        r0.x = lazy_reduce(acc[j][0][0], split, m);
+        r0.y = lazy_reduce(acc[j][0][1], split, m);
+        r1.x = lazy_reduce(acc[j][1][0], split, m);
+        r1.y = lazy_reduce(acc[j][1][1], split, m);
+        if (p.norm) {
+            const long long b = p.pair_block[pair];
+            const ulonglong2 nv =
+                ldg_stream(reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
+            r0.x = addmod(r0.x, nv.x, m.q);
+            r0.y = addmod(r0.y, nv.y, m.q);
+        }
+        u64 *o = p.out + pair * 2 * LN + coef0;
+        stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
+        stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
+    }
+}
+
+template <int TX>
+__device__ __forceinline__ void mac_pair_wide(const MacParams &p, const ulonglong2 *sct, const DevModulus &m,
+                                              size_t coef0, size_t LN, int tx, size_t pair) {
+    const long long b = p.pair_block[pair];
+    const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(p.diag + (size_t)b * p.diag_sb + coef0) + tx;
+    WideAcc a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+    const size_t sk2 = (size_t)p.diag_sk / 2;
+    for (int k = 0; k < p.K; k++) {
+        const ulonglong2 c0 = sct[(size_t)(k * 2 + 0) * TX];
+        const ulonglong2 c1 = sct[(size_t)(k * 2 + 1) * TX];
+        const ulonglong2 pt = ldg_stream(bp + (size_t)k * sk2);
+        wide_mac(a00, c0.x, pt.x);
+        wide_mac(a01, c0.y, pt.y);
+        wide_mac(a10, c1.x, pt.x);
+        wide_mac(a11, c1.y, pt.y);
+        if ((k & 15) == 15) { // 16 * q^2 + q < 2^128 for q < 2^61
+            a00.lo = barrett128(a00.lo, a00.hi, m.q, m.ratio0, m.ratio1);
+            a01.lo = barrett128(a01.lo, a01.hi, m.q, m.ratio0, m.ratio1);
+            a10.lo = barrett128(a10.lo, a10.hi, m.q, m.ratio0, m.ratio1);
+            a11.lo = barrett128(a11.lo, a11.hi, m.q, m.ratio0, m.ratio1);
+            a00.hi = a01.hi = a10.hi = a11.hi = 0;
+        }
+    }
+    ulonglong2 r0, r1;
+    r0.x = barrett128(a00.lo, a00.hi, m.q, m.ratio0, m.ratio1);
+    r0.y = barrett128(a01.lo, a01.hi, m.q, m.ratio0, m.ratio1);
+    r1.x = barrett128(a10.lo, a10.hi, m.q, m.ratio0, m.ratio1);
+    r1.y = barrett128(a11.lo, a11.hi, m.q, m.ratio0, m.ratio1);
+    if (p.norm) {
+        const ulonglong2 nv =
+            ldg_stream(reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
+        r0.x = addmod(r0.x, nv.x, m.q);
+        r0.y = addmod(r0.y, nv.y, m.q);
+    }
+    u64 *o = p.out + pair * 2 * LN + coef0;
+    stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
+    stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
+}
+
+// K is a power of two and UNROLL divides it: K/UNROLL is 1 or even (host picks UNROLL = min(K, 2)).
+template <int T, int UNROLL, bool WIDE>
+__global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
+    constexpr int TX = T / 2;    // threads along the slice (2 coefficients each)
+    constexpr int BY = 256 / TX; // block lanes (warp-uniform: TX >= 32)
     extern __shared__ __align__(16) u64 smem_ct[]; // [K][2][T]
     const MacChunk ch = p.chunks[blockIdx.x];
     const int slices = p.N / T;
@@ -90,7 +226,7 @@ __global__ void __launch_bounds__(256) mac_kernel(const MacParams p) {
     const size_t LN = (size_t)p.L * p.N;
     const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
 
-    // stage the query's rotated-ciphertext slice
+    // stage the query's rotated-ciphertext slice once; every block of the chunk reuses it
     {
         const u64 *src = p.rot + (size_t)ch.query * p.K * 2 * LN + coef0;
         const int rows = p.K * 2;
@@ -103,116 +239,27 @@ __global__ void __launch_bounds__(256) mac_kernel(const MacParams p) {
     __syncthreads();
 
     const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(smem_ct) + tx;
-    for (int pi = by * BT; pi < ch.pair_count; pi += BY * BT) {
-        const ulonglong2 *bp[BT];
-        bool valid[BT];
-#pragma unroll
-        for (int j = 0; j < BT; j++) {
-            valid[j] = (pi + j) < ch.pair_count;
-            const long long b = p.pair_block[ch.pair_start + (valid[j] ? pi + j : pi)];
-            bp[j] = reinterpret_cast<const ulonglong2 *>(p.diag + (size_t)b * p.diag_sb + coef0) + tx;
-        }
-        if (!WIDE) {
-            LazyAcc acc[BT][2][2];
-#pragma unroll
-            for (int j = 0; j < BT; j++)
-#pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    lazy_zero(acc[j][c][0]);
-                    lazy_zero(acc[j][c][1]);
-                }
-            const size_t sk2 = (size_t)p.diag_sk / 2;
-            for (int k0 = 0; k0 < p.K; k0 += UNROLL) {
-                ulonglong2 pt[UNROLL][BT];
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++)
-#pragma unroll
-                    for (int j = 0; j < BT; j++)
-                        if (k0 + u < p.K) pt[u][j] = ldg_stream(bp[j] + (size_t)(k0 + u) * sk2);
-#pragma unroll
-                for (int u = 0; u < UNROLL; u++) {
-                    if (k0 + u < p.K) {
-                        const ulonglong2 c0 = sct[(size_t)((k0 + u) * 2 + 0) * TX];
-                        const ulonglong2 c1 = sct[(size_t)((k0 + u) * 2 + 1) * TX];
-#pragma unroll
-                        for (int j = 0; j < BT; j++) {
-                            lazy_mac(acc[j][0][0], c0.x, pt[u][j].x);
-                            lazy_mac(acc[j][0][1], c0.y, pt[u][j].y);
-                            lazy_mac(acc[j][1][0], c1.x, pt[u][j].x);
-                            lazy_mac(acc[j][1][1], c1.y, pt[u][j].y);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                if (!valid[j]) continue;
-                const size_t pair = (size_t)ch.pair_start + pi + j;
-                ulonglong2 r0, r1;
-                r0.x = lazy_reduce(acc[j][0][0], m);
-                r0.y = lazy_reduce(acc[j][0][1], m);
-                r1.x = lazy_reduce(acc[j][1][0], m);
-                r1.y = lazy_reduce(acc[j][1][1], m);
-                if (p.norm) {
-                    const long long b = p.pair_block[pair];
-                    const ulonglong2 nv =
-                        ldg_stream(reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
-                    r0.x = addmod(r0.x, nv.x, m.q);
-                    r0.y = addmod(r0.y, nv.y, m.q);
-                }
-                u64 *o = p.out + pair * 2 * LN + coef0;
-                stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
-                stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
-            }
-        } else {
-            // generic path: 128-bit accumulators, one Barrett-128 every 16 terms (16 * q^2 < 2^128 for q < 2^62)
-            WideAcc acc[BT][2][2];
-#pragma unroll
-            for (int j = 0; j < BT; j++)
-#pragma unroll
-                for (int c = 0; c < 2; c++) acc[j][c][0].lo = acc[j][c][0].hi = acc[j][c][1].lo = acc[j][c][1].hi = 0;
-            const size_t sk2 = (size_t)p.diag_sk / 2;
-            for (int k = 0; k < p.K; k++) {
-                const ulonglong2 c0 = sct[(size_t)(k * 2 + 0) * TX];
-                const ulonglong2 c1 = sct[(size_t)(k * 2 + 1) * TX];
-#pragma unroll
-                for (int j = 0; j < BT; j++) {
-                    const ulonglong2 pt = ldg_stream(bp[j] + (size_t)k * sk2);
-                    wide_mac(acc[j][0][0], c0.x, pt.x);
-                    wide_mac(acc[j][0][1], c0.y, pt.y);
-                    wide_mac(acc[j][1][0], c1.x, pt.x);
-                    wide_mac(acc[j][1][1], c1.y, pt.y);
-                    if ((k & 15) == 15) {
-#pragma unroll
-                        for (int c = 0; c < 2; c++)
-#pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                acc[j][c][h].lo = barrett128(acc[j][c][h].lo, acc[j][c][h].hi, m.q, m.ratio0, m.ratio1);
-                                acc[j][c][h].hi = 0;
-                            }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                if (!valid[j]) continue;
-                const size_t pair = (size_t)ch.pair_start + pi + j;
-                ulonglong2 r0, r1;
-                r0.x = barrett128(acc[j][0][0].lo, acc[j][0][0].hi, m.q, m.ratio0, m.ratio1);
-                r0.y = barrett128(acc[j][0][1].lo, acc[j][0][1].hi, m.q, m.ratio0, m.ratio1);
-                r1.x = barrett128(acc[j][1][0].lo, acc[j][1][0].hi, m.q, m.ratio0, m.ratio1);
-                r1.y = barrett128(acc[j][1][1].lo, acc[j][1][1].hi, m.q, m.ratio0, m.ratio1);
-                if (p.norm) {
-                    const long long b = p.pair_block[pair];
-                    const ulonglong2 nv =
-                        ldg_stream(reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
-                    r0.x = addmod(r0.x, nv.x, m.q);
-                    r0.y = addmod(r0.y, nv.y, m.q);
-                }
-                u64 *o = p.out + pair * 2 * LN + coef0;
-                stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
-                stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
-            }
-        }
+    if (WIDE) {
+        for (int pi = by; pi < ch.pair_count; pi += BY)
+            mac_pair_wide<TX>(p, sct, m, coef0, LN, tx, (size_t)ch.pair_start + pi);
+    } else {
+        const int split = (int)m.split_shift;
+        int pi = by * 2;
+        for (; pi + 1 < ch.pair_count; pi += BY * 2)
+            mac_pairs_split<2, UNROLL, TX>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
+        if (pi < ch.pair_count) // odd tail: one pair left for this lane
+            mac_pairs_split<1, UNROLL, TX>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
     }
+}
+
+// canonical <-> split conversion of polynomial arrays: chunk y (blockIdx.y) of `chunk_words` words is
+// read at in + y*in_stride and written at out + y*out_stride; limb of word i of a chunk = (i / N) % L
+__global__ void __launch_bounds__(256) split_convert_kernel(const u64 *in, u64 *out, size_t chunk_words,
+                                                            size_t in_stride, size_t out_stride,
+                                                            const DevModulus *mods, int L, int N, int to_split) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= chunk_words) return;
+    const int s = (int)mods[(i / N) % L].split_shift;
+    const u64 x = in[(size_t)blockIdx.y * in_stride + i];
+    out[(size_t)blockIdx.y * out_stride + i] = to_split ? split_word(x, s) : unsplit_word(x, s);
 }

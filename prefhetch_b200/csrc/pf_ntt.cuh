@@ -23,6 +23,8 @@ struct NttParams {
     int src_map[PF_NTT_MAXMAP];  // blockIdx.y -> modulus index the input limb is reduced under (GALOIS_REDUCE)
     u64 lift_t, lift_thr;        // NTT_IN_LIFT: plain modulus and (t+1)/2
     const struct RotJob *jobs;   // NTT_IN_GALOIS_REDUCE: per blockIdx.z source polynomial and element
+    int out_split;               // forward only: store results in the MAC's split operand format
+    int *zero_flags;             // NTT_IN_REDUCE: zero_flags[blockIdx.z] = 1 if an input coefficient is 0
 };
 
 // one rotation = Evaluator::apply_galois_inplace on one ciphertext (see pf_keyswitch.cuh)
@@ -34,6 +36,10 @@ struct RotJob {
     u64 *out;           // [2][L][N] NTT form
     u32 einv;           // element^{-1} mod 2N
     u32 pad;
+    // hoisted path (pf_keyswitch.cuh): digits of the un-rotated c1, shared by every rotation of it
+    const u64 *D;       // [L][L+1][N]: NTT_I(c1_J mod q_I); nullptr -> exact per-rotation digits
+    const u64 *KM;      // [2][L+1][N]: per-key correction term
+    const int *flag;    // *flag != 0 -> c1 has a zero coefficient: use the exact per-rotation digits
 };
 
 __device__ __forceinline__ int sm_phys(int i) { return i + (i >> 5); }
@@ -176,10 +182,18 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
     const u64 q = m.q;
     const u32 gal_einv = (INMODE == NTT_IN_GALOIS_REDUCE) ? p.jobs[blockIdx.z].einv : 0u;
+    if (INMODE == NTT_IN_GALOIS_REDUCE) { // exact digits are only needed where hoisting does not apply
+        const RotJob &jb = p.jobs[blockIdx.z];
+        if (jb.D && !*jb.flag) return;
+    }
 
     auto gload = [&](int idx) -> u64 {
         if (INMODE == NTT_IN_PLAIN) return in[idx];
-        if (INMODE == NTT_IN_REDUCE) return barrett64(in[idx], q, m.ratio1);
+        if (INMODE == NTT_IN_REDUCE) {
+            const u64 x = in[idx];
+            if (x == 0 && p.zero_flags) p.zero_flags[blockIdx.z] = 1;
+            return barrett64(x, q, m.ratio1);
+        }
         if (INMODE == NTT_IN_LIFT) {
             u64 x = in[idx];
             return x >= p.lift_thr ? x + (q - p.lift_t) : x;
@@ -204,6 +218,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         const u64 two_q = q << 1;
         x = x >= two_q ? x - two_q : x;
         x = x >= q ? x - q : x;
+        if (p.out_split) x = ((x >> m.split_shift) << 32) | (x & ((1ull << m.split_shift) - 1));
         sm[sm_phys(idx)] = x;
     };
     ntt_fwd_pass<LOGN, Cfg::K3, 4>(tw, q, sload, fstore);

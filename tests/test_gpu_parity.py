@@ -140,6 +140,14 @@ def test_rotate_rows_bit_exact(pf, oracle, n):
         half = n // 2
         assert np.array_equal(cl.ctx.decode(plain),
                               np.concatenate([np.roll(vals[:half], -step), np.roll(vals[half:], -step)]))
+    # a c1 with zero coefficients leaves the hoisted path (its residue identity needs x != 0) and must
+    # still match SEAL's semantics bit for bit
+    ctz = ct.copy()
+    ctz[1, 0, 5] = 0
+    ctz[1, 2, n - 1] = 0
+    ctz[1, 1, 0] = 0
+    for step in (1, 3):
+        assert np.array_equal(eng.rotate_rows(ctz, step), cl.ctx.rotate_rows(ctz, step, cl.galois_key(step)))
     with pytest.raises(pf.PfError):
         eng.rotate_rows(ct, 7)  # no key loaded for this step
     eng.close()
