@@ -14,6 +14,10 @@ struct DevModulus {
     u64 n_inv, n_inv_sh; // N^{-1} mod q and its Shoup quotient
     u64 inv_last_w, inv_last_w_sh; // irp[1] * N^{-1} (last inverse stage with the scaling folded in)
     u64 split_shift; // s = ceil(bits(q)/2): operand split point of the MAC storage format (0 = canonical)
+    // key-switch mod-down constants of a data limb (special prime P = last prime of the chain)
+    u64 p_half_mod;        // (P >> 1) mod q
+    u64 p_inv, p_inv_sh;   // P^{-1} mod q and its Shoup quotient
+    u64 pad2;
 };
 
 // twiddle tables per modulus: fwd[N] then inv[N], each entry {w, floor(w*2^64/q)}

@@ -213,6 +213,8 @@ cudaError_t set_ntt_attrs() {
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_REDUCE>));
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
     SETATTR((ntt_inv_kernel<LOGN>));
+    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
+    SETATTR((ntt_inv_kernel<LOGN, NTT_OUT_KS>));
 #undef SETATTR
     return cudaSuccess;
 }
@@ -221,8 +223,12 @@ template <int LOGN>
 void launch_ntt_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
     const size_t smem = NttCfg<LOGN>::SMEM;
     const int nt = NttCfg<LOGN>::NT;
-    if (inverse)
+    if (inverse && p.ks_W)
+        ntt_inv_kernel<LOGN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
+    else if (inverse)
         ntt_inv_kernel<LOGN><<<grid, nt, smem, s>>>(p);
+    else if (p.ks_S)
+        ntt_fwd_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_PLAIN)
         ntt_fwd_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_LIFT)
@@ -298,6 +304,13 @@ int build_tables(pf_engine *e) {
         m.inv_last_w = pfh::mulmod(inv[1].x, n_inv, q);
         m.inv_last_w_sh = shoup(m.inv_last_w, q);
         m.split_shift = (u64)((64 - __builtin_clzll(q) + 1) / 2);
+        m.p_half_mod = m.p_inv = m.p_inv_sh = m.pad2 = 0;
+        if (j < L) {
+            const u64 P = e->h_q[k - 1];
+            m.p_half_mod = (P >> 1) % q;
+            m.p_inv = invmod(P % q, q);
+            m.p_inv_sh = shoup(m.p_inv, q);
+        }
     }
     CK(e->d_mods.ensure(mods.size() * sizeof(DevModulus)));
     CK(cudaMemcpy(e->d_mods.p, mods.data(), mods.size() * sizeof(DevModulus), cudaMemcpyHostToDevice));
@@ -360,6 +373,8 @@ int set_galois_key_words(pf_engine *e, u32 elt, const u64 *words, bool device_sr
     CK(gk.key.ensure(words_n * 8));
     CK(cudaMemcpyAsync(gk.key.p, words, words_n * 8, device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                        e->stream));
+    key_split_kernel<<<dim3(N / 256, e->L * 2 * e->k), 256, 0, e->stream>>>(gk.key.as<u64>(), e->d_mods.as<DevModulus>(), e->k, (int)N);
+    e->launches++;
     std::vector<u32> perm(N); // SEAL GaloisTool::generate_table_ntt
     for (u32 i = 0; i < N; i++) {
         const u32 rev = pfh::bitrev(i, e->logn);
@@ -434,11 +449,19 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         np.out_sz = (long long)per_d;
         for (int I = 0; I <= L; I++) np.mod_map[I] = (I == L) ? k - 1 : I;
         for (int J = 0; J < L; J++) np.src_map[J] = J;
+        np.out_split = 1;
         launch_ntt(e, NTT_IN_GALOIS_REDUCE, false, np, dim3(L + 1, L, nz));
         // 2. S_c[I]
-        ks_accumulate_kernel<<<dim3(N / 512, L + 1, nz), 256, 0, e->stream>>>(kp);
+        {
+            const dim3 g(N / 512, L + 1, (nz + KS_QT - 1) / KS_QT);
+            if (L <= 4) ks_accumulate_kernel<4><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else if (L <= 8) ks_accumulate_kernel<8><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else ks_accumulate_kernel<KS_MAXL><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+        }
         e->launches++;
-        // 3. u_c = INTT_P(S_c[L]) in place: grid (1, 2, z)
+        // 3. u_c = INTT_P(S_c[L]) in place, then W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).
+        // (The fused NTT_OUT_KS inverse epilogue exists but measured slower than this pair on B200:
+        // 0.69 ms vs 0.40 ms per step, profiles/r1_launches_step_v4.txt.)
         NttParams ip{};
         ip.in = kp.S + (size_t)L * N;
         ip.out = kp.S + (size_t)L * N;
@@ -448,7 +471,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(1, 2, nz));
         ks_moddown_prep_kernel<<<dim3(N / 256, 2, nz), 256, 0, e->stream>>>(kp);
         e->launches++;
-        // NTT_j(W_c[j]) in place: grid (L, 2, z)
+        // 4. NTT_j(W_c[j]) with the key-switch finish fused into its copy-out: writes the rotated ciphertext
         NttParams wp{};
         wp.in = kp.W;
         wp.out = kp.W;
@@ -456,10 +479,11 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         wp.in_sy = wp.out_sy = (long long)L * N;
         wp.in_sz = wp.out_sz = (long long)per_W;
         for (int j = 0; j < L; j++) wp.mod_map[j] = j;
+        wp.jobs = dj;
+        wp.ks_S = kp.S;
+        wp.ks_L = L;
+        wp.out_split = out_split ? 1 : 0;
         launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
-        // 4. finish
-        ks_finish_kernel<<<dim3(N / 256, 2 * L, nz), 256, 0, e->stream>>>(kp);
-        e->launches++;
     }
     CK(cudaGetLastError());
     return PF_OK;
@@ -484,6 +508,7 @@ int hoist_digits(pf_engine *e, const u64 *d_cts, size_t ncts, size_t ct_stride) 
         p.out_sy = (long long)(L + 1) * N;
         p.out_sz = (long long)per_d;
         p.zero_flags = e->s_flags.as<int>() + off;
+        p.out_split = 1;
         for (int I = 0; I <= L; I++) p.mod_map[I] = (I == L) ? k - 1 : I;
         launch_ntt(e, NTT_IN_REDUCE, false, p, dim3(L + 1, L, (unsigned)cnt));
     }
@@ -558,9 +583,9 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
         if (hrc) return hrc;
         const size_t per_d = (size_t)L * (L + 1) * N;
         jobs.reserve(nq * m * (R - 1));
-        for (size_t i = 0; i < nq; i++)
-            for (size_t a = 0; a < m; a++)
-                for (size_t r = 1; r < R; r++) {
+        for (size_t r = 1; r < R; r++) // rotation-major: consecutive jobs share the Galois key
+            for (size_t i = 0; i < nq; i++)
+                for (size_t a = 0; a < m; a++) {
                     const GaloisKey *gk = find_key(e, (int)r);
                     RotJob j{};
                     j.c1_coef = d_cts + (i * m + a) * ctw + (size_t)L * N;

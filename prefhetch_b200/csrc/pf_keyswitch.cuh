@@ -34,63 +34,86 @@ struct KsParams {
     int out_split; // write the rotated ciphertext in the MAC's split operand format
 };
 
-// grid (N/512, L+1, z); thread = 2 coefficients of output limb I, both key components
-__global__ void __launch_bounds__(256) ks_accumulate_kernel(const KsParams p) {
-    const int I = blockIdx.y, z = blockIdx.z, L = p.L, N = p.N;
+// S_c[I] for KS_QT consecutive jobs per CTA.  Jobs are ordered rotation-major, so consecutive jobs
+// share the Galois key: its 2*L words per coefficient stay in registers across the KS_QT queries and
+// the key stream (2.5 MiB per rotation at N=8192) is read once per KS_QT jobs instead of once per job.
+// Keys, hoisted digits D and exact digits d are all stored in the split operand format of their limb.
+// grid (N/512, L+1, ceil(z/KS_QT)); thread = 2 coefficients of output limb I, both key components
+#define KS_QT 8
+#define KS_MAXL 15
+template <int LT>
+__global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
+    const int I = blockIdx.y, L = p.L, N = p.N;
     const int ki = (I == L) ? p.k - 1 : I;
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
-    const RotJob job = p.jobs[z];
-    const bool hoisted = job.D && !*job.flag;
-    LazyAcc a00, a01, a10, a11;
-    lazy_zero(a00);
-    lazy_zero(a01);
-    lazy_zero(a10);
-    lazy_zero(a11);
     const int sh = (int)m.split_shift;
-    const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
-    u32 px = 0, py = 0;
-    if (hoisted) {
-        const uint2 pp = reinterpret_cast<const uint2 *>(job.perm)[c2];
-        px = pp.x;
-        py = pp.y;
-    }
-    for (int J = 0; J < L; J++) {
-        ulonglong2 dv;
-        if (hoisted) {
-            const u64 *dj = job.D + ((size_t)J * (L + 1) + I) * N;
-            dv.x = dj[px];
-            dv.y = dj[py];
-        } else {
-            dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
+    const int z0 = blockIdx.z * KS_QT, z1 = min(z0 + KS_QT, njobs);
+    ulonglong2 k0[LT], k1[LT];
+    const u64 *cur_key = nullptr;
+    for (int z = z0; z < z1; z++) {
+        const RotJob job = p.jobs[z];
+        if (job.key != cur_key) { // uniform across the CTA
+            cur_key = job.key;
+#pragma unroll
+            for (int J = 0; J < LT; J++) {
+                if (J < L) {
+                    const u64 *kj = job.key + (size_t)J * 2 * p.k * N;
+                    k0[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
+                    k1[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(p.k + ki) * N) + c2);
+                }
+            }
         }
-        const u64 *kj = job.key + (size_t)J * 2 * p.k * N;
-        const ulonglong2 k0 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
-        const ulonglong2 k1 = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(p.k + ki) * N) + c2);
-        const SplitOp dx = make_op(split_word(dv.x, sh)), dy = make_op(split_word(dv.y, sh));
-        const SplitOp k0x = make_op(split_word(k0.x, sh)), k0y = make_op(split_word(k0.y, sh));
-        const SplitOp k1x = make_op(split_word(k1.x, sh)), k1y = make_op(split_word(k1.y, sh));
-        lazy_mac(a00, dx.x0, dx.x1, dx.xs, k0x.x0, k0x.x1, k0x.xs);
-        lazy_mac(a01, dy.x0, dy.x1, dy.xs, k0y.x0, k0y.x1, k0y.xs);
-        lazy_mac(a10, dx.x0, dx.x1, dx.xs, k1x.x0, k1x.x1, k1x.xs);
-        lazy_mac(a11, dy.x0, dy.x1, dy.xs, k1y.x0, k1y.x1, k1y.xs);
+        const bool hoisted = job.D && !*job.flag;
+        LazyAcc a00, a01, a10, a11;
+        lazy_zero(a00);
+        lazy_zero(a01);
+        lazy_zero(a10);
+        lazy_zero(a11);
+        const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
+        u32 px = 0, py = 0;
+        if (hoisted) {
+            const uint2 pp = reinterpret_cast<const uint2 *>(job.perm)[c2];
+            px = pp.x;
+            py = pp.y;
+        }
+#pragma unroll
+        for (int J = 0; J < LT; J++) {
+            if (J < L) {
+                ulonglong2 dv;
+                if (hoisted) {
+                    const u64 *dj = job.D + ((size_t)J * (L + 1) + I) * N;
+                    dv.x = dj[px];
+                    dv.y = dj[py];
+                } else {
+                    dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
+                }
+                const SplitOp dx = make_op(dv.x), dy = make_op(dv.y);
+                const SplitOp k0x = make_op(k0[J].x), k0y = make_op(k0[J].y);
+                const SplitOp k1x = make_op(k1[J].x), k1y = make_op(k1[J].y);
+                lazy_mac(a00, dx.x0, dx.x1, dx.xs, k0x.x0, k0x.x1, k0x.xs);
+                lazy_mac(a01, dy.x0, dy.x1, dy.xs, k0y.x0, k0y.x1, k0y.xs);
+                lazy_mac(a10, dx.x0, dx.x1, dx.xs, k1x.x0, k1x.x1, k1x.xs);
+                lazy_mac(a11, dy.x0, dy.x1, dy.xs, k1y.x0, k1y.x1, k1y.xs);
+            }
+        }
+        u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
+        ulonglong2 r0, r1;
+        r0.x = lazy_reduce(a00, sh, m);
+        r0.y = lazy_reduce(a01, sh, m);
+        r1.x = lazy_reduce(a10, sh, m);
+        r1.y = lazy_reduce(a11, sh, m);
+        if (hoisted) {
+            const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
+            const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
+            r0.x = addmod(r0.x, m0.x, m.q);
+            r0.y = addmod(r0.y, m0.y, m.q);
+            r1.x = addmod(r1.x, m1.x, m.q);
+            r1.y = addmod(r1.y, m1.y, m.q);
+        }
+        reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
+        reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
     }
-    u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
-    ulonglong2 r0, r1;
-    r0.x = lazy_reduce(a00, sh, m);
-    r0.y = lazy_reduce(a01, sh, m);
-    r1.x = lazy_reduce(a10, sh, m);
-    r1.y = lazy_reduce(a11, sh, m);
-    if (hoisted) {
-        const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
-        const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
-        r0.x = addmod(r0.x, m0.x, m.q);
-        r0.y = addmod(r0.y, m0.y, m.q);
-        r1.x = addmod(r1.x, m1.x, m.q);
-        r1.y = addmod(r1.y, m1.y, m.q);
-    }
-    reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
-    reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
 }
 
 // neg[i] = 1 where coefficient position i of sigma(a) holds a negated coefficient.  grid (N/256)
@@ -100,7 +123,7 @@ __global__ void __launch_bounds__(256) galois_negmask_kernel(u64 *out, u32 einv,
     out[idx] = i0 >= (u32)N ? 1ull : 0ull;
 }
 
-// KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I].  M[L+1][N] NTT form.  grid (N/256, L+1, 2)
+// KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I].  M[L+1][N] NTT form; key in split format.  grid (N/256, L+1, 2)
 __global__ void __launch_bounds__(256) galois_km_kernel(const u64 *M, const u64 *key, u64 *KM, const DevModulus *mods,
                                                         int L, int k, int N) {
     const int i = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, c = blockIdx.z;
@@ -109,7 +132,7 @@ __global__ void __launch_bounds__(256) galois_km_kernel(const u64 *M, const u64 
     u64 acc = 0;
     for (int J = 0; J < L; J++) {
         const u64 f = mods[J].q % m.q;
-        const u64 kv = key[(((size_t)J * 2 + c) * k + ki) * N + i];
+        const u64 kv = unsplit_word(key[(((size_t)J * 2 + c) * k + ki) * N + i], (int)m.split_shift);
         acc = addmod(acc, mulmod(f, kv, m), m.q);
     }
     KM[((size_t)c * (L + 1) + I) * N + i] = mulmod(acc, M[(size_t)I * N + i], m);
@@ -155,4 +178,12 @@ __global__ void __launch_bounds__(256) ct_add_kernel(const u64 *a, const u64 *b,
     const int i = blockIdx.x * 256 + threadIdx.x;
     const size_t o = (size_t)blockIdx.y * N + i;
     out[o] = addmod(a[o], b[o], mods[blockIdx.y % L].q);
+}
+
+// Galois key words [L][2][k][N] canonical -> split operand format of each limb.  grid (N/256, L*2*k)
+__global__ void __launch_bounds__(256) key_split_kernel(u64 *key, const DevModulus *mods, int k, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int limb = blockIdx.y % k;
+    u64 *w = key + (size_t)blockIdx.y * N + i;
+    *w = split_word(*w, (int)mods[limb].split_shift);
 }

@@ -327,3 +327,13 @@ def test_encrypted_search_errors(pf, oracle):
         pf.Engine(128, 8192, [17, 19], 16760833)
     with pytest.raises(pf.PfError):
         pf.Engine(128, 8192, partial_g=3)
+
+
+def test_cpp_host_mirror():
+    """prefhetch::Server (C++ mirror of the reference Server class) over the same C ABI"""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "prefhetch_b200" / "host" / "pf_server_check"
+    assert exe.exists(), "run __graft_entry__.build() first"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr

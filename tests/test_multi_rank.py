@@ -1,0 +1,84 @@
+"""world_size-2 checks of the multi-GPU host logic on CPU (gloo): list sharding by rank, the
+result-count exchange and the gather-to-rank-0 of per-shard result ciphertexts (bench.py's
+gather_results pattern) — with synthetic payloads standing in for ciphertexts (no GPU here)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def shard_plan(idx, list_sizes, C, rank, world):
+    """host-side mirror of plan_pairs() in pf_engine.cu: result ciphertexts of the lists rank owns"""
+    plan = []
+    for qi in range(idx.shape[0]):
+        for l in idx[qi]:
+            if l % world != rank:
+                continue
+            for b in range((int(list_sizes[l]) + C - 1) // C):
+                plan.append((qi, int(l), b))
+    return plan
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    nlist, nq, nprobe, C, words = 32, 6, 8, 64, 16
+    list_sizes = rng.integers(0, 200, size=nlist)
+    idx = np.stack([rng.choice(nlist, size=nprobe, replace=False) for _ in range(nq)])
+    plan = shard_plan(idx, list_sizes, C, rank, world)
+    # payload of result r = a deterministic function of (query, list, block): stands in for the ciphertext words
+    mine = torch.tensor([[qi * 1_000_000 + l * 1000 + b] * words for qi, l, b in plan], dtype=torch.int64).reshape(-1, words)
+    cnt = torch.tensor([len(plan)], dtype=torch.int64)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    gathered = {0: mine} if rank == 0 else None
+    if rank == 0:
+        for r in range(1, world):
+            c = int(cnts[r].item())
+            buf = torch.empty((c, words), dtype=torch.int64)
+            if c:
+                dist.recv(buf, src=r)
+            gathered[r] = buf
+    elif len(plan):
+        dist.send(mine, dst=0)
+    dist.barrier()
+    if rank == 0:
+        # the union over ranks must be exactly the single-rank plan, every (query, list, block) once
+        full = shard_plan(idx, list_sizes, C, 0, 1)
+        got = sorted(int(row[0]) for r in range(world) for row in gathered[r])
+        want = sorted(qi * 1_000_000 + l * 1000 + b for qi, l, b in full)
+        ok = got == want and sum(int(c.item()) for c in cnts) == len(full)
+        with open(out_path, "w") as f:
+            f.write("ok" if ok else f"mismatch {len(got)} {len(want)}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_shard_and_gather_gloo(tmp_path, world):
+    port = _free_port()
+    out = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(world, port, str(out)), nprocs=world, join=True)
+    assert out.read_text() == "ok"
+
+
+def test_shards_partition_the_lists():
+    rng = np.random.default_rng(1)
+    list_sizes = rng.integers(0, 3000, size=100)
+    idx = np.stack([rng.choice(100, size=16, replace=False) for _ in range(5)])
+    full = set(shard_plan(idx, list_sizes, 1024, 0, 1))
+    for world in (2, 4, 8):
+        parts = [set(shard_plan(idx, list_sizes, 1024, r, world)) for r in range(world)]
+        assert set().union(*parts) == full
+        assert sum(len(p) for p in parts) == len(full)
