@@ -229,7 +229,7 @@ def make_dataset_cpu_light(cfg, seed=1234):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=list(CONFIGS))
@@ -409,7 +409,7 @@ def main():
             qnp[c * ctb: c * ctb + len(hdr)] = hdr
             qnp[c * ctb + len(hdr): (c + 1) * ctb] = host_ct[c].view(np.uint8)
         offs = (np.arange(nq * m + 1, dtype=np.uint64) * ctb)
-        out_host = torch.empty(max_res * ctb, dtype=torch.uint8).pin_memory()
+        out_host = torch.empty(max_res * eng.slot_bytes, dtype=torch.uint8).pin_memory()
         out_np = out_host.numpy()
         e_steps = max(2, min(args.steps, 5))
         e_useful, h2d, d2h = 0, 0, 0

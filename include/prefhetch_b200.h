@@ -124,7 +124,10 @@ typedef struct {
  * query_cts holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level) back to back,
  * ct_offsets[nq*m+1] their byte offsets.  For query i and each of its lists idx[i][p] (in order, lists
  * not owned by this rank are skipped) one result ciphertext per block of the list is written to
- * out_cts in SEAL format (coefficient form), result_offsets[nresults+1].  results_per_query[nq].
+ * out_cts in SEAL format (coefficient form).  Result r is the pf_ct_serialized_size() bytes starting
+ * at result_offsets[r]; results sit in slots of pf_result_slot_size() bytes so that their words are
+ * 128-byte aligned for the device-to-host copy (out_cap >= nresults * slot; result_offsets[nresults]
+ * = bytes used).  Pinned, 128-byte aligned out_cts gives the fastest copies.  results_per_query[nq].
  * labels / list_sizes as in pf_search_lists_plain (ids of the owned probed lists, packed);
  * probed_sizes[nq][nprobe] = length of each probed list (0 when not owned) so the client can map
  * candidate j of a list to (result j / C, candidate j % C). */
@@ -173,6 +176,8 @@ int pf_batch_encode(pf_engine *e, const uint64_t *values, uint64_t *plain);
 int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *diag, uint64_t *norm);
 /* SEAL wire format (compr_mode none) of a coefficient-form size-2 ciphertext */
 size_t pf_ct_serialized_size(pf_engine *e);
+/* bytes of out_cts reserved per result ciphertext by pf_search_lists_encrypted */
+size_t pf_result_slot_size(pf_engine *e);
 int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written);
 int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, int *is_ntt, size_t *consumed);
 

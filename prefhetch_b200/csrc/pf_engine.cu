@@ -82,7 +82,9 @@ struct BlockInfo {
     u32 list;
 };
 
-constexpr size_t SEAL_CT_HEADER = 16 + 32 + 1 + 8 * 5 + 16 + 8; // bytes before the data words
+constexpr size_t SEAL_CT_HEADER = 16 + 32 + 1 + 8 * 5 + 16 + 8; // bytes before the data words (113)
+constexpr size_t PF_RESULT_DATA_OFFSET = 128;                      // words of result r start at r*slot + 128
+constexpr size_t PF_RESULT_PAD = PF_RESULT_DATA_OFFSET - SEAL_CT_HEADER; // its SEAL stream starts here
 
 } // namespace
 
@@ -128,6 +130,8 @@ struct pf_engine {
     DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_qcts, s_out, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_group[2] = {nullptr, nullptr};
 
     // timing
     bool timing = false;
@@ -698,14 +702,10 @@ int plan_pairs(pf_engine *e, uint64_t nq, const int64_t *idx, uint32_t nprobe, P
     return PF_OK;
 }
 
-// The device-resident step: rotations, MAC, inverse NTT.  d_out must hold P ciphertexts.
-int search_core(pf_engine *e, uint64_t nq, const u64 *d_cts, const PairPlan &pl, u64 *d_out) {
-    const int L = e->L, N = e->N;
-    const size_t ctw = (size_t)2 * L * N, P = pl.pair_block.size();
-    CK(e->s_rot.ensure(nq * e->K * ctw * 8));
-    u64 *rot = e->s_rot.as<u64>();
-    int rc = build_rotated_sets(e, d_cts, nq, rot, 0, false);
-    if (rc) return rc;
+// chunk table and pair->block map of a whole plan to the device (pageable sources: the copies are
+// complete on return)
+int upload_plan(pf_engine *e, const PairPlan &pl) {
+    const size_t P = pl.pair_block.size();
     if (!P) return PF_OK;
     CK(e->s_chunks.ensure(pl.chunks.size() * sizeof(MacChunk)));
     CK(e->s_pairblock.ensure(P * sizeof(long long)));
@@ -713,6 +713,29 @@ int search_core(pf_engine *e, uint64_t nq, const u64 *d_cts, const PairPlan &pl,
                        e->stream));
     CK(cudaMemcpyAsync(e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long), cudaMemcpyHostToDevice,
                        e->stream));
+    return PF_OK;
+}
+
+// The device-resident step for queries [q0, q0+nq) of a plan: rotations, MAC, inverse NTT.  Result of
+// pair i lands at d_out + i*out_stride (coefficient form); d_cts points at query q0's ciphertexts.
+int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const PairPlan &pl, u64 *d_out,
+                size_t out_stride) {
+    const int L = e->L, N = e->N;
+    const size_t ctw = (size_t)2 * L * N;
+    CK(e->s_rot.ensure(nq * e->K * ctw * 8));
+    u64 *rot = e->s_rot.as<u64>();
+    int rc = build_rotated_sets(e, d_cts, nq, rot, 0, false);
+    if (rc) return rc;
+    // chunks / pairs of this query range (chunks are ordered by query)
+    size_t c0 = 0, c1 = 0;
+    while (c0 < pl.chunks.size() && (uint64_t)pl.chunks[c0].query < q0) c0++;
+    c1 = c0;
+    while (c1 < pl.chunks.size() && (uint64_t)pl.chunks[c1].query < q0 + nq) c1++;
+    if (c1 == c0) return PF_OK;
+    const size_t p0 = (size_t)pl.chunks[c0].pair_start;
+    const size_t p1 = (size_t)pl.chunks[c1 - 1].pair_start + pl.chunks[c1 - 1].pair_count;
+    const size_t P = p1 - p0;
+    u64 *out = d_out + p0 * out_stride;
     {
         PhaseTimer pt(e, PF_T_MAC);
         MacParams mp{};
@@ -722,18 +745,29 @@ int search_core(pf_engine *e, uint64_t nq, const u64 *d_cts, const PairPlan &pl,
         mp.diag_sb = (long long)e->diag_block_words;
         mp.diag_sk = (long long)L * N;
         mp.norm_sb = (long long)e->norm_block_words;
-        mp.chunks = e->s_chunks.as<MacChunk>();
+        mp.chunks = e->s_chunks.as<MacChunk>() + c0; // absolute pair / query indices (upload_plan)
         mp.pair_block = e->s_pairblock.as<long long>();
         mp.out = d_out;
+        mp.out_stride = (long long)out_stride;
         mp.mods = e->d_mods.as<DevModulus>();
         mp.K = e->K;
         mp.L = L;
         mp.N = N;
-        launch_mac(e, mp, (unsigned)pl.chunks.size());
+        mp.query_base = (int)q0;
+        launch_mac(e, mp, (unsigned)(c1 - c0));
     }
     {
         PhaseTimer pt(e, PF_T_INTT);
-        ntt_limbs(e, d_out, d_out, 2 * P, true);
+        for (size_t off = 0; off < P; off += 32768) {
+            const unsigned cnt = (unsigned)std::min<size_t>(32768, P - off);
+            NttParams ip{};
+            ip.in = ip.out = out + off * out_stride;
+            ip.in_sx = ip.out_sx = N;
+            ip.in_sy = ip.out_sy = (long long)L * N;
+            ip.in_sz = ip.out_sz = (long long)out_stride;
+            for (int i = 0; i < L; i++) ip.mod_map[i] = i;
+            launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(L, 2, cnt));
+        }
     }
     CK(cudaGetLastError());
     return PF_OK;
@@ -879,6 +913,10 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "cudaStreamCreate failed"));
     e->own_stream = true;
+    if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_group[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_group[1], cudaEventDisableTiming) != cudaSuccess)
+        return bail(e->fail(PF_ERR_CUDA, "copy stream / event creation failed"));
     cudaError_t ar = cudaSuccess;
     switch (e->logn) {
     case 10: ar = set_ntt_attrs<10>(); break;
@@ -900,6 +938,9 @@ void pf_engine_destroy(pf_engine *e) {
     cudaStreamSynchronize(e->stream);
     drain_events(e);
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (auto ev : e->ev_group)
+        if (ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1295,7 +1336,9 @@ int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, con
     }
     if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
     if (P > cap_results || (P && !d_out)) return e->fail(PF_ERR_CAPACITY, "need room for %llu result ciphertexts, capacity %llu", (unsigned long long)P, (unsigned long long)cap_results);
-    return search_core(e, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out);
+    rc = upload_plan(e, pl);
+    if (rc) return rc;
+    return search_core(e, 0, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out, (size_t)2 * e->L * e->N);
 }
 
 int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
@@ -1314,6 +1357,9 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     if (rc) return rc;
     const uint64_t P = pl.pair_block.size();
     const size_t ct_bytes = SEAL_CT_HEADER + ctw * 8;
+    // Result r occupies a slot of `slot` bytes; its SEAL stream starts at r*slot + RESULT_PAD so that
+    // the ciphertext words sit at a 128-byte aligned offset (one aligned D2H per query group).
+    const size_t slot = PF_RESULT_DATA_OFFSET + ctw * 8;
     // labels / sizes of the owned probed lists (same packing as pf_search_lists_plain)
     uint64_t nlabels = 0;
     for (uint64_t i = 0; i < nq; i++) {
@@ -1332,13 +1378,13 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     }
     if (stats) {
         stats->nresults = P;
-        stats->out_bytes = P * ct_bytes;
+        stats->out_bytes = P * slot;
         stats->useful_distances = pl.useful;
         stats->slot_distances = P * e->C;
     }
     if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
-    if (P > max_results || P * ct_bytes > out_cap || (labels && nlabels > label_cap))
-        return e->fail(PF_ERR_CAPACITY, "need %llu results / %llu bytes / %llu labels", (unsigned long long)P, (unsigned long long)(P * ct_bytes), (unsigned long long)nlabels);
+    if (P > max_results || P * slot > out_cap || (labels && nlabels > label_cap))
+        return e->fail(PF_ERR_CAPACITY, "need %llu results / %llu bytes / %llu labels", (unsigned long long)P, (unsigned long long)(P * slot), (unsigned long long)nlabels);
     // parse + upload the query ciphertexts
     CK(e->s_qcts.ensure(std::max<size_t>(8, ncts * ctw * 8)));
     uint64_t parms_id[4] = {0, 0, 0, 0};
@@ -1354,18 +1400,37 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
         CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, src + SEAL_CT_HEADER, ctw * 8, cudaMemcpyHostToDevice, e->stream));
     }
-    CK(e->s_out.ensure(std::max<size_t>(8, P * ctw * 8)));
-    rc = search_core(e, nq, e->s_qcts.as<u64>(), pl, e->s_out.as<u64>());
+    CK(e->s_out.ensure(std::max<size_t>(8, P * slot)));
+    uint8_t *d_blob = e->s_out.as<uint8_t>();
+    u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
+    rc = upload_plan(e, pl);
     if (rc) return rc;
-    // serialize: header per result, words straight from the device into the stream
-    for (uint64_t r = 0; r < P; r++) {
-        uint8_t *dst = out_cts + r * ct_bytes;
-        write_ct_prefix(e, dst, 0, parms_id);
-        CK(cudaMemcpyAsync(dst + SEAL_CT_HEADER, e->s_out.as<u64>() + r * ctw, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
-        if (result_offsets) result_offsets[r] = r * ct_bytes;
+    // query groups: the D2H of group i (copy stream) overlaps the compute of group i+1 (engine stream)
+    const uint64_t ngroups = std::min<uint64_t>(nq, 4);
+    uint64_t pair_lo = 0, q_lo = 0;
+    for (uint64_t gi = 0; gi < ngroups; gi++) {
+        const uint64_t q_hi = nq * (gi + 1) / ngroups;
+        uint64_t pair_hi = pair_lo;
+        for (uint64_t q = q_lo; q < q_hi; q++) pair_hi += pl.results_per_query[q];
+        rc = search_core(e, q_lo, q_hi - q_lo, e->s_qcts.as<u64>() + q_lo * e->m * ctw, pl, d_words, slot / 8);
+        if (rc) return rc;
+        if (pair_hi > pair_lo) {
+            cudaEvent_t ev = e->ev_group[gi & 1];
+            CK(cudaEventRecord(ev, e->stream));
+            CK(cudaStreamWaitEvent(e->copy_stream, ev, 0));
+            CK(cudaMemcpyAsync(out_cts + pair_lo * slot, d_blob + pair_lo * slot, (pair_hi - pair_lo) * slot,
+                               cudaMemcpyDeviceToHost, e->copy_stream));
+        }
+        pair_lo = pair_hi;
+        q_lo = q_hi;
     }
-    if (result_offsets) result_offsets[P] = P * ct_bytes;
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaStreamSynchronize(e->copy_stream));
+    for (uint64_t r = 0; r < P; r++) { // SEAL stream headers (113 bytes each) in front of the aligned words
+        write_ct_prefix(e, out_cts + r * slot + PF_RESULT_PAD, 0, parms_id);
+        if (result_offsets) result_offsets[r] = r * slot + PF_RESULT_PAD;
+    }
+    if (result_offsets) result_offsets[P] = P * slot;
     return PF_OK;
 }
 
@@ -1445,6 +1510,7 @@ int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_
     mp.chunks = dch.as<MacChunk>();
     mp.pair_block = dpb.as<long long>();
     mp.out = dout.as<u64>();
+    mp.out_stride = (long long)ctw;
     mp.mods = e->d_mods.as<DevModulus>();
     mp.K = (int)K;
     mp.L = L;
@@ -1574,6 +1640,7 @@ int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *di
 }
 
 size_t pf_ct_serialized_size(pf_engine *e) { return e ? SEAL_CT_HEADER + (size_t)2 * e->L * e->N * 8 : 0; }
+size_t pf_result_slot_size(pf_engine *e) { return e ? PF_RESULT_DATA_OFFSET + (size_t)2 * e->L * e->N * 8 : 0; }
 
 int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written) {
     if (!e || !ct || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;

@@ -29,9 +29,11 @@ struct MacParams {
     long long diag_sb, diag_sk, norm_sb;
     const MacChunk *chunks;
     const long long *pair_block; // [P] block index of every pair
-    u64 *out;                    // [P][2][L][N] NTT form
+    u64 *out;                    // result of pair i at out + i*out_stride: [2][L][N] NTT form
+    long long out_stride;        // words between consecutive results (>= 2*L*N)
     const DevModulus *mods;      // limb l uses mods[l]
     int K, L, N;
+    int query_base;              // MacChunk.query - query_base indexes rot
 };
 
 // ---- split-operand lazy accumulation -------------------------------------------------------------
@@ -167,7 +169,7 @@ __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulongl
             r0.x = addmod(r0.x, nv.x, m.q);
             r0.y = addmod(r0.y, nv.y, m.q);
         }
-        u64 *o = p.out + pair * 2 * LN + coef0;
+        u64 *o = p.out + pair * (size_t)p.out_stride + coef0;
         stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
         stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
     }
@@ -207,7 +209,7 @@ __device__ __forceinline__ void mac_pair_wide(const MacParams &p, const ulonglon
         r0.x = addmod(r0.x, nv.x, m.q);
         r0.y = addmod(r0.y, nv.y, m.q);
     }
-    u64 *o = p.out + pair * 2 * LN + coef0;
+    u64 *o = p.out + pair * (size_t)p.out_stride + coef0;
     stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
     stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
 }
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
 
     // stage the query's rotated-ciphertext slice once; every block of the chunk reuses it
     {
-        const u64 *src = p.rot + (size_t)ch.query * p.K * 2 * LN + coef0;
+        const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
         const int rows = p.K * 2;
         for (int i = threadIdx.x; i < rows * TX; i += 256) {
             const int row = i / TX, c = i % TX;

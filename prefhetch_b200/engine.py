@@ -43,13 +43,18 @@ class PfError(RuntimeError):
 @dataclass
 class SearchResult:
     """Encrypted stage-2 response: SEAL-serialized result ciphertexts plus the plaintext envelope."""
-    blob: np.ndarray                # uint8, result ciphertexts back to back
-    result_offsets: np.ndarray      # [nresults+1]
+    blob: np.ndarray                # uint8, result ciphertexts in aligned slots
+    result_offsets: np.ndarray      # [nresults+1]: start of every SEAL stream; last = bytes used
+    ct_bytes: int                   # length of every result stream
     results_per_query: np.ndarray   # [nq]
     labels: np.ndarray              # ids of the owned probed lists, packed per query
     list_sizes: np.ndarray          # [nq]
     probed_sizes: np.ndarray        # [nq][nprobe]
     stats: dict
+
+    def result(self, r: int) -> bytes:
+        o = int(self.result_offsets[r])
+        return self.blob[o:o + self.ct_bytes].tobytes()
 
 
 def _ptr(a: np.ndarray, typ):
@@ -85,6 +90,7 @@ class Engine:
         self.m, self.g = query_cts, partial_g
         self.ctw = 2 * self.L * self.n
         self.ct_bytes = self.lib.pf_ct_serialized_size(self.h)
+        self.slot_bytes = self.lib.pf_result_slot_size(self.h)
         self.device, self.rank, self.world = device, rank, world
 
     def close(self):
@@ -185,7 +191,7 @@ class Engine:
         # worst case: every probed list owned here
         max_results = int(self._max_results(idx))
         if out is None:
-            out = np.zeros(max(1, max_results) * self.ct_bytes, dtype=np.uint8)
+            out = np.zeros(max(1, max_results) * self.slot_bytes, dtype=np.uint8)
         roff = np.zeros(max_results + 1, dtype=np.uint64)
         rpq = np.zeros(nq, dtype=np.uint64)
         label_cap = max(1, max_results * info["C"])
@@ -198,7 +204,7 @@ class Engine:
             out.ctypes.data_as(C.c_void_p), out.size, _ptr(roff, U64P), max_results, _ptr(rpq, U64P),
             _ptr(labels, I64P), label_cap, _ptr(sizes, U64P), _ptr(psz, U64P), C.byref(st)))
         nres = st.nresults
-        return SearchResult(out, roff[:nres + 1], rpq.astype(np.int64), labels[:int(sizes.sum())],
+        return SearchResult(out, roff[:nres + 1], self.ct_bytes, rpq.astype(np.int64), labels[:int(sizes.sum())],
                             sizes.astype(np.int64), psz.astype(np.int64),
                             {f: getattr(st, f) for f, _ in PfSearchStats._fields_})
 

@@ -20,7 +20,7 @@ namespace prefhetch {
 using idx_t = int64_t; // ref: faiss_idx_t, include/common/client_server_utils.h:22
 
 struct EncryptedCoarseResult {
-    std::vector<uint8_t> ciphertexts;        // SEAL-serialized result ciphertexts, back to back
+    std::vector<uint8_t> ciphertexts;        // SEAL-serialized result ciphertexts in aligned slots (pf_result_slot_size)
     std::vector<uint64_t> result_offsets;    // [nresults+1]
     std::vector<uint64_t> results_per_query; // [nq]
     std::vector<idx_t> coarse_vector_indexes; // ids of the probed lists, packed per query (ref field name)
@@ -114,7 +114,7 @@ class Server {
             max_results += (n + m_Info.C - 1) / m_Info.C;
             max_labels += n;
         }
-        const size_t ct_bytes = pf_ct_serialized_size(m_Engine.get());
+        const size_t ct_bytes = pf_result_slot_size(m_Engine.get());
         out.ciphertexts.resize(max_results * ct_bytes);
         out.result_offsets.resize(max_results + 1);
         out.results_per_query.resize(nq);

@@ -254,7 +254,7 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world):
                     xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + C_, n_l)].astype(np.int32)
                     diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
                     want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
-                    got_bytes = res.blob[int(res.result_offsets[r]):int(res.result_offsets[r + 1])].tobytes()
+                    got_bytes = res.result(r)
                     assert got_bytes == cl.ctx.ct_save(want_ct), f"rank {rank} query {qi} result {r}"
                     got_ct, is_ntt = eng.ct_deserialize(got_bytes)
                     dist, budget = cl.distances(got_ct, query[qi], len(xs))
