@@ -18,6 +18,8 @@ struct DevModulus {
     u64 p_half_mod;        // (P >> 1) mod q
     u64 p_inv, p_inv_sh;   // P^{-1} mod q and its Shoup quotient
     u64 pad2;
+    // FP64 NTT constants (pf_ntt_fp.cuh): q, 1/q, centred N^{-1}, centred irp[1]*N^{-1}
+    double fq, fqinv, fninv, flast_w;
 };
 
 // twiddle tables per modulus: fwd[N] then inv[N], each entry {w, floor(w*2^64/q)}

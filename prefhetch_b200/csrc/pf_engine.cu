@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -20,7 +21,12 @@
 #include "pf_keyswitch.cuh"
 #include "pf_mac.cuh"
 #include "pf_ntt.cuh"
+#include "pf_ntt_fp.cuh"
 #include "pf_plain.cuh"
+
+#ifndef PF_MAC_DEFAULT_VARIANT
+#define PF_MAC_DEFAULT_VARIANT 0
+#endif
 
 namespace {
 
@@ -102,6 +108,8 @@ struct pf_engine {
     // device tables
     DevBuf d_mods; // DevModulus[k+1] (index k = plain modulus)
     DevBuf d_tw;   // Twiddle[k+1][2][N]
+    DevBuf d_tw_fp; // double[k+1][2][N] centred twiddles
+    bool ntt_fp = false; // FP64-pipe NTT kernels eligible (pf_ntt_fp.cuh)
     DevBuf d_inv_index_map;
     std::vector<u64> h_q;
     u64 q_mod_t = 0;
@@ -109,6 +117,7 @@ struct pf_engine {
     u64 p_half = 0;
     int max_prime_bits = 0;
     bool mac_wide = false;
+    bool mac_fpred = false; // FP64-assisted final reduction applies (pf_mac.cuh)
 
     std::map<u32, GaloisKey> gkeys;
 
@@ -127,7 +136,7 @@ struct pf_engine {
 
     // scratch
     DevBuf s_x, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
-    DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_qcts, s_out, s_tmp, s_plain,
+    DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_out, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
     cudaStream_t copy_stream = nullptr;
@@ -219,8 +228,32 @@ cudaError_t set_ntt_attrs() {
     SETATTR((ntt_inv_kernel<LOGN>));
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
     SETATTR((ntt_inv_kernel<LOGN, NTT_OUT_KS>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_LIFT>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_REDUCE>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
+    SETATTR((ntt_inv_fp_kernel<LOGN>));
 #undef SETATTR
     return cudaSuccess;
+}
+
+template <int LOGN>
+void launch_ntt_fp_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
+    const size_t smem = NttCfg<LOGN>::SMEM;
+    const int nt = NttCfg<LOGN>::NT;
+    if (inverse)
+        ntt_inv_fp_kernel<LOGN><<<grid, nt, smem, s>>>(p);
+    else if (p.ks_S)
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_PLAIN)
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_LIFT)
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_LIFT><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_REDUCE)
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_REDUCE><<<grid, nt, smem, s>>>(p);
+    else
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE><<<grid, nt, smem, s>>>(p);
 }
 
 template <int LOGN>
@@ -246,6 +279,18 @@ void launch_ntt_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaS
 void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) {
     p.mods = e->d_mods.as<DevModulus>();
     p.tw = e->d_tw.as<Twiddle>();
+    p.tw_fp = e->d_tw_fp.as<double>();
+    e->launches++;
+    if (e->ntt_fp && !(inverse && p.ks_W)) {
+        switch (e->logn) {
+        case 10: launch_ntt_fp_t<10>(inmode, inverse, p, grid, e->stream); break;
+        case 11: launch_ntt_fp_t<11>(inmode, inverse, p, grid, e->stream); break;
+        case 12: launch_ntt_fp_t<12>(inmode, inverse, p, grid, e->stream); break;
+        case 13: launch_ntt_fp_t<13>(inmode, inverse, p, grid, e->stream); break;
+        case 14: launch_ntt_fp_t<14>(inmode, inverse, p, grid, e->stream); break;
+        }
+        return;
+    }
     // gridDim.y/z limits: z <= 65535, y <= 65535
     switch (e->logn) {
     case 10: launch_ntt_t<10>(inmode, inverse, p, grid, e->stream); break;
@@ -254,7 +299,6 @@ void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) 
     case 13: launch_ntt_t<13>(inmode, inverse, p, grid, e->stream); break;
     case 14: launch_ntt_t<14>(inmode, inverse, p, grid, e->stream); break;
     }
-    e->launches++;
 }
 
 // transform `count` consecutive [L][N] polynomials (limb of polynomial y*L + x is x), in place or not
@@ -281,6 +325,8 @@ int build_tables(pf_engine *e) {
     const int N = e->N, k = e->k, L = e->L, logn = e->logn;
     std::vector<DevModulus> mods(k + 1);
     std::vector<Twiddle> tw((size_t)(k + 1) * 2 * N);
+    std::vector<double> twd((size_t)(k + 1) * 2 * N);
+    auto centred = [](u64 x, u64 q) { return x > q / 2 ? -(double)(q - x) : (double)x; };
     for (int j = 0; j <= k; j++) {
         const u64 q = (j == k) ? e->t : e->h_q[j];
         const u64 psi = minimal_primitive_root(2ull * N, q);
@@ -307,6 +353,17 @@ int build_tables(pf_engine *e) {
         }
         m.inv_last_w = pfh::mulmod(inv[1].x, n_inv, q);
         m.inv_last_w_sh = shoup(m.inv_last_w, q);
+        m.fq = (double)q;
+        m.fqinv = 1.0 / (double)q;
+        m.fninv = centred(n_inv, q);
+        m.flast_w = centred(m.inv_last_w, q);
+        {
+            double *fd = twd.data() + (size_t)j * 2 * N;
+            for (int i = 0; i < N; i++) {
+                fd[i] = centred(f[i].x, q);
+                fd[N + i] = centred(inv[i].x, q);
+            }
+        }
         m.split_shift = (u64)((64 - __builtin_clzll(q) + 1) / 2);
         m.p_half_mod = m.p_inv = m.p_inv_sh = m.pad2 = 0;
         if (j < L) {
@@ -320,6 +377,8 @@ int build_tables(pf_engine *e) {
     CK(cudaMemcpy(e->d_mods.p, mods.data(), mods.size() * sizeof(DevModulus), cudaMemcpyHostToDevice));
     CK(e->d_tw.ensure(tw.size() * sizeof(Twiddle)));
     CK(cudaMemcpy(e->d_tw.p, tw.data(), tw.size() * sizeof(Twiddle), cudaMemcpyHostToDevice));
+    CK(e->d_tw_fp.ensure(twd.size() * sizeof(double)));
+    CK(cudaMemcpy(e->d_tw_fp.p, twd.data(), twd.size() * sizeof(double), cudaMemcpyHostToDevice));
 
     // BatchEncoder index map (SEAL batchencoder.cpp) and its inverse
     std::vector<u32> inv_map(N);
@@ -637,26 +696,54 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
 }
 
 // ---- MAC launch -----------------------------------------------------------------------------
-template <int T, int UNROLL, bool WIDE>
+template <int T, int UNROLL, bool WIDE, bool FPRED = false>
 void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const size_t smem = (size_t)p.K * 2 * T * 8;
-    auto kern = mac_kernel<T, UNROLL, WIDE>;
+    auto kern = mac_kernel<T, UNROLL, WIDE, FPRED>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
     e->launches++;
 }
 
-int mac_tile(const pf_engine *e) { return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64); }
+template <int T, int UNROLL, int NS>
+void launch_mac_async_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    const size_t smem = (size_t)p.K * 2 * T * 8 + (size_t)NS * UNROLL * 2 * 16 * 256;
+    auto kern = mac_kernel_async<T, UNROLL, NS>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
+    e->launches++;
+}
+
+// MAC variant: 0 = register-staged loads (mac_kernel), 1 = cp.async ring T=128, 2 = cp.async ring T=256
+int mac_variant(const pf_engine *e) {
+    static const int env = [] {
+        const char *v = getenv("PF_MAC_VARIANT");
+        return v ? atoi(v) : -1;
+    }();
+    if (e->mac_wide || e->K < 4 || e->K > 32) return 0;
+    return env >= 0 ? env : PF_MAC_DEFAULT_VARIANT;
+}
+
+int mac_tile(const pf_engine *e) {
+    const int v = mac_variant(e);
+    if (v == 1) return 128;
+    if (v == 2) return 256;
+    return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64);
+}
 
 template <int T>
 void launch_mac_tile(pf_engine *e, const MacParams &p, unsigned nchunks) {
     if (e->mac_wide) launch_mac_t<T, 1, true>(e, p, nchunks);
+    else if (p.K >= 4 && e->mac_fpred) launch_mac_t<T, 2, false, true>(e, p, nchunks);
     else if (p.K >= 4) launch_mac_t<T, 2, false>(e, p, nchunks);
     else if (p.K == 2) launch_mac_t<T, 1, false>(e, p, nchunks);
     else launch_mac_t<T, 1, false>(e, p, nchunks);
 }
 
 void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    const int v = mac_variant(e);
+    if (v == 1) return launch_mac_async_t<128, 2, 4>(e, p, nchunks);
+    if (v == 2) return launch_mac_async_t<256, 2, 3>(e, p, nchunks);
     const int T = mac_tile(e);
     if (T == 256) launch_mac_tile<256>(e, p, nchunks);
     else if (T == 128) launch_mac_tile<128>(e, p, nchunks);
@@ -665,7 +752,8 @@ void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
 
 // Build the (query, block) pair list for this rank and the chunk table.  Returns PF_OK.
 struct PairPlan {
-    std::vector<long long> pair_block;
+    std::vector<long long> pair_block; // processing order: per query sorted by block (L2 reuse across queries)
+    std::vector<int> pair_out;         // result slot (response order) of every processed pair
     std::vector<MacChunk> chunks;
     std::vector<uint64_t> results_per_query;
     uint64_t useful = 0;
@@ -688,6 +776,26 @@ int plan_pairs(pf_engine *e, uint64_t nq, const int64_t *idx, uint32_t nprobe, P
             }
         }
     const size_t P = pl.pair_block.size();
+    // Within a query, process blocks in ascending block order: CTAs of different queries that run
+    // concurrently (same limb / slice) then reach a shared block at about the same time, so its
+    // second fetch hits L2.  The response order (probe order) is kept through pair_out.
+    pl.pair_out.resize(P);
+    {
+        size_t a = 0;
+        std::vector<std::pair<long long, int>> tmp;
+        while (a < P) {
+            size_t b = a;
+            while (b < P && pair_query[b] == pair_query[a]) b++;
+            tmp.clear();
+            for (size_t i = a; i < b; i++) tmp.push_back({pl.pair_block[i], (int)i});
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t i = a; i < b; i++) {
+                pl.pair_block[i] = tmp[i - a].first;
+                pl.pair_out[i] = tmp[i - a].second;
+            }
+            a = b;
+        }
+    }
     const int T = mac_tile(e);
     const size_t ctas_per_chunk = (size_t)e->L * (e->N / T);
     const size_t want_chunks = (4 * 148 + ctas_per_chunk - 1) / ctas_per_chunk;
@@ -713,6 +821,8 @@ int upload_plan(pf_engine *e, const PairPlan &pl) {
                        e->stream));
     CK(cudaMemcpyAsync(e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long), cudaMemcpyHostToDevice,
                        e->stream));
+    CK(e->s_pairout.ensure(P * sizeof(int)));
+    CK(cudaMemcpyAsync(e->s_pairout.p, pl.pair_out.data(), P * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     return PF_OK;
 }
 
@@ -747,6 +857,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
         mp.norm_sb = (long long)e->norm_block_words;
         mp.chunks = e->s_chunks.as<MacChunk>() + c0; // absolute pair / query indices (upload_plan)
         mp.pair_block = e->s_pairblock.as<long long>();
+        mp.pair_out = e->s_pairout.as<int>();
         mp.out = d_out;
         mp.out_stride = (long long)out_stride;
         mp.mods = e->d_mods.as<DevModulus>();
@@ -907,6 +1018,12 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     while ((1u << logk) < e->K) logk++;
     while ((1 << logl) < e->L) logl++;
     e->mac_wide = sbits + logk > 64;
+    {
+        const int fp_limit = e->logn <= 13 ? 44 : 49;
+        const char *env = getenv("PF_NTT_FP");
+        e->ntt_fp = e->max_prime_bits <= fp_limit && (!env || atoi(env) != 0);
+    }
+    e->mac_fpred = !e->mac_wide && e->max_prime_bits + logk <= 50 && !getenv("PF_MAC_NO_FPRED");
     if (sbits + logl > 64)
         return bail(e->fail(PF_ERR_INVALID, "coefficient primes of %d bits with %d limbs overflow the key-switch accumulator", e->max_prime_bits, e->L));
     if (cudaSetDevice(prm->device) != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaSetDevice(%d) failed", prm->device));
@@ -1482,13 +1599,15 @@ int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_
     CK(cudaSetDevice(e->prm.device));
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N, ptw = (size_t)L * N;
-    DevBuf dc, dp, dn, dout, dch, dpb;
+    DevBuf dc, dp, dn, dout, dch, dpb, dpo;
     CK(dc.ensure(K * ctw * 8));
     CK(dp.ensure(K * ptw * 8));
     CK(dn.ensure(ptw * 8));
     CK(dout.ensure(ctw * 8));
     CK(dch.ensure(sizeof(MacChunk)));
     CK(dpb.ensure(8));
+    CK(dpo.ensure(4));
+    CK(cudaMemsetAsync(dpo.p, 0, 4, e->stream));
     CK(cudaMemcpyAsync(dc.p, cts, K * ctw * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(dp.p, pts, K * ptw * 8, cudaMemcpyHostToDevice, e->stream));
     if (addend) CK(cudaMemcpyAsync(dn.p, addend, ptw * 8, cudaMemcpyHostToDevice, e->stream));
@@ -1509,6 +1628,7 @@ int pf_ct_pt_mac(pf_engine *e, const uint64_t *cts, const uint64_t *pts, uint32_
     mp.norm_sb = (long long)ptw;
     mp.chunks = dch.as<MacChunk>();
     mp.pair_block = dpb.as<long long>();
+    mp.pair_out = dpo.as<int>();
     mp.out = dout.as<u64>();
     mp.out_stride = (long long)ctw;
     mp.mods = e->d_mods.as<DevModulus>();

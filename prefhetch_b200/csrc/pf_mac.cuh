@@ -28,7 +28,8 @@ struct MacParams {
     const u64 *norm; // [nblocks][L][N] or nullptr
     long long diag_sb, diag_sk, norm_sb;
     const MacChunk *chunks;
-    const long long *pair_block; // [P] block index of every pair
+    const long long *pair_block; // [P] block index of every pair (processing order)
+    const int *pair_out;         // [P] result slot of every pair (response order)
     u64 *out;                    // result of pair i at out + i*out_stride: [2][L][N] NTT form
     long long out_stride;        // words between consecutive results (>= 2*L*N)
     const DevModulus *mods;      // limb l uses mods[l]
@@ -75,6 +76,30 @@ __device__ __forceinline__ u64 lazy_reduce(const LazyAcc &a, int s, const DevMod
     return barrett128(vlo, vhi, m.q, m.ratio0, m.ratio1);
 }
 
+// FP64-assisted final reduction (B200 has full-rate FP64: 64 DFMA lanes/clk/SM, measured with
+// tools/pipe_ubench.cu, and the pipe is otherwise idle here).  Valid when V/q <= 2^50, i.e.
+// bits(q) + ceil(log2 K) <= 50 (every BFVDefault prime at N = 8192 with K <= 64): the quotient estimate
+// floor(double(V) * (1/q)) is then within +-1 of the true quotient, and the remainder is finished in
+// 64-bit integers with two corrections.  3 IMAD instead of ~26 per reduction: with K = 16 terms the
+// Barrett-128 epilogue was 35 % of the kernel's IMAD work.
+__device__ __forceinline__ double u52_to_double(u64 x) { // exact for x < 2^52
+    return __longlong_as_double((long long)(x | 0x4330000000000000ull)) - 4503599627370496.0;
+}
+__device__ __forceinline__ u64 lazy_reduce_fp(const LazyAcc &a, int s, u64 q, double qinv) {
+    const u64 mid = a.kz - a.lo - a.hi;
+    const double p2s = __longlong_as_double((long long)(1023 + s) << 52);
+    const double v = fma(u52_to_double(a.hi) * p2s, p2s, fma(u52_to_double(mid), p2s, u52_to_double(a.lo)));
+    const u64 qh = (u64)__double2ll_rd(v * qinv);
+    const u64 vlo = a.lo + (mid << s) + (a.hi << (2 * s)); // low 64 bits of V
+    u64 r = vlo - qh * q;                                  // true remainder is in [-q, 2q)
+    r = ((long long)r < 0) ? r + q : r;
+    return r >= q ? r - q : r;
+}
+template <bool FPRED>
+__device__ __forceinline__ u64 lazy_reduce_sel(const LazyAcc &a, int s, const DevModulus &m, double qinv) {
+    return FPRED ? lazy_reduce_fp(a, s, m.q, qinv) : lazy_reduce(a, s, m);
+}
+
 __device__ __forceinline__ u64 split_word(u64 x, int s) { return ((x >> s) << 32) | (x & ((1ull << s) - 1)); }
 __device__ __forceinline__ u64 unsplit_word(u64 w, int s) { return ((w >> 32) << s) | (w & 0xffffffffull); }
 
@@ -99,9 +124,10 @@ __device__ __forceinline__ SplitOp make_op(u64 w) {
     return o;
 }
 
-template <int BT, int UNROLL, int TX>
+template <int BT, int UNROLL, int TX, bool FPRED>
 __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulonglong2 *sct, const DevModulus &m,
                                                 int split, size_t coef0, size_t LN, int tx, size_t pair0) {
+    const double qinv = 1.0 / (double)m.q;
     const ulonglong2 *bp[BT];
 #pragma unroll
     for (int j = 0; j < BT; j++) {
@@ -157,11 +183,12 @@ __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulongl
 #pragma unroll
     for (int j = 0; j < BT; j++) {
         const size_t pair = pair0 + j;
+        const size_t slot = (size_t)p.pair_out[pair];
         ulonglong2 r0, r1;
-        r0.x = lazy_reduce(acc[j][0][0], split, m);
-        r0.y = lazy_reduce(acc[j][0][1], split, m);
-        r1.x = lazy_reduce(acc[j][1][0], split, m);
-        r1.y = lazy_reduce(acc[j][1][1], split, m);
+        r0.x = lazy_reduce_sel<FPRED>(acc[j][0][0], split, m, qinv);
+        r0.y = lazy_reduce_sel<FPRED>(acc[j][0][1], split, m, qinv);
+        r1.x = lazy_reduce_sel<FPRED>(acc[j][1][0], split, m, qinv);
+        r1.y = lazy_reduce_sel<FPRED>(acc[j][1][1], split, m, qinv);
         if (p.norm) {
             const long long b = p.pair_block[pair];
             const ulonglong2 nv =
@@ -169,7 +196,7 @@ __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulongl
             r0.x = addmod(r0.x, nv.x, m.q);
             r0.y = addmod(r0.y, nv.y, m.q);
         }
-        u64 *o = p.out + pair * (size_t)p.out_stride + coef0;
+        u64 *o = p.out + slot * (size_t)p.out_stride + coef0;
         stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
         stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
     }
@@ -209,13 +236,13 @@ __device__ __forceinline__ void mac_pair_wide(const MacParams &p, const ulonglon
         r0.x = addmod(r0.x, nv.x, m.q);
         r0.y = addmod(r0.y, nv.y, m.q);
     }
-    u64 *o = p.out + pair * (size_t)p.out_stride + coef0;
+    u64 *o = p.out + (size_t)p.pair_out[pair] * (size_t)p.out_stride + coef0;
     stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
     stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
 }
 
 // K is a power of two and UNROLL divides it: K/UNROLL is 1 or even (host picks UNROLL = min(K, 2)).
-template <int T, int UNROLL, bool WIDE>
+template <int T, int UNROLL, bool WIDE, bool FPRED = false>
 __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
     constexpr int TX = T / 2;    // threads along the slice (2 coefficients each)
     constexpr int BY = 256 / TX; // block lanes (warp-uniform: TX >= 32)
@@ -248,10 +275,141 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
         const int split = (int)m.split_shift;
         int pi = by * 2;
         for (; pi + 1 < ch.pair_count; pi += BY * 2)
-            mac_pairs_split<2, UNROLL, TX>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
+            mac_pairs_split<2, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
         if (pi < ch.pair_count) // odd tail: one pair left for this lane
-            mac_pairs_split<1, UNROLL, TX>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
+            mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
     }
+}
+
+// ---- cp.async variant -------------------------------------------------------------------------------
+// Same mapping as mac_kernel, but the plaintext words travel global -> shared with cp.async (LDGSTS)
+// into a per-thread private ring of NS stages (each stage = UNROLL k-rows x 2 blocks x 16 B), so the
+// loads in flight are bounded by shared memory, not by registers, and stay in flight across the MACs
+// and across block boundaries.  A thread reads back only what it copied itself: no barrier, just
+// cp.async.wait_group.  smem = ct slice K*2*T*8 + ring NS*UNROLL*2*16*256 bytes.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NPEND));
+}
+
+template <int T, int UNROLL, int NS>
+__global__ void __launch_bounds__(256, 2) mac_kernel_async(const MacParams p) {
+    constexpr int TX = T / 2, BY = 256 / TX, BT = 2;
+    extern __shared__ __align__(16) u64 smem_ct[]; // [K][2][T] then the ring
+    const MacChunk ch = p.chunks[blockIdx.x];
+    const int slices = p.N / T;
+    const int l = blockIdx.y / slices, s = blockIdx.y % slices;
+    const int tx = threadIdx.x % TX, by = threadIdx.x / TX;
+    const DevModulus m = p.mods[l];
+    const int split = (int)m.split_shift;
+    const size_t LN = (size_t)p.L * p.N;
+    const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
+    ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(smem_ct + (size_t)p.K * 2 * T) + threadIdx.x;
+    // ring slot (stage, u, j) of this thread: ring[((stage*UNROLL + u)*BT + j) * 256]
+    {
+        const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
+        const int rows = p.K * 2;
+        for (int i = threadIdx.x; i < rows * TX; i += 256) {
+            const int row = i / TX, c = i % TX;
+            cp_async16(reinterpret_cast<ulonglong2 *>(smem_ct) + (size_t)row * TX + c,
+                       reinterpret_cast<const ulonglong2 *>(src + (size_t)row * LN) + c);
+        }
+        cp_async_commit();
+    }
+    const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(smem_ct) + tx;
+    const int KG = p.K / UNROLL;                                      // k-groups per pair-group
+    const int npg = (ch.pair_count - by * BT + BY * BT - 1) / (BY * BT); // pair-groups of this lane (may be <= 0)
+    const int total = npg > 0 ? npg * KG : 0;
+    const size_t sk2 = (size_t)p.diag_sk / 2;
+
+    auto issue = [&](int g) { // copy k-group g of the flattened (pair-group, k-group) sequence
+        if (g < total) {
+            const int pg = g / KG, kg = g % KG, stage = g % NS;
+            const int pi = by * BT + pg * BY * BT;
+#pragma unroll
+            for (int j = 0; j < BT; j++) {
+                if (pi + j < ch.pair_count) {
+                    const long long b = p.pair_block[ch.pair_start + pi + j];
+                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.diag + (size_t)b * p.diag_sb + coef0) +
+                                            tx + (size_t)kg * UNROLL * sk2;
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++)
+                        cp_async16(ring + (size_t)((stage * UNROLL + u) * BT + j) * 256, src + (size_t)u * sk2);
+                }
+            }
+        }
+        cp_async_commit(); // always commit so the group count per iteration is fixed
+    };
+
+#pragma unroll
+    for (int g = 0; g < NS - 1; g++) issue(g);
+    cp_async_wait<NS - 1>(); // the ct slice group (oldest) has landed for this thread ...
+    __syncthreads();         // ... and for every thread
+
+    LazyAcc acc[BT][2][2];
+#pragma unroll
+    for (int j = 0; j < BT; j++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            lazy_zero(acc[j][c][0]);
+            lazy_zero(acc[j][c][1]);
+        }
+    for (int g = 0; g < total; g++) {
+        issue(g + NS - 1);
+        cp_async_wait<NS - 1>(); // group g is complete
+        const int pg = g / KG, kg = g % KG, stage = g % NS;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int k = kg * UNROLL + u;
+            const ulonglong2 c0 = sct[(size_t)(k * 2 + 0) * TX];
+            const ulonglong2 c1 = sct[(size_t)(k * 2 + 1) * TX];
+            const SplitOp a00 = make_op(c0.x), a01 = make_op(c0.y), a10 = make_op(c1.x), a11 = make_op(c1.y);
+#pragma unroll
+            for (int j = 0; j < BT; j++) {
+                const ulonglong2 pt = ring[(size_t)((stage * UNROLL + u) * BT + j) * 256];
+                const SplitOp b0 = make_op(pt.x), b1 = make_op(pt.y);
+                lazy_mac(acc[j][0][0], a00.x0, a00.x1, a00.xs, b0.x0, b0.x1, b0.xs);
+                lazy_mac(acc[j][0][1], a01.x0, a01.x1, a01.xs, b1.x0, b1.x1, b1.xs);
+                lazy_mac(acc[j][1][0], a10.x0, a10.x1, a10.xs, b0.x0, b0.x1, b0.xs);
+                lazy_mac(acc[j][1][1], a11.x0, a11.x1, a11.xs, b1.x0, b1.x1, b1.xs);
+            }
+        }
+        if (kg == KG - 1) { // last k-group of the pair-group: reduce, add norms, store, reset
+            const int pi = by * BT + pg * BY * BT;
+#pragma unroll
+            for (int j = 0; j < BT; j++) {
+                if (pi + j < ch.pair_count) {
+                    const size_t pair = (size_t)ch.pair_start + pi + j;
+                    const size_t slot = (size_t)p.pair_out[pair];
+                    ulonglong2 r0, r1;
+                    r0.x = lazy_reduce(acc[j][0][0], split, m);
+                    r0.y = lazy_reduce(acc[j][0][1], split, m);
+                    r1.x = lazy_reduce(acc[j][1][0], split, m);
+                    r1.y = lazy_reduce(acc[j][1][1], split, m);
+                    if (p.norm) {
+                        const long long b = p.pair_block[pair];
+                        const ulonglong2 nv = ldg_stream(
+                            reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
+                        r0.x = addmod(r0.x, nv.x, m.q);
+                        r0.y = addmod(r0.y, nv.y, m.q);
+                    }
+                    u64 *o = p.out + slot * (size_t)p.out_stride + coef0;
+                    stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
+                    stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
+                }
+                lazy_zero(acc[j][0][0]);
+                lazy_zero(acc[j][0][1]);
+                lazy_zero(acc[j][1][0]);
+                lazy_zero(acc[j][1][1]);
+            }
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // canonical <-> split conversion of polynomial arrays: chunk y (blockIdx.y) of `chunk_words` words is

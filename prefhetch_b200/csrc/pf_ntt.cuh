@@ -21,6 +21,7 @@ struct NttParams {
     long long out_sx, out_sy, out_sz;
     const DevModulus *mods;
     const Twiddle *tw; // [nmod][2][N]
+    const double *tw_fp; // [nmod][2][N] centred twiddles as doubles (FP64 NTT)
     int mod_map[PF_NTT_MAXMAP];  // blockIdx.x -> modulus index of the transform
     int src_map[PF_NTT_MAXMAP];  // blockIdx.y -> modulus index the input limb is reduced under (GALOIS_REDUCE)
     u64 lift_t, lift_thr;        // NTT_IN_LIFT: plain modulus and (t+1)/2

@@ -1,0 +1,266 @@
+// pf_ntt_fp.cuh — the same negacyclic NTT / inverse NTT as pf_ntt.cuh (same passes, same SEAL
+// ordering, same load modes and epilogues, bit-identical canonical results), with the butterflies
+// moved from the integer pipes to the FP64 pipe.
+//
+// Why: B200 (sm_100a) issues 64 DFMA lanes/clk/SM — the same rate as IMAD.WIDE — and the pipe is
+// idle in an integer NTT (measured: tools/pipe_ubench.cu).  A Shoup/Harvey butterfly on 64-bit
+// residues costs ~33 issued integer instructions (4 IMAD.WIDE for each 64x64 high product, carries,
+// compares, selects); with residues held as exact integers in doubles it is 8 FP64 operations and
+// no compares.  (B300/sm_103a would not have this option: its FP64 rate is vestigial.)
+//
+// Exactness (q < 2^50, every quantity an integer-valued double, no rounding anywhere that matters):
+//   mulmod(a, w), |a| < 2^52, |w| <= q/2 (twiddles are stored centred):
+//     h = a*w (rounded)            l = fma(a, w, -h)      -> a*w = h + l exactly (error-free product)
+//     k = rint(h / q) via fma(h, 1/q, 1.5*2^52) - 1.5*2^52  (|h/q| < 2^51)
+//     r = fma(-k, q, h)            exact: h, k*q are integers and |h - k*q| <= 0.75 q < 2^50
+//     result = r + l               |l| <= ulp(h)/2 <= q/8  =>  |result| < q,  == a*w (mod q)
+//   forward (Cooley-Tukey) butterflies add/subtract such values: magnitudes grow by < q per stage;
+//   inverse (Gentleman-Sande) sums double per stage.  Values are pulled back to [-q/2, q/2]
+//   (x - rint(x/q) q) at pass boundaries (inverse always, forward when N = 16384) and every second
+//   inverse stage when N = 16384, which keeps everything below 2^52.  Eligibility (host): primes
+//   <= 44 bits for N <= 8192, <= 49 bits for N = 16384 — all SEAL BFVDefault sets; other parameter
+//   sets use the integer kernels.  A final reduce + one conditional +q stores the canonical residue,
+//   identical to the integer kernels'.
+#pragma once
+#include "pf_ntt.cuh"
+
+#define PF_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+struct FpConsts {
+    double q, qinv;
+};
+
+__device__ __forceinline__ double fp_mulmod(double a, double w, double q, double qinv) {
+    const double h = __dmul_rn(a, w);
+    const double l = __fma_rn(a, w, -h);
+    const double k = __dadd_rn(__fma_rn(h, qinv, PF_FP_MAGIC), -PF_FP_MAGIC);
+    const double r = __fma_rn(-k, q, h);
+    return __dadd_rn(r, l);
+}
+__device__ __forceinline__ double fp_reduce(double x, double q, double qinv) { // -> [-q/2, q/2]
+    const double k = __dadd_rn(__fma_rn(x, qinv, PF_FP_MAGIC), -PF_FP_MAGIC);
+    return __fma_rn(-k, q, x);
+}
+__device__ __forceinline__ double fp_from_u64(u64 x) { // exact for x < 2^52
+    return __dadd_rn(__longlong_as_double((long long)(x | 0x4330000000000000ull)), -4503599627370496.0);
+}
+__device__ __forceinline__ u64 fp_to_u64(double x) { // exact for integer x in [0, 2^51)
+    return (u64)__double_as_longlong(__dadd_rn(x, 4503599627370496.0)) & 0x000fffffffffffffull;
+}
+__device__ __forceinline__ u64 fp_canonical(double x, double q, double qinv) {
+    double r = fp_reduce(x, q, qinv);
+    r = r < 0.0 ? __dadd_rn(r, q) : r;
+    return fp_to_u64(r);
+}
+
+template <int LOGN, int K, int P0, int U>
+struct FpFwdStages {
+    static __device__ __forceinline__ void run(double (&v)[32], const double *__restrict__ tw, double q, double qinv) {
+        constexpr int LB = P0 - K + 1, G = 32 >> K, S0 = LOGN - 1 - P0, NT = 1 << (LOGN - 5), E = 1 << K;
+        constexpr int half = 1 << (K - 1 - U);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int hi = (g * NT + (int)threadIdx.x) >> LB;
+#pragma unroll
+            for (int r = 0; r < (1 << U); r++) {
+                const double w = __ldg(tw + ((1 << (S0 + U)) + (hi << U) + r));
+#pragma unroll
+                for (int i = 0; i < half; i++) {
+                    const int e = g * E + ((r << (K - U)) | i);
+                    const double X = v[e];
+                    const double T = fp_mulmod(v[e + half], w, q, qinv);
+                    v[e] = __dadd_rn(X, T);
+                    v[e + half] = __dadd_rn(X, -T);
+                }
+            }
+        }
+        if constexpr (U + 1 < K) FpFwdStages<LOGN, K, P0, U + 1>::run(v, tw, q, qinv);
+    }
+};
+
+template <int LOGN, int K, int P0, class Load, class Store>
+__device__ __forceinline__ void fp_fwd_pass(const double *__restrict__ tw, double q, double qinv, Load load,
+                                            Store store) {
+    constexpr int LB = P0 - K + 1, G = 32 >> K, NT = 1 << (LOGN - 5), E = 1 << K;
+    double v[32];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int c = g * NT + (int)threadIdx.x, lo = c & ((1 << LB) - 1), hi = c >> LB;
+        const int base = (hi << (P0 + 1)) | lo;
+#pragma unroll
+        for (int e = 0; e < E; e++) v[g * E + e] = load(base | (e << LB));
+    }
+    FpFwdStages<LOGN, K, P0, 0>::run(v, tw, q, qinv);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int c = g * NT + (int)threadIdx.x, lo = c & ((1 << LB) - 1), hi = c >> LB;
+        const int base = (hi << (P0 + 1)) | lo;
+#pragma unroll
+        for (int e = 0; e < E; e++) store(base | (e << LB), v[g * E + e]);
+    }
+}
+
+template <int LOGN, int K, int LB, bool LAST, int B>
+struct FpInvStages {
+    static __device__ __forceinline__ void run(double (&v)[32], const double *__restrict__ itw, double q, double qinv,
+                                               double ninv, double last_w) {
+        constexpr int G = 32 >> K, NT = 1 << (LOGN - 5), E = 1 << K;
+        constexpr int half = 1 << B;
+        constexpr int s = LOGN - 1 - LB - B;
+        constexpr bool fold = LAST && (B == K - 1);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int hi = (g * NT + (int)threadIdx.x) >> LB;
+#pragma unroll
+            for (int r = 0; r < (1 << (K - 1 - B)); r++) {
+                const double w = fold ? last_w : __ldg(itw + ((1 << s) + (hi << (K - 1 - B)) + r));
+#pragma unroll
+                for (int i = 0; i < half; i++) {
+                    const int e = g * E + ((r << (B + 1)) | i);
+                    const double U = v[e], V = v[e + half];
+                    double sum = __dadd_rn(U, V);
+                    // the sum path doubles every stage: with 49-bit primes pull it back every second stage
+                    if (LOGN >= 14 && (B & 1) && !fold) sum = fp_reduce(sum, q, qinv);
+                    if (fold) sum = fp_mulmod(sum, ninv, q, qinv);
+                    v[e] = sum;
+                    v[e + half] = fp_mulmod(__dadd_rn(U, -V), w, q, qinv);
+                }
+            }
+        }
+        if constexpr (B + 1 < K) FpInvStages<LOGN, K, LB, LAST, B + 1>::run(v, itw, q, qinv, ninv, last_w);
+    }
+};
+
+template <int LOGN, int K, int LB, bool LAST, class Load, class Store>
+__device__ __forceinline__ void fp_inv_pass(const double *__restrict__ itw, double q, double qinv, double ninv,
+                                            double last_w, Load load, Store store) {
+    constexpr int G = 32 >> K, NT = 1 << (LOGN - 5), E = 1 << K, P0 = LB + K - 1;
+    double v[32];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int c = g * NT + (int)threadIdx.x, lo = c & ((1 << LB) - 1), hi = c >> LB;
+        const int base = (hi << (P0 + 1)) | lo;
+#pragma unroll
+        for (int e = 0; e < E; e++) v[g * E + e] = load(base | (e << LB));
+    }
+    FpInvStages<LOGN, K, LB, LAST, 0>::run(v, itw, q, qinv, ninv, last_w);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const int c = g * NT + (int)threadIdx.x, lo = c & ((1 << LB) - 1), hi = c >> LB;
+        const int base = (hi << (P0 + 1)) | lo;
+#pragma unroll
+        for (int e = 0; e < E; e++) store(base | (e << LB), v[g * E + e]);
+    }
+}
+
+// p.tw_fp: [nmod][2][N] doubles (centred twiddles); p.fp_consts: [nmod] {q, 1/q, centred N^-1, centred irp[1]*N^-1}
+template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_fp_kernel(const NttParams p) {
+    using Cfg = NttCfg<LOGN>;
+    extern __shared__ __align__(16) double smd[];
+    const int mi = p.mod_map[blockIdx.x];
+    const DevModulus m = p.mods[mi];
+    const double *tw = p.tw_fp + (size_t)mi * 2 * Cfg::N;
+    const u64 *in = (INMODE == NTT_IN_GALOIS_REDUCE)
+                        ? p.jobs[blockIdx.z].c1_coef + blockIdx.y * p.in_sy
+                        : p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
+    u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
+    const double q = m.fq, qinv = m.fqinv;
+    const u32 gal_einv = (INMODE == NTT_IN_GALOIS_REDUCE) ? p.jobs[blockIdx.z].einv : 0u;
+    if (INMODE == NTT_IN_GALOIS_REDUCE) {
+        const RotJob &jb = p.jobs[blockIdx.z];
+        if (jb.D && !*jb.flag) return;
+    }
+    constexpr bool MIDRED = LOGN >= 14; // keep magnitudes below 2^52 for 49-bit primes
+
+    auto gload = [&](int idx) -> double {
+        if (INMODE == NTT_IN_PLAIN) return fp_from_u64(in[idx]);
+        if (INMODE == NTT_IN_REDUCE) {
+            const u64 x = in[idx];
+            if (x == 0 && p.zero_flags) p.zero_flags[blockIdx.z] = 1;
+            return fp_reduce(fp_from_u64(x), q, qinv);
+        }
+        if (INMODE == NTT_IN_LIFT) {
+            const u64 x = in[idx];
+            return x >= p.lift_thr ? __dadd_rn(fp_from_u64(x), -(double)p.lift_t) : fp_from_u64(x); // centred value
+        }
+        const u32 i0 = (u32)(((u64)idx * gal_einv) & (2u * Cfg::N - 1));
+        u64 x = in[i0 & (Cfg::N - 1)];
+        if (i0 >= (u32)Cfg::N) {
+            const u64 qs = p.mods[p.src_map[blockIdx.y]].q;
+            x = x ? qs - x : 0;
+        }
+        return fp_reduce(fp_from_u64(x), q, qinv);
+    };
+    auto sload = [&](int idx) -> double {
+        const double x = smd[sm_phys(idx)];
+        return MIDRED ? fp_reduce(x, q, qinv) : x;
+    };
+    auto sstore = [&](int idx, double x) { smd[sm_phys(idx)] = x; };
+
+    fp_fwd_pass<LOGN, Cfg::K1, LOGN - 1>(tw, q, qinv, gload, sstore);
+    __syncthreads();
+    fp_fwd_pass<LOGN, Cfg::K2, 8>(tw, q, qinv, sload, sstore);
+    __syncthreads();
+    u64 *smu = reinterpret_cast<u64 *>(smd);
+    auto fstore = [&](int idx, double x) {
+        u64 r = fp_canonical(x, q, qinv);
+        if (OUTMODE == NTT_OUT_PLAIN && p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
+        smu[sm_phys(idx)] = r;
+    };
+    fp_fwd_pass<LOGN, Cfg::K3, 4>(tw, q, qinv, sload, fstore);
+    __syncthreads();
+    if (OUTMODE == NTT_OUT_KS) {
+        const int j = blockIdx.x, c = blockIdx.y, L = p.ks_L;
+        const RotJob job = p.jobs[blockIdx.z];
+        const u64 *S = p.ks_S + ((size_t)blockIdx.z * 2 + c) * (L + 1) * Cfg::N + (size_t)j * Cfg::N;
+        u64 *o = job.out + ((size_t)c * L + j) * Cfg::N;
+        const u64 pinv = m.p_inv, pinv_sh = m.p_inv_sh, qi = m.q;
+#pragma unroll 8
+        for (int i = 0; i < 32; i++) {
+            const int idx = i * Cfg::NT + threadIdx.x;
+            const u64 w = smu[sm_phys(idx)];
+            u64 r = mul_shoup(submod(S[idx], w, qi), pinv, pinv_sh, qi);
+            if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * Cfg::N + job.perm[idx]], qi);
+            if (p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
+            o[idx] = r;
+        }
+        return;
+    }
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+        const int idx = i * Cfg::NT + threadIdx.x;
+        out[idx] = smu[sm_phys(idx)];
+    }
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_inv_fp_kernel(const NttParams p) {
+    using Cfg = NttCfg<LOGN>;
+    extern __shared__ __align__(16) double smd[];
+    const int mi = p.mod_map[blockIdx.x];
+    const DevModulus m = p.mods[mi];
+    const double *itw = p.tw_fp + (size_t)mi * 2 * Cfg::N + Cfg::N;
+    const u64 *in = p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
+    u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
+    const double q = m.fq, qinv = m.fqinv;
+    constexpr bool MIDRED = true; // Gentleman-Sande sums double per stage: reduce at every pass boundary
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+        const int idx = i * Cfg::NT + threadIdx.x;
+        smd[sm_phys(idx)] = fp_from_u64(in[idx]);
+    }
+    __syncthreads();
+    auto sload0 = [&](int idx) -> double { return smd[sm_phys(idx)]; };
+    auto sload = [&](int idx) -> double {
+        const double x = smd[sm_phys(idx)];
+        return MIDRED ? fp_reduce(x, q, qinv) : x;
+    };
+    auto sstore = [&](int idx, double x) { smd[sm_phys(idx)] = x; };
+    auto gstore = [&](int idx, double x) { out[idx] = fp_canonical(x, q, qinv); };
+    fp_inv_pass<LOGN, Cfg::K3, 0, false>(itw, q, qinv, m.fninv, m.flast_w, sload0, sstore);
+    __syncthreads();
+    fp_inv_pass<LOGN, Cfg::K2, 5, false>(itw, q, qinv, m.fninv, m.flast_w, sload, sstore);
+    __syncthreads();
+    fp_inv_pass<LOGN, Cfg::K1, 9, true>(itw, q, qinv, m.fninv, m.flast_w, sload, gstore);
+}
