@@ -235,6 +235,8 @@ def main():
     ap.add_argument("--config", default=None, choices=list(CONFIGS))
     ap.add_argument("--nq", type=int, default=None, help="queries per step")
     ap.add_argument("--g", type=int, default=None, help="partial-sum factor of the layout")
+    ap.add_argument("--result-limbs", type=int, default=2,
+                    help="limbs of the result ciphertexts (SEAL mod_switch_to before save); 0 = no switching")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -272,7 +274,7 @@ def main():
     t_setup = time.perf_counter()
     data = make_dataset(cfg, dev)
     eng = pf.Engine(d, n, pf.bfv_default_primes(n), pf.batching_plain_modulus(n, cfg["tbits"]), m, g,
-                    device=local_rank, rank=rank, world=world)
+                    device=local_rank, rank=rank, world=world, result_limbs=args.result_limbs)
     info = eng.load_index(data["centroids"], data["offsets"], data["ids"], data["vectors"])
     eng.set_list_sizes(data["offsets"])
     L, k, K, C_ = eng.L, eng.k, info["K"], info["C"]
@@ -299,7 +301,7 @@ def main():
     nsteps_total = args.warmup + args.steps
     qsets = [queries[(s * nq) % (len(queries) - nq):][:nq] for s in range(nsteps_total)]
     max_res = int(eng._blocks_per_list.max()) * nprobe * nq
-    d_out = torch.empty((max_res, 2, L, n), dtype=torch.int64, device=dev)
+    d_out = torch.empty((max_res, 2, eng.Lr, n), dtype=torch.int64, device=dev)
     log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f}s  index: {info}  max_res {max_res}")
 
     def step(s):
@@ -462,7 +464,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": cfg_name, "nb": cfg["nb"], "d": d, "nlist": cfg["nlist"], "nprobe": nprobe,
-                       "poly_degree": n, "limbs": L, "g": g, "query_cts": m, "queries_per_step": nq,
+                       "poly_degree": n, "limbs": L, "result_limbs": eng.Lr, "g": g, "query_cts": m, "queries_per_step": nq,
                        "parallelism": f"lists%{world}" if world > 1 else "single",
                        "l2_policy": f"inputs larger than L2: NTT-domain DB {info['db_bytes'] / 2**30:.1f} GiB/rank "
                                     "streamed from HBM, query batches rotate through a pool"},

@@ -51,6 +51,9 @@ typedef struct {
     uint32_t partial_g;     /* g: partial sums per candidate, power of two dividing d_pad/m */
     uint32_t rank;          /* this engine keeps the IVF lists l with l % world == rank */
     uint32_t world;
+    uint32_t result_limbs;  /* 0 = L.  < L: results are mod-switched down to this many limbs before they
+                             * leave the GPU (SEAL Evaluator::mod_switch_to_inplace), shrinking the response */
+    uint32_t reserved;
 } pf_params;
 
 typedef struct {
@@ -124,7 +127,7 @@ typedef struct {
  * query_cts holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level) back to back,
  * ct_offsets[nq*m+1] their byte offsets.  For query i and each of its lists idx[i][p] (in order, lists
  * not owned by this rank are skipped) one result ciphertext per block of the list is written to
- * out_cts in SEAL format (coefficient form).  Result r is the pf_ct_serialized_size() bytes starting
+ * out_cts in SEAL format (coefficient form).  Result r is the pf_result_serialized_size() bytes starting
  * at result_offsets[r]; results sit in slots of pf_result_slot_size() bytes so that their words are
  * 128-byte aligned for the device-to-host copy (out_cap >= nresults * slot; result_offsets[nresults]
  * = bytes used).  Pinned, 128-byte aligned out_cts gives the fastest copies.  results_per_query[nq].
@@ -139,7 +142,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
 
 /* Device-resident form of the same step (what `value` in bench.py times): d_query_cts is a DEVICE
  * pointer to raw words [nq][m][2][L][N] (coefficient form); d_out a DEVICE buffer of
- * cap_results*2*L*N words receiving coefficient-form results in the order above.  idx is a host
+ * cap_results*2*result_limbs*N words receiving coefficient-form results in the order above.  idx is a host
  * array.  Asynchronous on the engine stream. */
 int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, const int64_t *idx, uint32_t nprobe,
                      uint64_t *d_out, uint64_t cap_results, uint64_t *results_per_query, pf_search_stats *stats);
@@ -176,10 +179,17 @@ int pf_batch_encode(pf_engine *e, const uint64_t *values, uint64_t *plain);
 int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *diag, uint64_t *norm);
 /* SEAL wire format (compr_mode none) of a coefficient-form size-2 ciphertext */
 size_t pf_ct_serialized_size(pf_engine *e);
-/* bytes of out_cts reserved per result ciphertext by pf_search_lists_encrypted */
+/* bytes of out_cts reserved per result ciphertext by pf_search_lists_encrypted, and the length of a
+ * result's SEAL stream (results have result_limbs limbs) */
 size_t pf_result_slot_size(pf_engine *e);
+size_t pf_result_serialized_size(pf_engine *e);
+/* parms_id written into result ciphertexts (SEAL: context_data(level)->parms_id()); defaults to the
+ * query's parms_id when result_limbs == L, zeros otherwise (parms_id hashing is not implemented here) */
+int pf_set_result_parms_id(pf_engine *e, const uint64_t parms_id[4]);
 int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written);
-int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, int *is_ntt, size_t *consumed);
+/* accepts ciphertexts with L (query level) or result_limbs limbs; *limbs receives the count */
+int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, size_t cap_words, int *limbs,
+                      int *is_ntt, size_t *consumed);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,8 @@ EXPORTS = [
     "pf_galois_elt_from_step", "pf_search_lists_encrypted", "pf_search_device", "pf_timing_enable", "pf_timing_read",
     "pf_launch_count", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
-    "pf_ct_serialized_size", "pf_result_slot_size", "pf_ct_serialize", "pf_ct_deserialize",
+    "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id",
+    "pf_ct_serialize", "pf_ct_deserialize",
 ]
 
 
@@ -31,7 +32,7 @@ class PfParams(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("poly_degree", C.c_uint64),
                 ("num_primes", C.c_uint32), ("dim", C.c_uint32), ("primes", C.c_uint64 * PF_MAX_PRIMES),
                 ("plain_modulus", C.c_uint64), ("query_cts", C.c_uint32), ("partial_g", C.c_uint32),
-                ("rank", C.c_uint32), ("world", C.c_uint32)]
+                ("rank", C.c_uint32), ("world", C.c_uint32), ("result_limbs", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class PfIndexInfo(C.Structure):
@@ -96,8 +97,10 @@ def load() -> C.CDLL:
         "pf_encode_block": ([vp, i32p, C.c_uint32, u64p, u64p], C.c_int),
         "pf_ct_serialized_size": ([vp], C.c_size_t),
         "pf_result_slot_size": ([vp], C.c_size_t),
+        "pf_result_serialized_size": ([vp], C.c_size_t),
+        "pf_set_result_parms_id": ([vp, u64p], C.c_int),
         "pf_ct_serialize": ([vp, u64p, C.c_int, u8p, C.c_size_t, szp], C.c_int),
-        "pf_ct_deserialize": ([vp, u8p, C.c_size_t, u64p, i32p, szp], C.c_int),
+        "pf_ct_deserialize": ([vp, u8p, C.c_size_t, u64p, C.c_size_t, i32p, i32p, szp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

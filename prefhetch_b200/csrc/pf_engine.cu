@@ -97,6 +97,10 @@ constexpr size_t PF_RESULT_PAD = PF_RESULT_DATA_OFFSET - SEAL_CT_HEADER; // its 
 struct pf_engine {
     pf_params prm{};
     int N = 0, logn = 0, k = 0, L = 0;
+    int Lr = 0; // limbs of result ciphertexts (<= L)
+    uint64_t result_pid[4] = {0, 0, 0, 0};
+    bool result_pid_set = false;
+    DevBuf d_mstab, s_full, s_dropped;
     u32 d = 0, d_pad = 0, m = 0, g = 0, dc = 0, R = 0, K = 0, C = 0;
     u64 t = 0;
     std::mutex mu;
@@ -234,6 +238,7 @@ cudaError_t set_ntt_attrs() {
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
     SETATTR((ntt_inv_fp_kernel<LOGN>));
+    SETATTR((ntt_inv_fp_kernel<LOGN, NTT_OUT_MODSWITCH>));
 #undef SETATTR
     return cudaSuccess;
 }
@@ -242,7 +247,9 @@ template <int LOGN>
 void launch_ntt_fp_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
     const size_t smem = NttCfg<LOGN>::SMEM;
     const int nt = NttCfg<LOGN>::NT;
-    if (inverse)
+    if (inverse && p.ms_dropped)
+        ntt_inv_fp_kernel<LOGN, NTT_OUT_MODSWITCH><<<grid, nt, smem, s>>>(p);
+    else if (inverse)
         ntt_inv_fp_kernel<LOGN><<<grid, nt, smem, s>>>(p);
     else if (p.ks_S)
         ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
@@ -402,6 +409,20 @@ int build_tables(pf_engine *e) {
     e->q_mod_t = big_div_word(quo, e->t);
     e->delta_mod_q.resize(L);
     for (int j = 0; j < L; j++) e->delta_mod_q[j] = big_mod_word(quo, e->h_q[j]);
+    // mod-switch tables (divide_and_round_q_last): dropping limb c, for j < c
+    {
+        std::vector<u64> tab((size_t)MS_MAXL * MS_MAXL * 3, 0);
+        for (int c = 1; c < L; c++)
+            for (int j = 0; j < c; j++) {
+                const u64 qc = e->h_q[c], qj = e->h_q[j];
+                u64 *t = tab.data() + ((size_t)c * MS_MAXL + j) * 3;
+                t[0] = (qc >> 1) % qj;
+                t[1] = invmod(qc % qj, qj);
+                t[2] = shoup(t[1], qj);
+            }
+        CK(e->d_mstab.ensure(tab.size() * 8));
+        CK(cudaMemcpy(e->d_mstab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    }
     // special prime constants
     const u64 P = e->h_q[k - 1];
     e->p_half = P >> 1;
@@ -845,7 +866,16 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     const size_t p0 = (size_t)pl.chunks[c0].pair_start;
     const size_t p1 = (size_t)pl.chunks[c1 - 1].pair_start + pl.chunks[c1 - 1].pair_count;
     const size_t P = p1 - p0;
-    u64 *out = d_out + p0 * out_stride;
+    // with result_limbs < L the full-level results live in scratch and the mod-switch writes the slots
+    const bool ms = e->Lr < L;
+    u64 *full = d_out;
+    size_t full_stride = out_stride, full_base = p0;
+    if (ms) {
+        CK(e->s_full.ensure(P * ctw * 8));
+        full = e->s_full.as<u64>();
+        full_stride = ctw;
+        full_base = 0;
+    }
     {
         PhaseTimer pt(e, PF_T_MAC);
         MacParams mp{};
@@ -858,8 +888,8 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
         mp.chunks = e->s_chunks.as<MacChunk>() + c0; // absolute pair / query indices (upload_plan)
         mp.pair_block = e->s_pairblock.as<long long>();
         mp.pair_out = e->s_pairout.as<int>();
-        mp.out = d_out;
-        mp.out_stride = (long long)out_stride;
+        mp.out = ms ? full - p0 * full_stride : d_out; // slot index is absolute
+        mp.out_stride = (long long)full_stride;
         mp.mods = e->d_mods.as<DevModulus>();
         mp.K = e->K;
         mp.L = L;
@@ -869,15 +899,68 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     }
     {
         PhaseTimer pt(e, PF_T_INTT);
+        u64 *base = full + full_base * full_stride;
+        const int nd = L - e->Lr;
+        // the fused store (NTT_OUT_MODSWITCH) is bit-exact but measured 2-6x slower than the pair
+        // INTT + modswitch_kernel_t (register pressure in the 32-point pass); kept behind PF_FUSED_MS
+        static const bool want_fused = getenv("PF_FUSED_MS") != nullptr;
+        const bool fused_ms = want_fused && ms && e->ntt_fp && nd <= 4;
+        if (fused_ms) CK(e->s_dropped.ensure(P * (size_t)2 * nd * N * 8));
         for (size_t off = 0; off < P; off += 32768) {
             const unsigned cnt = (unsigned)std::min<size_t>(32768, P - off);
             NttParams ip{};
-            ip.in = ip.out = out + off * out_stride;
+            ip.in = ip.out = base + off * full_stride;
             ip.in_sx = ip.out_sx = N;
             ip.in_sy = ip.out_sy = (long long)L * N;
-            ip.in_sz = ip.out_sz = (long long)out_stride;
+            ip.in_sz = ip.out_sz = (long long)full_stride;
             for (int i = 0; i < L; i++) ip.mod_map[i] = i;
-            launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(L, 2, cnt));
+            if (!fused_ms) {
+                launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(L, 2, cnt));
+                if (ms) {
+                    const u64 *src = base + off * full_stride;
+                    u64 *dst = d_out + (p0 + off) * out_stride;
+                    const DevModulus *dm = e->d_mods.as<DevModulus>();
+                    const u64 *tab = e->d_mstab.as<u64>();
+                    const dim3 g2(N / 512, 2, cnt);
+#define MS_CASE(LL, RR)                                                                                        \
+    else if (L == LL && e->Lr == RR) modswitch_kernel_t<LL, RR><<<g2, 256, 0, e->stream>>>(src, full_stride, dst, \
+                                                                                          out_stride, dm, tab, N)
+                    if (false) {
+                    }
+                    MS_CASE(4, 3);
+                    MS_CASE(4, 2);
+                    MS_CASE(4, 1);
+                    MS_CASE(8, 4);
+                    MS_CASE(8, 2);
+                    MS_CASE(8, 1);
+                    MS_CASE(3, 2);
+                    MS_CASE(3, 1);
+                    else modswitch_kernel<<<dim3(N / 256, 2, cnt), 256, 0, e->stream>>>(src, full_stride, dst, out_stride,
+                                                                                        dm, tab, L, e->Lr, N);
+#undef MS_CASE
+                    e->launches++;
+                }
+                continue;
+            }
+            // (a) the limbs that will be dropped -> coefficient form in scratch [result][poly][c][N]
+            NttParams dp = ip;
+            dp.in = base + off * full_stride + (size_t)e->Lr * N;
+            dp.out = e->s_dropped.as<u64>() + off * (size_t)2 * nd * N;
+            dp.out_sy = (long long)nd * N;
+            dp.out_sz = (long long)2 * nd * N;
+            for (int i = 0; i < nd; i++) dp.mod_map[i] = e->Lr + i;
+            launch_ntt(e, NTT_IN_PLAIN, true, dp, dim3(nd, 2, cnt));
+            // (b) the kept limbs: inverse NTT with SEAL's mod_switch_to folded into the store
+            NttParams kp2 = ip;
+            kp2.out = d_out + (p0 + off) * out_stride;
+            kp2.out_sy = (long long)e->Lr * N;
+            kp2.out_sz = (long long)out_stride;
+            kp2.ms_dropped = e->s_dropped.as<u64>() + off * (size_t)2 * nd * N;
+            kp2.ms_dropped_sz = (long long)2 * nd * N;
+            kp2.ms_tab = e->d_mstab.as<u64>();
+            kp2.ms_L = L;
+            kp2.ms_Lr = e->Lr;
+            launch_ntt(e, NTT_IN_PLAIN, true, kp2, dim3(e->Lr, 2, cnt));
         }
     }
     CK(cudaGetLastError());
@@ -896,8 +979,8 @@ void write_seal_header(uint8_t *p, uint64_t total) {
 }
 
 // SEAL Ciphertext::save_members, compr_mode none (ciphertext.cpp, dynarray.h)
-void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t parms_id[4]) {
-    const uint64_t words = (uint64_t)2 * e->L * e->N, total = SEAL_CT_HEADER + words * 8;
+void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t parms_id[4], int limbs) {
+    const uint64_t words = (uint64_t)2 * limbs * e->N, total = SEAL_CT_HEADER + words * 8;
     write_seal_header(p, total);
     p += 16;
     memcpy(p, parms_id, 32);
@@ -909,7 +992,7 @@ void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t 
     v = (uint64_t)e->N;
     memcpy(p, &v, 8);
     p += 8;
-    v = (uint64_t)e->L;
+    v = (uint64_t)limbs;
     memcpy(p, &v, 8);
     p += 8;
     const double scale = 1.0;
@@ -982,11 +1065,13 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     e->k = (int)prm->num_primes;
     e->L = e->k - 1;
     e->t = prm->plain_modulus;
+    e->Lr = prm->result_limbs ? (int)prm->result_limbs : e->L;
     auto bail = [&](int code) {
         g_tls_error = e->err;
         delete e;
         return code;
     };
+    if (e->Lr < 1 || e->Lr > e->L) return bail(e->fail(PF_ERR_INVALID, "result_limbs must be in [1, L]"));
     for (int j = 0; j < e->k; j++) {
         const u64 q = prm->primes[j];
         if (q >> 61 || q < 2 || (q - 1) % (2 * N) || !pfh::is_prime(q))
@@ -1447,7 +1532,7 @@ int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, con
     const uint64_t P = pl.pair_block.size();
     if (stats) {
         stats->nresults = P;
-        stats->out_bytes = P * 2ull * e->L * e->N * 8;
+        stats->out_bytes = P * 2ull * e->Lr * e->N * 8;
         stats->useful_distances = pl.useful;
         stats->slot_distances = P * e->C;
     }
@@ -1455,7 +1540,7 @@ int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, con
     if (P > cap_results || (P && !d_out)) return e->fail(PF_ERR_CAPACITY, "need room for %llu result ciphertexts, capacity %llu", (unsigned long long)P, (unsigned long long)cap_results);
     rc = upload_plan(e, pl);
     if (rc) return rc;
-    return search_core(e, 0, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out, (size_t)2 * e->L * e->N);
+    return search_core(e, 0, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out, (size_t)2 * e->Lr * e->N);
 }
 
 int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
@@ -1473,10 +1558,10 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     int rc = plan_pairs(e, nq, idx, nprobe, pl);
     if (rc) return rc;
     const uint64_t P = pl.pair_block.size();
-    const size_t ct_bytes = SEAL_CT_HEADER + ctw * 8;
+    const size_t rw = (size_t)2 * e->Lr * N; // words of a result ciphertext
     // Result r occupies a slot of `slot` bytes; its SEAL stream starts at r*slot + RESULT_PAD so that
     // the ciphertext words sit at a 128-byte aligned offset (one aligned D2H per query group).
-    const size_t slot = PF_RESULT_DATA_OFFSET + ctw * 8;
+    const size_t slot = PF_RESULT_DATA_OFFSET + rw * 8;
     // labels / sizes of the owned probed lists (same packing as pf_search_lists_plain)
     uint64_t nlabels = 0;
     for (uint64_t i = 0; i < nq; i++) {
@@ -1543,8 +1628,10 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->copy_stream));
+    const uint64_t zero_pid[4] = {0, 0, 0, 0};
+    const uint64_t *out_pid = e->result_pid_set ? e->result_pid : (e->Lr == L ? parms_id : zero_pid);
     for (uint64_t r = 0; r < P; r++) { // SEAL stream headers (113 bytes each) in front of the aligned words
-        write_ct_prefix(e, out_cts + r * slot + PF_RESULT_PAD, 0, parms_id);
+        write_ct_prefix(e, out_cts + r * slot + PF_RESULT_PAD, 0, out_pid, e->Lr);
         if (result_offsets) result_offsets[r] = r * slot + PF_RESULT_PAD;
     }
     if (result_offsets) result_offsets[P] = P * slot;
@@ -1760,7 +1847,15 @@ int pf_encode_block(pf_engine *e, const int32_t *xs, uint32_t nvec, uint64_t *di
 }
 
 size_t pf_ct_serialized_size(pf_engine *e) { return e ? SEAL_CT_HEADER + (size_t)2 * e->L * e->N * 8 : 0; }
-size_t pf_result_slot_size(pf_engine *e) { return e ? PF_RESULT_DATA_OFFSET + (size_t)2 * e->L * e->N * 8 : 0; }
+size_t pf_result_slot_size(pf_engine *e) { return e ? PF_RESULT_DATA_OFFSET + (size_t)2 * e->Lr * e->N * 8 : 0; }
+size_t pf_result_serialized_size(pf_engine *e) { return e ? SEAL_CT_HEADER + (size_t)2 * e->Lr * e->N * 8 : 0; }
+int pf_set_result_parms_id(pf_engine *e, const uint64_t parms_id[4]) {
+    if (!e || !parms_id) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    memcpy(e->result_pid, parms_id, 32);
+    e->result_pid_set = true;
+    return PF_OK;
+}
 
 int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written) {
     if (!e || !ct || !out) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
@@ -1768,19 +1863,22 @@ int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, 
     if (written) *written = need;
     if (cap < need) return e->fail(PF_ERR_CAPACITY, "need %zu bytes", need);
     const uint64_t pid[4] = {0, 0, 0, 0};
-    write_ct_prefix(e, out, is_ntt, pid);
+    write_ct_prefix(e, out, is_ntt, pid, e->L);
     memcpy(out + SEAL_CT_HEADER, ct, need - SEAL_CT_HEADER);
     return PF_OK;
 }
 
-int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, int *is_ntt, size_t *consumed) {
+int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, size_t cap_words, int *limbs,
+                      int *is_ntt, size_t *consumed) {
     if (!e || !in || !ct) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
     int ntt;
     uint64_t pid[4], cms;
     size_t total;
     const int pr = parse_ct_prefix(e, in, len, &ntt, pid, &cms, &total);
-    if (pr || cms != (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "malformed ciphertext (code %d)", pr);
+    if (pr || cms < 1 || cms > (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "malformed ciphertext (code %d)", pr);
+    if ((total - SEAL_CT_HEADER) / 8 > cap_words) return e->fail(PF_ERR_CAPACITY, "need %zu words", (total - SEAL_CT_HEADER) / 8);
     memcpy(ct, in + SEAL_CT_HEADER, total - SEAL_CT_HEADER);
+    if (limbs) *limbs = (int)cms;
     if (is_ntt) *is_ntt = ntt;
     if (consumed) *consumed = total;
     return PF_OK;

@@ -187,3 +187,71 @@ __global__ void __launch_bounds__(256) key_split_kernel(u64 *key, const DevModul
     u64 *w = key + (size_t)blockIdx.y * N + i;
     *w = split_word(*w, (int)mods[limb].split_shift);
 }
+
+// SEAL Evaluator::mod_switch_to_inplace on coefficient-form BFV results: drop limbs L-1 .. Lr
+// (RNSTool::divide_and_round_q_last_inplace per step).  tab[(c*16 + j)*3 + {0,1,2}] =
+// {(q_c >> 1) mod q_j, q_c^{-1} mod q_j, its Shoup quotient} for j < c.  grid (N/256, 2, results)
+#define MS_MAXL 16
+__global__ void __launch_bounds__(256) modswitch_kernel(const u64 *in, size_t in_stride, u64 *out, size_t out_stride,
+                                                        const DevModulus *mods, const u64 *tab, int L, int Lr, int N) {
+    const int i = blockIdx.x * 256 + threadIdx.x, p = blockIdx.y;
+    const u64 *src = in + (size_t)blockIdx.z * in_stride + (size_t)p * L * N + i;
+    u64 x[MS_MAXL];
+#pragma unroll
+    for (int j = 0; j < MS_MAXL; j++)
+        if (j < L) x[j] = src[(size_t)j * N];
+    for (int c = L - 1; c >= Lr; c--) {
+        u64 last = 0;
+#pragma unroll
+        for (int j = 0; j < MS_MAXL; j++)
+            if (j == c) last = x[j];
+        const u64 qc = mods[c].q;
+        last = addmod(last, qc >> 1, qc);
+#pragma unroll
+        for (int j = 0; j < MS_MAXL; j++) {
+            if (j < c) {
+                const u64 qj = mods[j].q;
+                const u64 *t = tab + ((size_t)c * MS_MAXL + j) * 3;
+                const u64 tmp = submod(barrett64(last, qj, mods[j].ratio1), t[0], qj);
+                x[j] = mul_shoup(submod(x[j], tmp, qj), t[1], t[2], qj);
+            }
+        }
+    }
+    u64 *dst = out + (size_t)blockIdx.z * out_stride + (size_t)p * Lr * N + i;
+#pragma unroll
+    for (int j = 0; j < MS_MAXL; j++)
+        if (j < Lr) dst[(size_t)j * N] = x[j];
+}
+
+// Compile-time (L, Lr) version of modswitch_kernel, two coefficients per thread.  grid (N/512, 2, results)
+template <int L, int LR>
+__global__ void __launch_bounds__(256) modswitch_kernel_t(const u64 *in, size_t in_stride, u64 *out, size_t out_stride,
+                                                          const DevModulus *mods, const u64 *tab, int N) {
+    const int i2 = blockIdx.x * 256 + threadIdx.x, p = blockIdx.y;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in + (size_t)blockIdx.z * in_stride + (size_t)p * L * N) + i2;
+    ulonglong2 x[L];
+    u64 q[L], ratio[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        x[j] = src[(size_t)j * (N / 2)];
+        q[j] = mods[j].q;
+        ratio[j] = mods[j].ratio1;
+    }
+#pragma unroll
+    for (int c = L - 1; c >= LR; c--) {
+        const u64 half = q[c] >> 1;
+        const u64 lx = addmod(x[c].x, half, q[c]), ly = addmod(x[c].y, half, q[c]);
+#pragma unroll
+        for (int j = 0; j < c; j++) {
+            const u64 *t = tab + ((size_t)c * MS_MAXL + j) * 3;
+            const u64 hm = t[0], inv = t[1], inv_sh = t[2];
+            const u64 tx = submod(barrett64(lx, q[j], ratio[j]), hm, q[j]);
+            const u64 ty = submod(barrett64(ly, q[j], ratio[j]), hm, q[j]);
+            x[j].x = mul_shoup(submod(x[j].x, tx, q[j]), inv, inv_sh, q[j]);
+            x[j].y = mul_shoup(submod(x[j].y, ty, q[j]), inv, inv_sh, q[j]);
+        }
+    }
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out + (size_t)blockIdx.z * out_stride + (size_t)p * LR * N) + i2;
+#pragma unroll
+    for (int j = 0; j < LR; j++) dst[(size_t)j * (N / 2)] = x[j];
+}

@@ -12,7 +12,7 @@
 
 enum { NTT_IN_PLAIN = 0, NTT_IN_REDUCE = 1, NTT_IN_LIFT = 2, NTT_IN_GALOIS_REDUCE = 3 };
 // epilogues fused into the transforms of the key-switch mod-down (pf_keyswitch.cuh steps 3 and 4)
-enum { NTT_OUT_PLAIN = 0, NTT_OUT_KS = 1 };
+enum { NTT_OUT_PLAIN = 0, NTT_OUT_KS = 1, NTT_OUT_MODSWITCH = 2 };
 
 struct NttParams {
     const u64 *in;
@@ -33,6 +33,12 @@ struct NttParams {
     const u64 *ks_S;             // [z][2][L+1][N]
     int ks_L;
     u64 ks_p_half;
+    // NTT_OUT_MODSWITCH (inverse, grid (kept limb j, poly, result)): the dropped limbs [ms_Lr, ms_L) are
+    // already in coefficient form at ms_dropped + z*ms_dropped_sz + poly*(ms_L-ms_Lr)*N + (c-ms_Lr)*N
+    const u64 *ms_dropped;
+    long long ms_dropped_sz;
+    const u64 *ms_tab; // [(c*16 + j)*3 + {half_c mod q_j, q_c^-1 mod q_j, Shoup}]
+    int ms_L, ms_Lr;
 };
 
 // one rotation = Evaluator::apply_galois_inplace on one ciphertext (see pf_keyswitch.cuh)

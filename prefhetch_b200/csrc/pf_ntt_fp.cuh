@@ -234,7 +234,19 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     }
 }
 
-template <int LOGN>
+// SEAL mod_switch_to_inplace folded into the store of a kept limb j: x is the canonical coefficient of
+// limb j; d[] are the coefficients of the dropped limbs [Lr, L) at the same position.  Dropping limb c
+// (RNSTool::divide_and_round_q_last_inplace): last = d_c + (q_c>>1) mod q_c, then every remaining limb i
+// becomes (x_i - ((last mod q_i) - ((q_c>>1) mod q_i))) * q_c^{-1} mod q_i — applied to the still-to-be-
+// dropped limbs too, because they are switched before they are dropped themselves.
+__device__ __forceinline__ u64 ms_step(u64 xi, u64 last, const DevModulus *mods, const u64 *tab, int c, int i) {
+    const u64 qi = mods[i].q;
+    const u64 *t = tab + ((size_t)c * 16 + i) * 3;
+    const u64 tmp = submod(barrett64(last, qi, mods[i].ratio1), t[0], qi);
+    return mul_shoup(submod(xi, tmp, qi), t[1], t[2], qi);
+}
+
+template <int LOGN, int OUTMODE = NTT_OUT_PLAIN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_inv_fp_kernel(const NttParams p) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) double smd[];
@@ -257,7 +269,30 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
         return MIDRED ? fp_reduce(x, q, qinv) : x;
     };
     auto sstore = [&](int idx, double x) { smd[sm_phys(idx)] = x; };
-    auto gstore = [&](int idx, double x) { out[idx] = fp_canonical(x, q, qinv); };
+    auto gstore = [&](int idx, double x) {
+        u64 r = fp_canonical(x, q, qinv);
+        if (OUTMODE == NTT_OUT_MODSWITCH) {
+            const int L = p.ms_L, Lr = p.ms_Lr, j = blockIdx.x;
+            const u64 *dp = p.ms_dropped + (size_t)blockIdx.z * p.ms_dropped_sz + (size_t)blockIdx.y * (L - Lr) * Cfg::N + idx;
+            u64 d[4]; // up to 4 dropped limbs on the fused path (host falls back to modswitch_kernel beyond)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c < L - Lr) d[c] = dp[(size_t)c * Cfg::N];
+#pragma unroll
+            for (int cc = 3; cc >= 0; cc--) {
+                if (cc < L - Lr) {
+                    const int c = Lr + cc;
+                    const u64 qc = p.mods[c].q;
+                    const u64 last = addmod(d[cc], qc >> 1, qc);
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; c2++)
+                        if (c2 < cc) d[c2] = ms_step(d[c2], last, p.mods, p.ms_tab, c, Lr + c2);
+                    r = ms_step(r, last, p.mods, p.ms_tab, c, j);
+                }
+            }
+        }
+        out[idx] = r;
+    };
     fp_inv_pass<LOGN, Cfg::K3, 0, false>(itw, q, qinv, m.fninv, m.flast_w, sload0, sstore);
     __syncthreads();
     fp_inv_pass<LOGN, Cfg::K2, 5, false>(itw, q, qinv, m.fninv, m.flast_w, sload, sstore);

@@ -70,7 +70,8 @@ class Engine:
     """One engine per GPU (one process per GPU).  Mirrors `Server` (ref: include/server/server_lib.h)."""
 
     def __init__(self, dim: int, poly_degree: int = 8192, primes=None, plain_modulus: int | None = None,
-                 query_cts: int = 1, partial_g: int = 8, device: int = 0, rank: int = 0, world: int = 1):
+                 query_cts: int = 1, partial_g: int = 8, device: int = 0, rank: int = 0, world: int = 1,
+                 result_limbs: int = 0):
         self.lib = _capi.load()
         primes = list(primes) if primes is not None else bfv_default_primes(poly_degree)
         if plain_modulus is None:
@@ -81,6 +82,7 @@ class Engine:
         for i, q in enumerate(primes):
             p.primes[i] = q
         p.plain_modulus, p.query_cts, p.partial_g, p.rank, p.world = plain_modulus, query_cts, partial_g, rank, world
+        p.result_limbs = result_limbs
         self.h = C.c_void_p()
         rc = self.lib.pf_engine_create(C.byref(p), C.byref(self.h))
         if rc:
@@ -91,6 +93,8 @@ class Engine:
         self.ctw = 2 * self.L * self.n
         self.ct_bytes = self.lib.pf_ct_serialized_size(self.h)
         self.slot_bytes = self.lib.pf_result_slot_size(self.h)
+        self.result_bytes = self.lib.pf_result_serialized_size(self.h)
+        self.Lr = result_limbs or self.L
         self.device, self.rank, self.world = device, rank, world
 
     def close(self):
@@ -204,7 +208,7 @@ class Engine:
             out.ctypes.data_as(C.c_void_p), out.size, _ptr(roff, U64P), max_results, _ptr(rpq, U64P),
             _ptr(labels, I64P), label_cap, _ptr(sizes, U64P), _ptr(psz, U64P), C.byref(st)))
         nres = st.nresults
-        return SearchResult(out, roff[:nres + 1], self.ct_bytes, rpq.astype(np.int64), labels[:int(sizes.sum())],
+        return SearchResult(out, roff[:nres + 1], self.result_bytes, rpq.astype(np.int64), labels[:int(sizes.sum())],
                             sizes.astype(np.int64), psz.astype(np.int64),
                             {f: getattr(st, f) for f, _ in PfSearchStats._fields_})
 
@@ -325,8 +329,14 @@ class Engine:
         return out[:w.value].tobytes()
 
     def ct_deserialize(self, blob) -> tuple[np.ndarray, bool]:
+        """-> (ct [2][limbs][n], is_ntt); limbs is L for queries, result_limbs for results"""
         b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
-        ct = np.zeros((2, self.L, self.n), dtype=np.uint64)
-        ntt, used = C.c_int32(), C.c_size_t()
-        self._ck(self.lib.pf_ct_deserialize(self.h, _ptr(b, U8P), b.size, _ptr(ct, U64P), C.byref(ntt), C.byref(used)))
-        return ct, bool(ntt.value)
+        ct = np.zeros(2 * self.L * self.n, dtype=np.uint64)
+        ntt, limbs, used = C.c_int32(), C.c_int32(), C.c_size_t()
+        self._ck(self.lib.pf_ct_deserialize(self.h, _ptr(b, U8P), b.size, _ptr(ct, U64P), ct.size, C.byref(limbs),
+                                            C.byref(ntt), C.byref(used)))
+        return ct[:2 * limbs.value * self.n].reshape(2, limbs.value, self.n), bool(ntt.value)
+
+    def set_result_parms_id(self, pid):
+        arr = (C.c_uint64 * 4)(*pid)
+        self._ck(self.lib.pf_set_result_parms_id(self.h, arr))

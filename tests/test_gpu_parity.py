@@ -212,9 +212,9 @@ def test_plain_stages_match_reference_semantics(pf, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("n,g,chain,world", [(2048, 16, False, 1), (8192, 8, False, 1), (2048, 16, True, 1),
-                                             (2048, 16, False, 2)])
-def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world):
+@pytest.mark.parametrize("n,g,chain,world,rl", [(2048, 16, False, 1, 0), (8192, 8, False, 1, 0), (2048, 16, True, 1, 0),
+                                                (2048, 16, False, 2, 0), (8192, 8, False, 1, 2), (2048, 16, False, 1, 1)])
+def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
     """serialized query ciphertexts -> pf_search_lists_encrypted -> bytes identical to the oracle's
     pipeline; decrypted distances == exact integer squared L2 of the plaintext path."""
     d, nprobe = 128, 5
@@ -228,7 +228,7 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world):
     C_ = cl.lay.C
     all_results = {}
     for rank in range(world):
-        eng, _, _ = _engine(pf, n, g=g, rank=rank, world=world)
+        eng, _, _ = _engine(pf, n, g=g, rank=rank, world=world, result_limbs=rl)
         eng.load_index(cent, offsets, ids, vecs)
         eng.set_list_sizes(offsets)
         for i, key in enumerate(keys):
@@ -254,6 +254,8 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world):
                     xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + C_, n_l)].astype(np.int32)
                     diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
                     want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
+                    if rl:
+                        want_ct = cl.mod_switch_to(want_ct, rl)  # SEAL mod_switch_to_inplace before save
                     got_bytes = res.result(r)
                     assert got_bytes == cl.ctx.ct_save(want_ct), f"rank {rank} query {qi} result {r}"
                     got_ct, is_ntt = eng.ct_deserialize(got_bytes)

@@ -100,7 +100,29 @@ class OracleClient:
         offs[1:] = np.cumsum([len(b) for b in blobs])
         return np.frombuffer(b"".join(blobs), dtype=np.uint8).copy(), offs
 
+    def mod_switch_to(self, ct, limbs):
+        """SEAL Evaluator::mod_switch_to_inplace down to `limbs` data limbs (oracle)"""
+        while ct.shape[1] > limbs:
+            ct = self.ctx.mod_switch_next(ct)
+        return ct
+
     def distances(self, result_ct, q, nvec):
+        limbs = result_ct.shape[1]
+        if limbs < self.ctx.L:   # decrypt at the lower level: context / secret key restricted to its primes
+            key = (limbs,)
+            if not hasattr(self, "_low"):
+                self._low = {}
+            if key not in self._low:
+                pr = self.ctx.primes[:limbs] + [self.ctx.primes[-1]]
+                self._low[key] = (self.o.Context(self.ctx.n, pr, self.ctx.t),
+                                  np.ascontiguousarray(self.sk[[*range(limbs), self.ctx.k - 1]]))
+            ctx, sk = self._low[key]
+            plain, budget = ctx.decrypt(sk, result_ct)
+            slots = ctx.decode(plain).astype(np.int64)
+            tab = self.lay.slot_table()
+            qi = np.asarray(q).astype(np.int64)
+            d = (slots[tab].sum(axis=1) + int((qi * qi).sum())) % self.ctx.t
+            return d[:nvec], budget
         plain, budget = self.ctx.decrypt(self.sk, result_ct)
         slots = self.ctx.decode(plain).astype(np.int64)
         tab = self.lay.slot_table()
