@@ -536,11 +536,12 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         np.out_split = 1;
         launch_ntt(e, NTT_IN_GALOIS_REDUCE, false, np, dim3(L + 1, L, nz));
         // 2. S_c[I]
+        // 2a. S_c[P] (special-prime limb only)
         {
-            const dim3 g(N / 512, L + 1, (nz + KS_QT - 1) / KS_QT);
-            if (L <= 4) ks_accumulate_kernel<4><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else if (L <= 8) ks_accumulate_kernel<8><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else ks_accumulate_kernel<KS_MAXL><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            const dim3 g(N / 512, 1, (nz + KS_QT - 1) / KS_QT);
+            if (L <= 4) ks_accumulate_kernel<4, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else if (L <= 8) ks_accumulate_kernel<8, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else ks_accumulate_kernel<KS_MAXL, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
         }
         e->launches++;
         // 3. u_c = INTT_P(S_c[L]) in place, then W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).
@@ -555,7 +556,9 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(1, 2, nz));
         ks_moddown_prep_kernel<<<dim3(N / 256, 2, nz), 256, 0, e->stream>>>(kp);
         e->launches++;
-        // 4. NTT_j(W_c[j]) with the key-switch finish fused into its copy-out: writes the rotated ciphertext
+        // 4. NTT_j(W_c[j]) in place, then 2b. S_c[j] for the data limbs with the finish fused:
+        //    out_c[j] = (S_c[j] - NTT_j(W_c[j])) * P^{-1} (+ sigma_ntt(c0)[j]); S_c[j] never hits memory.
+        //    (Fusing the finish into the NTT copy-out instead, NTT_OUT_KS, measured slower.)
         NttParams wp{};
         wp.in = kp.W;
         wp.out = kp.W;
@@ -563,11 +566,14 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         wp.in_sy = wp.out_sy = (long long)L * N;
         wp.in_sz = wp.out_sz = (long long)per_W;
         for (int j = 0; j < L; j++) wp.mod_map[j] = j;
-        wp.jobs = dj;
-        wp.ks_S = kp.S;
-        wp.ks_L = L;
-        wp.out_split = out_split ? 1 : 0;
         launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
+        {
+            const dim3 g(N / 512, L, (nz + KS_QT - 1) / KS_QT);
+            if (L <= 4) ks_accumulate_kernel<4, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else if (L <= 8) ks_accumulate_kernel<8, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            else ks_accumulate_kernel<KS_MAXL, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+        }
+        e->launches++;
     }
     CK(cudaGetLastError());
     return PF_OK;

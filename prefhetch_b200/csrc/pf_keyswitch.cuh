@@ -41,9 +41,14 @@ struct KsParams {
 // grid (N/512, L+1, ceil(z/KS_QT)); thread = 2 coefficients of output limb I, both key components
 #define KS_QT 8
 #define KS_MAXL 15
-template <int LT>
+// FINISH = false: only the special-prime limb I = L (grid.y = 1); S_c[L] is written for the mod-down.
+// FINISH = true : data limbs I < L (grid.y = L) with step 4 fused: W holds NTT_I(W_c[I]) and the
+//                 rotated ciphertext (S_c[I] - W) * P^{-1} (+ sigma_ntt(c0) for c = 0) is written
+//                 directly, so S of the data limbs never touches memory.
+template <int LT, bool FINISH>
 __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
-    const int I = blockIdx.y, L = p.L, N = p.N;
+    const int L = p.L, N = p.N;
+    const int I = FINISH ? (int)blockIdx.y : L;
     const int ki = (I == L) ? p.k - 1 : I;
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
         lazy_zero(a11);
         const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
         u32 px = 0, py = 0;
-        if (hoisted) {
+        if (hoisted || FINISH) {
             const uint2 pp = reinterpret_cast<const uint2 *>(job.perm)[c2];
             px = pp.x;
             py = pp.y;
@@ -111,8 +116,28 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
             r1.x = addmod(r1.x, m1.x, m.q);
             r1.y = addmod(r1.y, m1.y, m.q);
         }
-        reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
-        reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
+        if (!FINISH) {
+            reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
+            reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
+        } else {
+            const u64 *Wz = p.W + (size_t)z * 2 * L * N;
+            const ulonglong2 w0 = reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N)[c2];
+            const ulonglong2 w1 = reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N)[c2];
+            const u64 *c0 = job.c0_ntt + (size_t)I * N;
+            ulonglong2 o0, o1;
+            o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), c0[px], m.q);
+            o0.y = addmod(mul_shoup(submod(r0.y, w0.y, m.q), m.p_inv, m.p_inv_sh, m.q), c0[py], m.q);
+            o1.x = mul_shoup(submod(r1.x, w1.x, m.q), m.p_inv, m.p_inv_sh, m.q);
+            o1.y = mul_shoup(submod(r1.y, w1.y, m.q), m.p_inv, m.p_inv_sh, m.q);
+            if (p.out_split) {
+                o0.x = split_word(o0.x, sh);
+                o0.y = split_word(o0.y, sh);
+                o1.x = split_word(o1.x, sh);
+                o1.y = split_word(o1.y, sh);
+            }
+            reinterpret_cast<ulonglong2 *>(job.out + (size_t)I * N)[c2] = o0;
+            reinterpret_cast<ulonglong2 *>(job.out + (size_t)(L + I) * N)[c2] = o1;
+        }
     }
 }
 
