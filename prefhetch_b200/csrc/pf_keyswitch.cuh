@@ -56,10 +56,14 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
     const int z0 = blockIdx.z * KS_QT, z1 = min(z0 + KS_QT, njobs);
     ulonglong2 k0[LT], k1[LT];
     const u64 *cur_key = nullptr;
+    u32 px = 0, py = 0; // NTT-domain permutation of this thread's two coefficients: constant per key
     for (int z = z0; z < z1; z++) {
         const RotJob job = p.jobs[z];
         if (job.key != cur_key) { // uniform across the CTA
             cur_key = job.key;
+            const uint2 pp = __ldg(reinterpret_cast<const uint2 *>(job.perm) + c2);
+            px = pp.x;
+            py = pp.y;
 #pragma unroll
             for (int J = 0; J < LT; J++) {
                 if (J < L) {
@@ -76,20 +80,14 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
         lazy_zero(a10);
         lazy_zero(a11);
         const u64 *dz = p.d + (size_t)z * L * (L + 1) * N;
-        u32 px = 0, py = 0;
-        if (hoisted || FINISH) {
-            const uint2 pp = reinterpret_cast<const uint2 *>(job.perm)[c2];
-            px = pp.x;
-            py = pp.y;
-        }
 #pragma unroll
         for (int J = 0; J < LT; J++) {
             if (J < L) {
                 ulonglong2 dv;
                 if (hoisted) {
                     const u64 *dj = job.D + ((size_t)J * (L + 1) + I) * N;
-                    dv.x = dj[px];
-                    dv.y = dj[py];
+                    dv.x = __ldg(dj + px);
+                    dv.y = __ldg(dj + py);
                 } else {
                     dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
                 }
@@ -121,12 +119,12 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
             reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
         } else {
             const u64 *Wz = p.W + (size_t)z * 2 * L * N;
-            const ulonglong2 w0 = reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N)[c2];
-            const ulonglong2 w1 = reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N)[c2];
+            const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N) + c2);
+            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N) + c2);
             const u64 *c0 = job.c0_ntt + (size_t)I * N;
             ulonglong2 o0, o1;
-            o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), c0[px], m.q);
-            o0.y = addmod(mul_shoup(submod(r0.y, w0.y, m.q), m.p_inv, m.p_inv_sh, m.q), c0[py], m.q);
+            o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), __ldg(c0 + px), m.q);
+            o0.y = addmod(mul_shoup(submod(r0.y, w0.y, m.q), m.p_inv, m.p_inv_sh, m.q), __ldg(c0 + py), m.q);
             o1.x = mul_shoup(submod(r1.x, w1.x, m.q), m.p_inv, m.p_inv_sh, m.q);
             o1.y = mul_shoup(submod(r1.y, w1.y, m.q), m.p_inv, m.p_inv_sh, m.q);
             if (p.out_split) {
