@@ -80,6 +80,38 @@ def make_dataset(cfg, device, seed=1234):
                 queries=queries.cpu().numpy().astype(np.float32))
 
 
+def make_dataset_shard(cfg, device, rank, world, seed=1234):
+    """Weak-scaling data set: the index of configs[1] replicated `world` times — world*nb vectors,
+    world*nlist lists, list l owned by rank l % world.  Every rank generates the centres of ALL lists
+    (same seed) but the vectors of its own lists only; the lists of other ranks are empty here, which is
+    how a sharded deployment loads its shard.  Vectors stay in the list of the centre that generated
+    them; the centroid is the mean of the list (exchanged between ranks by the caller)."""
+    import torch
+    nb, d, nlist = cfg["nb"], cfg["d"], cfg["nlist"]
+    G = nlist * world
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    centres = torch.rand((G, d), generator=g, device=device) * 160.0          # identical on every rank
+    npool = 4096
+    qa = torch.randint(0, G, (npool,), generator=g, device=device)
+    queries = torch.clamp(torch.round(centres[qa] + torch.randn((npool, d), generator=g, device=device) * 24.0), 0, 255)
+    g2 = torch.Generator(device=device)
+    g2.manual_seed(seed + 7919 * (rank + 1))
+    own = torch.arange(rank, G, world, device=device)                           # lists of this rank
+    assign = own[torch.randint(0, nlist, (nb,), generator=g2, device=device)]
+    base = torch.clamp(torch.round(centres[assign] + torch.randn((nb, d), generator=g2, device=device) * 24.0), 0, 255)
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=G)
+    offsets = torch.zeros(G + 1, dtype=torch.long, device=device)
+    offsets[1:] = torch.cumsum(counts, 0)
+    vecs = base[order].contiguous()
+    cent = torch.zeros((G, d), device=device).index_add_(0, assign, base) / counts.clamp(min=1).unsqueeze(1)
+    ids = order + rank * nb                                                      # globally unique ids
+    return dict(centroids=cent, counts=counts, offsets=offsets.cpu().numpy().astype(np.int64),
+                ids=ids.cpu().numpy().astype(np.int64), vectors=vecs.cpu().numpy().astype(np.float32),
+                queries=queries.cpu().numpy().astype(np.float32))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -245,8 +277,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg_name = args.config or ("sift1m_nlist1024_nprobe16" if max(args.gpus, world) == 1 else "sift1m_nlist4096_nprobe64")
+    cfg_name = args.config or "sift1m_nlist1024_nprobe16"
     cfg = dict(CONFIGS[cfg_name])
+    # N > 1 default: WEAK scaling of configs[1] — every rank holds its own 1M-vector / 1024-list shard
+    # of a world x larger index and the query probes 16*world lists (16 per shard on average).
+    # `--config sift1m_nlist4096_nprobe64` runs BASELINE configs[2] instead (fixed 1M index, strong).
+    weak = world > 1 and args.config is None
     if args.nq:
         cfg["nq"] = args.nq
     if args.g:
@@ -267,12 +303,24 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
 
     n, d, g, m, nprobe, nq = cfg["n"], cfg["d"], cfg["g"], cfg["m"], cfg["nprobe"], cfg["nq"]
     t_setup = time.perf_counter()
-    data = make_dataset(cfg, dev)
+    if weak:
+        nprobe = nprobe * world
+        data = make_dataset_shard(cfg, dev, rank, world)
+        cent, counts = data["centroids"], data["counts"]
+        dist.all_reduce(cent)                       # every list is non-zero on exactly one rank
+        dist.all_reduce(counts)
+        data["centroids"] = cent.cpu().numpy().astype(np.float32)
+        global_list_sizes = counts.cpu().numpy().astype(np.int64)
+    else:
+        data = make_dataset(cfg, dev)
+        global_list_sizes = (data["offsets"][1:] - data["offsets"][:-1]).astype(np.int64)
     eng = pf.Engine(d, n, pf.bfv_default_primes(n), pf.batching_plain_modulus(n, cfg["tbits"]), m, g,
                     device=local_rank, rank=rank, world=world, result_limbs=args.result_limbs)
     info = eng.load_index(data["centroids"], data["offsets"], data["ids"], data["vectors"])
@@ -300,40 +348,68 @@ def main():
     queries = data["queries"]
     nsteps_total = args.warmup + args.steps
     qsets = [queries[(s * nq) % (len(queries) - nq):][:nq] for s in range(nsteps_total)]
-    max_res = int(eng._blocks_per_list.max()) * nprobe * nq
-    d_out = torch.empty((max_res, 2, eng.Lr, n), dtype=torch.int64, device=dev)
+    if world == 1:
+        max_res = int(eng._blocks_per_list.max()) * nprobe * nq
+    else:  # probes spread over the ranks: 3x the expected per-rank share is far beyond its fluctuation
+        mean_blocks = float(eng._blocks_per_list[eng._blocks_per_list > 0].mean())
+        max_res = int(3.0 * nq * nprobe / world * mean_blocks) + 256
+    NBUF = 2 if world > 1 else 1
+    d_outs = [torch.empty((max_res, 2, eng.Lr, n), dtype=torch.int64, device=dev) for _ in range(NBUF)]
     log(f"[rank {rank}] setup {time.perf_counter() - t_setup:.1f}s  index: {info}  max_res {max_res}")
+    # result ciphertexts every rank produces for a probe list (all ranks know all list sizes)
+    blocks_of_list = (global_list_sizes + C_ - 1) // C_
+
+    def counts_per_rank(idx):
+        flat = idx.reshape(-1)
+        return [int(blocks_of_list[flat[(flat % world) == r]].sum()) for r in range(world)]
+
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    sent_ev = [None] * NBUF
+    gather_bufs = None
+    if world > 1 and rank == 0:
+        gather_bufs = [[torch.empty((max_res, 2, eng.Lr, n), dtype=torch.int64, device=dev) for _ in range(world - 1)]
+                       for _ in range(NBUF)]
 
     def step(s):
         x = qsets[s]
+        b = s % NBUF
+        if sent_ev[b] is not None:              # the gather that last used this buffer must be done
+            stream.wait_event(sent_ev[b])
         idx = eng.coarse_quantize(x, nprobe)
-        rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, d_out.data_ptr(), max_res)
+        rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, d_outs[b].data_ptr(), max_res)
         return idx, st
 
-    def gather_results(st):
-        """result ciphertexts of every shard to rank 0 (the response is assembled there)"""
+    def gather_results(s, idx, st):
+        """result ciphertexts of every shard to rank 0 over NCCL/NVLink (the response is assembled there);
+        issued on a side stream so that it overlaps the next step's compute"""
         if world == 1:
             return
-        cnt = torch.tensor([st["nresults"]], device=dev, dtype=torch.int64)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        if rank == 0:
-            for r in range(1, world):
-                c = int(cnts[r].item())
-                if c:
-                    dist.recv(gather_buf[:c], src=r)
-        else:
-            c = int(st["nresults"])
-            if c:
-                dist.send(d_out[:c], dst=0)
-
-    gather_buf = torch.empty_like(d_out) if (world > 1 and rank == 0) else None
+        b = s % NBUF
+        cnts = counts_per_rank(idx)
+        assert cnts[rank] == st["nresults"], (cnts, st)
+        done = torch.cuda.Event()
+        done.record(stream)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(done)
+            ops = []
+            if rank == 0:
+                for r in range(1, world):
+                    if cnts[r]:
+                        ops.append(dist.P2POp(dist.irecv, gather_bufs[b][r - 1][:cnts[r]], r))
+            elif cnts[rank]:
+                ops.append(dist.P2POp(dist.isend, d_outs[b][:cnts[rank]], 0))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            sent_ev[b] = ev
 
     # ---- value: device-resident timed region --------------------------------------------------
     with torch.cuda.stream(stream):
         for s in range(args.warmup):
-            _, st = step(s)
-            gather_results(st)
+            idx, st = step(s)
+            gather_results(s, idx, st)
         eng.synchronize()
         torch.cuda.synchronize()
         if world > 1:
@@ -349,10 +425,12 @@ def main():
         ev0.record(stream)
         for s in range(args.warmup, nsteps_total):
             idx, st = step(s)
-            gather_results(st)
+            gather_results(s, idx, st)
             useful += st["useful_distances"]
             slots += st["slot_distances"]
             nres += st["nresults"]
+        if comm_stream is not None:             # the timed region ends when the last gather has landed
+            stream.wait_stream(comm_stream)
         ev1.record(stream)
         eng.synchronize()
         torch.cuda.synchronize()
@@ -461,9 +539,12 @@ def main():
         line = {
             "metric": "encrypted candidate distances/sec", "value": value, "unit": "distances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": cfg_name, "nb": cfg["nb"], "d": d, "nlist": cfg["nlist"], "nprobe": nprobe,
+            "config": {"workload": cfg_name + (f" x{world} shards (weak: {world}M vectors, nlist {cfg['nlist'] * world}, "
+                                                f"nprobe {nprobe})" if weak else ""),
+                       "nb": cfg["nb"] * (world if weak else 1), "d": d,
+                       "nlist": cfg["nlist"] * (world if weak else 1), "nprobe": nprobe,
                        "poly_degree": n, "limbs": L, "result_limbs": eng.Lr, "g": g, "query_cts": m, "queries_per_step": nq,
                        "parallelism": f"lists%{world}" if world > 1 else "single",
                        "l2_policy": f"inputs larger than L2: NTT-domain DB {info['db_bytes'] / 2**30:.1f} GiB/rank "
