@@ -303,6 +303,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the per-step flag all-reduce must not queue behind compute
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -363,44 +364,55 @@ def main():
         flat = idx.reshape(-1)
         return [int(blocks_of_list[flat[(flat % world) == r]].sum()) for r in range(world)]
 
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    # ---- multi-GPU gather: results are WRITTEN INTO RANK 0's HBM by the last kernel of every rank's
+    # step (peer-mapped buffer, CUDA IPC over NVLink); a tiny stream-ordered NCCL all-reduce per step is
+    # the only collective and tells rank 0 that the step's ciphertexts have landed.
+    comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     sent_ev = [None] * NBUF
-    gather_bufs = None
-    if world > 1 and rank == 0:
-        gather_bufs = [[torch.empty((max_res, 2, eng.Lr, n), dtype=torch.int64, device=dev) for _ in range(world - 1)]
-                       for _ in range(NBUF)]
+    out_ptrs = [t.data_ptr() for t in d_outs]
+    res_bytes = 2 * eng.Lr * n * 8
+    ipc_local, ipc_mapped = [], []
+    if world > 1:
+        handles = [None]
+        if rank == 0:
+            handles = [[None] * world for _ in range(NBUF)]
+            for b in range(NBUF):
+                for r in range(1, world):
+                    ptr, h = eng.ipc_alloc(max_res * res_bytes)
+                    ipc_local.append(ptr)
+                    handles[b][r] = h
+            handles = [handles]
+        dist.broadcast_object_list(handles, src=0)
+        if rank != 0:
+            for b in range(NBUF):
+                p_ = eng.ipc_open(handles[0][b][rank])
+                ipc_mapped.append(p_)
+                out_ptrs[b] = p_            # this rank's results go straight into rank 0's gather buffer
+        flag = torch.zeros(1, device=dev)
+
+    next_idx = {}
 
     def step(s):
-        x = qsets[s]
+        """stage 1 of batch s+1 is issued right after stage 2 of batch s was enqueued, so the host-side
+        planning of the next batch overlaps the GPU work of this one (a serving loop does the same)"""
         b = s % NBUF
-        if sent_ev[b] is not None:              # the gather that last used this buffer must be done
+        if sent_ev[b] is not None:              # rank 0 has seen the step that last used this buffer
             stream.wait_event(sent_ev[b])
-        idx = eng.coarse_quantize(x, nprobe)
-        rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, d_outs[b].data_ptr(), max_res)
+        idx = next_idx.pop(s) if s in next_idx else eng.coarse_quantize(qsets[s], nprobe)
+        rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, out_ptrs[b], max_res)
+        # always one stage-1 call per step (the last one quantizes a batch that is never searched)
+        next_idx[s + 1] = eng.coarse_quantize(qsets[(s + 1) % nsteps_total], nprobe)
         return idx, st
 
     def gather_results(s, idx, st):
-        """result ciphertexts of every shard to rank 0 over NCCL/NVLink (the response is assembled there);
-        issued on a side stream so that it overlaps the next step's compute"""
         if world == 1:
             return
         b = s % NBUF
-        cnts = counts_per_rank(idx)
-        assert cnts[rank] == st["nresults"], (cnts, st)
         done = torch.cuda.Event()
         done.record(stream)
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(done)
-            ops = []
-            if rank == 0:
-                for r in range(1, world):
-                    if cnts[r]:
-                        ops.append(dist.P2POp(dist.irecv, gather_bufs[b][r - 1][:cnts[r]], r))
-            elif cnts[rank]:
-                ops.append(dist.P2POp(dist.isend, d_outs[b][:cnts[rank]], 0))
-            if ops:
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+            dist.all_reduce(flag)               # stream-ordered: every rank's writes of step s precede it
             ev = torch.cuda.Event()
             ev.record(comm_stream)
             sent_ev[b] = ev
@@ -441,6 +453,7 @@ def main():
         launches = eng.launch_count() - launches0
         phases = eng.timing_read(reset=True)
         eng.timing_enable(False)
+        log(f"[rank {rank}] {ms_total / args.steps:.3f} ms/step; phases " + ", ".join(f"{k} {v['ms'] / args.steps:.3f}" for k, v in phases.items()))
 
     # distinct blocks per step for the algorithmic-bytes formula (host-side bookkeeping, untimed)
     bpl = eng._blocks_per_list
@@ -558,6 +571,14 @@ def main():
             "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        for p_ in ipc_mapped:
+            eng.ipc_close(p_)
+        dist.barrier()
+        for p_ in ipc_local:
+            eng.ipc_free(p_)
     eng.close()
     if world > 1:
         dist.barrier()

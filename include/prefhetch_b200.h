@@ -147,6 +147,19 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
 int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, const int64_t *idx, uint32_t nprobe,
                      uint64_t *d_out, uint64_t cap_results, uint64_t *results_per_query, pf_search_stats *stats);
 
+/* ---- multi-GPU: peer-memory gather of result ciphertexts ---------------------------------------
+ * One process per GPU.  Rank 0 allocates the gather buffer with pf_ipc_alloc and ships the 64-byte
+ * handle to the other processes (any host channel); they map it with pf_ipc_open and pass the mapped
+ * pointer as d_out of pf_search_device: the last kernel of the step (mod-switch / inverse NTT) then
+ * stores the result ciphertexts straight into rank 0's HBM over NVLink — the compute step and the
+ * gather are one kernel, no copy kernels competing for SMs.  A stream-ordered barrier (any NCCL
+ * collective) tells rank 0 that a step's results have landed. */
+#define PF_IPC_HANDLE_BYTES 64
+int pf_ipc_alloc(pf_engine *e, size_t bytes, void **dptr, uint8_t handle[PF_IPC_HANDLE_BYTES]);
+int pf_ipc_open(pf_engine *e, const uint8_t handle[PF_IPC_HANDLE_BYTES], void **dptr);
+int pf_ipc_close(pf_engine *e, void *dptr);
+int pf_ipc_free(pf_engine *e, void *dptr);
+
 /* per-phase device timers (CUDA events on the engine stream), accumulated since the last reset */
 enum { PF_T_COARSE = 0, PF_T_TONTT = 1, PF_T_ROTATE = 2, PF_T_MAC = 3, PF_T_INTT = 4, PF_T_COUNT = 8 };
 int pf_timing_enable(pf_engine *e, int on);

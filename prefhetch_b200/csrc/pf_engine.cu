@@ -139,11 +139,12 @@ struct pf_engine {
     size_t diag_block_words = 0, norm_block_words = 0;
 
     // scratch
-    DevBuf s_x, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
+    DevBuf s_x, s_cx, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
     DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_out, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t coarse_stream = nullptr; // stage 1 runs beside the encrypted pipeline of the previous batch
     cudaEvent_t ev_group[2] = {nullptr, nullptr};
 
     // timing
@@ -181,7 +182,9 @@ struct PhaseTimer {
     int phase;
     cudaEvent_t a = nullptr, b = nullptr;
     uint64_t launches0;
-    PhaseTimer(pf_engine *e_, int phase_) : e(e_), phase(phase_), launches0(e_->launches) {
+    cudaStream_t st;
+    PhaseTimer(pf_engine *e_, int phase_, cudaStream_t st_ = nullptr)
+        : e(e_), phase(phase_), launches0(e_->launches), st(st_ ? st_ : e_->stream) {
         if (!e->timing) return;
         auto get = [&]() {
             cudaEvent_t ev;
@@ -195,12 +198,12 @@ struct PhaseTimer {
         };
         a = get();
         b = get();
-        cudaEventRecord(a, e->stream);
+        cudaEventRecord(a, st);
     }
     ~PhaseTimer() {
         e->t_launch[phase] += e->launches - launches0;
         if (!e->timing) return;
-        cudaEventRecord(b, e->stream);
+        cudaEventRecord(b, st);
         e->pending_events.push_back({phase, {a, b}});
     }
 };
@@ -1122,6 +1125,7 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
         return bail(e->fail(PF_ERR_CUDA, "cudaStreamCreate failed"));
     e->own_stream = true;
     if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&e->coarse_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_group[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_group[1], cudaEventDisableTiming) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "copy stream / event creation failed"));
@@ -1147,6 +1151,7 @@ void pf_engine_destroy(pf_engine *e) {
     drain_events(e);
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->coarse_stream) cudaStreamDestroy(e->coarse_stream);
     for (auto ev : e->ev_group)
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -1195,6 +1200,51 @@ int pf_timing_read(pf_engine *e, float *ms, uint64_t *launches, int reset) {
 }
 
 uint64_t pf_launch_count(pf_engine *e) { return e ? e->launches : 0; }
+
+// ---- peer-memory gather buffers (CUDA IPC over NVLink) -------------------------------------------
+int pf_ipc_alloc(pf_engine *e, size_t bytes, void **dptr, uint8_t handle[PF_IPC_HANDLE_BYTES]) {
+    if (!e || !dptr || !handle || !bytes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PF_IPC_HANDLE_BYTES, "IPC handle size");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t r = cudaIpcGetMemHandle(&h, p);
+    if (r != cudaSuccess) {
+        cudaFree(p);
+        return e->fail(PF_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(r));
+    }
+    memcpy(handle, &h, sizeof(h));
+    *dptr = p;
+    return PF_OK;
+}
+
+int pf_ipc_open(pf_engine *e, const uint8_t handle[PF_IPC_HANDLE_BYTES], void **dptr) {
+    if (!e || !dptr || !handle) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PF_OK;
+}
+
+int pf_ipc_close(pf_engine *e, void *dptr) {
+    if (!e || !dptr) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    CK(cudaIpcCloseMemHandle(dptr));
+    return PF_OK;
+}
+
+int pf_ipc_free(pf_engine *e, void *dptr) {
+    if (!e || !dptr) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    CK(cudaFree(dptr));
+    return PF_OK;
+}
 
 uint32_t pf_galois_elt_from_step(pf_engine *e, int step) { return e ? galois_elt_from_step(e, step) : 0; }
 
@@ -1393,25 +1443,28 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
     CK(cudaSetDevice(e->prm.device));
     const u32 d = e->d;
     const int nlist = (int)e->nlist;
-    PhaseTimer pt(e, PF_T_COARSE);
-    CK(e->s_x.ensure(nq * d * sizeof(float)));
+    // Stage 1 only reads the centroid table: it runs on its own stream so that the next batch can be
+    // quantized while the encrypted pipeline of the current batch still occupies the engine stream.
+    cudaStream_t cs = e->coarse_stream;
+    PhaseTimer pt(e, PF_T_COARSE, cs);
+    CK(e->s_cx.ensure(nq * d * sizeof(float)));
     CK(e->s_dist.ensure(nq * (size_t)nlist * sizeof(float)));
     CK(e->s_keys.ensure(nq * (size_t)nlist * sizeof(u64)));
     CK(e->s_idx.ensure(nq * nprobe * sizeof(long long)));
     CK(e->s_outdist.ensure(nq * nprobe * sizeof(float)));
-    CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->s_cx.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, cs));
     for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
         const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
-        coarse_dist_kernel<<<dim3((nlist + 127) / 128, nqb), 128, d * sizeof(float), e->stream>>>(
-            e->s_x.as<float>() + q0 * d, e->d_centroids.as<float>(), e->s_dist.as<float>() + q0 * nlist, nlist, (int)d);
-        topk_select_kernel<<<nqb, 256, 0, e->stream>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
-                                                       e->s_idx.as<long long>() + q0 * nprobe,
-                                                       e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
+        coarse_dist_kernel<<<dim3((nlist + 127) / 128, nqb), 128, d * sizeof(float), cs>>>(
+            e->s_cx.as<float>() + q0 * d, e->d_centroids.as<float>(), e->s_dist.as<float>() + q0 * nlist, nlist, (int)d);
+        topk_select_kernel<<<nqb, 256, 0, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
+                                                 e->s_idx.as<long long>() + q0 * nprobe,
+                                                 e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
         e->launches += 2;
     }
-    CK(cudaMemcpyAsync(out_idx, e->s_idx.p, nq * nprobe * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
-    if (out_dist) CK(cudaMemcpyAsync(out_dist, e->s_outdist.p, nq * nprobe * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(out_idx, e->s_idx.p, nq * nprobe * sizeof(long long), cudaMemcpyDeviceToHost, cs));
+    if (out_dist) CK(cudaMemcpyAsync(out_dist, e->s_outdist.p, nq * nprobe * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CK(cudaStreamSynchronize(cs));
     return PF_OK;
 }
 

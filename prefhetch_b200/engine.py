@@ -234,6 +234,26 @@ class Engine:
                                            C.c_void_p(d_out_ptr), cap_results, _ptr(rpq, U64P), C.byref(st)))
         return rpq.astype(np.int64), {f: getattr(st, f) for f, _ in PfSearchStats._fields_}
 
+    # ---- peer-memory gather buffers (multi-GPU) ------------------------------------------------
+    def ipc_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte handle) of a buffer other processes can map with ipc_open"""
+        ptr = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        self._ck(self.lib.pf_ipc_alloc(self.h, nbytes, C.byref(ptr), h))
+        return ptr.value, bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        h = (C.c_uint8 * 64)(*handle)
+        self._ck(self.lib.pf_ipc_open(self.h, h, C.byref(ptr)))
+        return ptr.value
+
+    def ipc_close(self, ptr: int):
+        self._ck(self.lib.pf_ipc_close(self.h, C.c_void_p(ptr)))
+
+    def ipc_free(self, ptr: int):
+        self._ck(self.lib.pf_ipc_free(self.h, C.c_void_p(ptr)))
+
     # ---- stream / timing ---------------------------------------------------------------------
     def stream(self) -> int:
         return self.lib.pf_engine_stream(self.h) or 0
