@@ -124,7 +124,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -401,7 +401,8 @@ def main():
         idx = next_idx.pop(s) if s in next_idx else eng.coarse_quantize(qsets[s], nprobe)
         rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, out_ptrs[b], max_res)
         # always one stage-1 call per step (the last one quantizes a batch that is never searched)
-        next_idx[s + 1] = eng.coarse_quantize(qsets[(s + 1) % nsteps_total], nprobe)
+        if not os.environ.get("PF_BENCH_NO_PREFETCH"):
+            next_idx[s + 1] = eng.coarse_quantize(qsets[(s + 1) % nsteps_total], nprobe)
         return idx, st
 
     def gather_results(s, idx, st):
@@ -412,7 +413,8 @@ def main():
         done.record(stream)
         with torch.cuda.stream(comm_stream):
             comm_stream.wait_event(done)
-            dist.all_reduce(flag)               # stream-ordered: every rank's writes of step s precede it
+            if not os.environ.get("PF_BENCH_NO_FLAG"):
+                dist.all_reduce(flag)           # stream-ordered: every rank's writes of step s precede it
             ev = torch.cuda.Event()
             ev.record(comm_stream)
             sent_ev[b] = ev
@@ -429,7 +431,8 @@ def main():
         eng.timing_enable(True)
         eng.timing_read(reset=True)
         sampler = ClockSampler(local_rank)
-        sampler.start()
+        if rank == 0:                          # one nvidia-smi poller per job: it takes driver locks
+            sampler.start()
         launches0 = eng.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         useful = slots = nres = 0
@@ -449,7 +452,7 @@ def main():
         if world > 1:
             dist.barrier()
         ms_total = ev0.elapsed_time(ev1)
-        clocks = sampler.stop()
+        clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count() - launches0
         phases = eng.timing_read(reset=True)
         eng.timing_enable(False)
