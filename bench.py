@@ -365,10 +365,10 @@ def main():
         return [int(blocks_of_list[flat[(flat % world) == r]].sum()) for r in range(world)]
 
     # ---- multi-GPU gather: results are WRITTEN INTO RANK 0's HBM by the last kernel of every rank's
-    # step (peer-mapped buffer, CUDA IPC over NVLink); a tiny stream-ordered NCCL all-reduce per step is
-    # the only collective and tells rank 0 that the step's ciphertexts have landed.
+    # step (peer-mapped buffer, CUDA IPC over NVLink); stream-ordered arrival / ack flags (one-thread
+    # kernels on peer memory) tell rank 0 that a step's ciphertexts have landed and the shards that their
+    # buffer may be reused.  NCCL (torch.distributed) only carries the set-up exchange and the timing reduce.
     comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
-    sent_ev = [None] * NBUF
     out_ptrs = [t.data_ptr() for t in d_outs]
     res_bytes = 2 * eng.Lr * n * 8
     ipc_local, ipc_mapped = [], []
@@ -388,36 +388,70 @@ def main():
                 p_ = eng.ipc_open(handles[0][b][rank])
                 ipc_mapped.append(p_)
                 out_ptrs[b] = p_            # this rank's results go straight into rank 0's gather buffer
-        flag = torch.zeros(1, device=dev)
+        # arrival flags live on rank 0 (one 128-byte line per rank), ack flags on every rank: one-thread
+        # kernels write / wait on them in stream order — no NCCL collective on the data path
+        FL = 128
+        arr_ptr, arr_h = eng.ipc_alloc(FL * world) if rank == 0 else (None, None)
+        ack_ptr, ack_h = eng.ipc_alloc(FL)
+        torch.cuda.synchronize()
+        allh = [None] * world
+        dist.all_gather_object(allh, (arr_h, ack_h))
+        if rank == 0:
+            ipc_local += [arr_ptr, ack_ptr]
+            ack_peer = [None] + [eng.ipc_open(allh[r][1]) for r in range(1, world)]
+            ipc_mapped += ack_peer[1:]
+        else:
+            ipc_local.append(ack_ptr)
+            arr_ptr = eng.ipc_open(allh[0][0])
+            ipc_mapped.append(arr_ptr)
+        # zero the flags with the flag kernels (raw IPC pointers, no torch view)
+        if rank == 0:
+            for r in range(world):
+                eng.flag_write(arr_ptr + FL * r, 0)
+        eng.flag_write(ack_ptr, 0)
+        eng.synchronize()
+        dist.barrier()
 
     next_idx = {}
+    host_t = {"wait": 0.0, "search": 0.0, "coarse": 0.0, "gather": 0.0, "n": 0}
 
     def step(s):
         """stage 1 of batch s+1 is issued right after stage 2 of batch s was enqueued, so the host-side
         planning of the next batch overlaps the GPU work of this one (a serving loop does the same)"""
         b = s % NBUF
-        if sent_ev[b] is not None:              # rank 0 has seen the step that last used this buffer
-            stream.wait_event(sent_ev[b])
+        t0 = time.perf_counter()
+        if world > 1 and rank != 0 and s >= NBUF:   # rank 0 has acknowledged the step that last used this buffer
+            eng.flag_wait(ack_ptr, s - NBUF + 1)
         idx = next_idx.pop(s) if s in next_idx else eng.coarse_quantize(qsets[s], nprobe)
+        t1 = time.perf_counter()
         rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, out_ptrs[b], max_res)
+        t2 = time.perf_counter()
         # always one stage-1 call per step (the last one quantizes a batch that is never searched)
         if not os.environ.get("PF_BENCH_NO_PREFETCH"):
             next_idx[s + 1] = eng.coarse_quantize(qsets[(s + 1) % nsteps_total], nprobe)
+        t3 = time.perf_counter()
+        host_t["wait"] += t1 - t0
+        host_t["search"] += t2 - t1
+        host_t["coarse"] += t3 - t2
+        host_t["n"] += 1
         return idx, st
 
     def gather_results(s, idx, st):
         if world == 1:
             return
-        b = s % NBUF
-        done = torch.cuda.Event()
-        done.record(stream)
-        with torch.cuda.stream(comm_stream):
+        tg = time.perf_counter()
+        if rank != 0:
+            eng.flag_write(arr_ptr + FL * rank, s + 1)      # after this rank's last kernel of step s
+        else:
+            done = torch.cuda.Event()
+            done.record(stream)
             comm_stream.wait_event(done)
-            if not os.environ.get("PF_BENCH_NO_FLAG"):
-                dist.all_reduce(flag)           # stream-ordered: every rank's writes of step s precede it
-            ev = torch.cuda.Event()
-            ev.record(comm_stream)
-            sent_ev[b] = ev
+            cs = comm_stream.cuda_stream
+            for r in range(1, world):
+                eng.flag_wait(arr_ptr + FL * r, s + 1, cs)   # every shard's ciphertexts of step s are in HBM
+            for r in range(1, world):
+                eng.flag_write(ack_peer[r], s + 1, cs)       # ... the response can be assembled; buffer free
+        host_t["gather"] += time.perf_counter() - tg
 
     # ---- value: device-resident timed region --------------------------------------------------
     with torch.cuda.stream(stream):
@@ -444,7 +478,7 @@ def main():
             useful += st["useful_distances"]
             slots += st["slot_distances"]
             nres += st["nresults"]
-        if comm_stream is not None:             # the timed region ends when the last gather has landed
+        if comm_stream is not None and rank == 0:  # the timed region ends when the last gather has landed
             stream.wait_stream(comm_stream)
         ev1.record(stream)
         eng.synchronize()
@@ -456,6 +490,7 @@ def main():
         launches = eng.launch_count() - launches0
         phases = eng.timing_read(reset=True)
         eng.timing_enable(False)
+        log(f"[rank {rank}] host ms/step: " + ", ".join(f"{k} {1e3 * v / max(1, host_t['n']):.3f}" for k, v in host_t.items() if k != "n"))
         log(f"[rank {rank}] {ms_total / args.steps:.3f} ms/step; phases " + ", ".join(f"{k} {v['ms'] / args.steps:.3f}" for k, v in phases.items()))
 
     # distinct blocks per step for the algorithmic-bytes formula (host-side bookkeeping, untimed)

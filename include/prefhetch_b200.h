@@ -159,6 +159,13 @@ int pf_ipc_alloc(pf_engine *e, size_t bytes, void **dptr, uint8_t handle[PF_IPC_
 int pf_ipc_open(pf_engine *e, const uint8_t handle[PF_IPC_HANDLE_BYTES], void **dptr);
 int pf_ipc_close(pf_engine *e, void *dptr);
 int pf_ipc_free(pf_engine *e, void *dptr);
+/* Stream-ordered flags in (peer-mapped) device memory: one-thread kernels, so they slip in beside the
+ * compute kernels where an NCCL collective would queue behind them.  write: *flag = value after all
+ * prior work of the stream (system-scope release).  wait: the stream blocks until *flag >= value.
+ * cuda_stream NULL = the engine stream.  Waits must only target flags whose writer does not itself
+ * wait on this stream's later work (the bench protocol: arrival flags -> rank 0 -> ack flags). */
+int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream);
+int pf_flag_wait(pf_engine *e, const void *flag, uint32_t value, void *cuda_stream);
 
 /* per-phase device timers (CUDA events on the engine stream), accumulated since the last reset */
 enum { PF_T_COARSE = 0, PF_T_TONTT = 1, PF_T_ROTATE = 2, PF_T_MAC = 3, PF_T_INTT = 4, PF_T_COUNT = 8 };

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -143,6 +144,13 @@ struct pf_engine {
     DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_out, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
+    // pinned upload arena: pageable cudaMemcpyAsync would synchronise the stream (and the host) on every
+    // small table upload; 4 call slots, a slot is reused only after the call that used it has finished
+    PinBuf h_arena;
+    size_t arena_slot_bytes = 0, arena_off = 0;
+    int arena_slot = 0;
+    cudaEvent_t arena_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool arena_ev_used[4] = {false, false, false, false};
     cudaStream_t copy_stream = nullptr;
     cudaStream_t coarse_stream = nullptr; // stage 1 runs beside the encrypted pipeline of the previous batch
     cudaEvent_t ev_group[2] = {nullptr, nullptr};
@@ -175,6 +183,47 @@ namespace {
             return e->fail(PF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
                            __LINE__);                                                                    \
     } while (0)
+
+struct HostTick { // PF_DEBUG_HOST=1: host-side time of the sections of a search call
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char *what;
+    explicit HostTick(const char *w) : what(w) {}
+    ~HostTick() {
+        static const bool on = getenv("PF_DEBUG_HOST") != nullptr;
+        if (on) fprintf(stderr, "[pf host] %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
+// ---- pinned upload arena --------------------------------------------------------------------
+constexpr size_t ARENA_SLOT = (size_t)8 << 20;
+
+int arena_begin(pf_engine *e) { // call once at the start of an API call that uploads tables
+    if (!e->h_arena.p) {
+        CK(e->h_arena.ensure(4 * ARENA_SLOT));
+        for (auto &ev : e->arena_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    e->arena_slot = (e->arena_slot + 1) & 3;
+    if (e->arena_ev_used[e->arena_slot]) CK(cudaEventSynchronize(e->arena_ev[e->arena_slot]));
+    e->arena_off = 0;
+    return PF_OK;
+}
+
+void arena_end(pf_engine *e) { // after the last upload of the call has been enqueued
+    cudaEventRecord(e->arena_ev[e->arena_slot], e->stream);
+    e->arena_ev_used[e->arena_slot] = true;
+}
+
+// async host->device copy of a small table through the pinned arena (falls back to a direct copy,
+// which synchronises, when the slot is exhausted)
+cudaError_t upload_async(pf_engine *e, void *dst, const void *src, size_t bytes) {
+    const size_t aligned = (bytes + 255) & ~(size_t)255;
+    if (!e->h_arena.p || e->arena_off + aligned > ARENA_SLOT)
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream);
+    char *stage = e->h_arena.as<char>() + (size_t)e->arena_slot * ARENA_SLOT + e->arena_off;
+    memcpy(stage, src, bytes);
+    e->arena_off += aligned;
+    return cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, e->stream);
+}
 
 // ---- timing -------------------------------------------------------------------------------
 struct PhaseTimer {
@@ -502,7 +551,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
     const size_t per_d = (size_t)L * (L + 1) * N, per_S = (size_t)2 * (L + 1) * N, per_W = (size_t)2 * L * N;
     const size_t zmax = std::max<size_t>(1, std::min<size_t>(512, ((size_t)1 << 30) / ((per_d + per_S + per_W) * 8)));
     CK(e->s_rotjobs.ensure(jobs.size() * sizeof(RotJob)));
-    CK(cudaMemcpyAsync(e->s_rotjobs.p, jobs.data(), jobs.size() * sizeof(RotJob), cudaMemcpyHostToDevice, e->stream));
+    CK(upload_async(e, e->s_rotjobs.p, jobs.data(), jobs.size() * sizeof(RotJob)));
     const size_t zb = std::min(zmax, jobs.size());
     CK(e->s_ks_d.ensure(zb * per_d * 8));
     CK(e->s_ks_S.ensure(zb * per_S * 8));
@@ -672,7 +721,11 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
     PhaseTimer pt(e, PF_T_ROTATE);
     std::vector<RotJob> jobs;
     if (direct) {
-        int hrc = hoist_digits(e, d_cts, nq * m, ctw);
+        int hrc;
+        {
+            HostTick ht("hoist_digits");
+            hrc = hoist_digits(e, d_cts, nq * m, ctw);
+        }
         if (hrc) return hrc;
         const size_t per_d = (size_t)L * (L + 1) * N;
         jobs.reserve(nq * m * (R - 1));
@@ -692,6 +745,7 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
                     j.flag = e->s_flags.as<int>() + (i * m + a);
                     jobs.push_back(j);
                 }
+        HostTick ht("run_rot_jobs");
         return run_rot_jobs(e, jobs, want_split);
     }
     // chain: rot_r = rotate(rot_{r-1}, 1); needs c1 of the previous member in coefficient form
@@ -847,12 +901,10 @@ int upload_plan(pf_engine *e, const PairPlan &pl) {
     if (!P) return PF_OK;
     CK(e->s_chunks.ensure(pl.chunks.size() * sizeof(MacChunk)));
     CK(e->s_pairblock.ensure(P * sizeof(long long)));
-    CK(cudaMemcpyAsync(e->s_chunks.p, pl.chunks.data(), pl.chunks.size() * sizeof(MacChunk), cudaMemcpyHostToDevice,
-                       e->stream));
-    CK(cudaMemcpyAsync(e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long), cudaMemcpyHostToDevice,
-                       e->stream));
+    CK(upload_async(e, e->s_chunks.p, pl.chunks.data(), pl.chunks.size() * sizeof(MacChunk)));
+    CK(upload_async(e, e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long)));
     CK(e->s_pairout.ensure(P * sizeof(int)));
-    CK(cudaMemcpyAsync(e->s_pairout.p, pl.pair_out.data(), P * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(upload_async(e, e->s_pairout.p, pl.pair_out.data(), P * sizeof(int)));
     return PF_OK;
 }
 
@@ -864,8 +916,13 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     const size_t ctw = (size_t)2 * L * N;
     CK(e->s_rot.ensure(nq * e->K * ctw * 8));
     u64 *rot = e->s_rot.as<u64>();
-    int rc = build_rotated_sets(e, d_cts, nq, rot, 0, false);
+    int rc;
+    {
+        HostTick ht("rotated_sets");
+        rc = build_rotated_sets(e, d_cts, nq, rot, 0, false);
+    }
     if (rc) return rc;
+    HostTick ht2("mac+intt");
     // chunks / pairs of this query range (chunks are ordered by query)
     size_t c0 = 0, c1 = 0;
     while (c0 < pl.chunks.size() && (uint64_t)pl.chunks[c0].query < q0) c0++;
@@ -1150,6 +1207,8 @@ void pf_engine_destroy(pf_engine *e) {
     cudaStreamSynchronize(e->stream);
     drain_events(e);
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    for (auto ev : e->arena_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->coarse_stream) cudaStreamDestroy(e->coarse_stream);
     for (auto ev : e->ev_group)
@@ -1235,6 +1294,22 @@ int pf_ipc_close(pf_engine *e, void *dptr) {
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     CK(cudaIpcCloseMemHandle(dptr));
+    return PF_OK;
+}
+
+int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream) {
+    if (!e || !flag) return PF_ERR_INVALID;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    flag_write_kernel<<<1, 1, 0, st>>>((volatile unsigned *)flag, value);
+    e->launches++;
+    return PF_OK;
+}
+
+int pf_flag_wait(pf_engine *e, const void *flag, uint32_t value, void *cuda_stream) {
+    if (!e || !flag) return PF_ERR_INVALID;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    flag_wait_kernel<<<1, 1, 0, st>>>((const volatile unsigned *)flag, value);
+    e->launches++;
     return PF_OK;
 }
 
@@ -1582,11 +1657,19 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
 int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, const int64_t *idx, uint32_t nprobe,
                      uint64_t *d_out, uint64_t cap_results, uint64_t *results_per_query, pf_search_stats *stats) {
     if (!e || !d_query_cts || !idx) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    HostTick htall("pf_search_device");
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->has_index || (!e->d_diag.p && e->ntotal)) return e->fail(PF_ERR_STATE, "no encodable index loaded");
-    CK(cudaSetDevice(e->prm.device));
+    {
+        HostTick ht("cudaSetDevice");
+        CK(cudaSetDevice(e->prm.device));
+    }
     PairPlan pl;
-    int rc = plan_pairs(e, nq, idx, nprobe, pl);
+    int rc;
+    {
+        HostTick ht("plan_pairs");
+        rc = plan_pairs(e, nq, idx, nprobe, pl);
+    }
     if (rc) return rc;
     const uint64_t P = pl.pair_block.size();
     if (stats) {
@@ -1597,9 +1680,19 @@ int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, con
     }
     if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
     if (P > cap_results || (P && !d_out)) return e->fail(PF_ERR_CAPACITY, "need room for %llu result ciphertexts, capacity %llu", (unsigned long long)P, (unsigned long long)cap_results);
-    rc = upload_plan(e, pl);
+    {
+        HostTick ht("arena_begin");
+        rc = arena_begin(e);
+    }
     if (rc) return rc;
-    return search_core(e, 0, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out, (size_t)2 * e->Lr * e->N);
+    {
+        HostTick ht("upload_plan");
+        rc = upload_plan(e, pl);
+    }
+    if (rc) return rc;
+    rc = search_core(e, 0, nq, (const u64 *)d_query_cts, pl, (u64 *)d_out, (size_t)2 * e->Lr * e->N);
+    arena_end(e);
+    return rc;
 }
 
 int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
@@ -1664,6 +1757,8 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     CK(e->s_out.ensure(std::max<size_t>(8, P * slot)));
     uint8_t *d_blob = e->s_out.as<uint8_t>();
     u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
+    rc = arena_begin(e);
+    if (rc) return rc;
     rc = upload_plan(e, pl);
     if (rc) return rc;
     // query groups: the D2H of group i (copy stream) overlaps the compute of group i+1 (engine stream)
@@ -1685,6 +1780,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         pair_lo = pair_hi;
         q_lo = q_hi;
     }
+    arena_end(e);
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->copy_stream));
     const uint64_t zero_pid[4] = {0, 0, 0, 0};

@@ -148,3 +148,14 @@ __global__ void __launch_bounds__(128) precise_l2_kernel(const float *__restrict
     for (int k = 0; k < d; k++) acc = ref_l2_step(acc, __ldg(b + k), sq[k]);
     out[(size_t)qi * nids + j] = acc;
 }
+
+// stream-ordered flags for the multi-GPU result gather (see include/prefhetch_b200.h)
+__global__ void flag_write_kernel(volatile unsigned *flag, unsigned value) {
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+__global__ void flag_wait_kernel(const volatile unsigned *flag, unsigned value) {
+    while (*flag < value) __nanosleep(500);
+    __threadfence_system();
+}

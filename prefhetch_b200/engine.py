@@ -248,6 +248,12 @@ class Engine:
         self._ck(self.lib.pf_ipc_open(self.h, h, C.byref(ptr)))
         return ptr.value
 
+    def flag_write(self, ptr: int, value: int, cuda_stream: int = 0):
+        self._ck(self.lib.pf_flag_write(self.h, C.c_void_p(ptr), value, C.c_void_p(cuda_stream)))
+
+    def flag_wait(self, ptr: int, value: int, cuda_stream: int = 0):
+        self._ck(self.lib.pf_flag_wait(self.h, C.c_void_p(ptr), value, C.c_void_p(cuda_stream)))
+
     def ipc_close(self, ptr: int):
         self._ck(self.lib.pf_ipc_close(self.h, C.c_void_p(ptr)))
 
