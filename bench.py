@@ -364,14 +364,19 @@ def main():
         flat = idx.reshape(-1)
         return [int(blocks_of_list[flat[(flat % world) == r]].sum()) for r in range(world)]
 
-    # ---- multi-GPU gather: results are WRITTEN INTO RANK 0's HBM by the last kernel of every rank's
-    # step (peer-mapped buffer, CUDA IPC over NVLink); stream-ordered arrival / ack flags (one-thread
-    # kernels on peer memory) tell rank 0 that a step's ciphertexts have landed and the shards that their
-    # buffer may be reused.  NCCL (torch.distributed) only carries the set-up exchange and the timing reduce.
+    # ---- multi-GPU gather: every rank's result ciphertexts go into RANK 0's HBM through a peer-mapped
+    # buffer (CUDA IPC over NVLink).  Default: copy-engine DMA on a side stream, overlapped with the next
+    # step (rank 0's NVLink ingest, ~0.75 TB/s, is the shared resource: 7 writers bursting from inside
+    # their last kernel stall each other, measured 68 % efficiency at 8 GPUs).  PF_BENCH_FUSED_GATHER=1
+    # lets the last kernel store straight into the peer buffer instead.  Stream-ordered arrival / ack
+    # flags (one-thread kernels on peer memory) tell rank 0 that a step has landed and the shards that
+    # their buffer is free.  NCCL only carries the set-up exchange and the timing reduce.
     comm_stream = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
     out_ptrs = [t.data_ptr() for t in d_outs]
     res_bytes = 2 * eng.Lr * n * 8
     ipc_local, ipc_mapped = [], []
+    fused_gather = bool(os.environ.get("PF_BENCH_FUSED_GATHER"))
+    copied_ev = [None] * NBUF
     if world > 1:
         handles = [None]
         if rank == 0:
@@ -387,7 +392,8 @@ def main():
             for b in range(NBUF):
                 p_ = eng.ipc_open(handles[0][b][rank])
                 ipc_mapped.append(p_)
-                out_ptrs[b] = p_            # this rank's results go straight into rank 0's gather buffer
+                if fused_gather:
+                    out_ptrs[b] = p_        # this rank's results go straight into rank 0's gather buffer
         # arrival flags live on rank 0 (one 128-byte line per rank), ack flags on every rank: one-thread
         # kernels write / wait on them in stream order — no NCCL collective on the data path
         FL = 128
@@ -420,8 +426,11 @@ def main():
         planning of the next batch overlaps the GPU work of this one (a serving loop does the same)"""
         b = s % NBUF
         t0 = time.perf_counter()
-        if world > 1 and rank != 0 and s >= NBUF:   # rank 0 has acknowledged the step that last used this buffer
-            eng.flag_wait(ack_ptr, s - NBUF + 1)
+        if world > 1 and rank != 0 and s >= NBUF:
+            if fused_gather:                    # rank 0 has acknowledged the step that last used this buffer
+                eng.flag_wait(ack_ptr, s - NBUF + 1)
+            elif copied_ev[b] is not None:      # the DMA that last read this local buffer is done
+                stream.wait_event(copied_ev[b])
         idx = next_idx.pop(s) if s in next_idx else eng.coarse_quantize(qsets[s], nprobe)
         t1 = time.perf_counter()
         rpq, st = eng.search_device(ct_pool[s % npool_steps].data_ptr(), nq, idx, out_ptrs[b], max_res)
@@ -440,8 +449,21 @@ def main():
         if world == 1:
             return
         tg = time.perf_counter()
-        if rank != 0:
+        if rank != 0 and fused_gather:
             eng.flag_write(arr_ptr + FL * rank, s + 1)      # after this rank's last kernel of step s
+        elif rank != 0:
+            b = s % NBUF
+            done = torch.cuda.Event()
+            done.record(stream)
+            comm_stream.wait_event(done)
+            cs = comm_stream.cuda_stream
+            if s >= NBUF:
+                eng.flag_wait(ack_ptr, s - NBUF + 1, cs)     # rank 0 is done with the peer buffer
+            eng.copy_async(ipc_mapped[b], d_outs[b].data_ptr(), int(st["nresults"]) * res_bytes, cs)
+            eng.flag_write(arr_ptr + FL * rank, s + 1, cs)
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            copied_ev[b] = ev
         else:
             done = torch.cuda.Event()
             done.record(stream)
@@ -478,7 +500,7 @@ def main():
             useful += st["useful_distances"]
             slots += st["slot_distances"]
             nres += st["nresults"]
-        if comm_stream is not None and rank == 0:  # the timed region ends when the last gather has landed
+        if comm_stream is not None:             # the timed region ends when the last gather has landed
             stream.wait_stream(comm_stream)
         ev1.record(stream)
         eng.synchronize()

@@ -164,6 +164,9 @@ int pf_ipc_free(pf_engine *e, void *dptr);
  * prior work of the stream (system-scope release).  wait: the stream blocks until *flag >= value.
  * cuda_stream NULL = the engine stream.  Waits must only target flags whose writer does not itself
  * wait on this stream's later work (the bench protocol: arrival flags -> rank 0 -> ack flags). */
+/* copy-engine (DMA) device-to-device copy, e.g. local results -> peer-mapped gather buffer, on a
+ * caller stream so that it overlaps the next step's kernels without using SMs */
+int pf_copy_async(pf_engine *e, void *dst, const void *src, size_t bytes, void *cuda_stream);
 int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream);
 int pf_flag_wait(pf_engine *e, const void *flag, uint32_t value, void *cuda_stream);
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "pf_engine_set_stream", "pf_engine_synchronize", "pf_load_index", "pf_get_index_info", "pf_retrieve_centroids",
     "pf_coarse_quantize", "pf_search_lists_plain", "pf_precise_search", "pf_set_galois_key", "pf_load_galois_keys",
     "pf_galois_elt_from_step", "pf_search_lists_encrypted", "pf_search_device", "pf_timing_enable", "pf_timing_read",
-    "pf_launch_count", "pf_ipc_alloc", "pf_ipc_open", "pf_ipc_close", "pf_ipc_free", "pf_flag_write", "pf_flag_wait", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
+    "pf_launch_count", "pf_ipc_alloc", "pf_ipc_open", "pf_ipc_close", "pf_ipc_free", "pf_copy_async", "pf_flag_write", "pf_flag_wait", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
     "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id",
     "pf_ct_serialize", "pf_ct_deserialize",
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
         "pf_ipc_open": ([vp, u8p, C.POINTER(vp)], C.c_int),
         "pf_ipc_close": ([vp, vp], C.c_int),
         "pf_ipc_free": ([vp, vp], C.c_int),
+        "pf_copy_async": ([vp, vp, vp, C.c_size_t, vp], C.c_int),
         "pf_flag_write": ([vp, vp, C.c_uint32, vp], C.c_int),
         "pf_flag_wait": ([vp, vp, C.c_uint32, vp], C.c_int),
         "pf_ntt_forward": ([vp, u64p, C.c_uint64, i32p], C.c_int),

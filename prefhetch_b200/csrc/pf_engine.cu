@@ -1297,6 +1297,13 @@ int pf_ipc_close(pf_engine *e, void *dptr) {
     return PF_OK;
 }
 
+int pf_copy_async(pf_engine *e, void *dst, const void *src, size_t bytes, void *cuda_stream) {
+    if (!e || !dst || !src) return PF_ERR_INVALID;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+    return PF_OK;
+}
+
 int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream) {
     if (!e || !flag) return PF_ERR_INVALID;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;

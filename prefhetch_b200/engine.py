@@ -248,6 +248,9 @@ class Engine:
         self._ck(self.lib.pf_ipc_open(self.h, h, C.byref(ptr)))
         return ptr.value
 
+    def copy_async(self, dst: int, src: int, nbytes: int, cuda_stream: int = 0):
+        self._ck(self.lib.pf_copy_async(self.h, C.c_void_p(dst), C.c_void_p(src), nbytes, C.c_void_p(cuda_stream)))
+
     def flag_write(self, ptr: int, value: int, cuda_stream: int = 0):
         self._ck(self.lib.pf_flag_write(self.h, C.c_void_p(ptr), value, C.c_void_p(cuda_stream)))
 

@@ -339,3 +339,47 @@ def test_cpp_host_mirror():
     assert exe.exists(), "run __graft_entry__.build() first"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("n,d,m,g,tbits", [(16384, 128, 1, 16, 24), (8192, 960, 8, 8, 27), (4096, 64, 2, 4, 24)])
+def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits):
+    """poly degree 16384 (L = 8, 49-bit primes: FP64 NTT with mid-pass reductions), GIST-shaped 960-d
+    vectors with 8 query ciphertexts (K = 128 diagonals per block), and a 2-ciphertext small case:
+    bytes identical to the oracle's pipeline, decrypted distances exact."""
+    from oracle.pf_oracle import BATCHING_T, BFV_DEFAULT_PRIMES
+    primes = BFV_DEFAULT_PRIMES[n]
+    t = BATCHING_T[(n, tbits)] if (n, tbits) in BATCHING_T else ntt_primes(n, tbits, 1)[0]
+    rng = np.random.default_rng(n + d)
+    nlist, nq, nprobe = 3, 2, 2
+    lay = oracle.LayoutPlan(n, d, m, g)
+    nb = lay.C + lay.C // 3
+    base, query, cent = sift_like(rng, nb, d, nlist, nq)
+    offsets, ids, vecs = build_ivf(base, cent)
+    eng = pf.Engine(d, n, primes, t, m, g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    cl = OracleClient(oracle, n, primes, t, d, m, g)
+    keys = cl.step_keys()
+    for i, key in enumerate(keys):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    cts = np.stack([cl.encrypt_query(q, 300 + 10 * i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    idx = eng.coarse_quantize(query, nprobe)
+    res = eng.coarseSearchEncrypted(blob, offs, idx)
+    r = 0
+    for qi in range(nq):
+        rot = oracle.rotate_query_set(cl.ctx, cl.lay, cts[qi], keys, False)
+        for l in idx[qi]:
+            n_l = int(offsets[l + 1] - offsets[l])
+            for b0 in range(0, n_l, lay.C):
+                xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + lay.C, n_l)].astype(np.int32)
+                diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
+                want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
+                assert res.result(r) == cl.ctx.ct_save(want_ct), f"query {qi} result {r}"
+                got_ct, _ = eng.ct_deserialize(res.result(r))
+                dist, budget = cl.distances(got_ct, query[qi], len(xs))
+                assert np.array_equal(dist, ((xs.astype(np.int64) - query[qi].astype(np.int64)) ** 2).sum(1))
+                assert budget > 0
+                r += 1
+    assert r == res.stats["nresults"] and r > 0
+    eng.close()
