@@ -798,7 +798,24 @@ void launch_mac_async_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     e->launches++;
 }
 
-// MAC variant: 0 = register-staged loads (mac_kernel), 1 = cp.async ring T=128, 2 = cp.async ring T=256
+template <int KS, int NST>
+void launch_mac_tma_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    constexpr int T = 256;
+    const size_t smem = (size_t)p.K * 2 * T * 8 + (size_t)NST * 4 * KS * T * 8 + 128;
+    if (e->mac_fpred) {
+        auto kern = mac_kernel_tma<T, KS, NST, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<dim3(nchunks, p.L * (p.N / T)), 288, smem, e->stream>>>(p);
+    } else {
+        auto kern = mac_kernel_tma<T, KS, NST, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<dim3(nchunks, p.L * (p.N / T)), 288, smem, e->stream>>>(p);
+    }
+    e->launches++;
+}
+
+// MAC variant: 0 = register-staged loads (mac_kernel), 1 = cp.async ring T=128, 2 = cp.async ring T=256,
+// 3 = TMA bulk-copy producer/consumer ring (T=256)
 int mac_variant(const pf_engine *e) {
     static const int env = [] {
         const char *v = getenv("PF_MAC_VARIANT");
@@ -811,7 +828,7 @@ int mac_variant(const pf_engine *e) {
 int mac_tile(const pf_engine *e) {
     const int v = mac_variant(e);
     if (v == 1) return 128;
-    if (v == 2) return 256;
+    if (v == 2 || v == 3) return 256;
     return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64);
 }
 
@@ -828,6 +845,7 @@ void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const int v = mac_variant(e);
     if (v == 1) return launch_mac_async_t<128, 2, 4>(e, p, nchunks);
     if (v == 2) return launch_mac_async_t<256, 2, 3>(e, p, nchunks);
+    if (v == 3) return launch_mac_tma_t<2, 3>(e, p, nchunks);
     const int T = mac_tile(e);
     if (T == 256) launch_mac_tile<256>(e, p, nchunks);
     else if (T == 128) launch_mac_tile<128>(e, p, nchunks);
