@@ -214,7 +214,7 @@ def run_reference(args, cfg, cfg_name):
     O.build()
     data = make_dataset(cfg, "cpu") if cfg["nb"] <= 200_000 else make_dataset_cpu_light(cfg)
     nthreads = O.max_threads()
-    nq_sample = min(cfg["nq"], 8)
+    nq_sample = min(cfg["nq"], 8)     # bounded sample: ~0.1-0.2 s per step on 16 cores, so K steps stay within minutes
     r = cpu_pipeline(cfg, data, nq_sample, nthreads, steps=args.steps, warmup=args.warmup)
     val = r["useful"] / r["seconds"]
     line = {
@@ -261,7 +261,7 @@ def make_dataset_cpu_light(cfg, seed=1234):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=None, choices=list(CONFIGS))
@@ -544,8 +544,12 @@ def main():
     alg_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * blocks_distinct + 2.0 * pairs) / args.steps  # rank-local
     streamed_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * pairs + 2.0 * pairs) / args.steps
     achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    traffic = None
+    tf = ROOT / "profiles" / "mac_traffic.json"
+    if tf.exists() and world == 1:   # dram__bytes_read+write per launch from the committed ncu --set full capture
+        traffic = json.loads(tf.read_text()).get(cfg_name, {}).get("traffic_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "mac_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "streamed_bytes_per_launch": streamed_bytes,
                 "streamed_gbs": streamed_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
                 "ms_per_launch": mac_ms}
@@ -597,9 +601,9 @@ def main():
             from oracle import pf_oracle as O
             O.build()
             nthreads = O.max_threads()
-            nq_s = min(nq, 8)
+            nq_s = min(nq, 32)   # ~10 s of CPU work on the host cores
             r = cpu_pipeline(cfg, data, nq_s, nthreads)
-            r1 = cpu_pipeline(cfg, data, 1, 1)
+            r1 = cpu_pipeline(cfg, data, 2, 1)
             cpu = {"value": r["useful"] / r["seconds"], "unit": "distances/s", "cores": nthreads, "kind": "port",
                    "sample": f"{nq_s} queries / {r['pairs']} (query,block) pairs of the same workload, whole hot path, "
                              f"{nthreads} OpenMP threads ({r['seconds']:.2f}s: rotations {r['rot_s']:.2f}s, MAC+INTT "
