@@ -120,6 +120,16 @@ class Engine:
         self.nlist = c.shape[0]
         return self.index_info()
 
+    def load_index_from_faiss(self, path: str, base_vectors):
+        """Server::init_index's cached-file branch (ref: src/server/server_lib.cpp:88-100): centroids and
+        inverted lists come from the .faiss file, raw vectors from the base set addressed by id."""
+        from . import faiss_io
+        f = faiss_io.read_ivfpq(path)
+        if f.d != self.dim:
+            raise PfError(1, f"index dimension {f.d} does not match the engine ({self.dim})")
+        offsets, ids, vecs = f.csr(np.asarray(base_vectors))
+        return self.load_index(f.centroids, offsets, ids, vecs)
+
     def index_info(self) -> dict:
         o = PfIndexInfo()
         self._ck(self.lib.pf_get_index_info(self.h, C.byref(o)))

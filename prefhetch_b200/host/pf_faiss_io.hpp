@@ -1,0 +1,120 @@
+// pf_faiss_io.hpp — reader for the FAISS IndexIVFPQ file the reference server caches on disk
+// (ref: src/server/server_lib.cpp:38-42 builds the file name, :82 writes it, :91-95 reads it and
+// rejects anything that is not an IndexIVFPQ).  Only what the GPU engine consumes is kept: the
+// coarse centroids and the ids of every inverted list; PQ codebooks and codes are skipped.
+// [EXT, UNVERIFIED] layout restated from the published faiss/impl/index_read.cpp (SURVEY.md
+// App. B.3); FAISS itself is not available here, so it is only checked against the writer in
+// prefhetch_b200/faiss_io.py.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace prefhetch {
+
+struct IvfFile {
+    uint32_t d = 0;
+    uint64_t ntotal = 0, nlist = 0, nprobe = 0, code_size = 0;
+    std::vector<float> centroids;      // [nlist][d]
+    std::vector<int64_t> list_offsets; // [nlist+1]
+    std::vector<int64_t> ids;          // list order
+};
+
+namespace detail {
+class Cursor {
+  public:
+    explicit Cursor(const std::string &path) {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        m_Buf.resize(static_cast<size_t>(f.tellg()));
+        f.seekg(0);
+        f.read(reinterpret_cast<char *>(m_Buf.data()), static_cast<std::streamsize>(m_Buf.size()));
+    }
+    template <class T> T get() {
+        T v;
+        copy(&v, sizeof(T));
+        return v;
+    }
+    void copy(void *dst, size_t n) {
+        if (n > m_Buf.size() - m_Pos) throw std::runtime_error("truncated index file");
+        if (dst) std::memcpy(dst, m_Buf.data() + m_Pos, n);
+        m_Pos += n;
+    }
+    void skip(size_t n) { copy(nullptr, n); }
+
+  private:
+    std::vector<uint8_t> m_Buf;
+    size_t m_Pos = 0;
+};
+constexpr uint32_t fourcc(const char (&s)[5]) {
+    return uint32_t(uint8_t(s[0])) | uint32_t(uint8_t(s[1])) << 8 | uint32_t(uint8_t(s[2])) << 16 |
+           uint32_t(uint8_t(s[3])) << 24;
+}
+inline void index_header(Cursor &c, uint32_t &d, uint64_t &ntotal) {
+    d = static_cast<uint32_t>(c.get<int32_t>());
+    ntotal = static_cast<uint64_t>(c.get<int64_t>());
+    c.skip(16);
+    c.skip(1); // is_trained
+    if (c.get<int32_t>() > 1) c.skip(4); // metric_arg
+}
+} // namespace detail
+
+inline IvfFile read_ivfpq_file(const std::string &path) {
+    using namespace detail;
+    Cursor c(path);
+    IvfFile out;
+    if (c.get<uint32_t>() != fourcc("IwPQ")) throw std::runtime_error("Loaded index is not of type IndexIVFPQ");
+    index_header(c, out.d, out.ntotal);
+    out.nlist = c.get<uint64_t>();
+    out.nprobe = c.get<uint64_t>();
+    const uint32_t qcc = c.get<uint32_t>();
+    if (qcc != fourcc("IxF2") && qcc != fourcc("IxFI")) throw std::runtime_error("coarse quantizer is not an IndexFlat");
+    uint32_t qd;
+    uint64_t qn;
+    index_header(c, qd, qn);
+    const uint64_t nfloats = c.get<uint64_t>();
+    if (qd != out.d || qn != out.nlist || nfloats != out.nlist * out.d)
+        throw std::runtime_error("quantizer shape does not match the IVF header");
+    out.centroids.resize(nfloats);
+    c.copy(out.centroids.data(), nfloats * sizeof(float));
+    const uint8_t dm = c.get<uint8_t>();
+    c.skip(c.get<uint64_t>() * 8);
+    if (dm == 2) c.skip(c.get<uint64_t>() * 16);
+    c.skip(1); // by_residual
+    out.code_size = c.get<uint64_t>();
+    c.skip(24); // pq.d, pq.M, pq.nbits
+    c.skip(c.get<uint64_t>() * sizeof(float));
+    if (c.get<uint32_t>() != fourcc("ilar")) throw std::runtime_error("unsupported inverted-list container");
+    if (c.get<uint64_t>() != out.nlist || c.get<uint64_t>() != out.code_size)
+        throw std::runtime_error("inverted lists do not match the index header");
+    std::vector<uint64_t> sizes(out.nlist, 0);
+    const uint32_t kind = c.get<uint32_t>();
+    const uint64_t nsz = c.get<uint64_t>();
+    if (kind == fourcc("full")) {
+        if (nsz != out.nlist) throw std::runtime_error("bad list size table");
+        c.copy(sizes.data(), nsz * 8);
+    } else if (kind == fourcc("sprs")) {
+        for (uint64_t i = 0; i < nsz / 2; i++) {
+            const uint64_t l = c.get<uint64_t>(), n = c.get<uint64_t>();
+            if (l >= out.nlist) throw std::runtime_error("bad list size table");
+            sizes[l] = n;
+        }
+    } else {
+        throw std::runtime_error("unknown list size encoding");
+    }
+    out.list_offsets.assign(out.nlist + 1, 0);
+    for (uint64_t l = 0; l < out.nlist; l++) out.list_offsets[l + 1] = out.list_offsets[l] + static_cast<int64_t>(sizes[l]);
+    if (static_cast<uint64_t>(out.list_offsets[out.nlist]) != out.ntotal)
+        throw std::runtime_error("ntotal does not match the inverted lists");
+    out.ids.resize(out.ntotal);
+    for (uint64_t l = 0; l < out.nlist; l++) {
+        c.skip(sizes[l] * out.code_size);
+        c.copy(out.ids.data() + out.list_offsets[l], sizes[l] * 8);
+    }
+    return out;
+}
+
+} // namespace prefhetch

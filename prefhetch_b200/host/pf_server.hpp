@@ -6,6 +6,7 @@
 // -lprefhetch_b200.  This is the code a maintainer drops into src/server/server_lib.cpp
 // (see INTEGRATION.md); it needs neither FAISS nor SEAL on the server.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 #include <span>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "../../include/prefhetch_b200.h"
+#include "pf_faiss_io.hpp"
 
 namespace prefhetch {
 
@@ -58,6 +60,20 @@ class Server {
         m_ListOffsets.assign(list_offsets, list_offsets + nlist + 1);
         check(pf_load_index(m_Engine.get(), nlist, centroids, list_offsets, ids, vectors));
         check(pf_get_index_info(m_Engine.get(), &m_Info));
+    }
+
+    // ref: the cached-file branch of Server::init_index (src/server/server_lib.cpp:88-99): centroids and
+    // inverted lists from the .faiss file, raw vectors from the base set addressed by id (:154-156)
+    void init_index(const std::string &faiss_path, std::span<const float> dataset_base) {
+        const IvfFile f = read_ivfpq_file(faiss_path);
+        if (f.d != m_Dim) throw std::runtime_error("index dimension does not match PRECISE_VECTOR_DIMENSIONS");
+        std::vector<float> vectors(f.ntotal * m_Dim);
+        for (uint64_t i = 0; i < f.ntotal; i++) {
+            const uint64_t row = static_cast<uint64_t>(f.ids[i]);
+            if (f.ids[i] < 0 || (row + 1) * m_Dim > dataset_base.size()) throw std::runtime_error("id outside the base set");
+            std::copy_n(dataset_base.data() + row * m_Dim, m_Dim, vectors.data() + i * m_Dim);
+        }
+        init_index(f.nlist, f.centroids.data(), f.list_offsets.data(), f.ids.data(), vectors.data());
     }
 
     // ref: Server::retrieve_centroids (src/server/server_lib.cpp:101-109)

@@ -282,6 +282,23 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
     eng.close()
 
 
+def test_index_from_faiss_file(pf, oracle, tmp_path):
+    """Cached-index branch of Server::init_index (ref: src/server/server_lib.cpp:88-100)."""
+    from prefhetch_b200 import faiss_io
+    base, query, cent, offsets, ids, vecs = _dataset(11, nb=3000, nlist=32)
+    lists = [ids[offsets[l]:offsets[l + 1]] for l in range(32)]
+    f = faiss_io.IVFPQFile(128, len(ids), 32, 20, cent, lists, [np.zeros((len(x), 32), np.uint8) for x in lists])
+    faiss_io.write_ivfpq(str(tmp_path / "idx.faiss"), f)
+    eng, _, _ = _engine(pf, 2048)
+    info = eng.load_index_from_faiss(str(tmp_path / "idx.faiss"), base)
+    assert info["nlist"] == 32 and info["ntotal"] == len(ids)
+    idx = eng.coarse_quantize(query, 4)
+    dist, labels, sizes = eng.coarseSearch(query, idx)
+    odist, olabels, osizes = oracle.search_lists_plain(query, idx, offsets, ids, vecs)
+    assert np.array_equal(labels, olabels) and np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
+    eng.close()
+
+
 def test_encrypted_search_errors(pf, oracle):
     n, g = 2048, 16
     base, query, cent, offsets, ids, vecs = _dataset(9, nb=2000, nlist=8, nq=2)
