@@ -70,6 +70,23 @@ __device__ __forceinline__ ulonglong2 ldg_stream(const ulonglong2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
     return r;
 }
+// L2 evict-first policy for data that is touched once per launch, so that re-used operands
+// (Galois keys, hoisted digits) keep their L2 lines
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ ulonglong2 ldg_once(const ulonglong2 *p, u64 pol) {
+    ulonglong2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                 : "=l"(r.x), "=l"(r.y)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_once(ulonglong2 *p, ulonglong2 v, u64 pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(v.x), "l"(v.y), "l"(pol));
+}
 __device__ __forceinline__ void stg_stream(ulonglong2 *p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y));
 }

@@ -114,6 +114,7 @@ struct pf_engine {
     DevBuf d_mods; // DevModulus[k+1] (index k = plain modulus)
     DevBuf d_tw;   // Twiddle[k+1][2][N]
     DevBuf d_tw_fp; // double[k+1][2][N] centred twiddles
+    DevBuf d_tw_fp_lane; // double[k+1][2][N] lane-major copies for the pass over bits [4..0]
     bool ntt_fp = false; // FP64-pipe NTT kernels eligible (pf_ntt_fp.cuh)
     DevBuf d_inv_index_map;
     std::vector<u64> h_q;
@@ -123,6 +124,7 @@ struct pf_engine {
     int max_prime_bits = 0;
     bool mac_wide = false;
     bool mac_fpred = false; // FP64-assisted final reduction applies (pf_mac.cuh)
+    bool ks_fpred = false;  // same for the key-switch inner product (L terms)
 
     std::map<u32, GaloisKey> gkeys;
 
@@ -339,6 +341,7 @@ void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) 
     p.mods = e->d_mods.as<DevModulus>();
     p.tw = e->d_tw.as<Twiddle>();
     p.tw_fp = e->d_tw_fp.as<double>();
+    p.tw_fp_lane = e->d_tw_fp_lane.as<double>();
     e->launches++;
     if (e->ntt_fp && !(inverse && p.ks_W)) {
         switch (e->logn) {
@@ -438,6 +441,27 @@ int build_tables(pf_engine *e) {
     CK(cudaMemcpy(e->d_tw.p, tw.data(), tw.size() * sizeof(Twiddle), cudaMemcpyHostToDevice));
     CK(e->d_tw_fp.ensure(twd.size() * sizeof(double)));
     CK(cudaMemcpy(e->d_tw_fp.p, twd.data(), twd.size() * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        // Lane-major copies of the twiddles of the 5-stage pass over bits [4..0] (thread c owns points
+        // 32c..32c+31): entry j of thread c at [j*NT + c], so that every twiddle load of a warp is one
+        // contiguous 256-byte run instead of 32 addresses 2^U doubles apart (pf_ntt_fp.cuh).
+        const int NT = N / 32;
+        std::vector<double> lane((size_t)(k + 1) * 2 * N, 0.0);
+        for (int j = 0; j <= k; j++) {
+            const double *fd = twd.data() + (size_t)j * 2 * N, *id = fd + N;
+            double *lf = lane.data() + (size_t)j * 2 * N, *li = lf + N;
+            for (int c = 0; c < NT; c++) {
+                int slot = 0;
+                for (int U = 0; U < 5; U++) // forward: stage U uses tw[2^(logn-5+U) + (c << U) + r]
+                    for (int r = 0; r < (1 << U); r++) lf[(size_t)(slot++) * NT + c] = fd[(1 << (logn - 5 + U)) + (c << U) + r];
+                slot = 0;
+                for (int B = 0; B < 5; B++) // inverse: stage B uses itw[2^(logn-1-B) + (c << (4-B)) + r]
+                    for (int r = 0; r < (1 << (4 - B)); r++) li[(size_t)(slot++) * NT + c] = id[(1 << (logn - 1 - B)) + (c << (4 - B)) + r];
+            }
+        }
+        CK(e->d_tw_fp_lane.ensure(lane.size() * sizeof(double)));
+        CK(cudaMemcpy(e->d_tw_fp_lane.p, lane.data(), lane.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
 
     // BatchEncoder index map (SEAL batchencoder.cpp) and its inverse
     std::vector<u32> inv_map(N);
@@ -545,6 +569,20 @@ int set_galois_key_words(pf_engine *e, u32 elt, const u64 *words, bool device_sr
 }
 
 // ---- rotations ------------------------------------------------------------------------------
+template <bool FINISH>
+void launch_ks_accumulate(pf_engine *e, const KsParams &kp, dim3 g, int nz) {
+    const int L = e->L;
+    if (e->ks_fpred) {
+        if (L <= 4) ks_accumulate_kernel<4, FINISH, true><<<g, 256, 0, e->stream>>>(kp, nz);
+        else if (L <= 8) ks_accumulate_kernel<8, FINISH, true><<<g, 256, 0, e->stream>>>(kp, nz);
+        else ks_accumulate_kernel<KS_MAXL, FINISH, true><<<g, 256, 0, e->stream>>>(kp, nz);
+    } else {
+        if (L <= 4) ks_accumulate_kernel<4, FINISH, false><<<g, 256, 0, e->stream>>>(kp, nz);
+        else if (L <= 8) ks_accumulate_kernel<8, FINISH, false><<<g, 256, 0, e->stream>>>(kp, nz);
+        else ks_accumulate_kernel<KS_MAXL, FINISH, false><<<g, 256, 0, e->stream>>>(kp, nz);
+    }
+}
+
 // Run a batch of rotation jobs (already filled on the host) through the key-switch pipeline.
 int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) {
     const int L = e->L, N = e->N, k = e->k;
@@ -595,9 +633,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         // 2a. S_c[P] (special-prime limb only)
         {
             const dim3 g(N / 512, 1, (nz + KS_QT - 1) / KS_QT);
-            if (L <= 4) ks_accumulate_kernel<4, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else if (L <= 8) ks_accumulate_kernel<8, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else ks_accumulate_kernel<KS_MAXL, false><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            launch_ks_accumulate<false>(e, kp, g, (int)nz);
         }
         e->launches++;
         // 3. u_c = INTT_P(S_c[L]) in place, then W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).
@@ -625,9 +661,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
         {
             const dim3 g(N / 512, L, (nz + KS_QT - 1) / KS_QT);
-            if (L <= 4) ks_accumulate_kernel<4, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else if (L <= 8) ks_accumulate_kernel<8, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
-            else ks_accumulate_kernel<KS_MAXL, true><<<g, 256, 0, e->stream>>>(kp, (int)nz);
+            launch_ks_accumulate<true>(e, kp, g, (int)nz);
         }
         e->launches++;
     }
@@ -733,8 +767,16 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
         if (hrc) return hrc;
         const size_t per_d = (size_t)L * (L + 1) * N;
         jobs.reserve(nq * m * (R - 1));
-        for (size_t r = 1; r < R; r++) // rotation-major: consecutive jobs share the Galois key
-            for (size_t i = 0; i < nq; i++)
+        // Order: groups of QG queries, rotation-major inside a group.  Consecutive jobs share the Galois
+        // key (ks_accumulate keeps it in registers across KS_QT jobs), and the hoisted digits D of a group
+        // (QG*m x 1.3 MB at N=8192) stay in L2 across its R-1 rotations; with rotation-major order over the
+        // whole batch, D (84 MB for 64 queries) was evicted by the streamed W / output between two uses
+        // and re-read from HBM for every rotation (ncu: 1.8 GB read per launch instead of 0.6 GB).
+        static const size_t env_qg = getenv("PF_KS_QGROUP") ? (size_t)atoi(getenv("PF_KS_QGROUP")) : 0;
+        const size_t QG = env_qg ? env_qg : 16;
+        for (size_t i0 = 0; i0 < nq; i0 += QG)
+          for (size_t r = 1; r < R; r++)
+            for (size_t i = i0; i < std::min(nq, i0 + QG); i++)
                 for (size_t a = 0; a < m; a++) {
                     const GaloisKey *gk = find_key(e, (int)r);
                     RotJob j{};
@@ -906,6 +948,8 @@ int plan_pairs(pf_engine *e, uint64_t nq, const int64_t *idx, uint32_t nprobe, P
     const size_t ctas_per_chunk = (size_t)e->L * (e->N / T);
     const size_t want_chunks = (4 * 148 + ctas_per_chunk - 1) / ctas_per_chunk;
     size_t CH = std::max<size_t>(4, std::min<size_t>(64, P / std::max<size_t>(1, want_chunks)));
+    static const size_t env_ch = getenv("PF_MAC_CHUNK") ? (size_t)atoi(getenv("PF_MAC_CHUNK")) : 0;
+    if (env_ch) CH = env_ch;
     size_t s = 0;
     while (s < P) {
         size_t epos = s;
@@ -1197,6 +1241,7 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
         e->ntt_fp = e->max_prime_bits <= fp_limit && (!env || atoi(env) != 0);
     }
     e->mac_fpred = !e->mac_wide && e->max_prime_bits + logk <= 50 && !getenv("PF_MAC_NO_FPRED");
+    e->ks_fpred = e->max_prime_bits + logl <= 50 && !getenv("PF_KS_NO_FPRED");
     if (sbits + logl > 64)
         return bail(e->fail(PF_ERR_INVALID, "coefficient primes of %d bits with %d limbs overflow the key-switch accumulator", e->max_prime_bits, e->L));
     if (cudaSetDevice(prm->device) != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaSetDevice(%d) failed", prm->device));

@@ -45,7 +45,9 @@ struct KsParams {
 // FINISH = true : data limbs I < L (grid.y = L) with step 4 fused: W holds NTT_I(W_c[I]) and the
 //                 rotated ciphertext (S_c[I] - W) * P^{-1} (+ sigma_ntt(c0) for c = 0) is written
 //                 directly, so S of the data limbs never touches memory.
-template <int LT, bool FINISH>
+// FPRED: FP64-assisted reduction of the lazy sums (pf_mac.cuh lazy_reduce_fp; host enables it when
+//        bits(q) + ceil(log2 L) <= 50).  W and the rotated ciphertext are touched once: L2 evict-first.
+template <int LT, bool FINISH, bool FPRED>
 __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
     const int L = p.L, N = p.N;
     const int I = FINISH ? (int)blockIdx.y : L;
@@ -53,6 +55,8 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
     const int sh = (int)m.split_shift;
+    const double qinv = m.fqinv;
+    const u64 once = l2_evict_first_policy();
     const int z0 = blockIdx.z * KS_QT, z1 = min(z0 + KS_QT, njobs);
     ulonglong2 k0[LT], k1[LT];
     const u64 *cur_key = nullptr;
@@ -102,10 +106,10 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
         }
         u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
         ulonglong2 r0, r1;
-        r0.x = lazy_reduce(a00, sh, m);
-        r0.y = lazy_reduce(a01, sh, m);
-        r1.x = lazy_reduce(a10, sh, m);
-        r1.y = lazy_reduce(a11, sh, m);
+        r0.x = lazy_reduce_sel<FPRED>(a00, sh, m, qinv);
+        r0.y = lazy_reduce_sel<FPRED>(a01, sh, m, qinv);
+        r1.x = lazy_reduce_sel<FPRED>(a10, sh, m, qinv);
+        r1.y = lazy_reduce_sel<FPRED>(a11, sh, m, qinv);
         if (hoisted) {
             const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
             const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
@@ -119,8 +123,8 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
             reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
         } else {
             const u64 *Wz = p.W + (size_t)z * 2 * L * N;
-            const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N) + c2);
-            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N) + c2);
+            const ulonglong2 w0 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N) + c2, once);
+            const ulonglong2 w1 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N) + c2, once);
             const u64 *c0 = job.c0_ntt + (size_t)I * N;
             ulonglong2 o0, o1;
             o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), __ldg(c0 + px), m.q);
@@ -133,8 +137,8 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
                 o1.x = split_word(o1.x, sh);
                 o1.y = split_word(o1.y, sh);
             }
-            reinterpret_cast<ulonglong2 *>(job.out + (size_t)I * N)[c2] = o0;
-            reinterpret_cast<ulonglong2 *>(job.out + (size_t)(L + I) * N)[c2] = o1;
+            stg_once(reinterpret_cast<ulonglong2 *>(job.out + (size_t)I * N) + c2, o0, once);
+            stg_once(reinterpret_cast<ulonglong2 *>(job.out + (size_t)(L + I) * N) + c2, o1, once);
         }
     }
 }

@@ -22,6 +22,7 @@ struct NttParams {
     const DevModulus *mods;
     const Twiddle *tw; // [nmod][2][N]
     const double *tw_fp; // [nmod][2][N] centred twiddles as doubles (FP64 NTT)
+    const double *tw_fp_lane; // [nmod][2][N] lane-major twiddles of the pass over bits [4..0]
     int mod_map[PF_NTT_MAXMAP];  // blockIdx.x -> modulus index of the transform
     int src_map[PF_NTT_MAXMAP];  // blockIdx.y -> modulus index the input limb is reduced under (GALOIS_REDUCE)
     u64 lift_t, lift_thr;        // NTT_IN_LIFT: plain modulus and (t+1)/2

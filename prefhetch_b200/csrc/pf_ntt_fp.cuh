@@ -58,12 +58,14 @@ struct FpFwdStages {
     static __device__ __forceinline__ void run(double (&v)[32], const double *__restrict__ tw, double q, double qinv) {
         constexpr int LB = P0 - K + 1, G = 32 >> K, S0 = LOGN - 1 - P0, NT = 1 << (LOGN - 5), E = 1 << K;
         constexpr int half = 1 << (K - 1 - U);
+        constexpr bool LANE = (LB == 0 && K == 5); // tw is the lane-major table: entry j of thread c at [j*NT + c]
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int hi = (g * NT + (int)threadIdx.x) >> LB;
 #pragma unroll
             for (int r = 0; r < (1 << U); r++) {
-                const double w = __ldg(tw + ((1 << (S0 + U)) + (hi << U) + r));
+                const double w = LANE ? __ldg(tw + (((1 << U) - 1 + r) * NT + (int)threadIdx.x))
+                                      : __ldg(tw + ((1 << (S0 + U)) + (hi << U) + r));
 #pragma unroll
                 for (int i = 0; i < half; i++) {
                     const int e = g * E + ((r << (K - U)) | i);
@@ -108,12 +110,16 @@ struct FpInvStages {
         constexpr int half = 1 << B;
         constexpr int s = LOGN - 1 - LB - B;
         constexpr bool fold = LAST && (B == K - 1);
+        constexpr bool LANE = (LB == 0 && K == 5); // itw is the lane-major table (see FpFwdStages)
+        constexpr int lane0 = 32 - (32 >> B);      // first entry of stage B: 0, 16, 24, 28, 30
 #pragma unroll
         for (int g = 0; g < G; g++) {
             const int hi = (g * NT + (int)threadIdx.x) >> LB;
 #pragma unroll
             for (int r = 0; r < (1 << (K - 1 - B)); r++) {
-                const double w = fold ? last_w : __ldg(itw + ((1 << s) + (hi << (K - 1 - B)) + r));
+                const double w = fold ? last_w
+                                      : (LANE ? __ldg(itw + ((lane0 + r) * NT + (int)threadIdx.x))
+                                              : __ldg(itw + ((1 << s) + (hi << (K - 1 - B)) + r)));
 #pragma unroll
                 for (int i = 0; i < half; i++) {
                     const int e = g * E + ((r << (B + 1)) | i);
@@ -153,6 +159,10 @@ __device__ __forceinline__ void fp_inv_pass(const double *__restrict__ itw, doub
     }
 }
 
+// p.tw_fp_lane: the same twiddles of the pass over bits [4..0] in lane-major order: thread c's j-th twiddle
+// at [j*NT + c].  In natural order a warp's 32 loads of one stage-U twiddle are 2^U doubles apart (up to
+// 32 cache lines per instruction; ncu: 682 L1 wavefronts per warp per transform, half the kernel's LSU
+// traffic); lane-major makes every load one 256-byte run (62 wavefronts).
 // p.tw_fp: [nmod][2][N] doubles (centred twiddles); p.fp_consts: [nmod] {q, 1/q, centred N^-1, centred irp[1]*N^-1}
 template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_fp_kernel(const NttParams p) {
@@ -161,6 +171,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     const int mi = p.mod_map[blockIdx.x];
     const DevModulus m = p.mods[mi];
     const double *tw = p.tw_fp + (size_t)mi * 2 * Cfg::N;
+    const double *twl = p.tw_fp_lane + (size_t)mi * 2 * Cfg::N;
     const u64 *in = (INMODE == NTT_IN_GALOIS_REDUCE)
                         ? p.jobs[blockIdx.z].c1_coef + blockIdx.y * p.in_sy
                         : p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
@@ -208,7 +219,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         if (OUTMODE == NTT_OUT_PLAIN && p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
         smu[sm_phys(idx)] = r;
     };
-    fp_fwd_pass<LOGN, Cfg::K3, 4>(tw, q, qinv, sload, fstore);
+    fp_fwd_pass<LOGN, Cfg::K3, 4>(twl, q, qinv, sload, fstore);
     __syncthreads();
     if (OUTMODE == NTT_OUT_KS) {
         const int j = blockIdx.x, c = blockIdx.y, L = p.ks_L;
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
     const int mi = p.mod_map[blockIdx.x];
     const DevModulus m = p.mods[mi];
     const double *itw = p.tw_fp + (size_t)mi * 2 * Cfg::N + Cfg::N;
+    const double *itwl = p.tw_fp_lane + (size_t)mi * 2 * Cfg::N + Cfg::N;
     const u64 *in = p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
     u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
     const double q = m.fq, qinv = m.fqinv;
@@ -293,7 +305,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
         }
         out[idx] = r;
     };
-    fp_inv_pass<LOGN, Cfg::K3, 0, false>(itw, q, qinv, m.fninv, m.flast_w, sload0, sstore);
+    fp_inv_pass<LOGN, Cfg::K3, 0, false>(itwl, q, qinv, m.fninv, m.flast_w, sload0, sstore);
     __syncthreads();
     fp_inv_pass<LOGN, Cfg::K2, 5, false>(itw, q, qinv, m.fninv, m.flast_w, sload, sstore);
     __syncthreads();
