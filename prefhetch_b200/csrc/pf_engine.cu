@@ -875,6 +875,8 @@ int mac_tile(const pf_engine *e) {
     const int v = mac_variant(e);
     if (v == 1) return 128;
     if (v == 2 || v == 3) return 256;
+    static const int env_t = getenv("PF_MAC_TILE") ? atoi(getenv("PF_MAC_TILE")) : 0;
+    if (env_t == 256 || env_t == 128 || env_t == 64) return env_t;
     return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64);
 }
 
@@ -1027,6 +1029,8 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
         mp.L = L;
         mp.N = N;
         mp.query_base = (int)q0;
+        static const int env_hint = getenv("PF_MAC_L2HINT") ? atoi(getenv("PF_MAC_L2HINT")) : 0;
+        mp.l2hint = env_hint;
         launch_mac(e, mp, (unsigned)(c1 - c0));
     }
     {

@@ -35,6 +35,7 @@ struct MacParams {
     const DevModulus *mods;      // limb l uses mods[l]
     int K, L, N;
     int query_base;              // MacChunk.query - query_base indexes rot
+    int l2hint;                  // 1: results and the ciphertext slice are L2 evict-first; 2: + plaintexts evict-last
 };
 
 // ---- split-operand lazy accumulation -------------------------------------------------------------
@@ -137,7 +138,8 @@ __device__ __forceinline__ SplitOp make_op(u64 w) {
 
 template <int BT, int UNROLL, int TX, bool FPRED>
 __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulonglong2 *sct, const DevModulus &m,
-                                                int split, size_t coef0, size_t LN, int tx, size_t pair0) {
+                                                int split, size_t coef0, size_t LN, int tx, size_t pair0,
+                                                u64 pol_once, u64 pol_keep) {
     const double qinv = 1.0 / (double)m.q;
     const ulonglong2 *bp[BT];
 #pragma unroll
@@ -162,7 +164,7 @@ __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulongl
         for (int u = 0; u < UNROLL; u++)
 #pragma unroll
             for (int j = 0; j < BT; j++) {
-                dst[u][j] = ldg_stream(bp[j]);
+                dst[u][j] = ldg_once(bp[j], pol_keep);
                 bp[j] += sk2;
             }
     };
@@ -208,8 +210,8 @@ __device__ __forceinline__ void mac_pairs_split(const MacParams &p, const ulongl
             r0.y = addmod(r0.y, nv.y, m.q);
         }
         u64 *o = p.out + slot * (size_t)p.out_stride + coef0;
-        stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
-        stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
+        stg_once(reinterpret_cast<ulonglong2 *>(o) + tx, r0, pol_once);
+        stg_once(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1, pol_once);
     }
 }
 
@@ -266,13 +268,15 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
     const size_t LN = (size_t)p.L * p.N;
     const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
 
+    const u64 pol_once = p.l2hint ? l2_evict_first_policy() : l2_evict_normal_policy();
+    const u64 pol_keep = p.l2hint == 2 ? l2_evict_last_policy() : l2_evict_normal_policy();
     // stage the query's rotated-ciphertext slice once; every block of the chunk reuses it
     {
         const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
         const int rows = p.K * 2;
         for (int i = threadIdx.x; i < rows * TX; i += 256) {
             const int row = i / TX, c = i % TX;
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(src + (size_t)row * LN) + c);
+            const ulonglong2 v = ldg_once(reinterpret_cast<const ulonglong2 *>(src + (size_t)row * LN) + c, pol_once);
             reinterpret_cast<ulonglong2 *>(smem_ct)[(size_t)row * TX + c] = v;
         }
     }
@@ -286,9 +290,9 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
         const int split = (int)m.split_shift;
         int pi = by * 2;
         for (; pi + 1 < ch.pair_count; pi += BY * 2)
-            mac_pairs_split<2, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
+            mac_pairs_split<2, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi, pol_once, pol_keep);
         if (pi < ch.pair_count) // odd tail: one pair left for this lane
-            mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi);
+            mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi, pol_once, pol_keep);
     }
 }
 
