@@ -267,7 +267,7 @@ def main():
     ap.add_argument("--config", default=None, choices=list(CONFIGS))
     ap.add_argument("--nq", type=int, default=None, help="queries per step")
     ap.add_argument("--g", type=int, default=None, help="partial-sum factor of the layout")
-    ap.add_argument("--result-limbs", type=int, default=2,
+    ap.add_argument("--result-limbs", type=int, default=1,
                     help="limbs of the result ciphertexts (SEAL mod_switch_to before save); 0 = no switching")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -568,7 +568,7 @@ def main():
         offs = (np.arange(nq * m + 1, dtype=np.uint64) * ctb)
         out_host = torch.empty(max_res * eng.slot_bytes, dtype=torch.uint8).pin_memory()
         out_np = out_host.numpy()
-        e_steps = max(2, min(args.steps, 5))
+        e_steps = max(2, min(args.steps, 20))
         e_useful, h2d, d2h = 0, 0, 0
         for s in range(2 + e_steps):
             if s == 2:

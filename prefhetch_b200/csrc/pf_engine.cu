@@ -95,6 +95,8 @@ constexpr size_t PF_RESULT_PAD = PF_RESULT_DATA_OFFSET - SEAL_CT_HEADER; // its 
 
 } // namespace
 
+#define PF_E2E_GROUPS 4 // query groups of pf_search_lists_encrypted (copy / compute overlap)
+
 struct pf_engine {
     pf_params prm{};
     int N = 0, logn = 0, k = 0, L = 0;
@@ -156,6 +158,8 @@ struct pf_engine {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t coarse_stream = nullptr; // stage 1 runs beside the encrypted pipeline of the previous batch
     cudaEvent_t ev_group[2] = {nullptr, nullptr};
+    cudaStream_t upload_stream = nullptr; // H2D of the query ciphertexts (pf_search_lists_encrypted)
+    cudaEvent_t ev_up[PF_E2E_GROUPS] = {};
 
     // timing
     bool timing = false;
@@ -1255,8 +1259,12 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     if (cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&e->coarse_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_group[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_group[1], cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&e->ev_group[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "copy stream / event creation failed"));
+    for (auto &ev : e->ev_up)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+            return bail(e->fail(PF_ERR_CUDA, "event creation failed"));
     cudaError_t ar = cudaSuccess;
     switch (e->logn) {
     case 10: ar = set_ntt_attrs<10>(); break;
@@ -1281,6 +1289,9 @@ void pf_engine_destroy(pf_engine *e) {
     for (auto ev : e->arena_ev)
         if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->upload_stream) cudaStreamDestroy(e->upload_stream);
+    for (auto ev : e->ev_up)
+        if (ev) cudaEventDestroy(ev);
     if (e->coarse_stream) cudaStreamDestroy(e->coarse_stream);
     for (auto ev : e->ev_group)
         if (ev) cudaEventDestroy(ev);
@@ -1793,6 +1804,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     // the ciphertext words sit at a 128-byte aligned offset (one aligned D2H per query group).
     const size_t slot = PF_RESULT_DATA_OFFSET + rw * 8;
     // labels / sizes of the owned probed lists (same packing as pf_search_lists_plain)
+    // (the label copy itself happens further down, while the GPU works)
     uint64_t nlabels = 0;
     for (uint64_t i = 0; i < nq; i++) {
         uint64_t cnt = 0;
@@ -1801,8 +1813,6 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
             const bool owned = (uint64_t)l % e->prm.world == e->prm.rank;
             const uint64_t n = owned ? (uint64_t)(e->h_list_offsets[l + 1] - e->h_list_offsets[l]) : 0;
             if (probed_sizes) probed_sizes[i * nprobe + p] = n;
-            if (labels && nlabels + n <= label_cap)
-                memcpy(labels + nlabels, e->h_ids.data() + e->h_list_offsets[l], n * sizeof(int64_t));
             nlabels += n;
             cnt += n;
         }
@@ -1830,7 +1840,15 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is compressed; save with compr_mode_type::none", c);
         if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
         if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
-        CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, src + SEAL_CT_HEADER, ctw * 8, cudaMemcpyHostToDevice, e->stream));
+    }
+    // Query groups: the H2D of group i+1 (upload stream) and the D2H of group i-1 (copy stream) overlap
+    // the compute of group i (engine stream).
+    const uint64_t ngroups = std::min<uint64_t>(nq, PF_E2E_GROUPS);
+    for (uint64_t gi = 0; gi < ngroups; gi++) {
+        for (size_t c = nq * gi / ngroups * e->m; c < nq * (gi + 1) / ngroups * e->m; c++)
+            CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, query_cts + ct_offsets[c] + SEAL_CT_HEADER, ctw * 8,
+                               cudaMemcpyHostToDevice, e->upload_stream));
+        CK(cudaEventRecord(e->ev_up[gi], e->upload_stream));
     }
     CK(e->s_out.ensure(std::max<size_t>(8, P * slot)));
     uint8_t *d_blob = e->s_out.as<uint8_t>();
@@ -1839,11 +1857,10 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     if (rc) return rc;
     rc = upload_plan(e, pl);
     if (rc) return rc;
-    // query groups: the D2H of group i (copy stream) overlaps the compute of group i+1 (engine stream)
-    const uint64_t ngroups = std::min<uint64_t>(nq, 4);
     uint64_t pair_lo = 0, q_lo = 0;
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         const uint64_t q_hi = nq * (gi + 1) / ngroups;
+        CK(cudaStreamWaitEvent(e->stream, e->ev_up[gi], 0));
         uint64_t pair_hi = pair_lo;
         for (uint64_t q = q_lo; q < q_hi; q++) pair_hi += pl.results_per_query[q];
         rc = search_core(e, q_lo, q_hi - q_lo, e->s_qcts.as<u64>() + q_lo * e->m * ctw, pl, d_words, slot / 8);
@@ -1859,6 +1876,17 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         q_lo = q_hi;
     }
     arena_end(e);
+    // labels of the owned probed lists (same packing as pf_search_lists_plain), copied while the GPU works
+    if (labels) {
+        uint64_t pos = 0;
+        for (uint64_t i = 0; i < nq * nprobe; i++) {
+            const int64_t l = idx[i];
+            if ((uint64_t)l % e->prm.world != e->prm.rank) continue;
+            const uint64_t n = (uint64_t)(e->h_list_offsets[l + 1] - e->h_list_offsets[l]);
+            memcpy(labels + pos, e->h_ids.data() + e->h_list_offsets[l], n * sizeof(int64_t));
+            pos += n;
+        }
+    }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->copy_stream));
     const uint64_t zero_pid[4] = {0, 0, 0, 0};

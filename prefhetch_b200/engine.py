@@ -201,17 +201,24 @@ class Engine:
         offs = np.ascontiguousarray(ct_offsets, dtype=np.uint64)
         idx = np.ascontiguousarray(nearest_centroid_idx, dtype=np.int64)
         nq, nprobe = idx.shape
-        info = self.index_info()
+        if not hasattr(self, "_C"):
+            self._C = self.index_info()["C"]
         # worst case: every probed list owned here
         max_results = int(self._max_results(idx))
         if out is None:
             out = np.zeros(max(1, max_results) * self.slot_bytes, dtype=np.uint8)
-        roff = np.zeros(max_results + 1, dtype=np.uint64)
-        rpq = np.zeros(nq, dtype=np.uint64)
-        label_cap = max(1, max_results * info["C"])
-        labels = np.zeros(label_cap, dtype=np.int64)
-        sizes = np.zeros(nq, dtype=np.uint64)
-        psz = np.zeros((nq, nprobe), dtype=np.uint64)
+        label_cap = max(1, max_results * self._C)
+        # response arrays are reused across calls (fresh 9 MB label arrays cost more page faults than the
+        # copy itself); the returned views stay valid until the next call on this engine
+        key = (nq, nprobe)
+        bufs = getattr(self, "_enc_bufs", None)
+        if bufs is None or bufs["key"] != key or len(bufs["roff"]) < max_results + 1 or len(bufs["labels"]) < label_cap:
+            bufs = {"key": key, "roff": np.empty(max_results + 1 + 64, dtype=np.uint64), "rpq": np.empty(nq, dtype=np.uint64),
+                    "labels": np.empty(label_cap + label_cap // 8, dtype=np.int64), "sizes": np.empty(nq, dtype=np.uint64),
+                    "psz": np.empty((nq, nprobe), dtype=np.uint64)}
+            self._enc_bufs = bufs
+        roff, rpq, labels, sizes, psz = bufs["roff"], bufs["rpq"], bufs["labels"], bufs["sizes"], bufs["psz"]
+        label_cap = len(labels)
         st = PfSearchStats()
         self._ck(self.lib.pf_search_lists_encrypted(
             self.h, nq, qb.ctypes.data_as(C.c_void_p), _ptr(offs, U64P), _ptr(idx, I64P), nprobe,

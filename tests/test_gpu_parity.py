@@ -213,7 +213,8 @@ def test_plain_stages_match_reference_semantics(pf, oracle):
 
 
 @pytest.mark.parametrize("n,g,chain,world,rl", [(2048, 16, False, 1, 0), (8192, 8, False, 1, 0), (2048, 16, True, 1, 0),
-                                                (2048, 16, False, 2, 0), (8192, 8, False, 1, 2), (2048, 16, False, 1, 1)])
+                                                (2048, 16, False, 2, 0), (8192, 8, False, 1, 2), (2048, 16, False, 1, 1),
+                                                (8192, 8, False, 1, 1)])
 def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
     """serialized query ciphertexts -> pf_search_lists_encrypted -> bytes identical to the oracle's
     pipeline; decrypted distances == exact integer squared L2 of the plaintext path."""

@@ -149,6 +149,38 @@ def test_encrypted_block_distance_exact(oracle, chain):
     assert budget > 10
 
 
+def test_result_mod_switched_to_one_limb_keeps_exact_distances(oracle):
+    """The bench / server default ships results at 1 data limb (SEAL mod_switch_to_inplace before save).
+    At the production parameters (N=8192, BFVDefault, t=Batching(N,24)) the switch adds at most
+    t*(1+N)/2 / q0 = 2^-7 of invariant noise in the WORST case, so decryption stays exact; the test pins
+    the budget that is actually left with extreme inputs (all-255 data against an all-0 query)."""
+    n, d, g = 8192, 128, 8
+    primes, t = oracle.BFV_DEFAULT_PRIMES[n], oracle.BATCHING_T[(n, 24)]
+    ctx = oracle.Context(n, primes, t)
+    lay = oracle.LayoutPlan(n, d, 1, g)
+    rng = np.random.default_rng(9)
+    xs = rng.integers(0, 256, size=(lay.C, d), dtype=np.int32)
+    xs[:8] = 255
+    xs[8:16] = 0
+    sk = ctx.keygen(1)
+    keys = [ctx.galois_keygen(sk, ctx.galois_elt(r), 100 + r) for r in range(1, lay.R)]
+    diag, norm = oracle.encode_block(ctx, lay, xs)
+    low = oracle.Context(n, [primes[0], primes[-1]], t)
+    sk_low = np.ascontiguousarray(sk[[0, ctx.k - 1]])
+    for q in (np.zeros(d, np.int64), np.full(d, 255, np.int64), rng.integers(0, 256, size=d).astype(np.int64)):
+        ct = ctx.encrypt(sk, ctx.encode(lay.query_slots(t, q, 0)), 2)
+        rot = oracle.rotate_query_set(ctx, lay, ct[None], keys, False)
+        res = oracle.block_distance(ctx, lay, rot, diag, norm)
+        _, full_budget = _client_distances(ctx, lay, sk, res, int((q * q).sum()), len(xs))
+        while res.shape[1] > 1:
+            res = ctx.mod_switch_next(res) if res.shape[1] == ctx.L else \
+                oracle.Context(n, primes[:res.shape[1]] + [primes[-1]], t).mod_switch_next(res)
+        got, budget = _client_distances(low, lay, sk_low, res, int((q * q).sum()), len(xs))
+        want = ((xs.astype(np.int64) - q) ** 2).sum(axis=1)
+        assert np.array_equal(got, want)
+        assert full_budget > 60 and budget >= 6, (full_budget, budget)
+
+
 def test_plain_path_matches_numpy(oracle):
     rng = np.random.default_rng(6)
     base, query, cent = sift_like(rng, 3000, 128, 32, 9)
