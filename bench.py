@@ -570,6 +570,7 @@ def main():
         out_np = out_host.numpy()
         e_steps = max(2, min(args.steps, 20))
         e_useful, h2d, d2h = 0, 0, 0
+        t_cq = t_se = 0.0
         for s in range(2 + e_steps):
             if s == 2:
                 if world > 1:
@@ -577,14 +578,20 @@ def main():
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
             x = qsets[s % nsteps_total]
+            ta = time.perf_counter()
             idx = eng.coarse_quantize(x, nprobe)
+            tb = time.perf_counter()
             res = eng.coarseSearchEncrypted(qnp, offs, idx, out=out_np)
             if s >= 2:
+                t_cq += tb - ta
+                t_se += time.perf_counter() - tb
                 e_useful += res.stats["useful_distances"]
                 h2d += nq * m * ctb + x.nbytes
                 d2h += res.stats["out_bytes"] + idx.nbytes
         torch.cuda.synchronize()
         e_dt = time.perf_counter() - t0
+        log(f"[rank {rank}] e2e {e_dt / e_steps * 1e3:.3f} ms/step: coarse_quantize {t_cq / e_steps * 1e3:.3f}, "
+            f"coarseSearchEncrypted {t_se / e_steps * 1e3:.3f}")
         et = torch.tensor([e_dt], device=dev, dtype=torch.float64)
         eu = torch.tensor([e_useful], device=dev, dtype=torch.float64)
         if world > 1:

@@ -95,7 +95,7 @@ constexpr size_t PF_RESULT_PAD = PF_RESULT_DATA_OFFSET - SEAL_CT_HEADER; // its 
 
 } // namespace
 
-#define PF_E2E_GROUPS 4 // query groups of pf_search_lists_encrypted (copy / compute overlap)
+#define PF_E2E_GROUPS 8 // max query groups of pf_search_lists_encrypted (copy / compute overlap)
 
 struct pf_engine {
     pf_params prm{};
@@ -1843,9 +1843,17 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     }
     // Query groups: the H2D of group i+1 (upload stream) and the D2H of group i-1 (copy stream) overlap
     // the compute of group i (engine stream).
-    const uint64_t ngroups = std::min<uint64_t>(nq, PF_E2E_GROUPS);
+    static const uint64_t env_groups = getenv("PF_E2E_GROUPS") ? (uint64_t)atoi(getenv("PF_E2E_GROUPS")) : 0;
+    const uint64_t ngroups = std::min<uint64_t>(nq, env_groups ? std::min<uint64_t>(env_groups, PF_E2E_GROUPS) : 4);
+    // group boundaries: with 4 groups the last one is the smallest (its D2H is the only copy nothing hides)
+    uint64_t q_end[PF_E2E_GROUPS + 1];
+    q_end[0] = 0;
     for (uint64_t gi = 0; gi < ngroups; gi++) {
-        for (size_t c = nq * gi / ngroups * e->m; c < nq * (gi + 1) / ngroups * e->m; c++)
+        static const uint64_t w4[4] = {5, 10, 14, 16};
+        q_end[gi + 1] = (ngroups == 4 && nq >= 16) ? nq * w4[gi] / 16 : nq * (gi + 1) / ngroups;
+    }
+    for (uint64_t gi = 0; gi < ngroups; gi++) {
+        for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
             CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, query_cts + ct_offsets[c] + SEAL_CT_HEADER, ctw * 8,
                                cudaMemcpyHostToDevice, e->upload_stream));
         CK(cudaEventRecord(e->ev_up[gi], e->upload_stream));
@@ -1859,7 +1867,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     if (rc) return rc;
     uint64_t pair_lo = 0, q_lo = 0;
     for (uint64_t gi = 0; gi < ngroups; gi++) {
-        const uint64_t q_hi = nq * (gi + 1) / ngroups;
+        const uint64_t q_hi = q_end[gi + 1];
         CK(cudaStreamWaitEvent(e->stream, e->ev_up[gi], 0));
         uint64_t pair_hi = pair_lo;
         for (uint64_t q = q_lo; q < q_hi; q++) pair_hi += pl.results_per_query[q];
