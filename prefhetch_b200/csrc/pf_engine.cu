@@ -294,6 +294,7 @@ cudaError_t set_ntt_attrs() {
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_LIFT>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_REDUCE>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
+    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_MODDOWN>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
     SETATTR((ntt_inv_fp_kernel<LOGN>));
     SETATTR((ntt_inv_fp_kernel<LOGN, NTT_OUT_MODSWITCH>));
@@ -317,6 +318,8 @@ void launch_ntt_fp_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cu
         ntt_fwd_fp_kernel<LOGN, NTT_IN_LIFT><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_REDUCE)
         ntt_fwd_fp_kernel<LOGN, NTT_IN_REDUCE><<<grid, nt, smem, s>>>(p);
+    else if (inmode == NTT_IN_MODDOWN)
+        ntt_fwd_fp_kernel<LOGN, NTT_IN_MODDOWN><<<grid, nt, smem, s>>>(p);
     else
         ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE><<<grid, nt, smem, s>>>(p);
 }
@@ -650,19 +653,36 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         ip.in_sz = ip.out_sz = (long long)per_S;
         ip.mod_map[0] = k - 1;
         launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(1, 2, nz));
-        ks_moddown_prep_kernel<<<dim3(N / 256, 2, nz), 256, 0, e->stream>>>(kp);
-        e->launches++;
-        // 4. NTT_j(W_c[j]) in place, then 2b. S_c[j] for the data limbs with the finish fused:
-        //    out_c[j] = (S_c[j] - NTT_j(W_c[j])) * P^{-1} (+ sigma_ntt(c0)[j]); S_c[j] never hits memory.
-        //    (Fusing the finish into the NTT copy-out instead, NTT_OUT_KS, measured slower.)
+        // 4. W_c[j] and NTT_j(W_c[j]): with the FP64 kernels W is formed while the transform loads u
+        //    (NTT_IN_MODDOWN), so neither the prep kernel nor a coefficient-form W exists; the integer
+        //    kernels keep the separate prep + in-place transform.  Then 2b. S_c[j] for the data limbs
+        //    with the finish fused: out_c[j] = (S_c[j] - NTT_j(W_c[j])) * P^{-1} (+ sigma_ntt(c0)[j]);
+        //    S_c[j] never hits memory.  (Fusing the finish into the NTT copy-out instead, NTT_OUT_KS,
+        //    measured slower.)
+        static const bool no_fuse = getenv("PF_KS_NO_FUSED_PREP") != nullptr;
         NttParams wp{};
-        wp.in = kp.W;
         wp.out = kp.W;
-        wp.in_sx = wp.out_sx = N;
-        wp.in_sy = wp.out_sy = (long long)L * N;
-        wp.in_sz = wp.out_sz = (long long)per_W;
+        wp.out_sx = N;
+        wp.out_sy = (long long)L * N;
+        wp.out_sz = (long long)per_W;
         for (int j = 0; j < L; j++) wp.mod_map[j] = j;
-        launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
+        if (e->ntt_fp && !no_fuse) {
+            wp.in = kp.S + (size_t)L * N;
+            wp.in_sx = 0;
+            wp.in_sy = (long long)(L + 1) * N;
+            wp.in_sz = (long long)per_S;
+            wp.ks_p_half = e->p_half;
+            wp.md_pmod = k - 1;
+            launch_ntt(e, NTT_IN_MODDOWN, false, wp, dim3(L, 2, nz));
+        } else {
+            ks_moddown_prep_kernel<<<dim3(N / 256, 2, nz), 256, 0, e->stream>>>(kp);
+            e->launches++;
+            wp.in = kp.W;
+            wp.in_sx = N;
+            wp.in_sy = (long long)L * N;
+            wp.in_sz = (long long)per_W;
+            launch_ntt(e, NTT_IN_PLAIN, false, wp, dim3(L, 2, nz));
+        }
         {
             const dim3 g(N / 512, L, (nz + KS_QT - 1) / KS_QT);
             launch_ks_accumulate<true>(e, kp, g, (int)nz);

@@ -10,7 +10,9 @@
 
 #define PF_NTT_MAXMAP 17
 
-enum { NTT_IN_PLAIN = 0, NTT_IN_REDUCE = 1, NTT_IN_LIFT = 2, NTT_IN_GALOIS_REDUCE = 3 };
+// NTT_IN_MODDOWN (FP64 kernels only): the input is u = INTT_P(S_c[P]); limb j transforms
+// W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j)  (pf_keyswitch.cuh step 3) computed on load
+enum { NTT_IN_PLAIN = 0, NTT_IN_REDUCE = 1, NTT_IN_LIFT = 2, NTT_IN_GALOIS_REDUCE = 3, NTT_IN_MODDOWN = 4 };
 // epilogues fused into the transforms of the key-switch mod-down (pf_keyswitch.cuh steps 3 and 4)
 enum { NTT_OUT_PLAIN = 0, NTT_OUT_KS = 1, NTT_OUT_MODSWITCH = 2 };
 
@@ -33,7 +35,8 @@ struct NttParams {
     u64 *ks_W;                   // [z][2][L][N]
     const u64 *ks_S;             // [z][2][L+1][N]
     int ks_L;
-    u64 ks_p_half;
+    u64 ks_p_half;               // also NTT_IN_MODDOWN: floor(P/2)
+    int md_pmod;                 // NTT_IN_MODDOWN: index of the special prime in mods
     // NTT_OUT_MODSWITCH (inverse, grid (kept limb j, poly, result)): the dropped limbs [ms_Lr, ms_L) are
     // already in coefficient form at ms_dropped + z*ms_dropped_sz + poly*(ms_L-ms_Lr)*N + (c-ms_Lr)*N
     const u64 *ms_dropped;

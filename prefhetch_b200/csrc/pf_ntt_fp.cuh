@@ -183,9 +183,18 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         if (jb.D && !*jb.flag) return;
     }
     constexpr bool MIDRED = LOGN >= 14; // keep magnitudes below 2^52 for 49-bit primes
+    u64 md_P = 0, md_Pratio = 0;
+    if (INMODE == NTT_IN_MODDOWN) {
+        md_P = p.mods[p.md_pmod].q;
+        md_Pratio = p.mods[p.md_pmod].ratio1;
+    }
 
     auto gload = [&](int idx) -> double {
         if (INMODE == NTT_IN_PLAIN) return fp_from_u64(in[idx]);
+        if (INMODE == NTT_IN_MODDOWN) {
+            const u64 v = barrett64(in[idx] + p.ks_p_half, md_P, md_Pratio);
+            return fp_from_u64(submod(barrett64(v, m.q, m.ratio1), m.p_half_mod, m.q));
+        }
         if (INMODE == NTT_IN_REDUCE) {
             const u64 x = in[idx];
             if (x == 0 && p.zero_flags) p.zero_flags[blockIdx.z] = 1;
