@@ -229,7 +229,7 @@ def run_reference(args, cfg, cfg_name):
         "e2e": {"value": val, "unit": "distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "queries_per_s": nq_sample / r["seconds"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -258,7 +258,16 @@ def make_dataset_cpu_light(cfg, seed=1234):
 
 
 # ----------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def emit(line):
+    """the one JSON line goes to the process's original stdout"""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    global _JSON_OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -272,6 +281,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    # stdout must carry exactly one JSON line: native libraries (NCCL prints its version banner with
+    # printf) write to fd 1, so fd 1 is pointed at stderr for the whole run and the line goes to a dup
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 0)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -641,7 +655,7 @@ def main():
             "phases_ms_per_step": {kk: v["ms"] / args.steps for kk, v in phases.items()},
             "e2e": e2e, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
