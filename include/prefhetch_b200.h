@@ -206,8 +206,13 @@ size_t pf_ct_serialized_size(pf_engine *e);
  * result's SEAL stream (results have result_limbs limbs) */
 size_t pf_result_slot_size(pf_engine *e);
 size_t pf_result_serialized_size(pf_engine *e);
+/* SEAL parms_id of the BFV parameter set {poly_degree, coeff_primes[0..nprimes), plain_modulus}: BLAKE2b-256
+ * of {scheme = 1, N, primes..., t} as 4 little-endian words (replaces EncryptionParameters::parms_id();
+ * [EXT] SEAL 4.1 encryptionparams.cpp compute_parms_id).  Needs no engine and no GPU. */
+int pf_parms_id(uint64_t poly_degree, const uint64_t *coeff_primes, uint32_t nprimes, uint64_t plain_modulus,
+                uint64_t out[4]);
 /* parms_id written into result ciphertexts (SEAL: context_data(level)->parms_id()); defaults to the
- * query's parms_id when result_limbs == L, zeros otherwise (parms_id hashing is not implemented here) */
+ * query's parms_id when result_limbs == L, else pf_parms_id of the first result_limbs data primes */
 int pf_set_result_parms_id(pf_engine *e, const uint64_t parms_id[4]);
 int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, size_t cap, size_t *written);
 /* accepts ciphertexts with L (query level) or result_limbs limbs; *limbs receives the count */

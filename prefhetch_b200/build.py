@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     cu, _ = sources()
-    cmd = [NVCC, *FLAGS, "-o", str(LIB), *[str(c) for c in cu]]
+    cmd = [NVCC, *FLAGS, "-o", str(LIB), *[str(c) for c in cu], "-lz"]  # zlib: SEAL compr_mode zlib streams
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = PKG / "build.log"
     log.write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)

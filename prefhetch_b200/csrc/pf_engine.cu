@@ -18,7 +18,9 @@
 #include "../../include/prefhetch_b200.h"
 #include "pf_common.cuh"
 #include "pf_encode.cuh"
+#include "pf_blake2b.h"
 #include "pf_host_math.h"
+#include <zlib.h>
 #include "pf_keyswitch.cuh"
 #include "pf_mac.cuh"
 #include "pf_ntt.cuh"
@@ -127,6 +129,7 @@ struct pf_engine {
     bool mac_wide = false;
     bool mac_fpred = false; // FP64-assisted final reduction applies (pf_mac.cuh)
     bool ks_fpred = false;  // same for the key-switch inner product (L terms)
+    uint64_t level_pid[PF_MAX_PRIMES + 1][4] = {}; // SEAL parms_id of the level with i data limbs (pf_blake2b.h)
 
     std::map<u32, GaloisKey> gkeys;
 
@@ -1167,11 +1170,52 @@ void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t 
 }
 
 // returns 0 on success; data_off = offset of the words, nlimbs = coeff_modulus_size
+// SEAL streams saved with compr_mode_type::zlib: the 16-byte SEALHeader is followed by one zlib
+// (RFC 1950) stream holding what an uncompressed save would have written after its header; nested
+// objects inside are saved uncompressed [EXT: SEAL 4.1 serialization.cpp / util/ztools.cpp].  Inflates
+// into `out` as the equivalent compr_mode none stream.  Returns 0, 1 (not zlib-compressed, untouched), <0 error.
+int inflate_seal_stream(const uint8_t *p, size_t len, std::vector<uint8_t> &out, size_t *consumed) {
+    if (len < 16 || p[0] != 0x5E || p[1] != 0xA1) return -2;
+    if (p[5] != 1) return 1;
+    uint64_t total;
+    memcpy(&total, p + 8, 8);
+    if (total > len || total < 16) return -1;
+    out.assign(16, 0);
+    z_stream zs{};
+    if (inflateInit(&zs) != Z_OK) return -5;
+    zs.next_in = const_cast<Bytef *>(p + 16);
+    zs.avail_in = (uInt)(total - 16);
+    int zr = Z_OK;
+    while (zr != Z_STREAM_END) {
+        const size_t have = out.size();
+        out.resize(have + std::max<size_t>(1 << 16, (total - 16) * 2));
+        zs.next_out = out.data() + have;
+        zs.avail_out = (uInt)(out.size() - have);
+        zr = inflate(&zs, Z_NO_FLUSH);
+        out.resize(out.size() - zs.avail_out);
+        if (zr != Z_OK && zr != Z_STREAM_END) {
+            inflateEnd(&zs);
+            return -6;
+        }
+        if (zr == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) {
+            inflateEnd(&zs);
+            return -1; // truncated
+        }
+    }
+    inflateEnd(&zs);
+    memcpy(out.data(), p, 16);
+    out[5] = 0;
+    const uint64_t new_total = out.size();
+    memcpy(out.data() + 8, &new_total, 8);
+    if (consumed) *consumed = (size_t)total;
+    return 0;
+}
+
 int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_ntt, uint64_t parms_id[4],
                     uint64_t *nlimbs, size_t *total_out) {
     if (len < SEAL_CT_HEADER) return -1;
     if (p[0] != 0x5E || p[1] != 0xA1 || p[2] != 0x10 || p[3] != 4) return -2;
-    if (p[5] != 0) return -3; // compressed streams are not accepted (zstd absent)
+    if (p[5] != 0) return -3; // zlib streams are inflated by the callers first; zstd is not available here
     uint64_t total, size, n, cms, words;
     memcpy(&total, p + 8, 8);
     if (total > len) return -1;
@@ -1198,6 +1242,12 @@ int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_nt
 extern "C" {
 
 int pf_abi_version(void) { return PF_ABI_VERSION; }
+
+int pf_parms_id(uint64_t poly_degree, const uint64_t *coeff_primes, uint32_t nprimes, uint64_t plain_modulus, uint64_t out[4]) {
+    if (!coeff_primes || !out || !nprimes || nprimes > 64) return PF_ERR_INVALID;
+    pfh::seal_parms_id(poly_degree, coeff_primes, nprimes, plain_modulus, out);
+    return PF_OK;
+}
 
 const char *pf_last_error(const pf_engine *e) { return e ? e->err.c_str() : g_tls_error.c_str(); }
 
@@ -1270,6 +1320,7 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
     }
     e->mac_fpred = !e->mac_wide && e->max_prime_bits + logk <= 50 && !getenv("PF_MAC_NO_FPRED");
     e->ks_fpred = e->max_prime_bits + logl <= 50 && !getenv("PF_KS_NO_FPRED");
+    for (int i = 1; i <= e->L; i++) pfh::seal_parms_id(N, prm->primes, (uint32_t)i, prm->plain_modulus, e->level_pid[i]);
     if (sbits + logl > 64)
         return bail(e->fail(PF_ERR_INVALID, "coefficient primes of %d bits with %d limbs overflow the key-switch accumulator", e->max_prime_bits, e->L));
     if (cudaSetDevice(prm->device) != cudaSuccess) return bail(e->fail(PF_ERR_CUDA, "cudaSetDevice(%d) failed", prm->device));
@@ -1729,8 +1780,17 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
     if (!e || !bytes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
+    std::vector<uint8_t> plain;
+    {
+        const int zr = inflate_seal_stream(bytes, len, plain, nullptr);
+        if (zr < 0) return e->fail(PF_ERR_FORMAT, "malformed compressed GaloisKeys stream (code %d)", zr);
+        if (zr == 0) {
+            bytes = plain.data();
+            len = plain.size();
+        }
+    }
     if (len < 16 + 32 + 8 || bytes[0] != 0x5E || bytes[1] != 0xA1 || bytes[5] != 0)
-        return e->fail(PF_ERR_FORMAT, "not an uncompressed SEAL stream");
+        return e->fail(PF_ERR_FORMAT, "not a SEAL stream with compr_mode none or zlib");
     uint64_t total;
     memcpy(&total, bytes + 8, 8);
     if (total > len) return e->fail(PF_ERR_FORMAT, "truncated GaloisKeys stream");
@@ -1850,14 +1910,24 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     // parse + upload the query ciphertexts
     CK(e->s_qcts.ensure(std::max<size_t>(8, ncts * ctw * 8)));
     uint64_t parms_id[4] = {0, 0, 0, 0};
+    std::vector<const uint8_t *> ct_src(ncts);
+    std::vector<std::vector<uint8_t>> inflated; // zlib-compressed queries (slow path: inflated on the host)
     for (size_t c = 0; c < ncts; c++) {
         const uint8_t *src = query_cts + ct_offsets[c];
-        const size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
+        size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
+        if (len >= 16 && src[5] == 1) {
+            inflated.emplace_back();
+            const int zr = inflate_seal_stream(src, len, inflated.back(), nullptr);
+            if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed zlib stream (code %d)", c, zr);
+            src = inflated.back().data();
+            len = inflated.back().size();
+        }
+        ct_src[c] = src;
         int is_ntt;
         uint64_t cms;
         size_t total;
         const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
-        if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is compressed; save with compr_mode_type::none", c);
+        if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu uses an unsupported compression (zstd); save with compr_mode_type::none or zlib", c);
         if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
         if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
     }
@@ -1874,7 +1944,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     }
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
-            CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, query_cts + ct_offsets[c] + SEAL_CT_HEADER, ctw * 8,
+            CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
                                cudaMemcpyHostToDevice, e->upload_stream));
         CK(cudaEventRecord(e->ev_up[gi], e->upload_stream));
     }
@@ -1917,8 +1987,9 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaStreamSynchronize(e->copy_stream));
-    const uint64_t zero_pid[4] = {0, 0, 0, 0};
-    const uint64_t *out_pid = e->result_pid_set ? e->result_pid : (e->Lr == L ? parms_id : zero_pid);
+    // result parms_id: caller's override, else the query's at full level, else SEAL's hash of the
+    // parameters of the level the results were switched to
+    const uint64_t *out_pid = e->result_pid_set ? e->result_pid : (e->Lr == L ? parms_id : e->level_pid[e->Lr]);
     for (uint64_t r = 0; r < P; r++) { // SEAL stream headers (113 bytes each) in front of the aligned words
         write_ct_prefix(e, out_cts + r * slot + PF_RESULT_PAD, 0, out_pid, e->Lr);
         if (result_offsets) result_offsets[r] = r * slot + PF_RESULT_PAD;
@@ -2162,14 +2233,21 @@ int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct,
     if (!e || !in || !ct) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
     int ntt;
     uint64_t pid[4], cms;
-    size_t total;
+    size_t total, zconsumed = 0;
+    std::vector<uint8_t> plain;
+    const int zr = inflate_seal_stream(in, len, plain, &zconsumed);
+    if (zr < 0) return e->fail(PF_ERR_FORMAT, "malformed compressed ciphertext (code %d)", zr);
+    if (zr == 0) {
+        in = plain.data();
+        len = plain.size();
+    }
     const int pr = parse_ct_prefix(e, in, len, &ntt, pid, &cms, &total);
     if (pr || cms < 1 || cms > (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "malformed ciphertext (code %d)", pr);
     if ((total - SEAL_CT_HEADER) / 8 > cap_words) return e->fail(PF_ERR_CAPACITY, "need %zu words", (total - SEAL_CT_HEADER) / 8);
     memcpy(ct, in + SEAL_CT_HEADER, total - SEAL_CT_HEADER);
     if (limbs) *limbs = (int)cms;
     if (is_ntt) *is_ntt = ntt;
-    if (consumed) *consumed = total;
+    if (consumed) *consumed = zr == 0 ? zconsumed : total;
     return PF_OK;
 }
 

@@ -30,6 +30,16 @@ def bfv_default_primes(n: int):
     return list(_BFV_DEFAULT[n])
 
 
+def parms_id(poly_degree: int, primes, plain_modulus: int):
+    """SEAL parms_id (4 x uint64) of a BFV parameter set; needs no GPU (pf_parms_id)"""
+    lib = _capi.load()
+    pr = (C.c_uint64 * len(primes))(*primes)
+    out = (C.c_uint64 * 4)()
+    if lib.pf_parms_id(poly_degree, pr, len(primes), plain_modulus, out):
+        raise ValueError("pf_parms_id: invalid arguments")
+    return tuple(int(x) for x in out)
+
+
 def batching_plain_modulus(n: int, bits: int) -> int:
     return _BATCHING[(n, bits)]
 

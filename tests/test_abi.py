@@ -50,3 +50,18 @@ def test_built_for_sm_100a():
     so = ROOT / "prefhetch_b200" / "libprefhetch_b200.so"
     out = subprocess.run(["cuobjdump", "-lelf", str(so)], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_parms_id_is_blake2b_of_the_parameter_words():
+    """pf_parms_id (host BLAKE2b, prefhetch_b200/csrc/pf_blake2b.h) against Python's hashlib on SEAL's
+    layout {scheme = 1, N, primes..., t}; also exercises multi-block messages (> 128 bytes)."""
+    import hashlib
+    import struct
+    import prefhetch_b200 as pf
+    from tests.util import ntt_primes
+    cases = [(8192, pf.bfv_default_primes(8192), 16760833), (8192, pf.bfv_default_primes(8192)[:1], 16760833),
+             (16384, pf.bfv_default_primes(16384), 16580609), (2048, ntt_primes(2048, 30, 14) + ntt_primes(2048, 31, 6), 65537)]
+    for n, primes, t in cases:
+        words = [1, n, *primes, t]
+        want = struct.unpack("<4Q", hashlib.blake2b(struct.pack(f"<{len(words)}Q", *words), digest_size=32).digest())
+        assert pf.parms_id(n, primes, t) == want

@@ -255,10 +255,12 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
                     xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + C_, n_l)].astype(np.int32)
                     diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
                     want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
+                    pid = (0, 0, 0, 0)
                     if rl:
                         want_ct = cl.mod_switch_to(want_ct, rl)  # SEAL mod_switch_to_inplace before save
+                        pid = _parms_id_py(n, primes[:rl], t)     # parms_id of the level switched to
                     got_bytes = res.result(r)
-                    assert got_bytes == cl.ctx.ct_save(want_ct), f"rank {rank} query {qi} result {r}"
+                    assert got_bytes == cl.ctx.ct_save(want_ct, parms_id=pid), f"rank {rank} query {qi} result {r}"
                     got_ct, is_ntt = eng.ct_deserialize(got_bytes)
                     dist, budget = cl.distances(got_ct, query[qi], len(xs))
                     want = ((xs.astype(np.int64) - query[qi].astype(np.int64)) ** 2).sum(1)
@@ -280,6 +282,54 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
         plain = dict(zip(labels[off:off + sizes[qi]].tolist(), dist[off:off + sizes[qi]].astype(np.int64).tolist()))
         assert plain == all_results[qi]
         off += sizes[qi]
+    eng.close()
+
+
+def _parms_id_py(n, primes, t):
+    import hashlib
+    import struct
+    words = [1, n, *primes, t]
+    return struct.unpack("<4Q", hashlib.blake2b(struct.pack(f"<{len(words)}Q", *words), digest_size=32).digest())
+
+
+def _zlib_stream(raw: bytes) -> bytes:
+    """what SEAL writes with compr_mode_type::zlib: header (compr_mode 1, new size) + deflate of the body"""
+    import struct
+    import zlib
+    body = zlib.compress(raw[16:], 6)
+    return raw[:5] + b"\x01" + raw[6:8] + struct.pack("<Q", 16 + len(body)) + body
+
+
+def test_zlib_compressed_streams(pf, oracle):
+    """SEAL compr_mode zlib on the request side: query ciphertexts, single ciphertexts and
+    GaloisKeys saved compressed give the same bytes out as their uncompressed form."""
+    n, g, d, nprobe = 2048, 16, 128, 3
+    base, query, cent, offsets, ids, vecs = _dataset(21, nb=3000, nlist=16, nq=2)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    cts = np.stack([cl.encrypt_query(q, 300 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    zparts = [_zlib_stream(bytes(blob[offs[i]:offs[i + 1]])) for i in range(len(cts))]
+    zblob = np.frombuffer(b"".join(zparts), dtype=np.uint8)
+    zoffs = np.concatenate([[0], np.cumsum([len(z) for z in zparts])]).astype(np.uint64)
+    assert len(zblob) < 0.8 * len(blob)
+    eng, _, _ = _engine(pf, n, g=g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(keys):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    idx = eng.coarse_quantize(query, nprobe)
+    plain = eng.coarseSearchEncrypted(blob, offs, idx)
+    want = [plain.result(r) for r in range(plain.stats["nresults"])]
+    comp = eng.coarseSearchEncrypted(zblob, zoffs, idx)
+    assert comp.stats["nresults"] == len(want) and all(comp.result(r) == want[r] for r in range(len(want)))
+    got, is_ntt = eng.ct_deserialize(zparts[0])
+    assert np.array_equal(got, cts[0][0]) and not is_ntt
+    with pytest.raises(pf.PfError):
+        eng.ct_deserialize(zparts[0][:-20])          # truncated deflate stream
+    with pytest.raises(pf.PfError):
+        eng.ct_deserialize(zparts[0][:5] + b"\x02" + zparts[0][6:])   # zstd: not available
     eng.close()
 
 
