@@ -150,6 +150,70 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+class NvmlSampler:
+    """Same quantities as ClockSampler read in-process through NVML (what nvidia-smi itself calls): SM clock
+    and clocks-event reasons every 100 ms DURING the timed region.  A polling nvidia-smi process queries far
+    more per sample and holds driver locks long enough to stall kernel launches for milliseconds on some
+    boxes (seen as steps of 4-6 ms with unchanged kernel times), which is why it is only the fallback."""
+
+    def __init__(self, torch_device):
+        self.dev, self.rows, self.ok, self.stop_flag = torch_device, [], False, threading.Event()
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = torch.device(self.dev).index or 0
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(vis.split(",")[idx]) if vis else idx)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+        except Exception:
+            self.ok = False
+        return self.ok
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def stop(self):
+        self.stop_flag.set()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.th.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml"}
+
+
+def make_sampler(local_rank, torch_device):
+    """PF_BENCH_CLOCKS = nvml (default) | smi | off"""
+    mode = os.environ.get("PF_BENCH_CLOCKS", "nvml")
+    if mode == "smi":
+        return ClockSampler(local_rank)
+    s = NvmlSampler(torch_device)
+    if mode == "off":
+        s.start = lambda: False
+    return s
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle's OpenMP whole-step driver on a bounded sample
 # ----------------------------------------------------------------------------------------------
@@ -500,9 +564,11 @@ def main():
             dist.barrier()
         eng.timing_enable(True)
         eng.timing_read(reset=True)
-        sampler = ClockSampler(local_rank)
-        if rank == 0:                          # one nvidia-smi poller per job: it takes driver locks
-            sampler.start()
+        sampler = make_sampler(local_rank, dev)
+        if rank == 0:                          # one poller per job: NVML queries take driver locks
+            if not sampler.start() and not isinstance(sampler, ClockSampler) and os.environ.get("PF_BENCH_CLOCKS", "nvml") != "off":
+                sampler = ClockSampler(local_rank)
+                sampler.start()
         launches0 = eng.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         useful = slots = nres = 0

@@ -354,6 +354,13 @@ void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) 
     p.tw_fp_lane = e->d_tw_fp_lane.as<double>();
     e->launches++;
     if (e->ntt_fp && !(inverse && p.ks_W)) {
+        if (!inverse && inmode == NTT_IN_GALOIS_REDUCE) {
+            // hoisted jobs need the exact digits only when flagged: 32 jobs per CTA; un-hoisted jobs
+            // (chain mode) always do: one job per CTA
+            p.njobs = (int)grid.z;
+            p.job_group = p.hoisted_jobs ? 32 : 1;
+            grid.z = (grid.z + p.job_group - 1) / p.job_group;
+        }
         switch (e->logn) {
         case 10: launch_ntt_fp_t<10>(inmode, inverse, p, grid, e->stream); break;
         case 11: launch_ntt_fp_t<11>(inmode, inverse, p, grid, e->stream); break;
@@ -638,6 +645,7 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         for (int I = 0; I <= L; I++) np.mod_map[I] = (I == L) ? k - 1 : I;
         for (int J = 0; J < L; J++) np.src_map[J] = J;
         np.out_split = 1;
+        np.hoisted_jobs = jobs[z0].D ? 1 : 0;
         launch_ntt(e, NTT_IN_GALOIS_REDUCE, false, np, dim3(L + 1, L, nz));
         // 2. S_c[I]
         // 2a. S_c[P] (special-prime limb only)

@@ -11,7 +11,8 @@
 #define PF_NTT_MAXMAP 17
 
 // NTT_IN_MODDOWN (FP64 kernels only): the input is u = INTT_P(S_c[P]); limb j transforms
-// W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j)  (pf_keyswitch.cuh step 3) computed on load
+// W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j)  (pf_keyswitch.cuh step 3), entered as the centred
+// representative of u mod P, which is congruent to it mod q_j
 enum { NTT_IN_PLAIN = 0, NTT_IN_REDUCE = 1, NTT_IN_LIFT = 2, NTT_IN_GALOIS_REDUCE = 3, NTT_IN_MODDOWN = 4 };
 // epilogues fused into the transforms of the key-switch mod-down (pf_keyswitch.cuh steps 3 and 4)
 enum { NTT_OUT_PLAIN = 0, NTT_OUT_KS = 1, NTT_OUT_MODSWITCH = 2 };
@@ -37,6 +38,8 @@ struct NttParams {
     int ks_L;
     u64 ks_p_half;               // also NTT_IN_MODDOWN: floor(P/2)
     int md_pmod;                 // NTT_IN_MODDOWN: index of the special prime in mods
+    int hoisted_jobs;            // NTT_IN_GALOIS_REDUCE: host hint, the jobs carry hoisted digits (RotJob.D)
+    int njobs, job_group;        // NTT_IN_GALOIS_REDUCE (FP64 kernels): CTA z covers jobs [z*job_group, ...) < njobs
     // NTT_OUT_MODSWITCH (inverse, grid (kept limb j, poly, result)): the dropped limbs [ms_Lr, ms_L) are
     // already in coefficient form at ms_dropped + z*ms_dropped_sz + poly*(ms_L-ms_Lr)*N + (c-ms_Lr)*N
     const u64 *ms_dropped;

@@ -164,8 +164,8 @@ __device__ __forceinline__ void fp_inv_pass(const double *__restrict__ itw, doub
 // 32 cache lines per instruction; ncu: 682 L1 wavefronts per warp per transform, half the kernel's LSU
 // traffic); lane-major makes every load one 256-byte run (62 wavefronts).
 // p.tw_fp: [nmod][2][N] doubles (centred twiddles); p.fp_consts: [nmod] {q, 1/q, centred N^-1, centred irp[1]*N^-1}
-template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
-__global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_fp_kernel(const NttParams p) {
+template <int LOGN, int INMODE, int OUTMODE>
+__device__ __forceinline__ void ntt_fwd_fp_body(const NttParams &p, const unsigned bz) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) double smd[];
     const int mi = p.mod_map[blockIdx.x];
@@ -173,31 +173,27 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     const double *tw = p.tw_fp + (size_t)mi * 2 * Cfg::N;
     const double *twl = p.tw_fp_lane + (size_t)mi * 2 * Cfg::N;
     const u64 *in = (INMODE == NTT_IN_GALOIS_REDUCE)
-                        ? p.jobs[blockIdx.z].c1_coef + blockIdx.y * p.in_sy
-                        : p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
-    u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
+                        ? p.jobs[bz].c1_coef + blockIdx.y * p.in_sy
+                        : p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + bz * p.in_sz;
+    u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + bz * p.out_sz;
     const double q = m.fq, qinv = m.fqinv;
-    const u32 gal_einv = (INMODE == NTT_IN_GALOIS_REDUCE) ? p.jobs[blockIdx.z].einv : 0u;
-    if (INMODE == NTT_IN_GALOIS_REDUCE) {
-        const RotJob &jb = p.jobs[blockIdx.z];
-        if (jb.D && !*jb.flag) return;
-    }
+    const u32 gal_einv = (INMODE == NTT_IN_GALOIS_REDUCE) ? p.jobs[bz].einv : 0u;
     constexpr bool MIDRED = LOGN >= 14; // keep magnitudes below 2^52 for 49-bit primes
-    u64 md_P = 0, md_Pratio = 0;
-    if (INMODE == NTT_IN_MODDOWN) {
-        md_P = p.mods[p.md_pmod].q;
-        md_Pratio = p.mods[p.md_pmod].ratio1;
-    }
+    const double md_P = (INMODE == NTT_IN_MODDOWN) ? p.mods[p.md_pmod].fq : 0.0;
+    bool saw_zero = false;
 
     auto gload = [&](int idx) -> double {
         if (INMODE == NTT_IN_PLAIN) return fp_from_u64(in[idx]);
         if (INMODE == NTT_IN_MODDOWN) {
-            const u64 v = barrett64(in[idx] + p.ks_p_half, md_P, md_Pratio);
-            return fp_from_u64(submod(barrett64(v, m.q, m.ratio1), m.p_half_mod, m.q));
+            // W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j) is congruent mod q_j to the centred
+            // representative of u mod P, and the transform takes any representative below 2^52: the
+            // canonical output is the same, no Barrett reduction is needed on the way in
+            const u64 u = in[idx];
+            return u > p.ks_p_half ? __dadd_rn(fp_from_u64(u), -md_P) : fp_from_u64(u);
         }
         if (INMODE == NTT_IN_REDUCE) {
             const u64 x = in[idx];
-            if (x == 0 && p.zero_flags) p.zero_flags[blockIdx.z] = 1;
+            saw_zero |= (x == 0); // one flag store after the pass: a store per element serialises the loads
             return fp_reduce(fp_from_u64(x), q, qinv);
         }
         if (INMODE == NTT_IN_LIFT) {
@@ -219,6 +215,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     auto sstore = [&](int idx, double x) { smd[sm_phys(idx)] = x; };
 
     fp_fwd_pass<LOGN, Cfg::K1, LOGN - 1>(tw, q, qinv, gload, sstore);
+    if (INMODE == NTT_IN_REDUCE && saw_zero && p.zero_flags) p.zero_flags[bz] = 1;
     __syncthreads();
     fp_fwd_pass<LOGN, Cfg::K2, 8>(tw, q, qinv, sload, sstore);
     __syncthreads();
@@ -232,8 +229,8 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     __syncthreads();
     if (OUTMODE == NTT_OUT_KS) {
         const int j = blockIdx.x, c = blockIdx.y, L = p.ks_L;
-        const RotJob job = p.jobs[blockIdx.z];
-        const u64 *S = p.ks_S + ((size_t)blockIdx.z * 2 + c) * (L + 1) * Cfg::N + (size_t)j * Cfg::N;
+        const RotJob job = p.jobs[bz];
+        const u64 *S = p.ks_S + ((size_t)bz * 2 + c) * (L + 1) * Cfg::N + (size_t)j * Cfg::N;
         u64 *o = job.out + ((size_t)c * L + j) * Cfg::N;
         const u64 pinv = m.p_inv, pinv_sh = m.p_inv_sh, qi = m.q;
 #pragma unroll 8
@@ -252,6 +249,36 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         const int idx = i * Cfg::NT + threadIdx.x;
         out[idx] = smu[sm_phys(idx)];
     }
+}
+
+// NTT_IN_GALOIS_REDUCE computes the exact per-rotation digits, needed only by jobs whose ciphertext has a
+// zero coefficient in c1 (pf_keyswitch.cuh): CTA z looks at jobs [z*G, z*G+G) (G = p.job_group <= 32) and
+// transforms the flagged ones, so the usual case costs one flag read per 32 jobs instead of one CTA per job.
+template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
+__global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_fp_kernel(const NttParams p) {
+    if (INMODE == NTT_IN_GALOIS_REDUCE) {
+        __shared__ unsigned need;
+        if (threadIdx.x < 32) {
+            const unsigned j = blockIdx.z * p.job_group + threadIdx.x;
+            bool n = false;
+            if ((int)threadIdx.x < p.job_group && j < (unsigned)p.njobs) {
+                const RotJob &jb = p.jobs[j];
+                n = !(jb.D && !*jb.flag);
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, n);
+            if (threadIdx.x == 0) need = mask;
+        }
+        __syncthreads();
+        unsigned mask = need;
+        while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            ntt_fwd_fp_body<LOGN, INMODE, OUTMODE>(p, blockIdx.z * p.job_group + b);
+            __syncthreads();
+        }
+        return;
+    }
+    ntt_fwd_fp_body<LOGN, INMODE, OUTMODE>(p, blockIdx.z);
 }
 
 // SEAL mod_switch_to_inplace folded into the store of a kept limb j: x is the canonical coefficient of
