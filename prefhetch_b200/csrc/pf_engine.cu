@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -50,6 +51,14 @@ struct DevBuf {
         cudaError_t e = cudaMalloc(&p, n);
         if (e == cudaSuccess) bytes = n;
         return e;
+    }
+    // per-step scratch whose size follows the batch (pairs, jobs): grow with 25 % headroom, so that a
+    // step slightly larger than every step before it does not pay cudaFree (a device-wide
+    // synchronisation) + cudaMalloc of hundreds of MB in the middle of a serving loop (measured: one
+    // such reallocation stalled the host for 170-670 ms)
+    cudaError_t ensure_grow(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        return ensure(n + n / 4 + ((size_t)1 << 20));
     }
     template <class T>
     T *as() const {
@@ -193,13 +202,35 @@ namespace {
                            __LINE__);                                                                    \
     } while (0)
 
-struct HostTick { // PF_DEBUG_HOST=1: host-side time of the sections of a search call
+// PF_DEBUG_HOST=1: host-side time of every section of a search call, printed as it happens;
+// PF_DEBUG_HOST=2: per-section totals (count, sum, max), printed when the process exits.
+struct HostTickTotals {
+    std::mutex mu;
+    std::map<std::string, std::array<double, 3>> t;
+    ~HostTickTotals() {
+        for (auto &kv : t)
+            fprintf(stderr, "[pf host total] %-18s n=%6.0f sum=%10.1f us avg=%8.1f us max=%9.1f us\n", kv.first.c_str(), kv.second[0],
+                    kv.second[1], kv.second[1] / std::max(1.0, kv.second[0]), kv.second[2]);
+    }
+};
+static HostTickTotals g_tick_totals;
+struct HostTick {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     const char *what;
     explicit HostTick(const char *w) : what(w) {}
     ~HostTick() {
-        static const bool on = getenv("PF_DEBUG_HOST") != nullptr;
-        if (on) fprintf(stderr, "[pf host] %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+        static const int mode = getenv("PF_DEBUG_HOST") ? std::max(1, atoi(getenv("PF_DEBUG_HOST"))) : 0;
+        if (!mode) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        if (mode == 1) {
+            fprintf(stderr, "[pf host] %-18s %8.1f us\n", what, us);
+        } else {
+            std::lock_guard<std::mutex> lk(g_tick_totals.mu);
+            auto &a = g_tick_totals.t[what];
+            a[0] += 1;
+            a[1] += us;
+            a[2] = std::max(a[2], us);
+        }
     }
 };
 
@@ -567,7 +598,7 @@ int set_galois_key_words(pf_engine *e, u32 elt, const u64 *words, bool device_sr
     // hoisting term: M[I] = NTT_I(negation mask of sigma), KM_c[I] = M[I] (.) sum_J (q_J mod q_I) key_J[c][I]
     const int L = e->L, k = e->k;
     CK(gk.km.ensure((size_t)2 * (L + 1) * N * 8));
-    CK(e->s_tmp.ensure((size_t)(L + 2) * N * 8));
+    CK(e->s_tmp.ensure_grow((size_t)(L + 2) * N * 8));
     u64 *mask = e->s_tmp.as<u64>(), *M = mask + N;
     galois_negmask_kernel<<<N / 256, 256, 0, e->stream>>>(mask, gk.einv, (int)N);
     e->launches++;
@@ -609,12 +640,12 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
     static const size_t env_zb = getenv("PF_KS_BATCH") ? (size_t)atoi(getenv("PF_KS_BATCH")) : 0;
     const size_t zmax = env_zb ? env_zb
                                : std::max<size_t>(1, std::min<size_t>(2048, ((size_t)3 << 30) / ((per_d + per_S + per_W) * 8)));
-    CK(e->s_rotjobs.ensure(jobs.size() * sizeof(RotJob)));
+    CK(e->s_rotjobs.ensure_grow(jobs.size() * sizeof(RotJob)));
     CK(upload_async(e, e->s_rotjobs.p, jobs.data(), jobs.size() * sizeof(RotJob)));
     const size_t zb = std::min(zmax, jobs.size());
-    CK(e->s_ks_d.ensure(zb * per_d * 8));
-    CK(e->s_ks_S.ensure(zb * per_S * 8));
-    CK(e->s_ks_W.ensure(zb * per_W * 8));
+    CK(e->s_ks_d.ensure_grow(zb * per_d * 8));
+    CK(e->s_ks_S.ensure_grow(zb * per_S * 8));
+    CK(e->s_ks_W.ensure_grow(zb * per_W * 8));
     KsParams kp{};
     kp.mods = e->d_mods.as<DevModulus>();
     kp.d = e->s_ks_d.as<u64>();
@@ -709,8 +740,8 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
 int hoist_digits(pf_engine *e, const u64 *d_cts, size_t ncts, size_t ct_stride) {
     const int L = e->L, N = e->N, k = e->k;
     const size_t per_d = (size_t)L * (L + 1) * N;
-    CK(e->s_hoistD.ensure(ncts * per_d * 8));
-    CK(e->s_flags.ensure(std::max<size_t>(4, ncts * sizeof(int))));
+    CK(e->s_hoistD.ensure_grow(ncts * per_d * 8));
+    CK(e->s_flags.ensure_grow(std::max<size_t>(4, ncts * sizeof(int))));
     CK(cudaMemsetAsync(e->s_flags.p, 0, ncts * sizeof(int), e->stream));
     for (size_t off = 0; off < ncts; off += 16384) {
         const size_t cnt = std::min<size_t>(16384, ncts - off);
@@ -768,7 +799,7 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
     u64 *ntt_dst = rot;
     size_t dst_stride = R * ctw;
     if (side_copy) {
-        CK(e->s_cqntt.ensure(nq * m * ctw * 8));
+        CK(e->s_cqntt.ensure_grow(nq * m * ctw * 8));
         ntt_dst = e->s_cqntt.as<u64>();
         dst_stride = ctw;
     }
@@ -831,7 +862,7 @@ int build_rotated_sets(pf_engine *e, const u64 *d_cts, size_t nq, u64 *rot, int 
     }
     // chain: rot_r = rotate(rot_{r-1}, 1); needs c1 of the previous member in coefficient form
     const GaloisKey *gk = find_key(e, 1);
-    CK(e->s_c1coef.ensure(nq * m * (size_t)L * N * 8));
+    CK(e->s_c1coef.ensure_grow(nq * m * (size_t)L * N * 8));
     u64 *c1c = e->s_c1coef.as<u64>();
     for (size_t r = 1; r < R; r++) {
         jobs.clear();
@@ -1002,11 +1033,11 @@ int plan_pairs(pf_engine *e, uint64_t nq, const int64_t *idx, uint32_t nprobe, P
 int upload_plan(pf_engine *e, const PairPlan &pl) {
     const size_t P = pl.pair_block.size();
     if (!P) return PF_OK;
-    CK(e->s_chunks.ensure(pl.chunks.size() * sizeof(MacChunk)));
-    CK(e->s_pairblock.ensure(P * sizeof(long long)));
+    CK(e->s_chunks.ensure_grow(pl.chunks.size() * sizeof(MacChunk)));
+    CK(e->s_pairblock.ensure_grow(P * sizeof(long long)));
     CK(upload_async(e, e->s_chunks.p, pl.chunks.data(), pl.chunks.size() * sizeof(MacChunk)));
     CK(upload_async(e, e->s_pairblock.p, pl.pair_block.data(), P * sizeof(long long)));
-    CK(e->s_pairout.ensure(P * sizeof(int)));
+    CK(e->s_pairout.ensure_grow(P * sizeof(int)));
     CK(upload_async(e, e->s_pairout.p, pl.pair_out.data(), P * sizeof(int)));
     return PF_OK;
 }
@@ -1017,7 +1048,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
                 size_t out_stride) {
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N;
-    CK(e->s_rot.ensure(nq * e->K * ctw * 8));
+    CK(e->s_rot.ensure_grow(nq * e->K * ctw * 8));
     u64 *rot = e->s_rot.as<u64>();
     int rc;
     {
@@ -1040,7 +1071,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     u64 *full = d_out;
     size_t full_stride = out_stride, full_base = p0;
     if (ms) {
-        CK(e->s_full.ensure(P * ctw * 8));
+        CK(e->s_full.ensure_grow(P * ctw * 8));
         full = e->s_full.as<u64>();
         full_stride = ctw;
         full_base = 0;
@@ -1076,7 +1107,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
         // INTT + modswitch_kernel_t (register pressure in the 32-point pass); kept behind PF_FUSED_MS
         static const bool want_fused = getenv("PF_FUSED_MS") != nullptr;
         const bool fused_ms = want_fused && ms && e->ntt_fp && nd <= 4;
-        if (fused_ms) CK(e->s_dropped.ensure(P * (size_t)2 * nd * N * 8));
+        if (fused_ms) CK(e->s_dropped.ensure_grow(P * (size_t)2 * nd * N * 8));
         for (size_t off = 0; off < P; off += 32768) {
             const unsigned cnt = (unsigned)std::min<size_t>(32768, P - off);
             NttParams ip{};
@@ -1531,7 +1562,7 @@ int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const in
     }
     // uint8 copy for the encoder; rejects non-integer / out-of-range values
     CK(e->d_base_u8.ensure(std::max<size_t>(4, ntotal * d)));
-    CK(e->s_tmp.ensure(sizeof(int)));
+    CK(e->s_tmp.ensure_grow(sizeof(int)));
     CK(cudaMemsetAsync(e->s_tmp.p, 0, sizeof(int), e->stream));
     if (ntotal) {
         const size_t n = ntotal * d;
@@ -1574,8 +1605,8 @@ int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const in
     // encode in batches of zb blocks
     const size_t plain_words = (size_t)(e->K + 1) * N;
     const size_t zb = std::max<size_t>(1, std::min<size_t>(nb ? nb : 1, ((size_t)256 << 20) / (plain_words * 8)));
-    CK(e->s_plain.ensure(zb * plain_words * 8));
-    CK(e->s_encblocks.ensure(std::max<size_t>(1, nb) * sizeof(EncodeBlock)));
+    CK(e->s_plain.ensure_grow(zb * plain_words * 8));
+    CK(e->s_encblocks.ensure_grow(std::max<size_t>(1, nb) * sizeof(EncodeBlock)));
     {
         std::vector<EncodeBlock> eb(nb);
         for (size_t b = 0; b < nb; b++) eb[b] = EncodeBlock{e->blocks[b].vec_offset, e->blocks[b].nvec, 0};
@@ -1690,11 +1721,11 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
     // quantized while the encrypted pipeline of the current batch still occupies the engine stream.
     cudaStream_t cs = e->coarse_stream;
     PhaseTimer pt(e, PF_T_COARSE, cs);
-    CK(e->s_cx.ensure(nq * d * sizeof(float)));
-    CK(e->s_dist.ensure(nq * (size_t)nlist * sizeof(float)));
-    CK(e->s_keys.ensure(nq * (size_t)nlist * sizeof(u64)));
-    CK(e->s_idx.ensure(nq * nprobe * sizeof(long long)));
-    CK(e->s_outdist.ensure(nq * nprobe * sizeof(float)));
+    CK(e->s_cx.ensure_grow(nq * d * sizeof(float)));
+    CK(e->s_dist.ensure_grow(nq * (size_t)nlist * sizeof(float)));
+    CK(e->s_keys.ensure_grow(nq * (size_t)nlist * sizeof(u64)));
+    CK(e->s_idx.ensure_grow(nq * nprobe * sizeof(long long)));
+    CK(e->s_outdist.ensure_grow(nq * nprobe * sizeof(float)));
     CK(cudaMemcpyAsync(e->s_cx.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, cs));
     for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
         const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
@@ -1737,10 +1768,10 @@ int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64
     if (w > cap || (w && (!dist || !labels))) return e->fail(PF_ERR_CAPACITY, "output needs %llu entries, capacity %llu", (unsigned long long)w, (unsigned long long)cap);
     if (!w) return PF_OK;
     const u32 d = e->d;
-    CK(e->s_x.ensure(nq * d * sizeof(float)));
-    CK(e->s_jobs.ensure(jobs.size() * sizeof(ListJob)));
-    CK(e->s_pl_dist.ensure(w * sizeof(float)));
-    CK(e->s_pl_labels.ensure(w * sizeof(long long)));
+    CK(e->s_x.ensure_grow(nq * d * sizeof(float)));
+    CK(e->s_jobs.ensure_grow(jobs.size() * sizeof(ListJob)));
+    CK(e->s_pl_dist.ensure_grow(w * sizeof(float)));
+    CK(e->s_pl_labels.ensure_grow(w * sizeof(long long)));
     CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->s_jobs.p, jobs.data(), jobs.size() * sizeof(ListJob), cudaMemcpyHostToDevice, e->stream));
     list_l2_kernel<<<(unsigned)jobs.size(), 128, d * sizeof(float), e->stream>>>(
@@ -1761,9 +1792,9 @@ int pf_precise_search(pf_engine *e, uint64_t nq, const float *x, const int64_t *
     if (!nq || !nids) return PF_OK;
     CK(cudaSetDevice(e->prm.device));
     const u32 d = e->d;
-    CK(e->s_x.ensure(nq * d * sizeof(float)));
-    CK(e->s_ids.ensure(nq * nids * sizeof(long long)));
-    CK(e->s_pl_dist.ensure(nq * nids * sizeof(float)));
+    CK(e->s_x.ensure_grow(nq * d * sizeof(float)));
+    CK(e->s_ids.ensure_grow(nq * nids * sizeof(long long)));
+    CK(e->s_pl_dist.ensure_grow(nq * nids * sizeof(float)));
     CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->s_ids.p, ids, nq * nids * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
     precise_l2_kernel<<<dim3((nids + 127) / 128, (unsigned)nq), 128, d * sizeof(float), e->stream>>>(
@@ -1916,7 +1947,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     if (P > max_results || P * slot > out_cap || (labels && nlabels > label_cap))
         return e->fail(PF_ERR_CAPACITY, "need %llu results / %llu bytes / %llu labels", (unsigned long long)P, (unsigned long long)(P * slot), (unsigned long long)nlabels);
     // parse + upload the query ciphertexts
-    CK(e->s_qcts.ensure(std::max<size_t>(8, ncts * ctw * 8)));
+    CK(e->s_qcts.ensure_grow(std::max<size_t>(8, ncts * ctw * 8)));
     uint64_t parms_id[4] = {0, 0, 0, 0};
     std::vector<const uint8_t *> ct_src(ncts);
     std::vector<std::vector<uint8_t>> inflated; // zlib-compressed queries (slow path: inflated on the host)
@@ -1956,7 +1987,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
                                cudaMemcpyHostToDevice, e->upload_stream));
         CK(cudaEventRecord(e->ev_up[gi], e->upload_stream));
     }
-    CK(e->s_out.ensure(std::max<size_t>(8, P * slot)));
+    CK(e->s_out.ensure_grow(std::max<size_t>(8, P * slot)));
     uint8_t *d_blob = e->s_out.as<uint8_t>();
     u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
     rc = arena_begin(e);
@@ -2012,7 +2043,7 @@ static int ntt_host(pf_engine *e, uint64_t *polys, uint64_t npoly, const int32_t
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     const size_t N = e->N;
-    CK(e->s_tmp.ensure(std::max<size_t>(8, npoly * N * 8)));
+    CK(e->s_tmp.ensure_grow(std::max<size_t>(8, npoly * N * 8)));
     CK(cudaMemcpyAsync(e->s_tmp.p, polys, npoly * N * 8, cudaMemcpyHostToDevice, e->stream));
     for (uint64_t i = 0; i < npoly; i++) {
         const int li = limb[i] < 0 ? e->k : limb[i];
@@ -2036,7 +2067,7 @@ static int ct_ntt_host(pf_engine *e, uint64_t *cts, uint64_t ncts, bool inverse)
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     const size_t ctw = (size_t)2 * e->L * e->N;
-    CK(e->s_tmp.ensure(std::max<size_t>(8, ncts * ctw * 8)));
+    CK(e->s_tmp.ensure_grow(std::max<size_t>(8, ncts * ctw * 8)));
     CK(cudaMemcpyAsync(e->s_tmp.p, cts, ncts * ctw * 8, cudaMemcpyHostToDevice, e->stream));
     ntt_limbs(e, e->s_tmp.as<u64>(), e->s_tmp.as<u64>(), 2 * ncts, inverse);
     CK(cudaMemcpyAsync(cts, e->s_tmp.p, ncts * ctw * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -2102,7 +2133,7 @@ int pf_ct_add(pf_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *out)
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     const size_t ctw = (size_t)2 * e->L * e->N;
-    CK(e->s_tmp.ensure(3 * ctw * 8));
+    CK(e->s_tmp.ensure_grow(3 * ctw * 8));
     u64 *da = e->s_tmp.as<u64>(), *db = da + ctw, *dc = db + ctw;
     CK(cudaMemcpyAsync(da, a, ctw * 8, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(db, b, ctw * 8, cudaMemcpyHostToDevice, e->stream));
@@ -2122,7 +2153,7 @@ int pf_rotate_rows(pf_engine *e, const uint64_t *ct, int step, uint64_t *out) {
     if (!gk) return e->fail(PF_ERR_STATE, "no Galois key for step %d", step);
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N;
-    CK(e->s_tmp.ensure(3 * ctw * 8));
+    CK(e->s_tmp.ensure_grow(3 * ctw * 8));
     u64 *din = e->s_tmp.as<u64>(), *dntt = din + ctw, *dout = dntt + ctw;
     CK(cudaMemcpyAsync(din, ct, ctw * 8, cudaMemcpyHostToDevice, e->stream));
     ntt_limbs(e, din, dntt, 2, false);
@@ -2152,8 +2183,8 @@ int pf_rotate_query_set(pf_engine *e, const uint64_t *cts, int chain, uint64_t *
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     const size_t ctw = (size_t)2 * e->L * e->N;
-    CK(e->s_qcts.ensure(e->m * ctw * 8));
-    CK(e->s_rot.ensure(e->K * ctw * 8));
+    CK(e->s_qcts.ensure_grow(e->m * ctw * 8));
+    CK(e->s_rot.ensure_grow(e->K * ctw * 8));
     CK(cudaMemcpyAsync(e->s_qcts.p, cts, e->m * ctw * 8, cudaMemcpyHostToDevice, e->stream));
     int rc = build_rotated_sets(e, e->s_qcts.as<u64>(), 1, e->s_rot.as<u64>(), chain, true);
     if (rc) return rc;
@@ -2168,7 +2199,7 @@ int pf_batch_encode(pf_engine *e, const uint64_t *values, uint64_t *plain) {
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->prm.device));
     const size_t N = e->N;
-    CK(e->s_tmp.ensure(2 * N * 8));
+    CK(e->s_tmp.ensure_grow(2 * N * 8));
     u64 *dv = e->s_tmp.as<u64>(), *dp = dv + N;
     CK(cudaMemcpyAsync(dv, values, N * 8, cudaMemcpyHostToDevice, e->stream));
     slot_scatter_kernel<<<(unsigned)(N / 256), 256, 0, e->stream>>>(dv, e->d_inv_index_map.as<u32>(), dp);

@@ -50,8 +50,9 @@ struct KsParams {
 template <int LT, bool FINISH, bool FPRED>
 __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
     const int L = p.L, N = p.N;
+    const int kk = p.k;
     const int I = FINISH ? (int)blockIdx.y : L;
-    const int ki = (I == L) ? p.k - 1 : I;
+    const int ki = (I == L) ? kk - 1 : I;
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
     const int sh = (int)m.split_shift;
@@ -71,9 +72,9 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
 #pragma unroll
             for (int J = 0; J < LT; J++) {
                 if (J < L) {
-                    const u64 *kj = job.key + (size_t)J * 2 * p.k * N;
+                    const u64 *kj = job.key + (size_t)J * 2 * kk * N;
                     k0[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
-                    k1[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(p.k + ki) * N) + c2);
+                    k1[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(kk + ki) * N) + c2);
                 }
             }
         }
