@@ -1731,9 +1731,17 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
         const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
         coarse_dist_kernel<<<dim3((nlist + 127) / 128, nqb), 128, d * sizeof(float), cs>>>(
             e->s_cx.as<float>() + q0 * d, e->d_centroids.as<float>(), e->s_dist.as<float>() + q0 * nlist, nlist, (int)d);
-        topk_select_kernel<<<nqb, 256, 0, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
-                                                 e->s_idx.as<long long>() + q0 * nprobe,
-                                                 e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
+        int M = 1;
+        while (M < (int)nprobe) M <<= 1;
+        const bool old_topk = getenv("PF_TOPK_ITER") != nullptr; // per call: tests flip it
+        if (M <= 4096 && !old_topk) // radix select + bitonic sort of the selected keys in shared memory
+            topk_radix_kernel<<<nqb, 256, (size_t)M * 8, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
+                                                              e->s_idx.as<long long>() + q0 * nprobe,
+                                                              e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe, M);
+        else
+            topk_select_kernel<<<nqb, 256, 0, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
+                                                     e->s_idx.as<long long>() + q0 * nprobe,
+                                                     e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
         e->launches += 2;
     }
     CK(cudaMemcpyAsync(out_idx, e->s_idx.p, nq * nprobe * sizeof(long long), cudaMemcpyDeviceToHost, cs));

@@ -285,6 +285,30 @@ def test_encrypted_search_end_to_end(pf, oracle, n, g, chain, world, rl):
     eng.close()
 
 
+@pytest.mark.parametrize("old", [False, True])
+def test_coarse_quantize_large_nlist(pf, oracle, old, monkeypatch):
+    """stage 1 at nlist / nprobe sizes of the multi-GPU configs (radix-select top-k and the iterative
+    kernel): same probed lists, same order, same float distances as the reference arithmetic."""
+    if old:
+        monkeypatch.setenv("PF_TOPK_ITER", "1")
+    rng = np.random.default_rng(77)
+    nlist, d = 1500, 128
+    cent = rng.integers(0, 200, size=(nlist, d)).astype(np.float32)
+    cent[700] = cent[3]          # ties
+    cent[1499] = cent[3]
+    query = np.concatenate([rng.integers(0, 200, size=(5, d)), cent[3:4], cent[900:901]]).astype(np.float32)
+    offsets = np.arange(nlist + 1, dtype=np.int64)
+    ids = np.arange(nlist, dtype=np.int64)
+    eng, _, _ = _engine(pf, 2048)
+    eng.load_index(cent, offsets, ids, cent.copy())
+    for nprobe in (1, 100, 257, 1500) if not old else (100,):
+        idx, dist = eng.coarse_quantize(query, nprobe, return_dist=True)
+        oidx, odist = oracle.coarse_quantize(query, cent, nprobe)
+        assert np.array_equal(idx, oidx)
+        assert np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
+    eng.close()
+
+
 def _parms_id_py(n, primes, t):
     import hashlib
     import struct
