@@ -127,6 +127,7 @@ struct pf_engine {
     DevBuf d_mods; // DevModulus[k+1] (index k = plain modulus)
     DevBuf d_tw;   // Twiddle[k+1][2][N]
     DevBuf d_tw_fp; // double[k+1][2][N] centred twiddles
+    DevBuf d_mstab_fp; // double[MS_MAXL][MS_MAXL][2] mod-switch constants for the FP64 kernel
     DevBuf d_tw_fp_lane; // double[k+1][2][N] lane-major copies for the pass over bits [4..0]
     bool ntt_fp = false; // FP64-pipe NTT kernels eligible (pf_ntt_fp.cuh)
     DevBuf d_inv_index_map;
@@ -546,6 +547,15 @@ int build_tables(pf_engine *e) {
             }
         CK(e->d_mstab.ensure(tab.size() * 8));
         CK(cudaMemcpy(e->d_mstab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+        std::vector<double> tabf((size_t)MS_MAXL * MS_MAXL * 2, 0.0); // the same constants for modswitch_fp_kernel_t
+        for (int c = 1; c < L; c++)
+            for (int j = 0; j < c; j++) {
+                const u64 *t = tab.data() + ((size_t)c * MS_MAXL + j) * 3;
+                tabf[((size_t)c * MS_MAXL + j) * 2] = (double)t[0];
+                tabf[((size_t)c * MS_MAXL + j) * 2 + 1] = centred(t[1], e->h_q[j]);
+            }
+        CK(e->d_mstab_fp.ensure(tabf.size() * 8));
+        CK(cudaMemcpy(e->d_mstab_fp.p, tabf.data(), tabf.size() * 8, cudaMemcpyHostToDevice));
     }
     // special prime constants
     const u64 P = e->h_q[k - 1];
@@ -1123,9 +1133,15 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
                     u64 *dst = d_out + (p0 + off) * out_stride;
                     const DevModulus *dm = e->d_mods.as<DevModulus>();
                     const u64 *tab = e->d_mstab.as<u64>();
+                    const double *tabf = e->d_mstab_fp.as<double>();
                     const dim3 g2(N / 512, 2, cnt);
-#define MS_CASE(LL, RR)                                                                                        \
-    else if (L == LL && e->Lr == RR) modswitch_kernel_t<LL, RR><<<g2, 256, 0, e->stream>>>(src, full_stride, dst, \
+                    // primes <= 49 bits: the FP64-pipe kernel (pf_ntt_fp.cuh); otherwise the integer one
+                    static const bool ms_int = getenv("PF_MS_INT") != nullptr;
+                    const bool ms_fp = e->max_prime_bits <= 49 && !ms_int;
+#define MS_CASE(LL, RR)                                                                                            \
+    else if (L == LL && e->Lr == RR && ms_fp) modswitch_fp_kernel_t<LL, RR><<<g2, 256, 0, e->stream>>>(src, full_stride, dst, \
+                                                                                                      out_stride, dm, tabf, N); \
+    else if (L == LL && e->Lr == RR) modswitch_kernel_t<LL, RR><<<g2, 256, 0, e->stream>>>(src, full_stride, dst,     \
                                                                                           out_stride, dm, tab, N)
                     if (false) {
                     }

@@ -22,6 +22,7 @@
 //   sets use the integer kernels.  A final reduce + one conditional +q stores the canonical residue,
 //   identical to the integer kernels'.
 #pragma once
+#include "pf_keyswitch.cuh"
 #include "pf_ntt.cuh"
 
 #define PF_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
@@ -346,4 +347,51 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
     fp_inv_pass<LOGN, Cfg::K2, 5, false>(itw, q, qinv, m.fninv, m.flast_w, sload, sstore);
     __syncthreads();
     fp_inv_pass<LOGN, Cfg::K1, 9, true>(itw, q, qinv, m.fninv, m.flast_w, sload, gstore);
+}
+
+// ---- result mod-switch on the FP64 pipe -------------------------------------------------------------
+// Same arithmetic as modswitch_kernel_t (pf_keyswitch.cuh; SEAL divide_and_round_q_last per dropped limb),
+// with every residue held as an exact integer in a double: dropping limb c,
+//   last = (x_c + (q_c >> 1)) mod q_c  (canonical),   x_j <- (x_j - last + ((q_c >> 1) mod q_j)) * q_c^{-1}  mod q_j
+// needs no reduction of `last` modulo q_j (|x_j - last + h| < 3 * 2^49 is fine for fp_mulmod) and no
+// 64x64 high products: 8 FP64 operations per step instead of ~35 integer ones.  The integer kernel was
+// IMAD-pipe bound (0.31 ms for the 1100 results of a step); this one is bound by its 0.7 GB of traffic.
+// Valid for primes <= 49 bits (every BFVDefault set); tabf[(c*MS_MAXL + j)*2] = {(q_c>>1) mod q_j, centred q_c^{-1} mod q_j}.
+// grid (N/512, 2, results), two coefficients per thread.
+template <int L, int LR>
+__global__ void __launch_bounds__(256) modswitch_fp_kernel_t(const u64 *in, size_t in_stride, u64 *out, size_t out_stride,
+                                                             const DevModulus *mods, const double *tabf, int N) {
+    const int i2 = blockIdx.x * 256 + threadIdx.x, p = blockIdx.y;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(in + (size_t)blockIdx.z * in_stride + (size_t)p * L * N) + i2;
+    double x0[L], x1[L], q[L], qinv[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        const ulonglong2 v = src[(size_t)j * (N / 2)];
+        x0[j] = fp_from_u64(v.x);
+        x1[j] = fp_from_u64(v.y);
+        q[j] = mods[j].fq;
+        qinv[j] = mods[j].fqinv;
+    }
+#pragma unroll
+    for (int c = L - 1; c >= LR; c--) {
+        const double half = (q[c] - 1.0) * 0.5; // q_c >> 1 (q_c is odd)
+        double l0 = fp_reduce(__dadd_rn(x0[c], half), q[c], qinv[c]);
+        double l1 = fp_reduce(__dadd_rn(x1[c], half), q[c], qinv[c]);
+        l0 = l0 < 0.0 ? __dadd_rn(l0, q[c]) : l0;
+        l1 = l1 < 0.0 ? __dadd_rn(l1, q[c]) : l1;
+#pragma unroll
+        for (int j = 0; j < c; j++) {
+            const double hm = tabf[((size_t)c * MS_MAXL + j) * 2], w = tabf[((size_t)c * MS_MAXL + j) * 2 + 1];
+            x0[j] = fp_mulmod(__dadd_rn(__dadd_rn(x0[j], -l0), hm), w, q[j], qinv[j]);
+            x1[j] = fp_mulmod(__dadd_rn(__dadd_rn(x1[j], -l1), hm), w, q[j], qinv[j]);
+        }
+    }
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(out + (size_t)blockIdx.z * out_stride + (size_t)p * LR * N) + i2;
+#pragma unroll
+    for (int j = 0; j < LR; j++) {
+        ulonglong2 r;
+        r.x = fp_canonical(x0[j], q[j], qinv[j]);
+        r.y = fp_canonical(x1[j], q[j], qinv[j]);
+        dst[(size_t)j * (N / 2)] = r;
+    }
 }
