@@ -624,11 +624,12 @@ def main():
     alg_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * blocks_distinct + 2.0 * pairs) / args.steps  # rank-local
     streamed_bytes = LN8 * (2.0 * K * nq * args.steps + (K + 1.0) * pairs + 2.0 * pairs) / args.steps
     achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
-    traffic = None
+    traffic, mac_name = None, "mac_kernel_occ" if K <= 16 else "mac_kernel"
     tf = ROOT / "profiles" / "mac_traffic.json"
     if tf.exists() and world == 1:   # dram__bytes_read+write per launch from the committed ncu --set full capture
-        traffic = json.loads(tf.read_text()).get(cfg_name, {}).get("traffic_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "mac_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        tj = json.loads(tf.read_text()).get(cfg_name, {})
+        traffic, mac_name = tj.get("traffic_bytes_per_launch"), tj.get("kernel", mac_name)
+    roofline = {"bound": "hbm", "kernel": mac_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg_bytes, "streamed_bytes_per_launch": streamed_bytes,
                 "streamed_gbs": streamed_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,

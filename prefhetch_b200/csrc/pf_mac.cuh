@@ -296,6 +296,38 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
     }
 }
 
+// Occupancy variant (PF_MAC_VARIANT=4): one block per lane at a time (12 accumulators instead of 24) so
+// that three CTAs fit an SM (<= 85 registers, 3 x 64 KiB of ciphertext slices): 24 warps instead of 16
+// to cover the load latency, at the price of reading the ciphertext slice from shared memory once per
+// block instead of once per two.  UNROLL4: four diagonals per load group.
+template <int T, int UNROLL, bool FPRED>
+__global__ void __launch_bounds__(256, 3) mac_kernel_occ(const MacParams p) {
+    constexpr int TX = T / 2, BY = 256 / TX;
+    extern __shared__ __align__(16) u64 smem_ct[]; // [K][2][T]
+    const MacChunk ch = p.chunks[blockIdx.x];
+    const int slices = p.N / T;
+    const int l = blockIdx.y / slices, s = blockIdx.y % slices;
+    const int tx = threadIdx.x % TX, by = threadIdx.x / TX;
+    const DevModulus m = p.mods[l];
+    const size_t LN = (size_t)p.L * p.N;
+    const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
+    const u64 pol = l2_evict_normal_policy();
+    {
+        const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
+        const int rows = p.K * 2;
+        for (int i = threadIdx.x; i < rows * TX; i += 256) {
+            const int row = i / TX, c = i % TX;
+            const ulonglong2 v = ldg_once(reinterpret_cast<const ulonglong2 *>(src + (size_t)row * LN) + c, pol);
+            reinterpret_cast<ulonglong2 *>(smem_ct)[(size_t)row * TX + c] = v;
+        }
+    }
+    __syncthreads();
+    const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(smem_ct) + tx;
+    const int split = (int)m.split_shift;
+    for (int pi = by; pi < ch.pair_count; pi += BY)
+        mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi, pol, pol);
+}
+
 // ---- cp.async variant -------------------------------------------------------------------------------
 // Same mapping as mac_kernel, but the plaintext words travel global -> shared with cp.async (LDGSTS)
 // into a per-thread private ring of NS stages (each stage = UNROLL k-rows x 2 blocks x 16 B), so the
