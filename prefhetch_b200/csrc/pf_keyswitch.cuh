@@ -47,8 +47,13 @@ struct KsParams {
 //                 directly, so S of the data limbs never touches memory.
 // FPRED: FP64-assisted reduction of the lazy sums (pf_mac.cuh lazy_reduce_fp; host enables it when
 //        bits(q) + ceil(log2 L) <= 50).  W and the rotated ciphertext are touched once: L2 evict-first.
+// LT <= 4: the key words of a thread live in its own shared-memory slots instead of 32 registers
+//          (no barrier: a thread reads back only what it wrote), which brings the kernel to 64
+//          registers and 4 CTAs/SM — it is bound by the latency of the digit gathers and W loads.
 template <int LT, bool FINISH, bool FPRED>
-__global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
+__global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
+    constexpr bool SMEMKEY = LT <= 4;
+    __shared__ ulonglong2 sk0[SMEMKEY ? LT : 1][SMEMKEY ? 256 : 1], sk1[SMEMKEY ? LT : 1][SMEMKEY ? 256 : 1];
     const int L = p.L, N = p.N;
     const int kk = p.k;
     const int I = FINISH ? (int)blockIdx.y : L;
@@ -59,7 +64,7 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
     const double qinv = m.fqinv;
     const u64 once = l2_evict_first_policy();
     const int z0 = blockIdx.z * KS_QT, z1 = min(z0 + KS_QT, njobs);
-    ulonglong2 k0[LT], k1[LT];
+    ulonglong2 k0[SMEMKEY ? 1 : LT], k1[SMEMKEY ? 1 : LT];
     const u64 *cur_key = nullptr;
     u32 px = 0, py = 0; // NTT-domain permutation of this thread's two coefficients: constant per key
     for (int z = z0; z < z1; z++) {
@@ -73,8 +78,15 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
             for (int J = 0; J < LT; J++) {
                 if (J < L) {
                     const u64 *kj = job.key + (size_t)J * 2 * kk * N;
-                    k0[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
-                    k1[J] = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(kk + ki) * N) + c2);
+                    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)ki * N) + c2);
+                    const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(kj + (size_t)(kk + ki) * N) + c2);
+                    if (SMEMKEY) {
+                        sk0[J][threadIdx.x] = a;
+                        sk1[J][threadIdx.x] = b;
+                    } else {
+                        k0[J] = a;
+                        k1[J] = b;
+                    }
                 }
             }
         }
@@ -97,8 +109,9 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 3 : (LT <= 8 ? 2 : 1))) ks_acc
                     dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
                 }
                 const SplitOp dx = make_op(dv.x), dy = make_op(dv.y);
-                const SplitOp k0x = make_op(k0[J].x), k0y = make_op(k0[J].y);
-                const SplitOp k1x = make_op(k1[J].x), k1y = make_op(k1[J].y);
+                const ulonglong2 ka = SMEMKEY ? sk0[J][threadIdx.x] : k0[J], kb = SMEMKEY ? sk1[J][threadIdx.x] : k1[J];
+                const SplitOp k0x = make_op(ka.x), k0y = make_op(ka.y);
+                const SplitOp k1x = make_op(kb.x), k1y = make_op(kb.y);
                 lazy_mac(a00, dx.x0, dx.x1, dx.xs, k0x.x0, k0x.x1, k0x.xs);
                 lazy_mac(a01, dy.x0, dy.x1, dy.xs, k0y.x0, k0y.x1, k0y.xs);
                 lazy_mac(a10, dx.x0, dx.x1, dx.xs, k1x.x0, k1x.x1, k1x.xs);
