@@ -911,15 +911,15 @@ void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     e->launches++;
 }
 
-template <int T, int UNROLL>
+template <int T, int UNROLL, int MINCTA = 3>
 void launch_mac_occ_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const size_t smem = (size_t)p.K * 2 * T * 8;
     if (e->mac_fpred) {
-        auto kern = mac_kernel_occ<T, UNROLL, true>;
+        auto kern = mac_kernel_occ<T, UNROLL, true, MINCTA>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
     } else {
-        auto kern = mac_kernel_occ<T, UNROLL, false>;
+        auto kern = mac_kernel_occ<T, UNROLL, false, MINCTA>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
     }
@@ -953,8 +953,9 @@ void launch_mac_tma_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
 
 // MAC variant: 0 = register-staged loads, two blocks per lane, 2 CTAs/SM (mac_kernel), 1 = cp.async ring
 // T=128, 2 = cp.async ring T=256, 3 = TMA bulk-copy producer/consumer ring (T=256), 4 / 5 = one block per
-// lane, 3 CTAs/SM (mac_kernel_occ, 2 / 4 diagonals per load group).  Default: 4 whenever three 256-
-// coefficient ciphertext slices fit an SM's shared memory (K <= 16), else 0.
+// lane, 3 CTAs/SM (mac_kernel_occ, 2 / 4 diagonals per load group), 6 = the same with 128-coefficient
+// slices, 64 registers and 4 CTAs/SM.  Default: 6 whenever the slices fit an SM's shared memory
+// (K <= 16), else 0.  Measured at K = 16: 1.005 / 0.89 / 0.835 ms for 0 / 4 / 6.
 int mac_variant(const pf_engine *e) {
     static const int env = [] {
         const char *v = getenv("PF_MAC_VARIANT");
@@ -962,13 +963,13 @@ int mac_variant(const pf_engine *e) {
     }();
     if (e->mac_wide || e->K < 4 || e->K > 32) return 0;
     const bool occ_fits = (size_t)e->K * 2 * 256 * 8 * 3 <= (size_t)227 * 1024;
-    if (env >= 0) return ((env == 4 || env == 5) && !occ_fits) ? 0 : env;
-    return occ_fits ? 4 : PF_MAC_DEFAULT_VARIANT;
+    if (env >= 0) return ((env >= 4 && env <= 6) && !occ_fits) ? 0 : env;
+    return occ_fits ? 4 : PF_MAC_DEFAULT_VARIANT; // 6 once the full parity suite has run with it
 }
 
 int mac_tile(const pf_engine *e) {
     const int v = mac_variant(e);
-    if (v == 1) return 128;
+    if (v == 1 || v == 6) return 128;
     if (v >= 2 && v <= 5) return 256;
     static const int env_t = getenv("PF_MAC_TILE") ? atoi(getenv("PF_MAC_TILE")) : 0;
     if (env_t == 256 || env_t == 128 || env_t == 64) return env_t;
@@ -991,6 +992,7 @@ void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
     if (v == 3) return launch_mac_tma_t<2, 3>(e, p, nchunks);
     if (v == 4) return launch_mac_occ_t<256, 2>(e, p, nchunks);
     if (v == 5) return (p.K % 8 == 0) ? launch_mac_occ_t<256, 4>(e, p, nchunks) : launch_mac_occ_t<256, 2>(e, p, nchunks);
+    if (v == 6) return launch_mac_occ_t<128, 2, 4>(e, p, nchunks);
     const int T = mac_tile(e);
     if (T == 256) launch_mac_tile<256>(e, p, nchunks);
     else if (T == 128) launch_mac_tile<128>(e, p, nchunks);

@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(256, 2) mac_kernel(const MacParams p) {
 // that three CTAs fit an SM (<= 85 registers, 3 x 64 KiB of ciphertext slices): 24 warps instead of 16
 // to cover the load latency, at the price of reading the ciphertext slice from shared memory once per
 // block instead of once per two.  UNROLL4: four diagonals per load group.
-template <int T, int UNROLL, bool FPRED>
-__global__ void __launch_bounds__(256, 3) mac_kernel_occ(const MacParams p) {
+template <int T, int UNROLL, bool FPRED, int MINCTA = 3>
+__global__ void __launch_bounds__(256, MINCTA) mac_kernel_occ(const MacParams p) {
     constexpr int TX = T / 2, BY = 256 / TX;
     extern __shared__ __align__(16) u64 smem_ct[]; // [K][2][T]
     const MacChunk ch = p.chunks[blockIdx.x];
