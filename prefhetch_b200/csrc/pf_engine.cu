@@ -964,7 +964,7 @@ int mac_variant(const pf_engine *e) {
     if (e->mac_wide || e->K < 4 || e->K > 32) return 0;
     const bool occ_fits = (size_t)e->K * 2 * 256 * 8 * 3 <= (size_t)227 * 1024;
     if (env >= 0) return ((env >= 4 && env <= 6) && !occ_fits) ? 0 : env;
-    return occ_fits ? 4 : PF_MAC_DEFAULT_VARIANT; // 6 once the full parity suite has run with it
+    return occ_fits ? 6 : PF_MAC_DEFAULT_VARIANT;
 }
 
 int mac_tile(const pf_engine *e) {
