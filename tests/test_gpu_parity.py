@@ -433,11 +433,13 @@ def test_cpp_host_mirror():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("n,d,m,g,tbits", [(16384, 128, 1, 16, 24), (8192, 960, 8, 8, 27), (4096, 64, 2, 4, 24)])
-def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits):
+@pytest.mark.parametrize("n,d,m,g,tbits,rl", [(16384, 128, 1, 16, 24, 0), (8192, 960, 8, 8, 27, 0), (4096, 64, 2, 4, 24, 0),
+                                              (16384, 128, 1, 16, 24, 2), (4096, 64, 2, 4, 24, 1)])
+def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits, rl):
     """poly degree 16384 (L = 8, 49-bit primes: FP64 NTT with mid-pass reductions), GIST-shaped 960-d
     vectors with 8 query ciphertexts (K = 128 diagonals per block), and a 2-ciphertext small case:
-    bytes identical to the oracle's pipeline, decrypted distances exact."""
+    bytes identical to the oracle's pipeline, decrypted distances exact.  rl > 0: results mod-switched
+    to rl limbs (8 -> 2 on the FP64 kernel with 49-bit primes; 2 -> 1 on the generic integer kernel)."""
     from oracle.pf_oracle import BATCHING_T, BFV_DEFAULT_PRIMES
     primes = BFV_DEFAULT_PRIMES[n]
     t = BATCHING_T[(n, tbits)] if (n, tbits) in BATCHING_T else ntt_primes(n, tbits, 1)[0]
@@ -447,7 +449,7 @@ def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits):
     nb = lay.C + lay.C // 3
     base, query, cent = sift_like(rng, nb, d, nlist, nq)
     offsets, ids, vecs = build_ivf(base, cent)
-    eng = pf.Engine(d, n, primes, t, m, g)
+    eng = pf.Engine(d, n, primes, t, m, g, result_limbs=rl)
     eng.load_index(cent, offsets, ids, vecs)
     eng.set_list_sizes(offsets)
     cl = OracleClient(oracle, n, primes, t, d, m, g)
@@ -467,7 +469,11 @@ def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits):
                 xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + lay.C, n_l)].astype(np.int32)
                 diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
                 want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
-                assert res.result(r) == cl.ctx.ct_save(want_ct), f"query {qi} result {r}"
+                pid = (0, 0, 0, 0)
+                if rl:
+                    want_ct = cl.mod_switch_to(want_ct, rl)
+                    pid = _parms_id_py(n, primes[:rl], t)
+                assert res.result(r) == cl.ctx.ct_save(want_ct, parms_id=pid), f"query {qi} result {r}"
                 got_ct, _ = eng.ct_deserialize(res.result(r))
                 dist, budget = cl.distances(got_ct, query[qi], len(xs))
                 assert np.array_equal(dist, ((xs.astype(np.int64) - query[qi].astype(np.int64)) ** 2).sum(1))
