@@ -285,8 +285,12 @@ def run_reference(args, cfg, cfg_name):
         "metric": "encrypted candidate distances/sec", "value": val, "unit": "distances/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg_name, **{k: cfg[k] for k in ("nb", "d", "nlist", "nprobe", "n", "g")},
-                   "queries_per_step": nq_sample},
+        # same keys as the GPU arm's config; the CPU arm times a bounded sample of the same workload
+        "config": {"workload": cfg_name, "nb": cfg["nb"], "d": cfg["d"], "nlist": cfg["nlist"], "nprobe": cfg["nprobe"],
+                   "poly_degree": cfg["n"], "limbs": len(O.BFV_DEFAULT_PRIMES[cfg["n"]]) - 1,
+                   "result_limbs": len(O.BFV_DEFAULT_PRIMES[cfg["n"]]) - 1, "g": cfg["g"], "query_cts": cfg["m"],
+                   "queries_per_step": nq_sample, "parallelism": f"{nthreads} host threads (OpenMP)",
+                   "l2_policy": "n/a (CPU)"},
         "cpu_baseline": {"value": val, "unit": "distances/s", "cores": nthreads, "kind": "port",
                          "sample": f"{nq_sample} queries x {r['pairs']} (query,block) pairs per step, whole hot path "
                                    f"(rotations {r['rot_s']:.2f}s + MAC/INTT {r['mac_s']:.2f}s)"},
