@@ -2028,6 +2028,18 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         static const uint64_t w4[4] = {5, 10, 14, 16};
         q_end[gi + 1] = (ngroups == 4 && nq >= 16) ? nq * w4[gi] / 16 : nq * (gi + 1) / ngroups;
     }
+    // From here on copies that touch the caller's buffers are in flight on three streams: whatever way
+    // this function is left, they are drained first (and the upload arena slot is closed).
+    struct DrainOnExit {
+        pf_engine *e;
+        bool arena_open = false;
+        ~DrainOnExit() {
+            if (arena_open) arena_end(e);
+            cudaStreamSynchronize(e->upload_stream);
+            cudaStreamSynchronize(e->stream);
+            cudaStreamSynchronize(e->copy_stream);
+        }
+    } drain{e};
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
             CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
@@ -2039,6 +2051,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
     u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
     rc = arena_begin(e);
     if (rc) return rc;
+    drain.arena_open = true;
     rc = upload_plan(e, pl);
     if (rc) return rc;
     uint64_t pair_lo = 0, q_lo = 0;
@@ -2060,6 +2073,7 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         q_lo = q_hi;
     }
     arena_end(e);
+    drain.arena_open = false;
     // labels of the owned probed lists (same packing as pf_search_lists_plain), copied while the GPU works
     if (labels) {
         uint64_t pos = 0;
