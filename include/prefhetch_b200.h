@@ -206,6 +206,11 @@ size_t pf_ct_serialized_size(pf_engine *e);
  * result's SEAL stream (results have result_limbs limbs) */
 size_t pf_result_slot_size(pf_engine *e);
 size_t pf_result_serialized_size(pf_engine *e);
+/* Normalises one SEAL stream (16-byte SEALHeader + body) to compr_mode none: zlib-compressed streams are
+ * inflated, uncompressed ones copied; zstd or corrupt input -> PF_ERR_FORMAT; too small a buffer ->
+ * PF_ERR_CAPACITY with *written = bytes needed.  (What seal::Serialization::Load does before the members
+ * are read; [EXT] SEAL 4.1 serialization.cpp.)  Needs no engine and no GPU. */
+int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t cap, size_t *written, size_t *consumed);
 /* SEAL parms_id of the BFV parameter set {poly_degree, coeff_primes[0..nprimes), plain_modulus}: BLAKE2b-256
  * of {scheme = 1, N, primes..., t} as 4 little-endian words (replaces EncryptionParameters::parms_id();
  * [EXT] SEAL 4.1 encryptionparams.cpp compute_parms_id).  Needs no engine and no GPU. */

@@ -23,7 +23,7 @@ EXPORTS = [
     "pf_galois_elt_from_step", "pf_search_lists_encrypted", "pf_search_device", "pf_timing_enable", "pf_timing_read",
     "pf_launch_count", "pf_ipc_alloc", "pf_ipc_open", "pf_ipc_close", "pf_ipc_free", "pf_copy_async", "pf_flag_write", "pf_flag_wait", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
-    "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id", "pf_parms_id",
+    "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id", "pf_parms_id", "pf_seal_stream_inflate",
     "pf_ct_serialize", "pf_ct_deserialize",
 ]
 
@@ -107,6 +107,7 @@ def load() -> C.CDLL:
         "pf_result_serialized_size": ([vp], C.c_size_t),
         "pf_set_result_parms_id": ([vp, u64p], C.c_int),
         "pf_parms_id": ([C.c_uint64, u64p, C.c_uint32, C.c_uint64, u64p], C.c_int),
+        "pf_seal_stream_inflate": ([vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)], C.c_int),
         "pf_ct_serialize": ([vp, u64p, C.c_int, u8p, C.c_size_t, szp], C.c_int),
         "pf_ct_deserialize": ([vp, u8p, C.c_size_t, u64p, C.c_size_t, i32p, i32p, szp], C.c_int),
     }

@@ -1321,6 +1321,29 @@ extern "C" {
 
 int pf_abi_version(void) { return PF_ABI_VERSION; }
 
+int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t cap, size_t *written, size_t *consumed) {
+    if (!in || !written) return PF_ERR_INVALID;
+    if (len < 16 || in[0] != 0x5E || in[1] != 0xA1) return PF_ERR_FORMAT;
+    uint64_t total;
+    memcpy(&total, in + 8, 8);
+    if (total > len || total < 16) return PF_ERR_FORMAT;
+    if (in[5] == 0) { // already compr_mode none
+        *written = (size_t)total;
+        if (consumed) *consumed = (size_t)total;
+        if (!out || cap < total) return PF_ERR_CAPACITY;
+        memcpy(out, in, (size_t)total);
+        return PF_OK;
+    }
+    std::vector<uint8_t> plain;
+    size_t used = 0;
+    if (inflate_seal_stream(in, len, plain, &used) != 0) return PF_ERR_FORMAT; // zstd, truncated or corrupt
+    *written = plain.size();
+    if (consumed) *consumed = used;
+    if (!out || cap < plain.size()) return PF_ERR_CAPACITY;
+    memcpy(out, plain.data(), plain.size());
+    return PF_OK;
+}
+
 int pf_parms_id(uint64_t poly_degree, const uint64_t *coeff_primes, uint32_t nprimes, uint64_t plain_modulus, uint64_t out[4]) {
     if (!coeff_primes || !out || !nprimes || nprimes > 64) return PF_ERR_INVALID;
     pfh::seal_parms_id(poly_degree, coeff_primes, nprimes, plain_modulus, out);

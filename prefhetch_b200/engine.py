@@ -40,6 +40,22 @@ def parms_id(poly_degree: int, primes, plain_modulus: int):
     return tuple(int(x) for x in out)
 
 
+def seal_stream_inflate(blob) -> bytes:
+    """one SEAL stream -> its compr_mode none form (zlib streams inflated); needs no GPU"""
+    lib = _capi.load()
+    b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+    need, used = C.c_size_t(), C.c_size_t()
+    rc = lib.pf_seal_stream_inflate(b.ctypes.data_as(C.c_void_p), b.size, None, 0, C.byref(need), C.byref(used))
+    if rc != _capi.PF_ERR_CAPACITY:
+        raise PfError(rc, "malformed SEAL stream")
+    out = np.empty(need.value, dtype=np.uint8)
+    rc = lib.pf_seal_stream_inflate(b.ctypes.data_as(C.c_void_p), b.size, out.ctypes.data_as(C.c_void_p), out.size,
+                                    C.byref(need), C.byref(used))
+    if rc:
+        raise PfError(rc, "malformed SEAL stream")
+    return out.tobytes()
+
+
 def batching_plain_modulus(n: int, bits: int) -> int:
     return _BATCHING[(n, bits)]
 

@@ -3,6 +3,7 @@ include/prefhetch_b200.h declares.  No compute calls (no GPU here)."""
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -65,3 +66,25 @@ def test_parms_id_is_blake2b_of_the_parameter_words():
         words = [1, n, *primes, t]
         want = struct.unpack("<4Q", hashlib.blake2b(struct.pack(f"<{len(words)}Q", *words), digest_size=32).digest())
         assert pf.parms_id(n, primes, t) == want
+
+
+def test_seal_stream_inflate_matches_python_zlib(oracle):
+    """compr_mode zlib handling of the product (host code, no GPU) against Python's zlib on a stream the
+    oracle serialised; corrupt / truncated / zstd streams are refused."""
+    import struct
+    import zlib
+    import prefhetch_b200 as pf
+    from tests.util import toy_params
+    n, primes, t = toy_params()
+    ctx = oracle.Context(n, primes, t)
+    rng = np.random.default_rng(1)
+    ct = np.stack([[rng.integers(0, q, size=n, dtype=np.uint64) for q in primes[:-1]] for _ in range(2)])
+    raw = ctx.ct_save(ct)
+    body = zlib.compress(raw[16:], 6)
+    z = raw[:5] + b"\x01" + raw[6:8] + struct.pack("<Q", 16 + len(body)) + body
+    assert pf.seal_stream_inflate(z) == raw          # inflated, header rewritten to compr none + new size
+    assert pf.seal_stream_inflate(raw) == raw        # uncompressed streams pass through
+    assert pf.seal_stream_inflate(z + b"tail") == raw  # trailing bytes of a longer buffer are not consumed
+    for bad in (z[:-9], z[:5] + b"\x02" + z[6:], z[:40] + bytes(8) + z[48:], b"\x00" * 32):
+        with pytest.raises(pf.PfError):
+            pf.seal_stream_inflate(bad)
