@@ -181,6 +181,28 @@ def test_result_mod_switched_to_one_limb_keeps_exact_distances(oracle):
         assert full_budget > 60 and budget >= 6, (full_budget, budget)
 
 
+@pytest.mark.parametrize("n,d,m,g,tbits,floor", [(8192, 128, 1, 8, 24, 90), (16384, 128, 1, 16, 24, 300),
+                                                  (8192, 960, 8, 8, 27, 80)])
+def test_noise_budget_at_baseline_parameter_sets(oracle, n, d, m, g, tbits, floor):
+    """exact distances and a comfortable noise budget at every BASELINE parameter set
+    (SIFT N=8192 / N=16384 with Batching(N,24), GIST-shaped 960-d with the 27-bit plain modulus)."""
+    from tests.util import OracleClient
+    primes, t = oracle.BFV_DEFAULT_PRIMES[n], oracle.BATCHING_T[(n, tbits)]
+    cl = OracleClient(oracle, n, primes, t, d, m, g)
+    rng = np.random.default_rng(n + d)
+    xs = rng.integers(0, 256, size=(min(cl.lay.C, 96), d), dtype=np.int32)
+    xs[0], xs[1] = 255, 0
+    q = rng.integers(0, 256, size=d).astype(np.int64)
+    keys = cl.step_keys()
+    cts = cl.encrypt_query(q.astype(np.float32), 77)
+    rot = oracle.rotate_query_set(cl.ctx, cl.lay, cts, keys, False)
+    diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
+    res = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
+    dist, budget = cl.distances(res, q, len(xs))
+    assert np.array_equal(dist, ((xs.astype(np.int64) - q) ** 2).sum(axis=1))
+    assert budget >= floor, budget
+
+
 def test_plain_path_matches_numpy(oracle):
     rng = np.random.default_rng(6)
     base, query, cent = sift_like(rng, 3000, 128, 32, 9)
