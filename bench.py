@@ -325,6 +325,37 @@ def make_dataset_cpu_light(cfg, seed=1234):
                 vectors=np.ascontiguousarray(base[order]), queries=queries)
 
 
+def recall_at_10(eng, data, nprobe, dev, nq_r=64):
+    """recall@10 of the two-stage search against exact brute force over the whole base set (untimed, world 1).
+    Stage 2 here is the engine's plaintext path: the encrypted results decrypt to exactly these distances
+    (tests/test_gpu_parity.py::test_encrypted_search_end_to_end), so both pipelines have this recall.
+    Ties are broken by the lower id on both sides."""
+    import torch
+    x = np.ascontiguousarray(data["queries"][:nq_r], dtype=np.float32)
+    idx = eng.coarse_quantize(x, nprobe)
+    dist, labels, sizes = eng.coarseSearch(x, idx)
+    base = torch.from_numpy(data["vectors"]).to(dev)
+    ids = torch.from_numpy(data["ids"]).to(dev)
+    xq = torch.from_numpy(x).to(dev).double()
+    q2 = (xq * xq).sum(1)
+    best = None
+    for s0 in range(0, base.shape[0], 131072):      # exact integer distances in float64, chunked
+        b = base[s0:s0 + 131072].double()
+        d2 = q2[:, None] + (b * b).sum(1)[None, :] - 2.0 * xq @ b.T
+        key = d2.round().long() * (1 << 21) + ids[s0:s0 + 131072][None, :]
+        key = key if best is None else torch.cat([best, key], dim=1)
+        best = key.topk(10, dim=1, largest=False).values
+    gt = (best % (1 << 21)).cpu().numpy()
+    hits, off = 0, 0
+    for i in range(len(x)):
+        n = int(sizes[i])
+        k = dist[off:off + n].astype(np.int64) * (1 << 21) + labels[off:off + n]
+        found = np.sort(k)[:10] % (1 << 21)
+        hits += len(set(found.tolist()) & set(gt[i].tolist()))
+        off += n
+    return hits / (10.0 * len(x))
+
+
 # ----------------------------------------------------------------------------------------------
 _JSON_OUT = None
 
@@ -639,6 +670,15 @@ def main():
                 "streamed_gbs": streamed_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
                 "ms_per_launch": mac_ms}
 
+    # ---- recall@10 of the search (BASELINE metric, untimed; single GPU: the whole index is local) ----
+    recall = None
+    if world == 1 and cfg["nb"] < (1 << 21):
+        try:
+            recall = recall_at_10(eng, data, nprobe, dev)
+            log(f"[rank {rank}] recall@10 = {recall:.4f} (nprobe {nprobe} of {cfg['nlist']} lists, 64 queries, exact brute-force ground truth)")
+        except Exception as ex:  # the metric line must not depend on this bookkeeping
+            log(f"[rank {rank}] recall@10 not computed: {ex}")
+
     # ---- e2e: host buffers through the public C-ABI call ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -719,6 +759,7 @@ def main():
                        "l2_policy": f"inputs larger than L2: NTT-domain DB {info['db_bytes'] / 2**30:.1f} GiB/rank "
                                     "streamed from HBM, query batches rotate through a pool"},
             "queries_per_s": nq * args.steps / (ms_total * 1e-3),
+            "recall_at_10": recall,
             "slot_distances_per_s": slots_all / (ms_total * 1e-3),
             "result_cts_per_step": nres_all / args.steps,
             "gpu_launches": int(launches_all),
