@@ -151,25 +151,42 @@ class ClockSampler:
 
 
 class NvmlSampler:
-    """Same quantities as ClockSampler read in-process through NVML (what nvidia-smi itself calls): SM clock
-    and clocks-event reasons every 100 ms DURING the timed region.  A polling nvidia-smi process queries far
-    more per sample and holds driver locks long enough to stall kernel launches for milliseconds on some
-    boxes (seen as steps of 4-6 ms with unchanged kernel times), which is why it is only the fallback."""
+    """Opt-in alternative to ClockSampler (PF_BENCH_CLOCKS=nvml): the same quantities read in-process
+    through NVML (what nvidia-smi itself calls) every 100 ms, without a second process."""
 
     def __init__(self, torch_device):
         self.dev, self.rows, self.ok, self.stop_flag = torch_device, [], False, threading.Event()
+
+    def _handle(self, nv):
+        import torch
+        idx = torch.device(self.dev).index or 0
+        try:   # containers usually expose exactly the assigned GPUs to NVML: same numbering as CUDA
+            if nv.nvmlDeviceGetCount() == torch.cuda.device_count():
+                return nv.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            pass
+        cands = []
+        try:
+            cands.append("GPU-" + str(torch.cuda.get_device_properties(self.dev).uuid))
+        except Exception:
+            pass
+        ents = [x.strip() for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip()]
+        ent = ents[idx] if idx < len(ents) else ""
+        if ent.startswith(("GPU-", "MIG-")):
+            cands.append(ent)
+        for u in cands:
+            for arg in (u, u.encode()):
+                try:
+                    return nv.nvmlDeviceGetHandleByUUID(arg)
+                except Exception:
+                    continue
+        return nv.nvmlDeviceGetHandleByIndex(int(ent) if ent.isdigit() else idx)
 
     def start(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(self.dev).uuid)
-            try:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
-            except Exception:
-                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-                idx = torch.device(self.dev).index or 0
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(vis.split(",")[idx]) if vis else idx)
+            self.h = self._handle(pynvml)
             self.nv = pynvml
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.ok = True
@@ -179,14 +196,17 @@ class NvmlSampler:
             self.ok = False
         return self.ok
 
-    def _poll(self):
+    def _sample(self):
         nv = self.nv
+        try:
+            self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                              int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop_flag.is_set():
-            try:
-                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
-                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
-            except Exception:
-                pass
+            self._sample()
             self.stop_flag.wait(0.1)
 
     def stop(self):
@@ -194,6 +214,7 @@ class NvmlSampler:
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
         self.th.join(timeout=2)
+        self._sample()   # one more while the queued steps still run (covers very short timed regions)
         nv = self.nv
         names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
@@ -204,13 +225,13 @@ class NvmlSampler:
 
 
 def make_sampler(local_rank, torch_device):
-    """PF_BENCH_CLOCKS = nvml (default) | smi | off"""
-    mode = os.environ.get("PF_BENCH_CLOCKS", "nvml")
-    if mode == "smi":
-        return ClockSampler(local_rank)
-    s = NvmlSampler(torch_device)
+    """PF_BENCH_CLOCKS = smi (default: the nvidia-smi poller every number in profiles/ was taken with) | nvml | off"""
+    mode = os.environ.get("PF_BENCH_CLOCKS", "smi")
+    if mode == "nvml":
+        return NvmlSampler(torch_device)
+    s = ClockSampler(local_rank)
     if mode == "off":
-        s.start = lambda: False
+        s.start = lambda: None
     return s
 
 
@@ -601,7 +622,7 @@ def main():
         eng.timing_read(reset=True)
         sampler = make_sampler(local_rank, dev)
         if rank == 0:                          # one poller per job: NVML queries take driver locks
-            if not sampler.start() and not isinstance(sampler, ClockSampler) and os.environ.get("PF_BENCH_CLOCKS", "nvml") != "off":
+            if sampler.start() is False:       # NVML requested but unusable: fall back to nvidia-smi
                 sampler = ClockSampler(local_rank)
                 sampler.start()
         launches0 = eng.launch_count()
@@ -618,12 +639,12 @@ def main():
         if comm_stream is not None:             # the timed region ends when the last gather has landed
             stream.wait_stream(comm_stream)
         ev1.record(stream)
+        clocks = sampler.stop() if rank == 0 else None   # last sample while the queued steps still run
         eng.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ms_total = ev0.elapsed_time(ev1)
-        clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count() - launches0
         phases = eng.timing_read(reset=True)
         eng.timing_enable(False)
