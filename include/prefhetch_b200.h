@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PF_ABI_VERSION 1
+#define PF_ABI_VERSION 2
 #define PF_MAX_PRIMES 16
 
 enum {
@@ -124,21 +124,42 @@ typedef struct {
 } pf_search_stats;
 
 /* The encrypted variant of Server::coarseSearch (additive to ref: src/server/controllers/Query.cc:29-63):
- * query_cts holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level) back to back,
- * ct_offsets[nq*m+1] their byte offsets.  For query i and each of its lists idx[i][p] (in order, lists
- * not owned by this rank are skipped) one result ciphertext per block of the list is written to
- * out_cts in SEAL format (coefficient form).  Result r is the pf_result_serialized_size() bytes starting
- * at result_offsets[r]; results sit in slots of pf_result_slot_size() bytes so that their words are
- * 128-byte aligned for the device-to-host copy (out_cap >= nresults * slot; result_offsets[nresults]
- * = bytes used).  Pinned, 128-byte aligned out_cts gives the fastest copies.  results_per_query[nq].
- * labels / list_sizes as in pf_search_lists_plain (ids of the owned probed lists, packed);
- * probed_sizes[nq][nprobe] = length of each probed list (0 when not owned) so the client can map
- * candidate j of a list to (result j / C, candidate j % C). */
-int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
-                              const int64_t *idx, uint32_t nprobe, uint8_t *out_cts, uint64_t out_cap,
-                              uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
-                              int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
-                              pf_search_stats *stats);
+ * query_cts[0, query_bytes) holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level),
+ * ct_offsets[nq*m+1] their byte offsets (ascending, all <= query_bytes, else PF_ERR_INVALID).  For query i
+ * and each of its lists idx[i][p] (in order, lists not owned by this rank are skipped) one result
+ * ciphertext per block of the list is written to out_cts in SEAL format (coefficient form).  Result r is
+ * the pf_result_serialized_size() bytes starting at result_offsets[r]; results sit in slots of
+ * pf_result_slot_size() bytes so that their words are 128-byte aligned for the device-to-host copy
+ * (out_cap >= nresults * slot; result_offsets[nresults] = bytes used).  Pinned, 128-byte aligned out_cts
+ * gives the fastest copies.  results_per_query[nq].  labels / list_sizes as in pf_search_lists_plain (ids
+ * of the owned probed lists, packed); probed_sizes[nq][nprobe] = length of each probed list (0 when not
+ * owned) so the client can map candidate j of a list to (result j / C, candidate j % C). */
+int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, uint64_t query_bytes,
+                              const uint64_t *ct_offsets, const int64_t *idx, uint32_t nprobe, uint8_t *out_cts,
+                              uint64_t out_cap, uint64_t *result_offsets, uint64_t max_results,
+                              uint64_t *results_per_query, int64_t *labels, uint64_t label_cap, uint64_t *list_sizes,
+                              uint64_t *probed_sizes, pf_search_stats *stats);
+
+/* The same call split in two, for a handler thread that keeps the GPU busy across requests
+ * (ref: Query::coarse_search is invoked per request, src/server/controllers/Query.cc:29-63):
+ * pf_search_submit validates, plans, enqueues upload + compute + download and returns; every host-side
+ * output except out_cts (offsets, sizes, labels, stats) is final on return.  pf_search_collect waits until
+ * the result ciphertexts of that ticket are in out_cts.  Up to 4 searches may be in flight per engine
+ * (a fifth submit returns PF_ERR_STATE); with three, request i+2 is queued behind the compute of request
+ * i+1 while request i is downloaded, and neither the GPU nor the PCIe link waits for the host.  query_cts and out_cts must stay valid and untouched until collect returns. */
+int pf_search_submit(pf_engine *e, uint64_t nq, const uint8_t *query_cts, uint64_t query_bytes,
+                     const uint64_t *ct_offsets, const int64_t *idx, uint32_t nprobe, uint8_t *out_cts,
+                     uint64_t out_cap, uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
+                     int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
+                     pf_search_stats *stats, uint64_t *ticket);
+int pf_search_collect(pf_engine *e, uint64_t ticket);
+/* query groups a search is cut into (copy/compute overlap INSIDE one call): 0 = default (4, best latency
+ * for a lone call); 1 = whole-batch kernels, best throughput when calls are pipelined with submit/collect */
+int pf_search_set_groups(pf_engine *e, uint32_t groups);
+/* page-lock caller memory (e.g. a POSIX shared-memory response buffer that every rank of a node writes its
+ * share of the response into) so that copies to / from it are asynchronous DMA */
+int pf_host_register(pf_engine *e, void *ptr, size_t bytes);
+int pf_host_unregister(pf_engine *e, void *ptr);
 
 /* Device-resident form of the same step (what `value` in bench.py times): d_query_cts is a DEVICE
  * pointer to raw words [nq][m][2][L][N] (coefficient form); d_out a DEVICE buffer of
@@ -168,7 +189,13 @@ int pf_ipc_free(pf_engine *e, void *dptr);
  * caller stream so that it overlaps the next step's kernels without using SMs */
 int pf_copy_async(pf_engine *e, void *dst, const void *src, size_t bytes, void *cuda_stream);
 int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream);
+/* The wait is bounded (20 s, env PF_FLAG_TIMEOUT_MS): if the flag never arrives the kernel gives up, the
+ * stream continues, and this and every later call on the engine returns PF_ERR_CUDA — a dead peer does
+ * not hang the process. */
 int pf_flag_wait(pf_engine *e, const void *flag, uint32_t value, void *cuda_stream);
+/* position-weighted 64-bit checksum of nwords device words (verifies that what landed in a gather buffer is
+ * what the producing rank computed); synchronous on cuda_stream (NULL = engine stream) */
+int pf_device_checksum(pf_engine *e, const void *dptr, uint64_t nwords, uint64_t *out, void *cuda_stream);
 
 /* per-phase device timers (CUDA events on the engine stream), accumulated since the last reset */
 enum { PF_T_COARSE = 0, PF_T_TONTT = 1, PF_T_ROTATE = 2, PF_T_MAC = 3, PF_T_INTT = 4, PF_T_COUNT = 8 };

@@ -199,6 +199,12 @@ void pfo_search_pairs(const pfo_context *c, const pfo_layout *lay, size_t nq, co
                       const uint64_t *const *keys, int chain, size_t P, const int32_t *pair_query,
                       const int64_t *pair_block, const uint64_t *diag, const uint64_t *norm, uint64_t *rot,
                       uint64_t *out, int nthreads, double *times);
+/* the same with every result mod-switched down to result_limbs (SEAL Evaluator::mod_switch_to_inplace)
+ * before it is stored: out_ms[P][2][result_limbs][n] */
+void pfo_search_pairs_ms(const pfo_context *c, const pfo_layout *lay, size_t nq, const uint64_t *cts,
+                         const uint64_t *const *keys, int chain, size_t P, const int32_t *pair_query,
+                         const int64_t *pair_block, const uint64_t *diag, const uint64_t *norm, uint64_t *rot,
+                         int result_limbs, uint64_t *out_ms, int nthreads, double *times);
 
 #ifdef __cplusplus
 }

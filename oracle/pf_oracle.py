@@ -145,6 +145,8 @@ def _declare(l):
     l.pfo_encode_blocks.argtypes = [vp, C.POINTER(Layout), C.c_size_t, i32p, i64p, u32p, u64p, u64p, C.c_int]
     l.pfo_search_pairs.argtypes = [vp, C.POINTER(Layout), C.c_size_t, u64p, C.POINTER(u64p), C.c_int, C.c_size_t,
                                    i32p, i64p, u64p, u64p, u64p, u64p, C.c_int, dp]
+    l.pfo_search_pairs_ms.argtypes = [vp, C.POINTER(Layout), C.c_size_t, u64p, C.POINTER(u64p), C.c_int, C.c_size_t,
+                                      i32p, i64p, u64p, u64p, u64p, C.c_int, u64p, C.c_int, dp]
 
 
 def _p(a: np.ndarray, typ):
@@ -408,20 +410,38 @@ def block_distance(ctx: Context, lay: LayoutPlan, rot: np.ndarray, diag: np.ndar
 
 
 def max_threads() -> int:
+    """OpenMP's default team size (follows OMP_NUM_THREADS, which torchrun sets to 1)"""
     return min(lib().pfo_max_threads(), os.cpu_count() or 1)
 
 
+def host_cores() -> int:
+    """cores this process may run on — the thread count the CPU baseline uses (passed explicitly to the
+    num_threads clauses, so an inherited OMP_NUM_THREADS=1 does not shrink it)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def search_pairs(ctx: Context, lay: LayoutPlan, cts: np.ndarray, keys, chain: bool, pair_query, pair_block,
-                 diag: np.ndarray, norm: np.ndarray, nthreads: int = 1):
-    """Whole step on CPU.  cts [nq][m][2][L][n]; returns (out [P][2][L][n], (rot_s, mac_s))."""
+                 diag: np.ndarray, norm: np.ndarray, nthreads: int = 1, result_limbs: int = 0):
+    """Whole step on CPU.  cts [nq][m][2][L][n]; returns (out [P][2][Lr][n], (rot_s, mac_s)); result_limbs
+    in [1, L) mod-switches every result down (SEAL mod_switch_to_inplace) as the CUDA engine does."""
     nq = cts.shape[0]
     pq = np.ascontiguousarray(pair_query, dtype=np.int32)
     pb = np.ascontiguousarray(pair_block, dtype=np.int64)
     P = len(pq)
     rot = np.zeros((nq, lay.K, 2, ctx.L, ctx.n), dtype=np.uint64)
-    out = np.zeros((P, 2, ctx.L, ctx.n), dtype=np.uint64)
     times = (C.c_double * 2)()
     arr, keep = _key_ptrs(keys)
+    if result_limbs and result_limbs < ctx.L:
+        out = np.zeros((P, 2, result_limbs, ctx.n), dtype=np.uint64)
+        lib().pfo_search_pairs_ms(ctx.h, C.byref(lay.s), nq, _p(np.ascontiguousarray(cts, dtype=np.uint64), u64p), arr,
+                                  int(chain), P, _p(pq, i32p), _p(pb, i64p), _p(np.ascontiguousarray(diag), u64p),
+                                  _p(np.ascontiguousarray(norm), u64p), _p(rot, u64p), result_limbs, _p(out, u64p),
+                                  nthreads, times)
+        return out, (times[0], times[1])
+    out = np.zeros((P, 2, ctx.L, ctx.n), dtype=np.uint64)
     lib().pfo_search_pairs(ctx.h, C.byref(lay.s), nq, _p(np.ascontiguousarray(cts, dtype=np.uint64), u64p), arr,
                            int(chain), P, _p(pq, i32p), _p(pb, i64p), _p(np.ascontiguousarray(diag), u64p),
                            _p(np.ascontiguousarray(norm), u64p), _p(rot, u64p), _p(out, u64p), nthreads, times)

@@ -66,3 +66,48 @@ void pfo_search_pairs(const pfo_context *c, const pfo_layout *lay, size_t nq, co
         times[1] = t2 - t1;
     }
 }
+
+/*
+ * The same step with SEAL Evaluator::mod_switch_to_inplace applied to every result before it is
+ * stored (what the CUDA engine does for pf_params.result_limbs < L): out_ms[P][2][Lr][n].  scratch
+ * per thread is allocated inside.  times as above (mod-switch time is part of times[1]).
+ */
+void pfo_search_pairs_ms(const pfo_context *c, const pfo_layout *lay, size_t nq, const uint64_t *cts,
+                         const uint64_t *const *keys, int chain, size_t P, const int32_t *pair_query,
+                         const int64_t *pair_block, const uint64_t *diag, const uint64_t *norm, uint64_t *rot,
+                         int result_limbs, uint64_t *out_ms, int nthreads, double *times) {
+    const size_t ctw = (size_t)2 * c->L * c->n;
+    const size_t dw = (size_t)lay->K * c->L * c->n, nw = (size_t)c->L * c->n;
+    const int Lr = (result_limbs < 1 || result_limbs > c->L) ? c->L : result_limbs;
+    const size_t outw = (size_t)2 * Lr * c->n;
+    if (nthreads < 1) nthreads = 1;
+    double t0 = now_s();
+#pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+    for (size_t i = 0; i < nq; i++)
+        pfo_rotate_query_set(c, lay, cts + i * lay->m * ctw, keys, chain, rot + i * lay->K * ctw);
+    double t1 = now_s();
+#pragma omp parallel num_threads(nthreads)
+    {
+        uint64_t *a = (uint64_t *)malloc(ctw * sizeof(uint64_t)), *b = (uint64_t *)malloc(ctw * sizeof(uint64_t));
+#pragma omp for schedule(dynamic)
+        for (size_t p = 0; p < P; p++) {
+            pfo_block_distance(c, lay, rot + (size_t)pair_query[p] * lay->K * ctw, diag + (size_t)pair_block[p] * dw,
+                               norm + (size_t)pair_block[p] * nw, a);
+            uint64_t *cur = a, *nxt = b;
+            for (int Lin = c->L; Lin > Lr; Lin--) {
+                pfo_mod_switch_next(c, cur, Lin, nxt);
+                uint64_t *t = cur;
+                cur = nxt;
+                nxt = t;
+            }
+            memcpy(out_ms + p * outw, cur, outw * sizeof(uint64_t));
+        }
+        free(a);
+        free(b);
+    }
+    double t2 = now_s();
+    if (times) {
+        times[0] = t1 - t0;
+        times[1] = t2 - t1;
+    }
+}

@@ -24,7 +24,8 @@ EXPORTS = [
     "pf_launch_count", "pf_ipc_alloc", "pf_ipc_open", "pf_ipc_close", "pf_ipc_free", "pf_copy_async", "pf_flag_write", "pf_flag_wait", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
     "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id", "pf_parms_id", "pf_seal_stream_inflate",
-    "pf_ct_serialize", "pf_ct_deserialize",
+    "pf_ct_serialize", "pf_ct_deserialize", "pf_search_submit", "pf_search_collect", "pf_search_set_groups",
+    "pf_host_register", "pf_host_unregister", "pf_device_checksum",
 ]
 
 
@@ -78,8 +79,15 @@ def load() -> C.CDLL:
         "pf_set_galois_key": ([vp, C.c_uint32, u64p], C.c_int),
         "pf_load_galois_keys": ([vp, u8p, C.c_size_t], C.c_int),
         "pf_galois_elt_from_step": ([vp, C.c_int], C.c_uint32),
-        "pf_search_lists_encrypted": ([vp, C.c_uint64, vp, u64p, i64p, C.c_uint32, vp, C.c_uint64, u64p, C.c_uint64,
-                                       u64p, i64p, C.c_uint64, u64p, u64p, C.POINTER(PfSearchStats)], C.c_int),
+        "pf_search_lists_encrypted": ([vp, C.c_uint64, vp, C.c_uint64, u64p, i64p, C.c_uint32, vp, C.c_uint64, u64p,
+                                       C.c_uint64, u64p, i64p, C.c_uint64, u64p, u64p, C.POINTER(PfSearchStats)], C.c_int),
+        "pf_search_submit": ([vp, C.c_uint64, vp, C.c_uint64, u64p, i64p, C.c_uint32, vp, C.c_uint64, u64p, C.c_uint64,
+                              u64p, i64p, C.c_uint64, u64p, u64p, C.POINTER(PfSearchStats), u64p], C.c_int),
+        "pf_search_collect": ([vp, C.c_uint64], C.c_int),
+        "pf_search_set_groups": ([vp, C.c_uint32], C.c_int),
+        "pf_host_register": ([vp, vp, C.c_size_t], C.c_int),
+        "pf_host_unregister": ([vp, vp], C.c_int),
+        "pf_device_checksum": ([vp, vp, C.c_uint64, u64p, vp], C.c_int),
         "pf_search_device": ([vp, C.c_uint64, vp, i64p, C.c_uint32, vp, C.c_uint64, u64p, C.POINTER(PfSearchStats)],
                              C.c_int),
         "pf_timing_enable": ([vp, C.c_int], C.c_int),

@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -87,6 +88,28 @@ struct PinBuf {
     }
 };
 
+// host memory the GPU reads / writes in place (zero-copy): small results that must not queue behind a
+// large response download on the device-to-host copy engine
+struct MappedBuf {
+    void *h = nullptr, *d = nullptr;
+    size_t bytes = 0;
+    ~MappedBuf() {
+        if (h) cudaFreeHost(h);
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (h) cudaFreeHost(h);
+        h = d = nullptr;
+        bytes = 0;
+        n += n / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&h, n, cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        e = cudaHostGetDevicePointer(&d, h, 0);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+
 struct GaloisKey {
     DevBuf key;  // [L][2][k][N]
     DevBuf perm; // u32[N]
@@ -103,10 +126,15 @@ struct BlockInfo {
 constexpr size_t SEAL_CT_HEADER = 16 + 32 + 1 + 8 * 5 + 16 + 8; // bytes before the data words (113)
 constexpr size_t PF_RESULT_DATA_OFFSET = 128;                      // words of result r start at r*slot + 128
 constexpr size_t PF_RESULT_PAD = PF_RESULT_DATA_OFFSET - SEAL_CT_HEADER; // its SEAL stream starts here
+static_assert(SEAL_CT_HEADER == 113, "stamp_headers_kernel copies 113 bytes");
 
 } // namespace
 
-#define PF_E2E_GROUPS 8 // max query groups of pf_search_lists_encrypted (copy / compute overlap)
+// inflated-size ceilings for client-supplied zlib streams (inflate_seal_stream)
+#define PF_MAX_GALOIS_KEYS 256
+#define PF_INFLATE_HARD_CAP ((size_t)6 << 30)
+#define PF_E2E_GROUPS 8
+#define PF_MAX_FLIGHTS 4 // max query groups of pf_search_lists_encrypted (copy / compute overlap)
 
 struct pf_engine {
     pf_params prm{};
@@ -114,14 +142,18 @@ struct pf_engine {
     int Lr = 0; // limbs of result ciphertexts (<= L)
     uint64_t result_pid[4] = {0, 0, 0, 0};
     bool result_pid_set = false;
-    DevBuf d_mstab, s_full, s_dropped;
+    DevBuf d_mstab, s_full, s_cksum;
     u32 d = 0, d_pad = 0, m = 0, g = 0, dc = 0, R = 0, K = 0, C = 0;
     u64 t = 0;
     std::mutex mu;
     mutable std::string err;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    // host-mapped error word written by device code that gives up (flag_wait_kernel time-out); every
+    // API call that enqueues or waits for work looks at it first (check_device_error)
+    unsigned long long *h_err_word = nullptr, *d_err_word = nullptr;
+    unsigned long long flag_timeout_ns = 20ull * 1000 * 1000 * 1000;
 
     // device tables
     DevBuf d_mods; // DevModulus[k+1] (index k = plain modulus)
@@ -157,10 +189,11 @@ struct pf_engine {
     size_t diag_block_words = 0, norm_block_words = 0;
 
     // scratch
-    DevBuf s_x, s_cx, s_dist, s_keys, s_idx, s_outdist, s_jobs, s_pl_dist, s_pl_labels, s_ids;
-    DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_out, s_tmp, s_plain,
+    DevBuf s_x, s_cx, s_dist, s_keys, s_jobs, s_pl_dist, s_pl_labels, s_ids;
+    DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_tmp, s_plain,
         s_encblocks;
     PinBuf h_stage, h_stage2;
+    MappedBuf m_cx, m_cidx, m_cdist; // stage 1: query vectors in, probe ids / distances out (zero-copy)
     // pinned upload arena: pageable cudaMemcpyAsync would synchronise the stream (and the host) on every
     // small table upload; 4 call slots, a slot is reused only after the call that used it has finished
     PinBuf h_arena;
@@ -171,8 +204,17 @@ struct pf_engine {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t coarse_stream = nullptr; // stage 1 runs beside the encrypted pipeline of the previous batch
     cudaEvent_t ev_group[2] = {nullptr, nullptr};
-    cudaStream_t upload_stream = nullptr; // H2D of the query ciphertexts (pf_search_lists_encrypted)
-    cudaEvent_t ev_up[PF_E2E_GROUPS] = {};
+    cudaStream_t upload_stream = nullptr; // H2D of the query ciphertexts (pf_search_submit)
+    // searches in flight (pf_search_submit .. pf_search_collect): own query / result buffers each
+    struct Flight {
+        bool busy = false;
+        uint64_t id = 0;
+        DevBuf qcts, out;
+        cudaEvent_t ev_up[PF_E2E_GROUPS] = {};
+        cudaEvent_t done = nullptr;
+    } flights[PF_MAX_FLIGHTS];
+    uint64_t next_ticket = 0;
+    int groups_hint = 0; // pf_search_set_groups
 
     // timing
     bool timing = false;
@@ -234,6 +276,15 @@ struct HostTick {
         }
     }
 };
+
+// A device-side give-up (flag wait that timed out) is sticky: it surfaces as PF_ERR_CUDA on every later call.
+int check_device_error(pf_engine *e) {
+    if (!e->h_err_word) return PF_OK;
+    const unsigned long long w = *(volatile unsigned long long *)e->h_err_word;
+    if (!w) return PF_OK;
+    return e->fail(PF_ERR_CUDA, "peer flag wait timed out after %.1f s (flag value %u, waiting for %u): a peer rank is dead or out of protocol order",
+                   (double)e->flag_timeout_ns * 1e-9, (unsigned)((w >> 32) & 0x7fffffffu), (unsigned)(w & 0xffffffffu));
+}
 
 // ---- pinned upload arena --------------------------------------------------------------------
 constexpr size_t ARENA_SLOT = (size_t)8 << 20;
@@ -323,16 +374,12 @@ cudaError_t set_ntt_attrs() {
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_REDUCE>));
     SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
     SETATTR((ntt_inv_kernel<LOGN>));
-    SETATTR((ntt_fwd_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
-    SETATTR((ntt_inv_kernel<LOGN, NTT_OUT_KS>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_LIFT>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_REDUCE>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_GALOIS_REDUCE>));
     SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_MODDOWN>));
-    SETATTR((ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS>));
     SETATTR((ntt_inv_fp_kernel<LOGN>));
-    SETATTR((ntt_inv_fp_kernel<LOGN, NTT_OUT_MODSWITCH>));
 #undef SETATTR
     return cudaSuccess;
 }
@@ -341,12 +388,8 @@ template <int LOGN>
 void launch_ntt_fp_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
     const size_t smem = NttCfg<LOGN>::SMEM;
     const int nt = NttCfg<LOGN>::NT;
-    if (inverse && p.ms_dropped)
-        ntt_inv_fp_kernel<LOGN, NTT_OUT_MODSWITCH><<<grid, nt, smem, s>>>(p);
-    else if (inverse)
+    if (inverse)
         ntt_inv_fp_kernel<LOGN><<<grid, nt, smem, s>>>(p);
-    else if (p.ks_S)
-        ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_PLAIN)
         ntt_fwd_fp_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_LIFT)
@@ -363,12 +406,8 @@ template <int LOGN>
 void launch_ntt_t(int inmode, bool inverse, const NttParams &p, dim3 grid, cudaStream_t s) {
     const size_t smem = NttCfg<LOGN>::SMEM;
     const int nt = NttCfg<LOGN>::NT;
-    if (inverse && p.ks_W)
-        ntt_inv_kernel<LOGN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
-    else if (inverse)
+    if (inverse)
         ntt_inv_kernel<LOGN><<<grid, nt, smem, s>>>(p);
-    else if (p.ks_S)
-        ntt_fwd_kernel<LOGN, NTT_IN_PLAIN, NTT_OUT_KS><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_PLAIN)
         ntt_fwd_kernel<LOGN, NTT_IN_PLAIN><<<grid, nt, smem, s>>>(p);
     else if (inmode == NTT_IN_LIFT)
@@ -385,7 +424,7 @@ void launch_ntt(pf_engine *e, int inmode, bool inverse, NttParams p, dim3 grid) 
     p.tw_fp = e->d_tw_fp.as<double>();
     p.tw_fp_lane = e->d_tw_fp_lane.as<double>();
     e->launches++;
-    if (e->ntt_fp && !(inverse && p.ks_W)) {
+    if (e->ntt_fp) {
         if (!inverse && inmode == NTT_IN_GALOIS_REDUCE) {
             // hoisted jobs need the exact digits only when flagged: 32 jobs per CTA; un-hoisted jobs
             // (chain mode) always do: one job per CTA
@@ -696,8 +735,8 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         }
         e->launches++;
         // 3. u_c = INTT_P(S_c[L]) in place, then W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j).
-        // (The fused NTT_OUT_KS inverse epilogue exists but measured slower than this pair on B200:
-        // 0.69 ms vs 0.40 ms per step, profiles/r1_launches_step_v4.txt.)
+        // (An inverse NTT with this prep fused into its store measured slower than the pair on B200:
+        // 0.69 ms vs 0.40 ms per step, profiles/r1_launches_step_v4.txt; the variant was removed.)
         NttParams ip{};
         ip.in = kp.S + (size_t)L * N;
         ip.out = kp.S + (size_t)L * N;
@@ -709,9 +748,9 @@ int run_rot_jobs(pf_engine *e, const std::vector<RotJob> &jobs, bool out_split) 
         //    (NTT_IN_MODDOWN), so neither the prep kernel nor a coefficient-form W exists; the integer
         //    kernels keep the separate prep + in-place transform.  Then 2b. S_c[j] for the data limbs
         //    with the finish fused: out_c[j] = (S_c[j] - NTT_j(W_c[j])) * P^{-1} (+ sigma_ntt(c0)[j]);
-        //    S_c[j] never hits memory.  (Fusing the finish into the NTT copy-out instead, NTT_OUT_KS,
-        //    measured slower.)
-        static const bool no_fuse = getenv("PF_KS_NO_FUSED_PREP") != nullptr;
+        //    S_c[j] never hits memory.  (Fusing the finish into the NTT copy-out instead measured
+        //    slower and was removed.)
+        const bool no_fuse = getenv("PF_KS_NO_FUSED_PREP") != nullptr; // per call: tests flip it
         NttParams wp{};
         wp.out = kp.W;
         wp.out_sx = N;
@@ -926,52 +965,27 @@ void launch_mac_occ_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     e->launches++;
 }
 
-template <int T, int UNROLL, int NS>
-void launch_mac_async_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
-    const size_t smem = (size_t)p.K * 2 * T * 8 + (size_t)NS * UNROLL * 2 * 16 * 256;
-    auto kern = mac_kernel_async<T, UNROLL, NS>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
-    e->launches++;
-}
-
-template <int KS, int NST>
-void launch_mac_tma_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
-    constexpr int T = 256;
-    const size_t smem = (size_t)p.K * 2 * T * 8 + (size_t)NST * 4 * KS * T * 8 + 128;
-    if (e->mac_fpred) {
-        auto kern = mac_kernel_tma<T, KS, NST, true>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3(nchunks, p.L * (p.N / T)), 288, smem, e->stream>>>(p);
-    } else {
-        auto kern = mac_kernel_tma<T, KS, NST, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3(nchunks, p.L * (p.N / T)), 288, smem, e->stream>>>(p);
-    }
-    e->launches++;
-}
-
-// MAC variant: 0 = register-staged loads, two blocks per lane, 2 CTAs/SM (mac_kernel), 1 = cp.async ring
-// T=128, 2 = cp.async ring T=256, 3 = TMA bulk-copy producer/consumer ring (T=256), 4 / 5 = one block per
-// lane, 3 CTAs/SM (mac_kernel_occ, 2 / 4 diagonals per load group), 6 = the same with 128-coefficient
-// slices, 64 registers and 4 CTAs/SM.  Default: 6 whenever the slices fit an SM's shared memory
-// (K <= 16), else 0.  Measured at K = 16: 1.005 / 0.89 / 0.835 ms for 0 / 4 / 6.
+// MAC variant (PF_MAC_VARIANT, read per call so tests can flip it): 0 = two blocks per lane, 2 CTAs/SM
+// (mac_kernel), 4 / 5 = one block per lane, 256-coefficient slices, 3 CTAs/SM (mac_kernel_occ, 2 / 4
+// diagonals per load group), 6 = the same with 128-coefficient slices, 64 registers and 4 CTAs/SM.
+// Default: 6 whenever the slices fit an SM's shared memory (K <= 16), else 0.  Measured at K = 16:
+// 1.005 / 0.89 / 0.835 ms for 0 / 4 / 6.  (cp.async and TMA bulk-copy rings were measured slower — 1.5 /
+// 1.22 ms — and removed; profiles/README.md keeps the numbers.)
 int mac_variant(const pf_engine *e) {
-    static const int env = [] {
-        const char *v = getenv("PF_MAC_VARIANT");
-        return v ? atoi(v) : -1;
-    }();
+    const char *v = getenv("PF_MAC_VARIANT");
+    const int env = v ? atoi(v) : -1;
     if (e->mac_wide || e->K < 4 || e->K > 32) return 0;
     const bool occ_fits = (size_t)e->K * 2 * 256 * 8 * 3 <= (size_t)227 * 1024;
-    if (env >= 0) return ((env >= 4 && env <= 6) && !occ_fits) ? 0 : env;
+    if (env == 0) return 0;
+    if (env >= 4 && env <= 6) return occ_fits ? env : 0;
     return occ_fits ? 6 : PF_MAC_DEFAULT_VARIANT;
 }
 
 int mac_tile(const pf_engine *e) {
     const int v = mac_variant(e);
-    if (v == 1 || v == 6) return 128;
-    if (v >= 2 && v <= 5) return 256;
-    static const int env_t = getenv("PF_MAC_TILE") ? atoi(getenv("PF_MAC_TILE")) : 0;
+    if (v == 6) return 128;
+    if (v == 4 || v == 5) return 256;
+    const int env_t = getenv("PF_MAC_TILE") ? atoi(getenv("PF_MAC_TILE")) : 0;
     if (env_t == 256 || env_t == 128 || env_t == 64) return env_t;
     return e->K <= 32 ? 256 : (e->K <= 64 ? 128 : 64);
 }
@@ -987,9 +1001,6 @@ void launch_mac_tile(pf_engine *e, const MacParams &p, unsigned nchunks) {
 
 void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
     const int v = mac_variant(e);
-    if (v == 1) return launch_mac_async_t<128, 2, 4>(e, p, nchunks);
-    if (v == 2) return launch_mac_async_t<256, 2, 3>(e, p, nchunks);
-    if (v == 3) return launch_mac_tma_t<2, 3>(e, p, nchunks);
     if (v == 4) return launch_mac_occ_t<256, 2>(e, p, nchunks);
     if (v == 5) return (p.K % 8 == 0) ? launch_mac_occ_t<256, 4>(e, p, nchunks) : launch_mac_occ_t<256, 2>(e, p, nchunks);
     if (v == 6) return launch_mac_occ_t<128, 2, 4>(e, p, nchunks);
@@ -1136,11 +1147,8 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
         PhaseTimer pt(e, PF_T_INTT);
         u64 *base = full + full_base * full_stride;
         const int nd = L - e->Lr;
-        // the fused store (NTT_OUT_MODSWITCH) is bit-exact but measured 2-6x slower than the pair
-        // INTT + modswitch_kernel_t (register pressure in the 32-point pass); kept behind PF_FUSED_MS
-        static const bool want_fused = getenv("PF_FUSED_MS") != nullptr;
-        const bool fused_ms = want_fused && ms && e->ntt_fp && nd <= 4;
-        if (fused_ms) CK(e->s_dropped.ensure_grow(P * (size_t)2 * nd * N * 8));
+        // (an inverse NTT with the mod-switch folded into its store was bit-exact but 2-6x slower than the
+        // pair INTT + modswitch kernel — register pressure in the 32-point pass — and was removed)
         for (size_t off = 0; off < P; off += 32768) {
             const unsigned cnt = (unsigned)std::min<size_t>(32768, P - off);
             NttParams ip{};
@@ -1149,7 +1157,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
             ip.in_sy = ip.out_sy = (long long)L * N;
             ip.in_sz = ip.out_sz = (long long)full_stride;
             for (int i = 0; i < L; i++) ip.mod_map[i] = i;
-            if (!fused_ms) {
+            {
                 launch_ntt(e, NTT_IN_PLAIN, true, ip, dim3(L, 2, cnt));
                 if (ms) {
                     const u64 *src = base + off * full_stride;
@@ -1159,7 +1167,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
                     const double *tabf = e->d_mstab_fp.as<double>();
                     const dim3 g2(N / 512, 2, cnt);
                     // primes <= 49 bits: the FP64-pipe kernel (pf_ntt_fp.cuh); otherwise the integer one
-                    static const bool ms_int = getenv("PF_MS_INT") != nullptr;
+                    const bool ms_int = getenv("PF_MS_INT") != nullptr; // per call: tests flip it
                     const bool ms_fp = e->max_prime_bits <= 49 && !ms_int;
 #define MS_CASE(LL, RR)                                                                                            \
     else if (L == LL && e->Lr == RR && ms_fp) modswitch_fp_kernel_t<LL, RR><<<g2, 256, 0, e->stream>>>(src, full_stride, dst, \
@@ -1181,27 +1189,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
 #undef MS_CASE
                     e->launches++;
                 }
-                continue;
             }
-            // (a) the limbs that will be dropped -> coefficient form in scratch [result][poly][c][N]
-            NttParams dp = ip;
-            dp.in = base + off * full_stride + (size_t)e->Lr * N;
-            dp.out = e->s_dropped.as<u64>() + off * (size_t)2 * nd * N;
-            dp.out_sy = (long long)nd * N;
-            dp.out_sz = (long long)2 * nd * N;
-            for (int i = 0; i < nd; i++) dp.mod_map[i] = e->Lr + i;
-            launch_ntt(e, NTT_IN_PLAIN, true, dp, dim3(nd, 2, cnt));
-            // (b) the kept limbs: inverse NTT with SEAL's mod_switch_to folded into the store
-            NttParams kp2 = ip;
-            kp2.out = d_out + (p0 + off) * out_stride;
-            kp2.out_sy = (long long)e->Lr * N;
-            kp2.out_sz = (long long)out_stride;
-            kp2.ms_dropped = e->s_dropped.as<u64>() + off * (size_t)2 * nd * N;
-            kp2.ms_dropped_sz = (long long)2 * nd * N;
-            kp2.ms_tab = e->d_mstab.as<u64>();
-            kp2.ms_L = L;
-            kp2.ms_Lr = e->Lr;
-            launch_ntt(e, NTT_IN_PLAIN, true, kp2, dim3(e->Lr, 2, cnt));
         }
     }
     CK(cudaGetLastError());
@@ -1252,35 +1240,53 @@ void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t 
 // (RFC 1950) stream holding what an uncompressed save would have written after its header; nested
 // objects inside are saved uncompressed [EXT: SEAL 4.1 serialization.cpp / util/ztools.cpp].  Inflates
 // into `out` as the equivalent compr_mode none stream.  Returns 0, 1 (not zlib-compressed, untouched), <0 error.
-int inflate_seal_stream(const uint8_t *p, size_t len, std::vector<uint8_t> &out, size_t *consumed) {
+// `max_out` bounds the inflated size (header included): the streams come from clients, and a few KB of
+// deflate can expand a thousandfold — callers pass the size the object can legitimately have (-7 beyond
+// it).  Input and output are fed to zlib in chunks below its 32-bit avail_in / avail_out.
+int inflate_seal_stream(const uint8_t *p, size_t len, std::vector<uint8_t> &out, size_t *consumed, size_t max_out) {
     if (len < 16 || p[0] != 0x5E || p[1] != 0xA1) return -2;
     if (p[5] != 1) return 1;
     uint64_t total;
     memcpy(&total, p + 8, 8);
     if (total > len || total < 16) return -1;
+    if (max_out < 16) return -7;
     out.assign(16, 0);
-    z_stream zs{};
+    struct ZGuard {
+        z_stream zs{};
+        bool live = false;
+        ~ZGuard() {
+            if (live) inflateEnd(&zs);
+        }
+    } zg;
+    z_stream &zs = zg.zs;
     if (inflateInit(&zs) != Z_OK) return -5;
-    zs.next_in = const_cast<Bytef *>(p + 16);
-    zs.avail_in = (uInt)(total - 16);
-    int zr = Z_OK;
-    while (zr != Z_STREAM_END) {
+    zg.live = true;
+    const uint8_t *in_pos = p + 16;
+    size_t in_left = (size_t)(total - 16);
+    constexpr size_t ZCHUNK = (size_t)1 << 30;
+    for (;;) {
+        if (zs.avail_in == 0 && in_left) {
+            const size_t take = std::min(in_left, ZCHUNK);
+            zs.next_in = const_cast<Bytef *>(in_pos);
+            zs.avail_in = (uInt)take;
+            in_pos += take;
+            in_left -= take;
+        }
         const size_t have = out.size();
-        out.resize(have + std::max<size_t>(1 << 16, (total - 16) * 2));
-        zs.next_out = out.data() + have;
-        zs.avail_out = (uInt)(out.size() - have);
-        zr = inflate(&zs, Z_NO_FLUSH);
-        out.resize(out.size() - zs.avail_out);
-        if (zr != Z_OK && zr != Z_STREAM_END) {
-            inflateEnd(&zs);
-            return -6;
-        }
-        if (zr == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) {
-            inflateEnd(&zs);
-            return -1; // truncated
-        }
+        Bytef probe = 0;
+        const bool at_cap = have >= max_out; // the object cannot be larger: one probe byte tells "ended" from "more"
+        const size_t grow = at_cap ? 1 : std::min(std::min(max_out - have, ZCHUNK), std::max<size_t>(1 << 16, (size_t)(total - 16) * 2));
+        if (!at_cap) out.resize(have + grow);
+        zs.next_out = at_cap ? &probe : out.data() + have;
+        zs.avail_out = (uInt)grow;
+        const int zr = inflate(&zs, Z_NO_FLUSH);
+        const size_t produced = grow - zs.avail_out;
+        if (at_cap && produced) return -7;
+        if (!at_cap) out.resize(have + produced);
+        if (zr == Z_STREAM_END) break;
+        if (zr != Z_OK && zr != Z_BUF_ERROR) return -6;
+        if (zs.avail_in == 0 && in_left == 0 && zs.avail_out != 0) return -1; // truncated
     }
-    inflateEnd(&zs);
     memcpy(out.data(), p, 16);
     out[5] = 0;
     const uint64_t new_total = out.size();
@@ -1305,7 +1311,8 @@ int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_nt
     const uint8_t *in = p + 89;
     if (in[0] != 0x5E || in[1] != 0xA1 || in[5] != 0) return -2;
     memcpy(&words, in + 16, 8);
-    if (size != 2 || n != (uint64_t)e->N || words != size * n * cms) return -4;
+    if (size != 2 || n != (uint64_t)e->N || cms < 1 || cms > PF_MAX_PRIMES) return -4; // bounded before multiplying
+    if (words != size * n * cms) return -4;
     if (SEAL_CT_HEADER + words * 8 != total) return -4;
     *nlimbs = cms;
     *total_out = (size_t)total;
@@ -1336,7 +1343,17 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
     }
     std::vector<uint8_t> plain;
     size_t used = 0;
-    if (inflate_seal_stream(in, len, plain, &used) != 0) return PF_ERR_FORMAT; // zstd, truncated or corrupt
+    // engine-less utility: the caller's capacity bounds the output once it is known; the sizing call
+    // (out == NULL) is bounded by the largest object of this protocol (GaloisKeys at N = 16384)
+    const size_t bound = (out && cap) ? cap : PF_INFLATE_HARD_CAP;
+    const int zr = inflate_seal_stream(in, len, plain, &used, bound);
+    if (zr == -7 && out && cap) { // larger than the caller's buffer: report the need without inflating past the ceiling
+        if (inflate_seal_stream(in, len, plain, &used, PF_INFLATE_HARD_CAP) != 0) return PF_ERR_FORMAT;
+        *written = plain.size();
+        if (consumed) *consumed = used;
+        return PF_ERR_CAPACITY;
+    }
+    if (zr != 0) return PF_ERR_FORMAT; // zstd, truncated, corrupt or beyond the ceiling
     *written = plain.size();
     if (consumed) *consumed = used;
     if (!out || cap < plain.size()) return PF_ERR_CAPACITY;
@@ -1434,9 +1451,18 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
         cudaEventCreateWithFlags(&e->ev_group[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->upload_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "copy stream / event creation failed"));
-    for (auto &ev : e->ev_up)
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+    for (auto &fl : e->flights) {
+        for (auto &ev : fl.ev_up)
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+                return bail(e->fail(PF_ERR_CUDA, "event creation failed"));
+        if (cudaEventCreateWithFlags(&fl.done, cudaEventDisableTiming) != cudaSuccess)
             return bail(e->fail(PF_ERR_CUDA, "event creation failed"));
+    }
+    if (cudaHostAlloc((void **)&e->h_err_word, sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&e->d_err_word, e->h_err_word, 0) != cudaSuccess)
+        return bail(e->fail(PF_ERR_CUDA, "error word allocation failed"));
+    *e->h_err_word = 0;
+    if (const char *ft = getenv("PF_FLAG_TIMEOUT_MS")) e->flag_timeout_ns = (unsigned long long)std::max(1, atoi(ft)) * 1000000ull;
     cudaError_t ar = cudaSuccess;
     switch (e->logn) {
     case 10: ar = set_ntt_attrs<10>(); break;
@@ -1462,12 +1488,17 @@ void pf_engine_destroy(pf_engine *e) {
         if (ev) cudaEventDestroy(ev);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->upload_stream) cudaStreamDestroy(e->upload_stream);
-    for (auto ev : e->ev_up)
-        if (ev) cudaEventDestroy(ev);
+    for (auto &fl : e->flights) {
+        if (fl.busy && fl.done) cudaEventSynchronize(fl.done);
+        for (auto ev : fl.ev_up)
+            if (ev) cudaEventDestroy(ev);
+        if (fl.done) cudaEventDestroy(fl.done);
+    }
     if (e->coarse_stream) cudaStreamDestroy(e->coarse_stream);
     for (auto ev : e->ev_group)
         if (ev) cudaEventDestroy(ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    if (e->h_err_word) cudaFreeHost(e->h_err_word);
     delete e;
 }
 
@@ -1486,7 +1517,7 @@ int pf_engine_set_stream(pf_engine *e, void *s) {
 int pf_engine_synchronize(pf_engine *e) {
     if (!e) return PF_ERR_INVALID;
     CK(cudaStreamSynchronize(e->stream));
-    return PF_OK;
+    return check_device_error(e);
 }
 
 int pf_timing_enable(pf_engine *e, int on) {
@@ -1512,7 +1543,7 @@ int pf_timing_read(pf_engine *e, float *ms, uint64_t *launches, int reset) {
     return PF_OK;
 }
 
-uint64_t pf_launch_count(pf_engine *e) { return e ? e->launches : 0; }
+uint64_t pf_launch_count(pf_engine *e) { return e ? e->launches.load() : 0; }
 
 // ---- peer-memory gather buffers (CUDA IPC over NVLink) -------------------------------------------
 int pf_ipc_alloc(pf_engine *e, size_t bytes, void **dptr, uint8_t handle[PF_IPC_HANDLE_BYTES]) {
@@ -1560,18 +1591,42 @@ int pf_copy_async(pf_engine *e, void *dst, const void *src, size_t bytes, void *
 
 int pf_flag_write(pf_engine *e, void *flag, uint32_t value, void *cuda_stream) {
     if (!e || !flag) return PF_ERR_INVALID;
+    int rc = check_device_error(e);
+    if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
     flag_write_kernel<<<1, 1, 0, st>>>((volatile unsigned *)flag, value);
+    CK(cudaGetLastError());
     e->launches++;
     return PF_OK;
 }
 
 int pf_flag_wait(pf_engine *e, const void *flag, uint32_t value, void *cuda_stream) {
     if (!e || !flag) return PF_ERR_INVALID;
+    int rc = check_device_error(e);
+    if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
-    flag_wait_kernel<<<1, 1, 0, st>>>((const volatile unsigned *)flag, value);
+    flag_wait_kernel<<<1, 1, 0, st>>>((const volatile unsigned *)flag, value, e->flag_timeout_ns, e->d_err_word);
+    CK(cudaGetLastError());
     e->launches++;
     return PF_OK;
+}
+
+int pf_device_checksum(pf_engine *e, const void *dptr, uint64_t nwords, uint64_t *out, void *cuda_stream) {
+    if (!e || !dptr || !out) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : e->stream;
+    CK(e->s_cksum.ensure(8));
+    CK(cudaMemsetAsync(e->s_cksum.p, 0, 8, st));
+    if (nwords) {
+        const unsigned blocks = (unsigned)std::min<uint64_t>(148 * 8, (nwords + 255) / 256);
+        checksum_kernel<<<blocks, 256, 0, st>>>((const u64 *)dptr, (size_t)nwords, e->s_cksum.as<u64>());
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    CK(cudaMemcpyAsync(out, e->s_cksum.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return check_device_error(e);
 }
 
 int pf_ipc_free(pf_engine *e, void *dptr) {
@@ -1783,12 +1838,19 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
     // quantized while the encrypted pipeline of the current batch still occupies the engine stream.
     cudaStream_t cs = e->coarse_stream;
     PhaseTimer pt(e, PF_T_COARSE, cs);
+    // Inputs go through a pinned staging buffer (asynchronous H2D), outputs are written by the kernel straight
+    // into mapped host memory: a D2H copy of these few KB would queue behind the response download of the
+    // previous search on the copy engine (measured: 1.3 ms per call instead of 0.1 ms, and a GPU idle meanwhile).
     CK(e->s_cx.ensure_grow(nq * d * sizeof(float)));
     CK(e->s_dist.ensure_grow(nq * (size_t)nlist * sizeof(float)));
     CK(e->s_keys.ensure_grow(nq * (size_t)nlist * sizeof(u64)));
-    CK(e->s_idx.ensure_grow(nq * nprobe * sizeof(long long)));
-    CK(e->s_outdist.ensure_grow(nq * nprobe * sizeof(float)));
-    CK(cudaMemcpyAsync(e->s_cx.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CK(e->m_cx.ensure(nq * d * sizeof(float)));
+    CK(e->m_cidx.ensure(nq * nprobe * sizeof(long long)));
+    CK(e->m_cdist.ensure(nq * nprobe * sizeof(float)));
+    memcpy(e->m_cx.h, x, nq * d * sizeof(float));
+    CK(cudaMemcpyAsync(e->s_cx.p, e->m_cx.h, nq * d * sizeof(float), cudaMemcpyHostToDevice, cs));
+    long long *o_idx = (long long *)e->m_cidx.d;
+    float *o_dist = (float *)e->m_cdist.d;
     for (uint64_t q0 = 0; q0 < nq; q0 += 32768) {
         const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
         coarse_dist_kernel<<<dim3((nlist + 127) / 128, nqb), 128, d * sizeof(float), cs>>>(
@@ -1798,17 +1860,16 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
         const bool old_topk = getenv("PF_TOPK_ITER") != nullptr; // per call: tests flip it
         if (M <= 4096 && !old_topk) // radix select + bitonic sort of the selected keys in shared memory
             topk_radix_kernel<<<nqb, 256, (size_t)M * 8, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
-                                                              e->s_idx.as<long long>() + q0 * nprobe,
-                                                              e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe, M);
+                                                              o_idx + q0 * nprobe, o_dist + q0 * nprobe, nlist, (int)nprobe, M);
         else
             topk_select_kernel<<<nqb, 256, 0, cs>>>(e->s_dist.as<float>() + q0 * nlist, e->s_keys.as<u64>() + q0 * nlist,
-                                                     e->s_idx.as<long long>() + q0 * nprobe,
-                                                     e->s_outdist.as<float>() + q0 * nprobe, nlist, (int)nprobe);
+                                                     o_idx + q0 * nprobe, o_dist + q0 * nprobe, nlist, (int)nprobe);
         e->launches += 2;
     }
-    CK(cudaMemcpyAsync(out_idx, e->s_idx.p, nq * nprobe * sizeof(long long), cudaMemcpyDeviceToHost, cs));
-    if (out_dist) CK(cudaMemcpyAsync(out_dist, e->s_outdist.p, nq * nprobe * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(cs));
+    memcpy(out_idx, e->m_cidx.h, nq * nprobe * sizeof(long long));
+    if (out_dist) memcpy(out_dist, e->m_cdist.h, nq * nprobe * sizeof(float));
     return PF_OK;
 }
 
@@ -1848,6 +1909,7 @@ int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64
         e->s_x.as<float>(), e->d_base_f32.as<float>(), e->d_ids.as<long long>(), e->s_jobs.as<ListJob>(),
         e->s_pl_dist.as<float>(), e->s_pl_labels.as<long long>(), (int)d, w);
     e->launches++;
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dist, e->s_pl_dist.p, w * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(labels, e->s_pl_labels.p, w * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1867,10 +1929,15 @@ int pf_precise_search(pf_engine *e, uint64_t nq, const float *x, const int64_t *
     CK(e->s_pl_dist.ensure_grow(nq * nids * sizeof(float)));
     CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->s_ids.p, ids, nq * nids * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
-    precise_l2_kernel<<<dim3((nids + 127) / 128, (unsigned)nq), 128, d * sizeof(float), e->stream>>>(
-        e->s_x.as<float>(), e->d_base_f32.as<float>(), e->d_pos_of_id.as<long long>(), e->s_ids.as<long long>(),
-        e->s_pl_dist.as<float>(), (int)d, (int)nids, (long long)e->ntotal);
-    e->launches++;
+    for (uint64_t q0 = 0; q0 < nq; q0 += 32768) { // gridDim.y <= 65535
+        const unsigned nqb = (unsigned)std::min<uint64_t>(32768, nq - q0);
+        precise_l2_kernel<<<dim3((nids + 127) / 128, nqb), 128, d * sizeof(float), e->stream>>>(
+            e->s_x.as<float>() + q0 * d, e->d_base_f32.as<float>(), e->d_pos_of_id.as<long long>(),
+            e->s_ids.as<long long>() + q0 * nids, e->s_pl_dist.as<float>() + q0 * nids, (int)d, (int)nids,
+            (long long)e->ntotal);
+        e->launches++;
+    }
+    CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->s_pl_dist.p, nq * nids * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return PF_OK;
@@ -1891,7 +1958,12 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
     CK(cudaSetDevice(e->prm.device));
     std::vector<uint8_t> plain;
     {
-        const int zr = inflate_seal_stream(bytes, len, plain, nullptr);
+        // a GaloisKeys object of this parameter set: header + parms_id + dim1 + one count per possible
+        // element + at most PF_MAX_GALOIS_KEYS keys of L ciphertexts over k primes
+        const size_t key_bytes = (size_t)e->L * (SEAL_CT_HEADER + (size_t)2 * e->k * e->N * 8);
+        const size_t cap = 16 + 32 + 8 + (size_t)e->N * 8 + (size_t)PF_MAX_GALOIS_KEYS * key_bytes;
+        const int zr = inflate_seal_stream(bytes, len, plain, nullptr, cap);
+        if (zr == -7) return e->fail(PF_ERR_FORMAT, "compressed GaloisKeys stream inflates beyond %zu bytes (%d keys of this parameter set)", cap, PF_MAX_GALOIS_KEYS);
         if (zr < 0) return e->fail(PF_ERR_FORMAT, "malformed compressed GaloisKeys stream (code %d)", zr);
         if (zr == 0) {
             bytes = plain.data();
@@ -1907,6 +1979,7 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
     uint64_t dim1;
     memcpy(&dim1, bytes + off, 8);
     off += 8;
+    if (dim1 > (uint64_t)e->N) return e->fail(PF_ERR_FORMAT, "GaloisKeys stream holds %llu slots, at most N = %d possible", (unsigned long long)dim1, e->N);
     const size_t key_ct_words = (size_t)2 * e->k * e->N;
     std::vector<u64> words((size_t)e->L * key_ct_words);
     for (uint64_t index = 0; index < dim1; index++) {
@@ -1973,19 +2046,44 @@ int pf_search_device(pf_engine *e, uint64_t nq, const uint64_t *d_query_cts, con
     return rc;
 }
 
-int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, const uint64_t *ct_offsets,
-                              const int64_t *idx, uint32_t nprobe, uint8_t *out_cts, uint64_t out_cap,
-                              uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
-                              int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
-                              pf_search_stats *stats) {
-    if (!e || !query_cts || !ct_offsets || !idx) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+// The encrypted search is enqueued by pf_search_submit and completed by pf_search_collect: two calls may
+// be in flight, so the upload and the compute of call i+1 overlap the device-to-host copy of call i
+// (separate query / result buffers per flight; three streams: upload, engine, copy).  Everything that
+// touches the caller's host buffers on the CPU (labels, sizes, offsets) is done inside submit while the
+// GPU works; the SEAL stream headers in front of every result are stamped on the device, so collect is
+// just a wait on the last copy.
+static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, uint64_t query_bytes,
+                         const uint64_t *ct_offsets, const int64_t *idx, uint32_t nprobe, uint8_t *out_cts,
+                         uint64_t out_cap, uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
+                         int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
+                         pf_search_stats *stats, uint64_t *ticket) {
+    if (!e || !query_cts || !ct_offsets || !idx || !ticket) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    HostTick htall("search_submit");
     std::lock_guard<std::mutex> lk(e->mu);
+    int rc = check_device_error(e);
+    if (rc) return rc;
     if (!e->has_index || (!e->d_diag.p && e->ntotal)) return e->fail(PF_ERR_STATE, "no encodable index loaded");
+    int fi = -1;
+    for (int i = 0; i < PF_MAX_FLIGHTS; i++)
+        if (!e->flights[i].busy) {
+            fi = i;
+            break;
+        }
+    if (fi < 0) return e->fail(PF_ERR_STATE, "%d searches already in flight: collect one first", PF_MAX_FLIGHTS);
+    pf_engine::Flight &fl = e->flights[fi];
     CK(cudaSetDevice(e->prm.device));
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N, ncts = nq * e->m;
+    // the ciphertext streams sit inside [0, query_bytes): offsets ascending, every stream inside the blob
+    for (size_t c = 0; c < ncts; c++)
+        if (ct_offsets[c + 1] < ct_offsets[c] || ct_offsets[c + 1] > query_bytes)
+            return e->fail(PF_ERR_INVALID, "ct_offsets[%zu..%zu] = [%llu, %llu) is not an ascending range inside the %llu-byte query blob", c,
+                           c + 1, (unsigned long long)ct_offsets[c], (unsigned long long)ct_offsets[c + 1], (unsigned long long)query_bytes);
     PairPlan pl;
-    int rc = plan_pairs(e, nq, idx, nprobe, pl);
+    {
+        HostTick ht("plan_pairs");
+        rc = plan_pairs(e, nq, idx, nprobe, pl);
+    }
     if (rc) return rc;
     const uint64_t P = pl.pair_block.size();
     const size_t rw = (size_t)2 * e->Lr * N; // words of a result ciphertext
@@ -2014,36 +2112,41 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         stats->slot_distances = P * e->C;
     }
     if (results_per_query) memcpy(results_per_query, pl.results_per_query.data(), nq * sizeof(uint64_t));
-    if (P > max_results || P * slot > out_cap || (labels && nlabels > label_cap))
+    if (P > max_results || P * slot > out_cap || (P && !out_cts) || (labels && nlabels > label_cap))
         return e->fail(PF_ERR_CAPACITY, "need %llu results / %llu bytes / %llu labels", (unsigned long long)P, (unsigned long long)(P * slot), (unsigned long long)nlabels);
-    // parse + upload the query ciphertexts
-    CK(e->s_qcts.ensure_grow(std::max<size_t>(8, ncts * ctw * 8)));
+    // parse the query ciphertexts
+    CK(fl.qcts.ensure_grow(std::max<size_t>(8, ncts * ctw * 8)));
     uint64_t parms_id[4] = {0, 0, 0, 0};
     std::vector<const uint8_t *> ct_src(ncts);
     std::vector<std::vector<uint8_t>> inflated; // zlib-compressed queries (slow path: inflated on the host)
-    for (size_t c = 0; c < ncts; c++) {
-        const uint8_t *src = query_cts + ct_offsets[c];
-        size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
-        if (len >= 16 && src[5] == 1) {
-            inflated.emplace_back();
-            const int zr = inflate_seal_stream(src, len, inflated.back(), nullptr);
-            if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed zlib stream (code %d)", c, zr);
-            src = inflated.back().data();
-            len = inflated.back().size();
+    {
+        HostTick ht("parse_queries");
+        for (size_t c = 0; c < ncts; c++) {
+            const uint8_t *src = query_cts + ct_offsets[c];
+            size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
+            if (len >= 16 && src[5] == 1) {
+                inflated.emplace_back();
+                const int zr = inflate_seal_stream(src, len, inflated.back(), nullptr, SEAL_CT_HEADER + ctw * 8);
+                if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed zlib stream (code %d)", c, zr);
+                src = inflated.back().data();
+                len = inflated.back().size();
+            }
+            ct_src[c] = src;
+            int is_ntt;
+            uint64_t cms;
+            size_t total;
+            const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
+            if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu uses an unsupported compression (zstd); save with compr_mode_type::none or zlib", c);
+            if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
+            if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
         }
-        ct_src[c] = src;
-        int is_ntt;
-        uint64_t cms;
-        size_t total;
-        const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
-        if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu uses an unsupported compression (zstd); save with compr_mode_type::none or zlib", c);
-        if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
-        if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
     }
     // Query groups: the H2D of group i+1 (upload stream) and the D2H of group i-1 (copy stream) overlap
-    // the compute of group i (engine stream).
+    // the compute of group i (engine stream).  With calls pipelined through submit / collect the overlap
+    // comes from the neighbouring calls, and one group (whole-batch kernels) is the most efficient.
     static const uint64_t env_groups = getenv("PF_E2E_GROUPS") ? (uint64_t)atoi(getenv("PF_E2E_GROUPS")) : 0;
-    const uint64_t ngroups = std::min<uint64_t>(nq, env_groups ? std::min<uint64_t>(env_groups, PF_E2E_GROUPS) : 4);
+    const uint64_t want_groups = env_groups ? env_groups : (e->groups_hint ? (uint64_t)e->groups_hint : 4);
+    const uint64_t ngroups = std::max<uint64_t>(1, std::min<uint64_t>(nq, std::min<uint64_t>(want_groups, PF_E2E_GROUPS)));
     // group boundaries: with 4 groups the last one is the smallest (its D2H is the only copy nothing hides)
     uint64_t q_end[PF_E2E_GROUPS + 1];
     q_end[0] = 0;
@@ -2051,39 +2154,53 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         static const uint64_t w4[4] = {5, 10, 14, 16};
         q_end[gi + 1] = (ngroups == 4 && nq >= 16) ? nq * w4[gi] / 16 : nq * (gi + 1) / ngroups;
     }
-    // From here on copies that touch the caller's buffers are in flight on three streams: whatever way
-    // this function is left, they are drained first (and the upload arena slot is closed).
-    struct DrainOnExit {
+    // From here on copies that touch the caller's buffers are in flight on three streams: if this
+    // function fails they are drained before it returns (and the upload arena slot is closed).
+    struct DrainOnError {
         pf_engine *e;
-        bool arena_open = false;
-        ~DrainOnExit() {
+        bool armed = true, arena_open = false;
+        ~DrainOnError() {
             if (arena_open) arena_end(e);
+            if (!armed) return;
             cudaStreamSynchronize(e->upload_stream);
             cudaStreamSynchronize(e->stream);
             cudaStreamSynchronize(e->copy_stream);
         }
     } drain{e};
-    for (uint64_t gi = 0; gi < ngroups; gi++) {
-        for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
-            CK(cudaMemcpyAsync(e->s_qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
-                               cudaMemcpyHostToDevice, e->upload_stream));
-        CK(cudaEventRecord(e->ev_up[gi], e->upload_stream));
+    {
+        HostTick ht("enqueue_h2d");
+        for (uint64_t gi = 0; gi < ngroups; gi++) {
+            for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
+                CK(cudaMemcpyAsync(fl.qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
+                                   cudaMemcpyHostToDevice, e->upload_stream));
+            CK(cudaEventRecord(fl.ev_up[gi], e->upload_stream));
+        }
     }
-    CK(e->s_out.ensure_grow(std::max<size_t>(8, P * slot)));
-    uint8_t *d_blob = e->s_out.as<uint8_t>();
+    CK(fl.out.ensure_grow(std::max<size_t>(8, P * slot)));
+    uint8_t *d_blob = fl.out.as<uint8_t>();
     u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
     rc = arena_begin(e);
     if (rc) return rc;
     drain.arena_open = true;
     rc = upload_plan(e, pl);
     if (rc) return rc;
+    // SEAL stream headers (113 bytes in front of the aligned words of every result), written on the device
+    // so that they travel with the one D2H per group.  Result parms_id: caller's override, else the
+    // query's at full level, else SEAL's hash of the parameters of the level the results were switched to
+    if (P) {
+        const uint64_t *out_pid = e->result_pid_set ? e->result_pid : (e->Lr == L ? parms_id : e->level_pid[e->Lr]);
+        ResultHeader hd{};
+        write_ct_prefix(e, hd.b, 0, out_pid, e->Lr);
+        stamp_headers_kernel<<<(unsigned)((P + 127) / 128), 128, 0, e->stream>>>(d_blob, slot, PF_RESULT_PAD, P, hd);
+        e->launches++;
+    }
     uint64_t pair_lo = 0, q_lo = 0;
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         const uint64_t q_hi = q_end[gi + 1];
-        CK(cudaStreamWaitEvent(e->stream, e->ev_up[gi], 0));
+        CK(cudaStreamWaitEvent(e->stream, fl.ev_up[gi], 0));
         uint64_t pair_hi = pair_lo;
         for (uint64_t q = q_lo; q < q_hi; q++) pair_hi += pl.results_per_query[q];
-        rc = search_core(e, q_lo, q_hi - q_lo, e->s_qcts.as<u64>() + q_lo * e->m * ctw, pl, d_words, slot / 8);
+        rc = search_core(e, q_lo, q_hi - q_lo, fl.qcts.as<u64>() + q_lo * e->m * ctw, pl, d_words, slot / 8);
         if (rc) return rc;
         if (pair_hi > pair_lo) {
             cudaEvent_t ev = e->ev_group[gi & 1];
@@ -2095,9 +2212,24 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
         pair_lo = pair_hi;
         q_lo = q_hi;
     }
+    // the flight is complete when the engine stream (rotations of an empty plan included) and the last
+    // copy are done
+    CK(cudaEventRecord(e->ev_group[0], e->stream));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->ev_group[0], 0));
+    CK(cudaEventRecord(fl.done, e->copy_stream));
     arena_end(e);
     drain.arena_open = false;
-    // labels of the owned probed lists (same packing as pf_search_lists_plain), copied while the GPU works
+    drain.armed = false;
+    fl.busy = true;
+    fl.id = ++e->next_ticket;
+    *ticket = fl.id;
+    // host-side share of the response, while the GPU works: result offsets and the labels of the owned
+    // probed lists (same packing as pf_search_lists_plain)
+    HostTick htl("labels+offsets");
+    if (result_offsets) {
+        for (uint64_t r = 0; r < P; r++) result_offsets[r] = r * slot + PF_RESULT_PAD;
+        result_offsets[P] = P * slot;
+    }
     if (labels) {
         uint64_t pos = 0;
         for (uint64_t i = 0; i < nq * nprobe; i++) {
@@ -2108,16 +2240,69 @@ int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_ct
             pos += n;
         }
     }
-    CK(cudaStreamSynchronize(e->stream));
-    CK(cudaStreamSynchronize(e->copy_stream));
-    // result parms_id: caller's override, else the query's at full level, else SEAL's hash of the
-    // parameters of the level the results were switched to
-    const uint64_t *out_pid = e->result_pid_set ? e->result_pid : (e->Lr == L ? parms_id : e->level_pid[e->Lr]);
-    for (uint64_t r = 0; r < P; r++) { // SEAL stream headers (113 bytes each) in front of the aligned words
-        write_ct_prefix(e, out_cts + r * slot + PF_RESULT_PAD, 0, out_pid, e->Lr);
-        if (result_offsets) result_offsets[r] = r * slot + PF_RESULT_PAD;
+    return PF_OK;
+}
+
+int pf_search_submit(pf_engine *e, uint64_t nq, const uint8_t *query_cts, uint64_t query_bytes, const uint64_t *ct_offsets,
+                     const int64_t *idx, uint32_t nprobe, uint8_t *out_cts, uint64_t out_cap, uint64_t *result_offsets,
+                     uint64_t max_results, uint64_t *results_per_query, int64_t *labels, uint64_t label_cap,
+                     uint64_t *list_sizes, uint64_t *probed_sizes, pf_search_stats *stats, uint64_t *ticket) {
+    return submit_search(e, nq, query_cts, query_bytes, ct_offsets, idx, nprobe, out_cts, out_cap, result_offsets,
+                         max_results, results_per_query, labels, label_cap, list_sizes, probed_sizes, stats, ticket);
+}
+
+int pf_search_collect(pf_engine *e, uint64_t ticket) {
+    if (!e) return PF_ERR_INVALID;
+    HostTick ht("search_collect");
+    cudaEvent_t done = nullptr;
+    int fi = -1;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        for (int i = 0; i < PF_MAX_FLIGHTS; i++)
+            if (e->flights[i].busy && e->flights[i].id == ticket) fi = i;
+        if (fi < 0) return e->fail(PF_ERR_STATE, "no search in flight with ticket %llu", (unsigned long long)ticket);
+        done = e->flights[fi].done;
+        CK(cudaSetDevice(e->prm.device));
     }
-    if (result_offsets) result_offsets[P] = P * slot;
+    const cudaError_t ce = cudaEventSynchronize(done); // not under the lock: another thread may submit meanwhile
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->flights[fi].busy = false;
+    if (ce != cudaSuccess) return e->fail(PF_ERR_CUDA, "search %llu failed: %s", (unsigned long long)ticket, cudaGetErrorString(ce));
+    return check_device_error(e);
+}
+
+int pf_search_set_groups(pf_engine *e, uint32_t groups) {
+    if (!e || groups > PF_E2E_GROUPS) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->groups_hint = (int)groups;
+    return PF_OK;
+}
+
+int pf_search_lists_encrypted(pf_engine *e, uint64_t nq, const uint8_t *query_cts, uint64_t query_bytes,
+                              const uint64_t *ct_offsets, const int64_t *idx, uint32_t nprobe, uint8_t *out_cts,
+                              uint64_t out_cap, uint64_t *result_offsets, uint64_t max_results, uint64_t *results_per_query,
+                              int64_t *labels, uint64_t label_cap, uint64_t *list_sizes, uint64_t *probed_sizes,
+                              pf_search_stats *stats) {
+    uint64_t ticket = 0;
+    const int rc = submit_search(e, nq, query_cts, query_bytes, ct_offsets, idx, nprobe, out_cts, out_cap, result_offsets,
+                                 max_results, results_per_query, labels, label_cap, list_sizes, probed_sizes, stats, &ticket);
+    if (rc) return rc;
+    return pf_search_collect(e, ticket);
+}
+
+int pf_host_register(pf_engine *e, void *ptr, size_t bytes) {
+    if (!e || !ptr || !bytes) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return PF_OK;
+}
+
+int pf_host_unregister(pf_engine *e, void *ptr) {
+    if (!e || !ptr) return PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->prm.device));
+    CK(cudaHostUnregister(ptr));
     return PF_OK;
 }
 
@@ -2358,7 +2543,7 @@ int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct,
     uint64_t pid[4], cms;
     size_t total, zconsumed = 0;
     std::vector<uint8_t> plain;
-    const int zr = inflate_seal_stream(in, len, plain, &zconsumed);
+    const int zr = inflate_seal_stream(in, len, plain, &zconsumed, SEAL_CT_HEADER + (size_t)2 * e->L * e->N * 8);
     if (zr < 0) return e->fail(PF_ERR_FORMAT, "malformed compressed ciphertext (code %d)", zr);
     if (zr == 0) {
         in = plain.data();

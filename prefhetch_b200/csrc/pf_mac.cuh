@@ -328,310 +328,6 @@ __global__ void __launch_bounds__(256, MINCTA) mac_kernel_occ(const MacParams p)
         mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi, pol, pol);
 }
 
-// ---- cp.async variant -------------------------------------------------------------------------------
-// Same mapping as mac_kernel, but the plaintext words travel global -> shared with cp.async (LDGSTS)
-// into a per-thread private ring of NS stages (each stage = UNROLL k-rows x 2 blocks x 16 B), so the
-// loads in flight are bounded by shared memory, not by registers, and stay in flight across the MACs
-// and across block boundaries.  A thread reads back only what it copied itself: no barrier, just
-// cp.async.wait_group.  smem = ct slice K*2*T*8 + ring NS*UNROLL*2*16*256 bytes.
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int NPEND>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(NPEND));
-}
-
-template <int T, int UNROLL, int NS>
-__global__ void __launch_bounds__(256, 2) mac_kernel_async(const MacParams p) {
-    constexpr int TX = T / 2, BY = 256 / TX, BT = 2;
-    extern __shared__ __align__(16) u64 smem_ct[]; // [K][2][T] then the ring
-    const MacChunk ch = p.chunks[blockIdx.x];
-    const int slices = p.N / T;
-    const int l = blockIdx.y / slices, s = blockIdx.y % slices;
-    const int tx = threadIdx.x % TX, by = threadIdx.x / TX;
-    const DevModulus m = p.mods[l];
-    const int split = (int)m.split_shift;
-    const size_t LN = (size_t)p.L * p.N;
-    const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
-    ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(smem_ct + (size_t)p.K * 2 * T) + threadIdx.x;
-    // ring slot (stage, u, j) of this thread: ring[((stage*UNROLL + u)*BT + j) * 256]
-    {
-        const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
-        const int rows = p.K * 2;
-        for (int i = threadIdx.x; i < rows * TX; i += 256) {
-            const int row = i / TX, c = i % TX;
-            cp_async16(reinterpret_cast<ulonglong2 *>(smem_ct) + (size_t)row * TX + c,
-                       reinterpret_cast<const ulonglong2 *>(src + (size_t)row * LN) + c);
-        }
-        cp_async_commit();
-    }
-    const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(smem_ct) + tx;
-    const int KG = p.K / UNROLL;                                      // k-groups per pair-group
-    const int npg = (ch.pair_count - by * BT + BY * BT - 1) / (BY * BT); // pair-groups of this lane (may be <= 0)
-    const int total = npg > 0 ? npg * KG : 0;
-    const size_t sk2 = (size_t)p.diag_sk / 2;
-
-    auto issue = [&](int g) { // copy k-group g of the flattened (pair-group, k-group) sequence
-        if (g < total) {
-            const int pg = g / KG, kg = g % KG, stage = g % NS;
-            const int pi = by * BT + pg * BY * BT;
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                if (pi + j < ch.pair_count) {
-                    const long long b = p.pair_block[ch.pair_start + pi + j];
-                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.diag + (size_t)b * p.diag_sb + coef0) +
-                                            tx + (size_t)kg * UNROLL * sk2;
-#pragma unroll
-                    for (int u = 0; u < UNROLL; u++)
-                        cp_async16(ring + (size_t)((stage * UNROLL + u) * BT + j) * 256, src + (size_t)u * sk2);
-                }
-            }
-        }
-        cp_async_commit(); // always commit so the group count per iteration is fixed
-    };
-
-#pragma unroll
-    for (int g = 0; g < NS - 1; g++) issue(g);
-    cp_async_wait<NS - 1>(); // the ct slice group (oldest) has landed for this thread ...
-    __syncthreads();         // ... and for every thread
-
-    LazyAcc acc[BT][2][2];
-#pragma unroll
-    for (int j = 0; j < BT; j++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            lazy_zero(acc[j][c][0]);
-            lazy_zero(acc[j][c][1]);
-        }
-    for (int g = 0; g < total; g++) {
-        issue(g + NS - 1);
-        cp_async_wait<NS - 1>(); // group g is complete
-        const int pg = g / KG, kg = g % KG, stage = g % NS;
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const int k = kg * UNROLL + u;
-            const ulonglong2 c0 = sct[(size_t)(k * 2 + 0) * TX];
-            const ulonglong2 c1 = sct[(size_t)(k * 2 + 1) * TX];
-            const SplitOp a00 = make_op(c0.x), a01 = make_op(c0.y), a10 = make_op(c1.x), a11 = make_op(c1.y);
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                const ulonglong2 pt = ring[(size_t)((stage * UNROLL + u) * BT + j) * 256];
-                const SplitOp b0 = make_op(pt.x), b1 = make_op(pt.y);
-                lazy_mac(acc[j][0][0], a00.x0, a00.x1, a00.xs, b0.x0, b0.x1, b0.xs);
-                lazy_mac(acc[j][0][1], a01.x0, a01.x1, a01.xs, b1.x0, b1.x1, b1.xs);
-                lazy_mac(acc[j][1][0], a10.x0, a10.x1, a10.xs, b0.x0, b0.x1, b0.xs);
-                lazy_mac(acc[j][1][1], a11.x0, a11.x1, a11.xs, b1.x0, b1.x1, b1.xs);
-            }
-        }
-        if (kg == KG - 1) { // last k-group of the pair-group: reduce, add norms, store, reset
-            const int pi = by * BT + pg * BY * BT;
-#pragma unroll
-            for (int j = 0; j < BT; j++) {
-                if (pi + j < ch.pair_count) {
-                    const size_t pair = (size_t)ch.pair_start + pi + j;
-                    const size_t slot = (size_t)p.pair_out[pair];
-                    ulonglong2 r0, r1;
-                    r0.x = lazy_reduce(acc[j][0][0], split, m);
-                    r0.y = lazy_reduce(acc[j][0][1], split, m);
-                    r1.x = lazy_reduce(acc[j][1][0], split, m);
-                    r1.y = lazy_reduce(acc[j][1][1], split, m);
-                    if (p.norm) {
-                        const long long b = p.pair_block[pair];
-                        const ulonglong2 nv = ldg_stream(
-                            reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
-                        r0.x = addmod(r0.x, nv.x, m.q);
-                        r0.y = addmod(r0.y, nv.y, m.q);
-                    }
-                    u64 *o = p.out + slot * (size_t)p.out_stride + coef0;
-                    stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
-                    stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
-                }
-                lazy_zero(acc[j][0][0]);
-                lazy_zero(acc[j][0][1]);
-                lazy_zero(acc[j][1][0]);
-                lazy_zero(acc[j][1][1]);
-            }
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// ---- TMA (cp.async.bulk) variant ---------------------------------------------------------------------
-// Producer / consumer pipeline.  One elected thread of warp 8 streams the plaintext rows (T*8 = 2 KiB
-// contiguous each) of 4 blocks x KS diagonals per stage into a ring of NST stages with
-// cp.async.bulk...mbarrier::complete_tx; the 8 consumer warps wait on the stage's "full" mbarrier,
-// run the split-operand MACs out of shared memory and release the stage through its "empty" mbarrier.
-// Bytes in flight are set by the ring (NST-1 stages x 16 KiB per CTA, 2 CTAs per SM), not by registers
-// or by how many LDGs a warp can have outstanding; the query's ciphertext slice arrives the same way.
-// SASS: UBLKCP (bulk copy), SYNCS.* (mbarrier).
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(void *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, void *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-template <int T, int KS, int NST, bool FPRED>
-__global__ void __launch_bounds__(288, 2) mac_kernel_tma(const MacParams p) {
-    constexpr int TX = T / 2, BY = 256 / TX, BT = 2, PG = BY * BT; // PG pairs per pair-group
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    u64 *sct_base = reinterpret_cast<u64 *>(smem_raw);                         // [K][2][T]
-    u64 *ring = sct_base + (size_t)p.K * 2 * T;                               // [NST][PG][KS][T]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)NST * PG * KS * T);
-    unsigned long long *full = bars, *empty = bars + NST, *ctbar = bars + 2 * NST;
-    const MacChunk ch = p.chunks[blockIdx.x];
-    const int slices = p.N / T;
-    const int l = blockIdx.y / slices, s = blockIdx.y % slices;
-    const size_t LN = (size_t)p.L * p.N;
-    const size_t coef0 = (size_t)l * p.N + (size_t)s * T;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KG = p.K / KS;
-    const int npg = (ch.pair_count + PG - 1) / PG;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NST; i++) {
-            mbar_init(full + i, 1);
-            mbar_init(empty + i, 8);
-        }
-        mbar_init(ctbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp == 8) {
-        if (lane == 0) {
-            // the query's rotated-ciphertext slice: 2K rows of T*8 bytes
-            mbar_expect_tx(ctbar, (unsigned)(p.K * 2 * T * 8));
-            const u64 *src = p.rot + (size_t)(ch.query - p.query_base) * p.K * 2 * LN + coef0;
-            for (int row = 0; row < p.K * 2; row++) bulk_g2s(sct_base + (size_t)row * T, src + (size_t)row * LN, T * 8, ctbar);
-            int g = 0;
-            for (int pg = 0; pg < npg; pg++) {
-                const int nvalid = min(PG, ch.pair_count - pg * PG);
-                const u64 *bsrc[PG];
-#pragma unroll
-                for (int j = 0; j < PG; j++) {
-                    const long long b = p.pair_block[ch.pair_start + pg * PG + min(j, nvalid - 1)];
-                    bsrc[j] = p.diag + (size_t)b * p.diag_sb + coef0;
-                }
-                for (int kg = 0; kg < KG; kg++, g++) {
-                    const int stage = g % NST;
-                    mbar_wait(empty + stage, ((g / NST) & 1) ^ 1);
-                    mbar_expect_tx(full + stage, (unsigned)(nvalid * KS * T * 8));
-                    u64 *dst = ring + (size_t)stage * PG * KS * T;
-#pragma unroll
-                    for (int j = 0; j < PG; j++)
-                        if (j < nvalid)
-#pragma unroll
-                            for (int u = 0; u < KS; u++)
-                                bulk_g2s(dst + (size_t)(j * KS + u) * T, bsrc[j] + (size_t)(kg * KS + u) * p.diag_sk, T * 8,
-                                         full + stage);
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- consumers: 8 warps, thread = 2 coefficients x 2 blocks ----
-    const int tx = threadIdx.x % TX, by = threadIdx.x / TX;
-    const DevModulus m = p.mods[l];
-    const int split = (int)m.split_shift;
-    const double qinv = 1.0 / (double)m.q;
-    const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(sct_base) + tx;
-    LazyAcc acc[BT][2][2];
-#pragma unroll
-    for (int j = 0; j < BT; j++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {
-            lazy_zero(acc[j][c][0]);
-            lazy_zero(acc[j][c][1]);
-        }
-    mbar_wait(ctbar, 0);
-    int g = 0;
-    for (int pg = 0; pg < npg; pg++) {
-        const int nvalid = min(PG, ch.pair_count - pg * PG);
-        for (int kg = 0; kg < KG; kg++, g++) {
-            const int stage = g % NST;
-            mbar_wait(full + stage, (g / NST) & 1);
-            const ulonglong2 *st = reinterpret_cast<const ulonglong2 *>(ring + (size_t)stage * PG * KS * T) + tx;
-#pragma unroll
-            for (int u = 0; u < KS; u++) {
-                const int k = kg * KS + u;
-                const ulonglong2 c0 = sct[(size_t)(k * 2 + 0) * TX];
-                const ulonglong2 c1 = sct[(size_t)(k * 2 + 1) * TX];
-                const SplitOp a00 = make_op(c0.x), a01 = make_op(c0.y), a10 = make_op(c1.x), a11 = make_op(c1.y);
-#pragma unroll
-                for (int jj = 0; jj < BT; jj++) {
-                    const int j = by * BT + jj;
-                    if (j < nvalid) { // warp-uniform
-                        const ulonglong2 pt = st[(size_t)(j * KS + u) * TX];
-                        const SplitOp b0 = make_op(pt.x), b1 = make_op(pt.y);
-                        lazy_mac(acc[jj][0][0], a00.x0, a00.x1, a00.xs, b0.x0, b0.x1, b0.xs);
-                        lazy_mac(acc[jj][0][1], a01.x0, a01.x1, a01.xs, b1.x0, b1.x1, b1.xs);
-                        lazy_mac(acc[jj][1][0], a10.x0, a10.x1, a10.xs, b0.x0, b0.x1, b0.xs);
-                        lazy_mac(acc[jj][1][1], a11.x0, a11.x1, a11.xs, b1.x0, b1.x1, b1.xs);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-            if (kg == KG - 1) {
-#pragma unroll
-                for (int jj = 0; jj < BT; jj++) {
-                    const int j = by * BT + jj;
-                    if (j < nvalid) {
-                        const size_t pair = (size_t)ch.pair_start + pg * PG + j;
-                        const size_t slot = (size_t)p.pair_out[pair];
-                        ulonglong2 r0, r1;
-                        r0.x = lazy_reduce_sel<FPRED>(acc[jj][0][0], split, m, qinv);
-                        r0.y = lazy_reduce_sel<FPRED>(acc[jj][0][1], split, m, qinv);
-                        r1.x = lazy_reduce_sel<FPRED>(acc[jj][1][0], split, m, qinv);
-                        r1.y = lazy_reduce_sel<FPRED>(acc[jj][1][1], split, m, qinv);
-                        if (p.norm) {
-                            const long long b = p.pair_block[pair];
-                            const ulonglong2 nv = ldg_stream(
-                                reinterpret_cast<const ulonglong2 *>(p.norm + (size_t)b * p.norm_sb + coef0) + tx);
-                            r0.x = addmod(r0.x, nv.x, m.q);
-                            r0.y = addmod(r0.y, nv.y, m.q);
-                        }
-                        u64 *o = p.out + slot * (size_t)p.out_stride + coef0;
-                        stg_stream(reinterpret_cast<ulonglong2 *>(o) + tx, r0);
-                        stg_stream(reinterpret_cast<ulonglong2 *>(o + LN) + tx, r1);
-                    }
-                    lazy_zero(acc[jj][0][0]);
-                    lazy_zero(acc[jj][0][1]);
-                    lazy_zero(acc[jj][1][0]);
-                    lazy_zero(acc[jj][1][1]);
-                }
-            }
-        }
-    }
-}
-
 // canonical <-> split conversion of polynomial arrays: chunk y (blockIdx.y) of `chunk_words` words is
 // read at in + y*in_stride and written at out + y*out_stride; limb of word i of a chunk = (i / N) % L
 __global__ void __launch_bounds__(256) split_convert_kernel(const u64 *in, u64 *out, size_t chunk_words,

@@ -14,8 +14,6 @@
 // W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j)  (pf_keyswitch.cuh step 3), entered as the centred
 // representative of u mod P, which is congruent to it mod q_j
 enum { NTT_IN_PLAIN = 0, NTT_IN_REDUCE = 1, NTT_IN_LIFT = 2, NTT_IN_GALOIS_REDUCE = 3, NTT_IN_MODDOWN = 4 };
-// epilogues fused into the transforms of the key-switch mod-down (pf_keyswitch.cuh steps 3 and 4)
-enum { NTT_OUT_PLAIN = 0, NTT_OUT_KS = 1, NTT_OUT_MODSWITCH = 2 };
 
 struct NttParams {
     const u64 *in;
@@ -32,20 +30,10 @@ struct NttParams {
     const struct RotJob *jobs;   // NTT_IN_GALOIS_REDUCE: per blockIdx.z source polynomial and element
     int out_split;               // forward only: store results in the MAC's split operand format
     int *zero_flags;             // NTT_IN_REDUCE: zero_flags[blockIdx.z] = 1 if an input coefficient is 0
-    // NTT_OUT_KS (grid (.., c, z)): inverse = mod-down prep, forward = key-switch finish
-    u64 *ks_W;                   // [z][2][L][N]
-    const u64 *ks_S;             // [z][2][L+1][N]
-    int ks_L;
-    u64 ks_p_half;               // also NTT_IN_MODDOWN: floor(P/2)
+    u64 ks_p_half;               // NTT_IN_MODDOWN: floor(P/2)
     int md_pmod;                 // NTT_IN_MODDOWN: index of the special prime in mods
     int hoisted_jobs;            // NTT_IN_GALOIS_REDUCE: host hint, the jobs carry hoisted digits (RotJob.D)
     int njobs, job_group;        // NTT_IN_GALOIS_REDUCE (FP64 kernels): CTA z covers jobs [z*job_group, ...) < njobs
-    // NTT_OUT_MODSWITCH (inverse, grid (kept limb j, poly, result)): the dropped limbs [ms_Lr, ms_L) are
-    // already in coefficient form at ms_dropped + z*ms_dropped_sz + poly*(ms_L-ms_Lr)*N + (c-ms_Lr)*N
-    const u64 *ms_dropped;
-    long long ms_dropped_sz;
-    const u64 *ms_tab; // [(c*16 + j)*3 + {half_c mod q_j, q_c^-1 mod q_j, Shoup}]
-    int ms_L, ms_Lr;
 };
 
 // one rotation = Evaluator::apply_galois_inplace on one ciphertext (see pf_keyswitch.cuh)
@@ -190,7 +178,7 @@ __device__ __forceinline__ void ntt_inv_pass(const Twiddle *__restrict__ itw, co
     }
 }
 
-template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
+template <int LOGN, int INMODE>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_kernel(const NttParams p) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) u64 sm[];
@@ -239,30 +227,11 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         const u64 two_q = q << 1;
         x = x >= two_q ? x - two_q : x;
         x = x >= q ? x - q : x;
-        if (OUTMODE == NTT_OUT_PLAIN && p.out_split) x = ((x >> m.split_shift) << 32) | (x & ((1ull << m.split_shift) - 1));
+        if (p.out_split) x = ((x >> m.split_shift) << 32) | (x & ((1ull << m.split_shift) - 1));
         sm[sm_phys(idx)] = x;
     };
     ntt_fwd_pass<LOGN, Cfg::K3, 4>(tw, q, sload, fstore);
     __syncthreads();
-    if (OUTMODE == NTT_OUT_KS) {
-        // key-switch finish: x = blockIdx.x = data limb j, y = component c, z = job.  The transform just
-        // computed is NTT_j(W_c[j]);  out_c[j] = (S_c[j] - it) * P^{-1} (+ sigma_ntt(c0)[j] for c = 0)
-        const int j = blockIdx.x, c = blockIdx.y, L = p.ks_L;
-        const RotJob job = p.jobs[blockIdx.z];
-        const u64 *S = p.ks_S + ((size_t)blockIdx.z * 2 + c) * (L + 1) * Cfg::N + (size_t)j * Cfg::N;
-        u64 *o = job.out + ((size_t)c * L + j) * Cfg::N;
-        const u64 pinv = m.p_inv, pinv_sh = m.p_inv_sh;
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            const int idx = i * Cfg::NT + threadIdx.x;
-            const u64 w = sm[sm_phys(idx)];
-            u64 r = mul_shoup(submod(S[idx], w, q), pinv, pinv_sh, q);
-            if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * Cfg::N + job.perm[idx]], q);
-            if (p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
-            o[idx] = r;
-        }
-        return;
-    }
 #pragma unroll 8
     for (int i = 0; i < 32; i++) {
         const int idx = i * Cfg::NT + threadIdx.x;
@@ -270,7 +239,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
     }
 }
 
-template <int LOGN, int OUTMODE = NTT_OUT_PLAIN>
+template <int LOGN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_inv_kernel(const NttParams p) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) u64 sm[];
@@ -279,12 +248,6 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
     const Twiddle *itw = p.tw + (size_t)mi * 2 * Cfg::N + Cfg::N;
     const u64 *in = p.in + blockIdx.x * p.in_sx + blockIdx.y * p.in_sy + blockIdx.z * p.in_sz;
     u64 *out = p.out + blockIdx.x * p.out_sx + blockIdx.y * p.out_sy + blockIdx.z * p.out_sz;
-    __shared__ u64 epi_q[PF_NTT_MAXMAP], epi_ratio[PF_NTT_MAXMAP], epi_half[PF_NTT_MAXMAP];
-    if (OUTMODE == NTT_OUT_KS && (int)threadIdx.x < p.ks_L) {
-        epi_q[threadIdx.x] = p.mods[threadIdx.x].q;
-        epi_ratio[threadIdx.x] = p.mods[threadIdx.x].ratio1;
-        epi_half[threadIdx.x] = p.mods[threadIdx.x].p_half_mod;
-    }
 #pragma unroll 8
     for (int i = 0; i < 32; i++) {
         const int idx = i * Cfg::NT + threadIdx.x;
@@ -293,20 +256,7 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
     __syncthreads();
     auto sload = [&](int idx) -> u64 { return sm[sm_phys(idx)]; };
     auto sstore = [&](int idx, u64 x) { sm[sm_phys(idx)] = x; };
-    auto gstore = [&](int idx, u64 x) {
-        if (OUTMODE == NTT_OUT_KS) {
-            // mod-down prep: x = u_c = INTT_P(S_c[P]);  W_c[j] = ((u + P/2) mod P mod q_j) - (P/2 mod q_j)
-            const int L = p.ks_L;
-            u64 *W = p.ks_W + ((size_t)blockIdx.z * 2 + blockIdx.y) * L * Cfg::N;
-            const u64 v = barrett64(x + p.ks_p_half, m.q, m.ratio1);
-            for (int j = 0; j < L; j++) {
-                const u64 qj = epi_q[j];
-                W[(size_t)j * Cfg::N + idx] = submod(barrett64(v, qj, epi_ratio[j]), epi_half[j], qj);
-            }
-        } else {
-            out[idx] = x;
-        }
-    };
+    auto gstore = [&](int idx, u64 x) { out[idx] = x; };
     ntt_inv_pass<LOGN, Cfg::K3, 0, false>(itw, m, sload, sstore);
     __syncthreads();
     ntt_inv_pass<LOGN, Cfg::K2, 5, false>(itw, m, sload, sstore);

@@ -1,5 +1,5 @@
 // pf_ntt_fp.cuh — the same negacyclic NTT / inverse NTT as pf_ntt.cuh (same passes, same SEAL
-// ordering, same load modes and epilogues, bit-identical canonical results), with the butterflies
+// ordering, same load modes, bit-identical canonical results), with the butterflies
 // moved from the integer pipes to the FP64 pipe.
 //
 // Why: B200 (sm_100a) issues 64 DFMA lanes/clk/SM — the same rate as IMAD.WIDE — and the pipe is
@@ -165,7 +165,7 @@ __device__ __forceinline__ void fp_inv_pass(const double *__restrict__ itw, doub
 // 32 cache lines per instruction; ncu: 682 L1 wavefronts per warp per transform, half the kernel's LSU
 // traffic); lane-major makes every load one 256-byte run (62 wavefronts).
 // p.tw_fp: [nmod][2][N] doubles (centred twiddles); p.fp_consts: [nmod] {q, 1/q, centred N^-1, centred irp[1]*N^-1}
-template <int LOGN, int INMODE, int OUTMODE>
+template <int LOGN, int INMODE>
 __device__ __forceinline__ void ntt_fwd_fp_body(const NttParams &p, const unsigned bz) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) double smd[];
@@ -223,28 +223,11 @@ __device__ __forceinline__ void ntt_fwd_fp_body(const NttParams &p, const unsign
     u64 *smu = reinterpret_cast<u64 *>(smd);
     auto fstore = [&](int idx, double x) {
         u64 r = fp_canonical(x, q, qinv);
-        if (OUTMODE == NTT_OUT_PLAIN && p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
+        if (p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
         smu[sm_phys(idx)] = r;
     };
     fp_fwd_pass<LOGN, Cfg::K3, 4>(twl, q, qinv, sload, fstore);
     __syncthreads();
-    if (OUTMODE == NTT_OUT_KS) {
-        const int j = blockIdx.x, c = blockIdx.y, L = p.ks_L;
-        const RotJob job = p.jobs[bz];
-        const u64 *S = p.ks_S + ((size_t)bz * 2 + c) * (L + 1) * Cfg::N + (size_t)j * Cfg::N;
-        u64 *o = job.out + ((size_t)c * L + j) * Cfg::N;
-        const u64 pinv = m.p_inv, pinv_sh = m.p_inv_sh, qi = m.q;
-#pragma unroll 8
-        for (int i = 0; i < 32; i++) {
-            const int idx = i * Cfg::NT + threadIdx.x;
-            const u64 w = smu[sm_phys(idx)];
-            u64 r = mul_shoup(submod(S[idx], w, qi), pinv, pinv_sh, qi);
-            if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * Cfg::N + job.perm[idx]], qi);
-            if (p.out_split) r = ((r >> m.split_shift) << 32) | (r & ((1ull << m.split_shift) - 1));
-            o[idx] = r;
-        }
-        return;
-    }
 #pragma unroll 8
     for (int i = 0; i < 32; i++) {
         const int idx = i * Cfg::NT + threadIdx.x;
@@ -255,7 +238,7 @@ __device__ __forceinline__ void ntt_fwd_fp_body(const NttParams &p, const unsign
 // NTT_IN_GALOIS_REDUCE computes the exact per-rotation digits, needed only by jobs whose ciphertext has a
 // zero coefficient in c1 (pf_keyswitch.cuh): CTA z looks at jobs [z*G, z*G+G) (G = p.job_group <= 32) and
 // transforms the flagged ones, so the usual case costs one flag read per 32 jobs instead of one CTA per job.
-template <int LOGN, int INMODE, int OUTMODE = NTT_OUT_PLAIN>
+template <int LOGN, int INMODE>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fwd_fp_kernel(const NttParams p) {
     if (INMODE == NTT_IN_GALOIS_REDUCE) {
         __shared__ unsigned need;
@@ -274,27 +257,15 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_fw
         while (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            ntt_fwd_fp_body<LOGN, INMODE, OUTMODE>(p, blockIdx.z * p.job_group + b);
+            ntt_fwd_fp_body<LOGN, INMODE>(p, blockIdx.z * p.job_group + b);
             __syncthreads();
         }
         return;
     }
-    ntt_fwd_fp_body<LOGN, INMODE, OUTMODE>(p, blockIdx.z);
+    ntt_fwd_fp_body<LOGN, INMODE>(p, blockIdx.z);
 }
 
-// SEAL mod_switch_to_inplace folded into the store of a kept limb j: x is the canonical coefficient of
-// limb j; d[] are the coefficients of the dropped limbs [Lr, L) at the same position.  Dropping limb c
-// (RNSTool::divide_and_round_q_last_inplace): last = d_c + (q_c>>1) mod q_c, then every remaining limb i
-// becomes (x_i - ((last mod q_i) - ((q_c>>1) mod q_i))) * q_c^{-1} mod q_i — applied to the still-to-be-
-// dropped limbs too, because they are switched before they are dropped themselves.
-__device__ __forceinline__ u64 ms_step(u64 xi, u64 last, const DevModulus *mods, const u64 *tab, int c, int i) {
-    const u64 qi = mods[i].q;
-    const u64 *t = tab + ((size_t)c * 16 + i) * 3;
-    const u64 tmp = submod(barrett64(last, qi, mods[i].ratio1), t[0], qi);
-    return mul_shoup(submod(xi, tmp, qi), t[1], t[2], qi);
-}
-
-template <int LOGN, int OUTMODE = NTT_OUT_PLAIN>
+template <int LOGN>
 __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_inv_fp_kernel(const NttParams p) {
     using Cfg = NttCfg<LOGN>;
     extern __shared__ __align__(16) double smd[];
@@ -320,26 +291,6 @@ __global__ void __launch_bounds__(NttCfg<LOGN>::NT, (LOGN <= 13 ? 2 : 1)) ntt_in
     auto sstore = [&](int idx, double x) { smd[sm_phys(idx)] = x; };
     auto gstore = [&](int idx, double x) {
         u64 r = fp_canonical(x, q, qinv);
-        if (OUTMODE == NTT_OUT_MODSWITCH) {
-            const int L = p.ms_L, Lr = p.ms_Lr, j = blockIdx.x;
-            const u64 *dp = p.ms_dropped + (size_t)blockIdx.z * p.ms_dropped_sz + (size_t)blockIdx.y * (L - Lr) * Cfg::N + idx;
-            u64 d[4]; // up to 4 dropped limbs on the fused path (host falls back to modswitch_kernel beyond)
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (c < L - Lr) d[c] = dp[(size_t)c * Cfg::N];
-#pragma unroll
-            for (int cc = 3; cc >= 0; cc--) {
-                if (cc < L - Lr) {
-                    const int c = Lr + cc;
-                    const u64 qc = p.mods[c].q;
-                    const u64 last = addmod(d[cc], qc >> 1, qc);
-#pragma unroll
-                    for (int c2 = 0; c2 < 3; c2++)
-                        if (c2 < cc) d[c2] = ms_step(d[c2], last, p.mods, p.ms_tab, c, Lr + c2);
-                    r = ms_step(r, last, p.mods, p.ms_tab, c, j);
-                }
-            }
-        }
         out[idx] = r;
     };
     fp_inv_pass<LOGN, Cfg::K3, 0, false>(itwl, q, qinv, m.fninv, m.flast_w, sload0, sstore);

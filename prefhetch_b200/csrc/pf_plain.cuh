@@ -241,7 +241,51 @@ __global__ void flag_write_kernel(volatile unsigned *flag, unsigned value) {
     *flag = value;
     __threadfence_system();
 }
-__global__ void flag_wait_kernel(const volatile unsigned *flag, unsigned value) {
-    while (*flag < value) __nanosleep(500);
+// Bounded wait: a peer that died, hit an error or lost protocol order must not hang this stream (and
+// every later implicit device synchronisation of the process) for ever.  After timeout_ns the kernel
+// gives up, records {flag value seen, value wanted} in the engine's host-mapped error word and ends;
+// the next API call on the engine returns PF_ERR_CUDA (pf_engine.cu check_device_error).
+__global__ void flag_wait_kernel(const volatile unsigned *flag, unsigned value, unsigned long long timeout_ns,
+                                 volatile unsigned long long *err_word) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned seen = *flag;
+    while (seen < value) {
+        __nanosleep(500);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+            *err_word = 0x8000000000000000ull | ((unsigned long long)seen << 32) | value;
+            __threadfence_system();
+            return;
+        }
+        seen = *flag;
+    }
     __threadfence_system();
+}
+
+// 64-bit additive checksum of `n` words (gather verification: a rank's results against the copy that
+// landed in rank 0's buffer).  grid (blocks), 256 threads; out must be zeroed.
+__global__ void __launch_bounds__(256) checksum_kernel(const u64 *__restrict__ p, size_t n, u64 *out) {
+    u64 acc = 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        acc += p[i] * (2 * (u64)(i & 0xffff) + 1); // position-weighted: a permuted copy does not pass
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// The 113-byte SEAL stream header (SEALHeader + Ciphertext members + DynArray header, compr_mode none)
+// is the same for every result of a call: it is written in front of the 128-byte aligned ciphertext
+// words on the device, so the response leaves the GPU complete with one copy per query group instead of
+// the host writing ~1100 headers after the last copy has landed.
+struct ResultHeader {
+    unsigned char b[128];
+};
+__global__ void __launch_bounds__(128) stamp_headers_kernel(unsigned char *blob, size_t slot, size_t pad, size_t nresults,
+                                                            const ResultHeader hd) {
+    const size_t r = (size_t)blockIdx.x * 128 + threadIdx.x;
+    if (r >= nresults) return;
+    unsigned char *dst = blob + r * slot + pad;
+    for (int i = 0; i < 113; i++) dst[i] = hd.b[i];
 }

@@ -83,6 +83,19 @@ class SearchResult:
         return self.blob[o:o + self.ct_bytes].tobytes()
 
 
+class PendingSearch:
+    """A search in flight (pf_search_submit); collect() = pf_search_collect."""
+
+    def __init__(self, eng, ticket: int, result: SearchResult, keep):
+        self.eng, self.ticket, self.result, self._keep = eng, ticket, result, keep
+
+    def collect(self) -> SearchResult:
+        if self.ticket is not None:
+            self.eng._ck(self.eng.lib.pf_search_collect(self.eng.h, self.ticket))
+            self.ticket, self._keep = None, None
+        return self.result
+
+
 def _ptr(a: np.ndarray, typ):
     assert a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(typ)
@@ -223,6 +236,13 @@ class Engine:
                               ) -> SearchResult:
         """Encrypted variant of Server::coarseSearch: SEAL-serialized query ciphertexts in, SEAL-serialized
         result ciphertexts out (additive to ref: src/server/controllers/Query.cc:29-63)."""
+        return self.submitSearchEncrypted(query_blob, ct_offsets, nearest_centroid_idx, out).collect()
+
+    def submitSearchEncrypted(self, query_blob, ct_offsets, nearest_centroid_idx, out: np.ndarray | None = None
+                              ) -> "PendingSearch":
+        """pf_search_submit: enqueue the search and return; `.collect()` waits for the result ciphertexts.
+        Two searches may be in flight (upload + compute of one overlap the download of the other).  The
+        query blob and `out` must not be touched until collect() returns."""
         qb = query_blob if isinstance(query_blob, np.ndarray) else np.frombuffer(query_blob, dtype=np.uint8)
         offs = np.ascontiguousarray(ct_offsets, dtype=np.uint64)
         idx = np.ascontiguousarray(nearest_centroid_idx, dtype=np.int64)
@@ -235,25 +255,47 @@ class Engine:
             out = np.zeros(max(1, max_results) * self.slot_bytes, dtype=np.uint8)
         label_cap = max(1, max_results * self._C)
         # response arrays are reused across calls (fresh 9 MB label arrays cost more page faults than the
-        # copy itself); the returned views stay valid until the next call on this engine
+        # copy itself): a ring of 5 sets (one more than the searches that can be in flight), so the views of a
+        # result stay valid while the next four searches are submitted
         key = (nq, nprobe)
-        bufs = getattr(self, "_enc_bufs", None)
-        if bufs is None or bufs["key"] != key or len(bufs["roff"]) < max_results + 1 or len(bufs["labels"]) < label_cap:
-            bufs = {"key": key, "roff": np.empty(max_results + 1 + 64, dtype=np.uint64), "rpq": np.empty(nq, dtype=np.uint64),
-                    "labels": np.empty(label_cap + label_cap // 8, dtype=np.int64), "sizes": np.empty(nq, dtype=np.uint64),
-                    "psz": np.empty((nq, nprobe), dtype=np.uint64)}
-            self._enc_bufs = bufs
+        ring = getattr(self, "_enc_bufs", None)
+        if ring is None or ring["key"] != key or len(ring["sets"][0]["roff"]) < max_results + 1 \
+                or len(ring["sets"][0]["labels"]) < label_cap:
+            ring = {"key": key, "next": 0, "sets": [
+                {"roff": np.empty(max_results + 1 + 64, dtype=np.uint64), "rpq": np.empty(nq, dtype=np.uint64),
+                 "labels": np.empty(label_cap + label_cap // 8, dtype=np.int64), "sizes": np.empty(nq, dtype=np.uint64),
+                 "psz": np.empty((nq, nprobe), dtype=np.uint64)} for _ in range(5)]}
+            self._enc_bufs = ring
+        bufs = ring["sets"][ring["next"]]
         roff, rpq, labels, sizes, psz = bufs["roff"], bufs["rpq"], bufs["labels"], bufs["sizes"], bufs["psz"]
         label_cap = len(labels)
         st = PfSearchStats()
-        self._ck(self.lib.pf_search_lists_encrypted(
-            self.h, nq, qb.ctypes.data_as(C.c_void_p), _ptr(offs, U64P), _ptr(idx, I64P), nprobe,
+        ticket = C.c_uint64()
+        self._ck(self.lib.pf_search_submit(
+            self.h, nq, qb.ctypes.data_as(C.c_void_p), qb.size, _ptr(offs, U64P), _ptr(idx, I64P), nprobe,
             out.ctypes.data_as(C.c_void_p), out.size, _ptr(roff, U64P), max_results, _ptr(rpq, U64P),
-            _ptr(labels, I64P), label_cap, _ptr(sizes, U64P), _ptr(psz, U64P), C.byref(st)))
+            _ptr(labels, I64P), label_cap, _ptr(sizes, U64P), _ptr(psz, U64P), C.byref(st), C.byref(ticket)))
+        ring["next"] = (ring["next"] + 1) % 5          # a refused submit does not consume a set
         nres = st.nresults
-        return SearchResult(out, roff[:nres + 1], self.result_bytes, rpq.astype(np.int64), labels[:int(sizes.sum())],
-                            sizes.astype(np.int64), psz.astype(np.int64),
-                            {f: getattr(st, f) for f, _ in PfSearchStats._fields_})
+        res = SearchResult(out, roff[:nres + 1], self.result_bytes, rpq.astype(np.int64), labels[:int(sizes.sum())],
+                           sizes.astype(np.int64), psz.astype(np.int64),
+                           {f: getattr(st, f) for f, _ in PfSearchStats._fields_})
+        return PendingSearch(self, ticket.value, res, (qb, offs, idx))
+
+    def set_search_groups(self, groups: int):
+        """pf_search_set_groups: 1 = whole-batch kernels (pipelined calls), 0 = default (4 query groups)"""
+        self._ck(self.lib.pf_search_set_groups(self.h, groups))
+
+    def host_register(self, arr: np.ndarray):
+        self._ck(self.lib.pf_host_register(self.h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._ck(self.lib.pf_host_unregister(self.h, arr.ctypes.data_as(C.c_void_p)))
+
+    def device_checksum(self, dptr: int, nwords: int, cuda_stream: int = 0) -> int:
+        out = C.c_uint64()
+        self._ck(self.lib.pf_device_checksum(self.h, C.c_void_p(dptr), nwords, C.byref(out), C.c_void_p(cuda_stream)))
+        return out.value
 
     def _max_results(self, idx: np.ndarray) -> int:
         if not hasattr(self, "_blocks_per_list"):

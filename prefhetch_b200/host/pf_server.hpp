@@ -28,13 +28,15 @@ struct EncryptedCoarseResult {
     std::vector<idx_t> coarse_vector_indexes; // ids of the probed lists, packed per query (ref field name)
     std::vector<uint64_t> list_sizes_per_query;
     std::vector<uint64_t> probed_sizes;      // [nq][nprobe]
+    uint64_t nresults = 0, out_bytes = 0;
 };
 
 class Server {
   public:
     // ref: Server::Server (src/server/server_lib.cpp:32-46); parameters are run-time here
     Server(uint32_t dim, uint64_t poly_degree, const std::vector<uint64_t> &primes, uint64_t plain_modulus,
-           uint32_t query_cts = 1, uint32_t partial_g = 8, int device = 0, uint32_t rank = 0, uint32_t world = 1)
+           uint32_t query_cts = 1, uint32_t partial_g = 8, int device = 0, uint32_t rank = 0, uint32_t world = 1,
+           uint32_t result_limbs = 0)
         : m_Dim(dim) {
         pf_params p{};
         p.struct_size = sizeof(pf_params);
@@ -48,6 +50,7 @@ class Server {
         p.partial_g = partial_g;
         p.rank = rank;
         p.world = world;
+        p.result_limbs = result_limbs; // 0 = full level; 1 = what bench.py ships (SEAL mod_switch_to before save)
         pf_engine *e = nullptr;
         if (pf_engine_create(&p, &e) != PF_OK) throw std::runtime_error(pf_last_error(nullptr));
         m_Engine.reset(e);
@@ -119,10 +122,25 @@ class Server {
     // SEAL-serialized GaloisKeys of the client (compr_mode none)
     void loadGaloisKeys(std::span<const uint8_t> blob) { check(pf_load_galois_keys(m_Engine.get(), blob.data(), blob.size())); }
 
+    // one Galois key from raw words [L][2][k][N] (GaloisKeys::key(galois_elt) data, NTT form)
+    void setGaloisKey(uint32_t galois_elt, std::span<const uint64_t> words) {
+        check(pf_set_galois_key(m_Engine.get(), galois_elt, words.data()));
+    }
+    uint32_t galoisEltFromStep(int step) const { return pf_galois_elt_from_step(m_Engine.get(), step); }
+
     // encrypted variant of coarseSearch: SEAL-serialized query ciphertexts in, result ciphertexts out
     void coarseSearchEncrypted(uint64_t nq, std::span<const uint8_t> query_cts, std::span<const uint64_t> ct_offsets,
                                std::span<const idx_t> nearest_centroid_idx, uint32_t nprobe,
                                EncryptedCoarseResult &out) const {
+        collect(submitSearchEncrypted(nq, query_cts, ct_offsets, nearest_centroid_idx, nprobe, out), out);
+    }
+
+    // the same in two halves (pf_search_submit / pf_search_collect): a handler thread submits request i+1
+    // before it collects request i, so the GPU never waits for a download.  `out`, `query_cts` stay alive
+    // and untouched until collect() returns.
+    uint64_t submitSearchEncrypted(uint64_t nq, std::span<const uint8_t> query_cts, std::span<const uint64_t> ct_offsets,
+                                   std::span<const idx_t> nearest_centroid_idx, uint32_t nprobe,
+                                   EncryptedCoarseResult &out) const {
         uint64_t max_results = 0, max_labels = 0;
         for (idx_t l : nearest_centroid_idx) {
             if (l < 0 || static_cast<uint64_t>(l) >= m_Nlist) throw std::runtime_error("list id out of range");
@@ -138,17 +156,27 @@ class Server {
         out.list_sizes_per_query.resize(nq);
         out.probed_sizes.resize(nq * nprobe);
         pf_search_stats st{};
-        check(pf_search_lists_encrypted(m_Engine.get(), nq, query_cts.data(), ct_offsets.data(),
-                                        nearest_centroid_idx.data(), nprobe, out.ciphertexts.data(),
-                                        out.ciphertexts.size(), out.result_offsets.data(), max_results,
-                                        out.results_per_query.data(), out.coarse_vector_indexes.data(), max_labels,
-                                        out.list_sizes_per_query.data(), out.probed_sizes.data(), &st));
-        out.ciphertexts.resize(st.out_bytes);
-        out.result_offsets.resize(st.nresults + 1);
+        uint64_t ticket = 0;
+        check(pf_search_submit(m_Engine.get(), nq, query_cts.data(), query_cts.size(), ct_offsets.data(),
+                               nearest_centroid_idx.data(), nprobe, out.ciphertexts.data(), out.ciphertexts.size(),
+                               out.result_offsets.data(), max_results, out.results_per_query.data(),
+                               out.coarse_vector_indexes.data(), max_labels, out.list_sizes_per_query.data(),
+                               out.probed_sizes.data(), &st, &ticket));
+        out.nresults = st.nresults;
+        out.out_bytes = st.out_bytes;
+        return ticket;
+    }
+
+    void collect(uint64_t ticket, EncryptedCoarseResult &out) const {
+        check(pf_search_collect(m_Engine.get(), ticket));
+        out.ciphertexts.resize(out.out_bytes);
+        out.result_offsets.resize(out.nresults + 1);
         uint64_t labels = 0;
         for (uint64_t s : out.list_sizes_per_query) labels += s;
         out.coarse_vector_indexes.resize(labels);
     }
+
+    size_t resultSerializedSize() const { return pf_result_serialized_size(m_Engine.get()); }
 
     pf_engine *handle() const { return m_Engine.get(); }
     const pf_index_info &info() const { return m_Info; }

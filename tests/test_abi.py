@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pf_abi_version() == 1
+    assert lib.pf_abi_version() == 2
 
 
 def test_no_cpu_fallback(lib):
@@ -88,3 +88,28 @@ def test_seal_stream_inflate_matches_python_zlib(oracle):
     for bad in (z[:-9], z[:5] + b"\x02" + z[6:], z[:40] + bytes(8) + z[48:], b"\x00" * 32):
         with pytest.raises(pf.PfError):
             pf.seal_stream_inflate(bad)
+
+
+def test_seal_stream_inflate_is_bounded():
+    """a deflate bomb is refused once it exceeds the caller's capacity: PF_ERR_CAPACITY with the true size
+    (below the hard ceiling) and nothing written past the buffer; exact-capacity output still succeeds"""
+    import ctypes as C
+    import struct
+    import zlib
+    from prefhetch_b200 import _capi
+    lib = _capi.load()
+    payload = bytes(3 << 20)
+    body = zlib.compress(payload, 9)
+    z = bytes([0x5E, 0xA1, 0x10, 4, 1, 1, 0, 0]) + struct.pack("<Q", 16 + len(body)) + body
+    zin = np.frombuffer(z, dtype=np.uint8)
+    need, used = C.c_size_t(), C.c_size_t()
+    small = np.full(4096 + 64, 0xAB, dtype=np.uint8)
+    rc = lib.pf_seal_stream_inflate(zin.ctypes.data_as(C.c_void_p), zin.size, small.ctypes.data_as(C.c_void_p), 4096,
+                                    C.byref(need), C.byref(used))
+    assert rc == _capi.PF_ERR_CAPACITY and need.value == 16 + len(payload)
+    assert (small == 0xAB).all()
+    exact = np.zeros(16 + len(payload), dtype=np.uint8)
+    rc = lib.pf_seal_stream_inflate(zin.ctypes.data_as(C.c_void_p), zin.size, exact.ctypes.data_as(C.c_void_p), exact.size,
+                                    C.byref(need), C.byref(used))
+    assert rc == _capi.PF_OK and need.value == exact.size and used.value == len(z)
+    assert exact[5] == 0 and not exact[16:].any()

@@ -481,3 +481,266 @@ def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits, rl):
                 r += 1
     assert r == res.stats["nresults"] and r > 0
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: the benchmarked shape, the Galois-key loader, the kept kernel variants, submit / collect
+# ---------------------------------------------------------------------------------------------------------
+def _bench_shape_dataset(seed=5, nlist=256, d=128, C_=1024):
+    """SIFT-shaped index with bench.py's structure: ~1 block per list, a few lists of two blocks."""
+    rng = np.random.default_rng(seed)
+    centres = rng.uniform(0, 160, size=(nlist, d))
+    sizes = rng.integers(120, 200, size=nlist)
+    sizes[[3, 77, 200]] = [C_ + 40, C_ + 1, 2 * C_]        # multi-block lists (one of them exactly 2 blocks)
+    sizes[9] = 0                                           # an empty list
+    assign = np.repeat(np.arange(nlist), sizes)
+    base = np.clip(np.rint(centres[assign] + rng.normal(0, 24, size=(len(assign), d))), 0, 255).astype(np.float32)
+    offsets = np.zeros(nlist + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    ids = rng.permutation(len(assign)).astype(np.int64)
+    cent = np.stack([base[offsets[l]:offsets[l + 1]].mean(0) if sizes[l] else centres[l] for l in range(nlist)]).astype(np.float32)
+    qa = rng.integers(0, nlist, size=64)
+    query = np.clip(np.rint(centres[qa] + rng.normal(0, 24, size=(64, d))), 0, 255).astype(np.float32)
+    return cent, offsets, ids, base, query
+
+
+@pytest.mark.parametrize("rl", [1, 0])
+def test_encrypted_search_bench_shape(pf, oracle, rl):
+    """The shape bench.py times (64 queries x 16 probes, N = 8192, g = 8, ~1100 (query, block) pairs, real
+    encryptions): key-switch query groups of 16, the 4 e2e query groups (5/10/14/16 sixteenths), blocks
+    probed by several queries of the batch, multi-block lists.  EVERY result is decrypted and compared with
+    the exact integer distances; a sample of >= 32 results spread over all query groups is compared byte
+    for byte with the oracle pipeline (ref contract: src/server/server_lib.cpp:111-138)."""
+    n, d, g, nprobe, nq = 8192, 128, 8, 16, 64
+    primes, t = _params(n)
+    cent, offsets, ids, vecs, query = _bench_shape_dataset()
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    eng, _, _ = _engine(pf, n, g=g, result_limbs=rl)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(keys):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    cts = np.stack([cl.encrypt_query(q, 1000 + 3 * i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    idx = eng.coarse_quantize(query, nprobe)
+    idx[5, 2] = 3; idx[21, 0] = 3; idx[41, 15] = 77; idx[60, 7] = 200; idx[63, 1] = 9   # force the special lists in
+    res = eng.coarseSearchEncrypted(blob, offs, idx)
+    C_ = cl.lay.C
+    blocks_of = (offsets[1:] - offsets[:-1] + C_ - 1) // C_
+    assert res.stats["nresults"] == int(blocks_of[idx.reshape(-1)].sum()) > 900
+    probes_per_list = np.bincount(idx.reshape(-1), minlength=len(cent))
+    assert (probes_per_list > 1).sum() > 50            # blocks shared between queries of the batch
+    # walk the response in order; decrypt everything, byte-compare the sample
+    sample_q = {0, 4, 5, 15, 16, 19, 20, 21, 31, 32, 39, 40, 41, 47, 48, 55, 56, 60, 63}
+    checked, r = 0, 0
+    pid = _parms_id_py(n, primes[:rl], t) if rl else (0, 0, 0, 0)
+    for qi in range(nq):
+        rot = oracle.rotate_query_set(cl.ctx, cl.lay, cts[qi], keys, False) if qi in sample_q else None
+        assert res.results_per_query[qi] == int(blocks_of[idx[qi]].sum())
+        for p in range(nprobe):
+            l = idx[qi, p]
+            n_l = int(offsets[l + 1] - offsets[l])
+            for b0 in range(0, n_l, C_):
+                xs = vecs[offsets[l] + b0: offsets[l] + min(b0 + C_, n_l)].astype(np.int32)
+                got = res.result(r)
+                got_ct, is_ntt = eng.ct_deserialize(got)
+                dist, budget = cl.distances(got_ct, query[qi], len(xs))
+                assert np.array_equal(dist, ((xs.astype(np.int64) - query[qi].astype(np.int64)) ** 2).sum(1)), (qi, p, b0)
+                assert budget > 0 and not is_ntt
+                special = l in (3, 77, 200)
+                if rot is not None and (p in (0, 7, 15) or special):
+                    diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
+                    want_ct = oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm)
+                    if rl:
+                        want_ct = cl.mod_switch_to(want_ct, rl)
+                    assert got == cl.ctx.ct_save(want_ct, parms_id=pid), f"query {qi} probe {p} block {b0}"
+                    checked += 1
+                r += 1
+    assert r == res.stats["nresults"] and checked >= 32
+    eng.close()
+
+
+def test_load_galois_keys_stream(pf, oracle):
+    """pf_load_galois_keys: a SEAL GaloisKeys stream (compr_mode none and zlib) gives the same rotated query
+    set as the raw-word setter and the oracle; malformed streams are refused."""
+    from tests.util import galois_keys_save, zlib_stream
+    n, d, g = 2048, 128, 16
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    by_elt = {cl.ctx.galois_elt(i + 1): k for i, k in enumerate(keys)}
+    blob = galois_keys_save(cl.ctx, by_elt)
+    q = np.random.default_rng(2).integers(0, 256, size=d)
+    cts = cl.encrypt_query(q, 9)
+    want = oracle.rotate_query_set(cl.ctx, cl.lay, cts, keys, False)
+    for stream in (blob, zlib_stream(blob)):
+        eng, _, _ = _engine(pf, n, g=g)
+        eng.load_galois_keys(stream)
+        assert np.array_equal(eng.rotate_query_set(cts, False), want)
+        eng.close()
+    eng, _, _ = _engine(pf, n, g=g)
+    with pytest.raises(pf.PfError) as ei:
+        eng.load_galois_keys(blob[:len(blob) // 2])        # truncated
+    assert ei.value.code == 5
+    with pytest.raises(pf.PfError):
+        eng.load_galois_keys(zlib_stream(blob)[:-9])       # truncated deflate stream
+    bad = bytearray(blob)
+    bad[16 + 32:16 + 40] = (n + 1).to_bytes(8, "little")    # more key slots than Galois elements exist
+    with pytest.raises(pf.PfError):
+        eng.load_galois_keys(bytes(bad))
+    with pytest.raises(pf.PfError):                         # no keys loaded by any of the failed calls
+        eng.rotate_query_set(cts, False)
+    eng.close()
+
+
+_VARIANTS = [{"PF_MAC_VARIANT": "0"}, {"PF_MAC_VARIANT": "4"}, {"PF_MAC_VARIANT": "5"}, {"PF_MAC_VARIANT": "6"},
+             {"PF_NTT_FP": "0"}, {"PF_MS_INT": "1"}, {"PF_KS_NO_FUSED_PREP": "1"}, {"PF_MAC_NO_FPRED": "1"},
+             {"PF_KS_NO_FPRED": "1"}, {"PF_E2E_GROUPS": "1"}, {"PF_E2E_GROUPS": "7"}]
+
+
+@pytest.mark.parametrize("n,g,rl", [(8192, 8, 1), (16384, 16, 2)])
+def test_kernel_variants_bit_identical(pf, oracle, monkeypatch, n, g, rl):
+    """every kept non-default kernel (environment switches of DESIGN.md) gives the bytes of the default path,
+    which is itself checked against the oracle: MAC variants 0/4/5/6, integer NTT at N >= 8192, integer
+    mod-switch, un-fused mod-down prep, Barrett instead of FP64-assisted reductions, other group counts."""
+    d, nprobe, nq = 128, 3, 5
+    primes, t = _params(n)
+    lay = oracle.LayoutPlan(n, d, 1, g)
+    rng = np.random.default_rng(n)
+    base, query, cent = sift_like(rng, lay.C + 700, d, 4, nq)
+    offsets, ids, vecs = build_ivf(base, cent)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    cts = np.stack([cl.encrypt_query(q, 40 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+
+    def run():
+        eng, _, _ = _engine(pf, n, g=g, result_limbs=rl)     # PF_NTT_FP / *_NO_FPRED are read at creation
+        eng.load_index(cent, offsets, ids, vecs)
+        eng.set_list_sizes(offsets)
+        for i, key in enumerate(keys):
+            eng.set_galois_key(eng.galois_elt(i + 1), key)
+        idx = eng.coarse_quantize(query, nprobe)
+        res = eng.coarseSearchEncrypted(blob, offs, idx)
+        out = [res.result(r) for r in range(res.stats["nresults"])]
+        eng.close()
+        return idx, out
+
+    idx, ref = run()
+    # the default path against the oracle (first result of every query)
+    r = 0
+    for qi in range(nq):
+        rot = oracle.rotate_query_set(cl.ctx, cl.lay, cts[qi], keys, False)
+        l = idx[qi, 0]
+        xs = vecs[offsets[l]: offsets[l] + min(lay.C, int(offsets[l + 1] - offsets[l]))].astype(np.int32)
+        diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
+        want = cl.mod_switch_to(oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm), rl)
+        assert ref[r] == cl.ctx.ct_save(want, parms_id=_parms_id_py(n, primes[:rl], t))
+        r += sum(int((offsets[x + 1] - offsets[x] + lay.C - 1) // lay.C) for x in idx[qi])
+    for env in _VARIANTS:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, got = run()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert len(got) == len(ref) and all(a == b for a, b in zip(got, ref)), f"variant {env} differs from the default path"
+
+
+def test_submit_collect_pipelined(pf, oracle):
+    """pf_search_submit / pf_search_collect: searches in flight give the bytes of the one-call form; a
+    fifth submit is refused with PF_ERR_STATE until one is collected; an unknown ticket is refused."""
+    n, g, d, nprobe = 2048, 16, 128, 4
+    base, query, cent, offsets, ids, vecs = _dataset(31, nb=4000, nlist=16, nq=6)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    eng, _, _ = _engine(pf, n, g=g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(cl.step_keys()):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    batches = []
+    for b in range(3):
+        qs = query[2 * b: 2 * b + 2]
+        cts = np.stack([cl.encrypt_query(q, 500 + 10 * b + i) for i, q in enumerate(qs)])
+        blob, offs = cl.serialize_queries(cts)
+        idx = eng.coarse_quantize(qs, nprobe)
+        one = eng.coarseSearchEncrypted(blob, offs, idx)
+        batches.append((blob, offs, idx, [one.result(r) for r in range(one.stats["nresults"])], one.labels.copy()))
+    for groups in (0, 1):
+        eng.set_search_groups(groups)
+        p0 = eng.submitSearchEncrypted(*batches[0][:3])
+        p1 = eng.submitSearchEncrypted(*batches[1][:3])
+        extra = [eng.submitSearchEncrypted(*batches[2][:3]) for _ in range(2)]   # 4 in flight: the limit
+        with pytest.raises(pf.PfError) as ei:
+            eng.submitSearchEncrypted(*batches[2][:3])
+        assert ei.value.code == 4
+        r0 = p0.collect()
+        for x in extra:
+            x.collect()
+        p2 = eng.submitSearchEncrypted(*batches[2][:3])
+        for pend, (_, _, _, want, labels) in zip((p0, p1, p2), batches):
+            res = pend.collect()
+            assert [res.result(r) for r in range(res.stats["nresults"])] == want
+            assert np.array_equal(res.labels, labels)
+        assert r0 is p0.result
+    assert eng.lib.pf_search_collect(eng.h, 12345) == 4
+    eng.close()
+
+
+def test_hostile_inputs(pf, oracle):
+    """offsets outside the blob, a deflate bomb in place of a query ciphertext, a peer flag that
+    never arrives — each is an error code, never an out-of-bounds read, unbounded allocation or a hang."""
+    import struct
+    import zlib
+    n, g = 2048, 16
+    base, query, cent, offsets, ids, vecs = _dataset(9, nb=2000, nlist=8, nq=2)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, 128, 1, g)
+    eng, _, _ = _engine(pf, n, g=g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(cl.step_keys()):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    cts = np.stack([cl.encrypt_query(q, 5 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    idx = eng.coarse_quantize(query, 2)
+    for bad_offs in ([0, offs[1], offs[2] + 8], [0, offs[2], offs[1]], [offs[1], 0, offs[2]], [0, 2 ** 63, 2 ** 63 + 5]):
+        with pytest.raises(pf.PfError) as ei:
+            eng.coarseSearchEncrypted(blob, np.array(bad_offs, dtype=np.uint64), idx)
+        assert ei.value.code == 1
+    # 200 MB of zeros deflate to ~200 KB: must be refused at the size of one ciphertext, not inflated
+    bomb_body = zlib.compress(bytes(200 << 20), 9)
+    bomb = bytes(blob[:5]) + b"\x01" + bytes(blob[6:8]) + struct.pack("<Q", 16 + len(bomb_body)) + bomb_body
+    with pytest.raises(pf.PfError) as ei:
+        eng.ct_deserialize(bomb)
+    assert ei.value.code == 5
+    zb = np.frombuffer(bomb + bytes(blob[offs[1]:offs[2]]), dtype=np.uint8)
+    zo = np.array([0, len(bomb), len(zb)], dtype=np.uint64)
+    with pytest.raises(pf.PfError) as ei:
+        eng.coarseSearchEncrypted(zb, zo, idx)
+    assert ei.value.code == 5
+    res = eng.coarseSearchEncrypted(blob, offs, idx)       # the engine still works
+    assert res.stats["nresults"] > 0
+    eng.close()
+
+
+def test_flag_wait_times_out(pf, monkeypatch):
+    """a peer flag that never arrives: the wait kernel gives up after PF_FLAG_TIMEOUT_MS and the engine reports
+    PF_ERR_CUDA from then on instead of hanging the stream"""
+    monkeypatch.setenv("PF_FLAG_TIMEOUT_MS", "200")
+    eng, _, _ = _engine(pf, 2048)
+    ptr, _h = eng.ipc_alloc(128)
+    eng.flag_write(ptr, 3)
+    eng.flag_wait(ptr, 3)          # already there: returns at once
+    eng.synchronize()
+    words = np.arange(16, dtype=np.uint64)
+    assert eng.device_checksum(ptr, 0) == 0
+    eng.flag_wait(ptr, 4)          # never written
+    with pytest.raises(pf.PfError) as ei:
+        eng.synchronize()
+    assert ei.value.code == 2 and "timed out" in str(ei.value)
+    with pytest.raises(pf.PfError):
+        eng.flag_write(ptr, 5)     # sticky
+    eng.ipc_free(ptr)
+    eng.close()

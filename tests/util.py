@@ -129,3 +129,34 @@ class OracleClient:
         qi = np.asarray(q).astype(np.int64)
         d = (slots[tab].sum(axis=1) + int((qi * qi).sum())) % self.ctx.t
         return d[:nvec], budget
+
+
+def galois_keys_save(ctx, keys_by_elt: dict, parms_id=(0, 0, 0, 0)) -> bytes:
+    """SEAL 4.1 GaloisKeys::save with compr_mode none ([EXT] kswitchkeys.h KSwitchKeys::save_members inside a
+    Serialization::Save envelope): SEALHeader, parms_id, dim1 = N key slots (GaloisKeys resizes to
+    coeff_count), per slot dim2 and dim2 PublicKey streams — each a SEAL envelope around the members of a
+    size-2 NTT-form ciphertext over all k primes.  Slot of element e is (e - 1) / 2.
+    keys_by_elt: {galois_elt: words [L][2][k][n]}."""
+    import struct
+    n, k, L = ctx.n, ctx.k, ctx.L
+    parts = [struct.pack("<4Q", *parms_id), struct.pack("<Q", n)]
+    slots = {(e - 1) // 2: w for e, w in keys_by_elt.items()}
+    for i in range(n):
+        if i not in slots:
+            parts.append(struct.pack("<Q", 0))
+            continue
+        w = np.asarray(slots[i], dtype=np.uint64).reshape(L, 2, k, n)
+        parts.append(struct.pack("<Q", L))
+        for j in range(L):
+            parts.append(ctx.ct_save(w[j], is_ntt=True, parms_id=parms_id))
+    body = b"".join(parts)
+    total = 16 + len(body)
+    return bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0]) + struct.pack("<Q", total) + body
+
+
+def zlib_stream(raw: bytes) -> bytes:
+    """what SEAL writes with compr_mode_type::zlib: header (compr_mode 1, new size) + deflate of the body"""
+    import struct
+    import zlib
+    body = zlib.compress(raw[16:], 6)
+    return raw[:5] + b"\x01" + raw[6:8] + struct.pack("<Q", 16 + len(body)) + body
