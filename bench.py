@@ -1228,7 +1228,9 @@ def main():
         line = {
             "metric": "encrypted candidate distances/sec", "value": rec["value"], "unit": "distances/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak" if weak else ("strong" if world > 1 else "n/a (single GPU)"), "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if (world > 1 and not weak) else "weak", "vs_baseline": None,
+            "scaling_note": ("N = 1 point of the series: the default run at N GPUs is weak scaling of this workload (N list shards of 1M vectors), "
+                             "`--config X` at N > 1 is strong scaling of X") if world == 1 else None,
             "dtype": "u64", "data": "synthetic",
             "config": bench_config(cfg_name, cfg, rec["L"], rec["Lr"], cfg["nq"], world, weak, rec["nprobe"], grid),
             "queries_per_s": rec["queries_per_s"],

@@ -142,7 +142,7 @@ struct pf_engine {
     int Lr = 0; // limbs of result ciphertexts (<= L)
     uint64_t result_pid[4] = {0, 0, 0, 0};
     bool result_pid_set = false;
-    DevBuf d_mstab, s_full, s_cksum;
+    DevBuf d_mstab, s_full, s_cksum, s_ctoff;
     u32 d = 0, d_pad = 0, m = 0, g = 0, dc = 0, R = 0, K = 0, C = 0;
     u64 t = 0;
     std::mutex mu;
@@ -196,7 +196,7 @@ struct pf_engine {
     MappedBuf m_cx, m_cidx, m_cdist; // stage 1: query vectors in, probe ids / distances out (zero-copy)
     // pinned upload arena: pageable cudaMemcpyAsync would synchronise the stream (and the host) on every
     // small table upload; 4 call slots, a slot is reused only after the call that used it has finished
-    PinBuf h_arena;
+    MappedBuf h_arena; // host-mapped: the GPU fetches the tables with a kernel, no copy engine involved
     size_t arena_slot_bytes = 0, arena_off = 0;
     int arena_slot = 0;
     cudaEvent_t arena_ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -209,10 +209,13 @@ struct pf_engine {
     struct Flight {
         bool busy = false;
         uint64_t id = 0;
-        DevBuf qcts, out;
+        DevBuf qcts, out, qraw; // qraw: the uploaded byte range of the query blob (headers still in place)
         cudaEvent_t ev_up[PF_E2E_GROUPS] = {};
         cudaEvent_t done = nullptr;
+        cudaEvent_t tl[6] = {}; // PF_DEBUG_TIMELINE: upload begin/end, compute begin/end, download begin/end
     } flights[PF_MAX_FLIGHTS];
+    bool timeline = false;
+    cudaEvent_t tl_base = nullptr;
     uint64_t next_ticket = 0;
     int groups_hint = 0; // pf_search_set_groups
 
@@ -290,7 +293,7 @@ int check_device_error(pf_engine *e) {
 constexpr size_t ARENA_SLOT = (size_t)8 << 20;
 
 int arena_begin(pf_engine *e) { // call once at the start of an API call that uploads tables
-    if (!e->h_arena.p) {
+    if (!e->h_arena.h) {
         CK(e->h_arena.ensure(4 * ARENA_SLOT));
         for (auto &ev : e->arena_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
@@ -305,16 +308,29 @@ void arena_end(pf_engine *e) { // after the last upload of the call has been enq
     e->arena_ev_used[e->arena_slot] = true;
 }
 
-// async host->device copy of a small table through the pinned arena (falls back to a direct copy,
-// which synchronises, when the slot is exhausted)
+// Small per-call tables (pair plan, rotation jobs; tens of KB) reach the device WITHOUT the copy engine:
+// they are written into a host-mapped arena slot and a few-CTA kernel on the engine stream pulls them into
+// device scratch.  A cudaMemcpyAsync here queues behind the bulk query-ciphertext uploads of the following
+// searches on the H2D engine — measured with PF_DEBUG_TIMELINE: the whole compute of a search stalled 2-3 ms
+// behind 34 MB of uploads it did not depend on.  (Falls back to a direct copy, which synchronises, when the
+// slot is exhausted.)
+__global__ void __launch_bounds__(256) fetch_words_kernel(u32 *dst, const u32 *src, size_t nwords) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < nwords) dst[i] = src[i];
+}
+
 cudaError_t upload_async(pf_engine *e, void *dst, const void *src, size_t bytes) {
     const size_t aligned = (bytes + 255) & ~(size_t)255;
-    if (!e->h_arena.p || e->arena_off + aligned > ARENA_SLOT)
+    if (!e->h_arena.h || e->arena_off + aligned > ARENA_SLOT || (bytes & 3))
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream);
-    char *stage = e->h_arena.as<char>() + (size_t)e->arena_slot * ARENA_SLOT + e->arena_off;
-    memcpy(stage, src, bytes);
+    const size_t off = (size_t)e->arena_slot * ARENA_SLOT + e->arena_off;
+    memcpy((char *)e->h_arena.h + off, src, bytes);
     e->arena_off += aligned;
-    return cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, e->stream);
+    const size_t nwords = bytes / 4;
+    if (!nwords) return cudaSuccess;
+    fetch_words_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, e->stream>>>((u32 *)dst, (const u32 *)((char *)e->h_arena.d + off), nwords);
+    e->launches++;
+    return cudaGetLastError();
 }
 
 // ---- timing -------------------------------------------------------------------------------
@@ -1457,7 +1473,10 @@ int pf_engine_create(const pf_params *prm, pf_engine **out) {
                 return bail(e->fail(PF_ERR_CUDA, "event creation failed"));
         if (cudaEventCreateWithFlags(&fl.done, cudaEventDisableTiming) != cudaSuccess)
             return bail(e->fail(PF_ERR_CUDA, "event creation failed"));
+        for (auto &ev : fl.tl) cudaEventCreate(&ev);
     }
+    e->timeline = getenv("PF_DEBUG_TIMELINE") != nullptr;
+    cudaEventCreate(&e->tl_base);
     if (cudaHostAlloc((void **)&e->h_err_word, sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&e->d_err_word, e->h_err_word, 0) != cudaSuccess)
         return bail(e->fail(PF_ERR_CUDA, "error word allocation failed"));
@@ -2167,21 +2186,50 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
             cudaStreamSynchronize(e->copy_stream);
         }
     } drain{e};
+    if (e->timeline) {
+        if (e->next_ticket == 0) cudaEventRecord(e->tl_base, e->upload_stream);
+        cudaEventRecord(fl.tl[0], e->upload_stream);
+    }
+    // Upload.  Uncompressed streams (the fast path) go up as ONE copy per query group — the byte range of
+    // the blob that holds the group's streams, SEAL headers included — and strip_headers_kernel moves the
+    // ciphertext words (at a byte offset of 113 inside every stream) to their aligned place; 64 separate
+    // 512 KB copies reached 37 GB/s alone and crawled next to a response download.  Streams that were
+    // inflated on the host are copied one by one.
+    rc = arena_begin(e);
+    if (rc) return rc;
+    drain.arena_open = true;
+    const bool raw_path = inflated.empty() && ncts > 0;
+    std::vector<u64> rel_off(ncts);
+    if (raw_path) {
+        const uint64_t lo = ct_offsets[0], hi = ct_offsets[ncts];
+        CK(fl.qraw.ensure_grow((size_t)(hi - lo) + 64));
+        CK(e->s_ctoff.ensure_grow(ncts * 8));
+        for (size_t c = 0; c < ncts; c++) rel_off[c] = ct_offsets[c] - lo + SEAL_CT_HEADER;
+        CK(upload_async(e, e->s_ctoff.p, rel_off.data(), ncts * 8)); // engine stream, ahead of the strip kernels
+    }
     {
         HostTick ht("enqueue_h2d");
         for (uint64_t gi = 0; gi < ngroups; gi++) {
-            for (size_t c = q_end[gi] * e->m; c < q_end[gi + 1] * e->m; c++)
-                CK(cudaMemcpyAsync(fl.qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
+            const size_t c_lo = q_end[gi] * e->m, c_hi = q_end[gi + 1] * e->m;
+            if (raw_path && c_hi > c_lo) {
+                const uint64_t b_lo = ct_offsets[c_lo] - ct_offsets[0], b_hi = ct_offsets[c_hi] - ct_offsets[0];
+                CK(cudaMemcpyAsync(fl.qraw.as<uint8_t>() + b_lo, query_cts + ct_offsets[c_lo], (size_t)(b_hi - b_lo),
                                    cudaMemcpyHostToDevice, e->upload_stream));
+            } else {
+                for (size_t c = c_lo; c < c_hi; c++)
+                    CK(cudaMemcpyAsync(fl.qcts.as<u64>() + c * ctw, ct_src[c] + SEAL_CT_HEADER, ctw * 8,
+                                       cudaMemcpyHostToDevice, e->upload_stream));
+            }
             CK(cudaEventRecord(fl.ev_up[gi], e->upload_stream));
         }
+    }
+    if (e->timeline) {
+        cudaEventRecord(fl.tl[1], e->upload_stream);
+        cudaEventRecord(fl.tl[2], e->stream);
     }
     CK(fl.out.ensure_grow(std::max<size_t>(8, P * slot)));
     uint8_t *d_blob = fl.out.as<uint8_t>();
     u64 *d_words = reinterpret_cast<u64 *>(d_blob + PF_RESULT_DATA_OFFSET);
-    rc = arena_begin(e);
-    if (rc) return rc;
-    drain.arena_open = true;
     rc = upload_plan(e, pl);
     if (rc) return rc;
     // SEAL stream headers (113 bytes in front of the aligned words of every result), written on the device
@@ -2198,6 +2246,12 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         const uint64_t q_hi = q_end[gi + 1];
         CK(cudaStreamWaitEvent(e->stream, fl.ev_up[gi], 0));
+        if (raw_path && q_hi > q_lo) {
+            const size_t c_lo = q_lo * e->m, nc = (q_hi - q_lo) * e->m;
+            strip_headers_kernel<<<dim3((unsigned)((ctw + 255) / 256), (unsigned)nc), 256, 0, e->stream>>>(
+                fl.qraw.as<uint8_t>(), e->s_ctoff.as<u64>() + c_lo, fl.qcts.as<u64>() + c_lo * ctw, ctw);
+            e->launches++;
+        }
         uint64_t pair_hi = pair_lo;
         for (uint64_t q = q_lo; q < q_hi; q++) pair_hi += pl.results_per_query[q];
         rc = search_core(e, q_lo, q_hi - q_lo, fl.qcts.as<u64>() + q_lo * e->m * ctw, pl, d_words, slot / 8);
@@ -2215,8 +2269,10 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
     // the flight is complete when the engine stream (rotations of an empty plan included) and the last
     // copy are done
     CK(cudaEventRecord(e->ev_group[0], e->stream));
+    if (e->timeline) cudaEventRecord(fl.tl[3], e->stream);
     CK(cudaStreamWaitEvent(e->copy_stream, e->ev_group[0], 0));
     CK(cudaEventRecord(fl.done, e->copy_stream));
+    if (e->timeline) cudaEventRecord(fl.tl[5], e->copy_stream);
     arena_end(e);
     drain.arena_open = false;
     drain.armed = false;
@@ -2268,6 +2324,13 @@ int pf_search_collect(pf_engine *e, uint64_t ticket) {
     std::lock_guard<std::mutex> lk(e->mu);
     e->flights[fi].busy = false;
     if (ce != cudaSuccess) return e->fail(PF_ERR_CUDA, "search %llu failed: %s", (unsigned long long)ticket, cudaGetErrorString(ce));
+    if (e->timeline) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 6; i++)
+            if (i != 4) cudaEventElapsedTime(&t[i], e->tl_base, e->flights[fi].tl[i]);
+        fprintf(stderr, "[pf timeline] ticket %3llu  upload %8.3f..%8.3f  compute %8.3f..%8.3f  download ..%8.3f ms\n",
+                (unsigned long long)ticket, t[0], t[1], t[2], t[3], t[5]);
+    }
     return check_device_error(e);
 }
 

@@ -289,3 +289,19 @@ __global__ void __launch_bounds__(128) stamp_headers_kernel(unsigned char *blob,
     unsigned char *dst = blob + r * slot + pad;
     for (int i = 0; i < 113; i++) dst[i] = hd.b[i];
 }
+
+// Query ciphertexts arrive as SEAL streams: 113 header bytes, then 2*L*N little-endian words — at a byte offset
+// that is not a multiple of 8.  The blob is uploaded as it is and this kernel moves the words of ciphertext y
+// (raw + src_off[y], any alignment) to dst + y*words: two aligned 8-byte loads and a funnel shift per word.
+// raw must be readable 8 bytes past the last word.  grid (ceil(words/256), ncts)
+__global__ void __launch_bounds__(256) strip_headers_kernel(const unsigned char *__restrict__ raw, const u64 *__restrict__ src_off,
+                                                            u64 *__restrict__ dst, size_t words) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= words) return;
+    const size_t off = (size_t)src_off[blockIdx.y] + 8 * i;
+    const unsigned sh = (unsigned)(off & 7) * 8;
+    const u64 *a = reinterpret_cast<const u64 *>(raw + (off & ~(size_t)7));
+    const u64 lo = a[0];
+    const u64 v = sh ? (lo >> sh) | (a[1] << (64 - sh)) : lo;
+    dst[(size_t)blockIdx.y * words + i] = v;
+}

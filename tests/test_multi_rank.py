@@ -82,3 +82,80 @@ def test_shards_partition_the_lists():
         parts = [set(shard_plan(idx, list_sizes, 1024, r, world)) for r in range(world)]
         assert set().union(*parts) == full
         assert sum(len(p) for p in parts) == len(full)
+
+
+# ---- round 2: the rank grid (list shards x query groups) and the one-buffer node response ----------------
+def test_grid_covers_every_query_list_pair_once():
+    """bench.py's grid: rank r serves list shard r % L and query group r // L; every (query, probed list)
+    pair is computed by exactly one rank, for every grid of 1, 2, 4 and 8 ranks"""
+    import bench
+    rng = np.random.default_rng(3)
+    nq, nlist, nprobe = 64, 256, 16
+    idx = np.stack([rng.choice(nlist, size=nprobe, replace=False) for _ in range(nq)])
+    for world in (1, 2, 4, 8):
+        grids = [(L, world // L) for L in (1, 2, 4, 8) if world % L == 0 and L <= world]
+        assert bench.default_strong_grid(world) in grids
+        for Lw, Qw in grids:
+            assert bench.parse_grid(f"{Lw}x{Qw}", world) == (Lw, Qw)
+            seen = np.zeros((nq, nlist), dtype=np.int32)
+            for rank in range(world):
+                lr, qg = rank % Lw, rank // Lw
+                lo, hi = bench.split_queries(nq, Qw, qg)
+                for qi in range(lo, hi):
+                    for l in idx[qi]:
+                        if l % Lw == lr:
+                            seen[qi, l] += 1
+            want = np.zeros_like(seen)
+            for qi in range(nq):
+                want[qi, idx[qi]] = 1
+            assert np.array_equal(seen, want), (Lw, Qw)
+    with pytest.raises(SystemExit):
+        bench.parse_grid("3x2", 8)
+    assert bench.parse_grid(None, 4) == (4, 1)
+
+
+def _response_worker(rank, world, port, name, out_path):
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shares = [1000 + 64 * r for r in range(world)]
+    qbytes = 5000
+    if rank != 0:
+        dist.barrier()                       # rank 0 creates the segment first
+    nr = bench.NodeResponse(rank, world, name, qbytes, shares)
+    if rank == 0:
+        nr.flags[:] = 0
+        nr.query[:] = np.arange(qbytes, dtype=np.uint32).astype(np.uint8)
+        dist.barrier()
+    dist.barrier()
+    ok = nr.share.size == shares[rank] and np.array_equal(nr.query, np.arange(qbytes, dtype=np.uint32).astype(np.uint8))
+    for step in range(3):                    # every rank writes its share of the response of `step`, then marks it
+        nr.share[:] = (17 * rank + step) & 0xFF
+        nr.mark_done(step)
+        if rank == 0:
+            nr.wait_all(step, timeout_s=30)
+            for r in range(world):
+                ok = ok and bool((nr.share_of(r) == ((17 * r + step) & 0xFF)).all())
+        dist.barrier()
+    if rank == 0:
+        try:
+            nr.flags[world - 1] = 0
+            nr.wait_all(5, timeout_s=0.2)    # a rank that never finishes: a time-out, not a hang
+            ok = False
+        except TimeoutError:
+            pass
+        with open(out_path, "w") as f:
+            f.write("ok" if ok else "mismatch")
+    dist.barrier()
+    nr.close()
+    dist.destroy_process_group()
+
+
+def test_node_response_shared_buffer_gloo(tmp_path):
+    """world-size-2 check of the e2e response path of bench.py at N > 1: one POSIX shared-memory buffer, every
+    rank writes its own share, rank 0 sees all of them once every rank has marked the step"""
+    port = _free_port()
+    out = tmp_path / "result.txt"
+    mp.spawn(_response_worker, args=(2, port, f"pf_test_{port}", str(out)), nprocs=2, join=True)
+    assert out.read_text() == "ok"
