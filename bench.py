@@ -312,6 +312,37 @@ def pin_to_gpu_numa_node(torch_device):
         return {"pinned": False, "why": f"{type(ex).__name__}: {ex}"}
 
 
+def bind_pages_to_gpu_node(arr, torch_device):
+    """mbind(2) the pages of a host buffer to the NUMA node of this rank's GPU BEFORE they are first touched
+    (the shared response buffer: a rank whose share sat on the other socket downloaded at 60 % of the local
+    rate).  Best effort: a container whose cpuset.mems excludes the node, or a kernel without NUMA, says no."""
+    try:
+        import ctypes
+        import torch
+        p = torch.cuda.get_device_properties(torch_device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text().strip())
+        if node < 0:
+            return {"bound": False, "why": "no NUMA node reported for the GPU"}
+        addr = arr.ctypes.data
+        page = 4096
+        start = (addr + page - 1) // page * page
+        length = (addr + arr.nbytes) // page * page - start
+        if length <= 0:
+            return {"bound": False, "why": "buffer smaller than a page"}
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        libc = ctypes.CDLL(None, use_errno=True)
+        MPOL_BIND, SYS_mbind = 2, 237
+        rc = libc.syscall(SYS_mbind, ctypes.c_void_p(start), ctypes.c_ulong(length), ctypes.c_int(MPOL_BIND), mask,
+                          ctypes.c_ulong(16 * 64), ctypes.c_uint(0))
+        if rc != 0:
+            return {"bound": False, "node": node, "why": f"mbind errno {ctypes.get_errno()}"}
+        return {"bound": True, "node": node}
+    except Exception as ex:
+        return {"bound": False, "why": f"{type(ex).__name__}: {ex}"}
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle's OpenMP whole-step driver on a bounded sample
 # ----------------------------------------------------------------------------------------------
@@ -833,7 +864,18 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
 
     # ---- e2e: host buffers through the public C-ABI calls --------------------------------------
     if want_e2e:
-        rec["e2e"] = run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag)
+        # every rank must take the same path: agree first that the flights' buffers fit beside the resident DB
+        free_b, _tot = torch.cuda.mem_get_info(dev)
+        depth = int(os.environ.get("PF_BENCH_E2E_DEPTH", "3"))
+        need = depth * (max_res * eng.slot_bytes + 2 * max(nq_loc, 1) * m * eng.ct_bytes) + (2 << 30)
+        fits = torch.tensor([1.0 if need <= free_b else 0.0], device=dev, dtype=torch.float64)
+        comm.all_reduce(fits)
+        if int(fits.item()) == world:
+            rec["e2e"] = run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag)
+        else:
+            rec["e2e"] = {"value": None, "unit": "distances/s", "skipped": f"{depth} searches in flight need {need / 2**30:.1f} GiB beside the "
+                          f"{info['db_bytes'] / 2**30:.1f} GiB DB; {free_b / 2**30:.1f} GiB free on this GPU (shard the index over more GPUs)"}
+            log(f"[{tag}rank {rank}] e2e skipped: {rec['e2e']['skipped']}")
 
     # ---- parity self-check on real encryptions (untimed; the oracle is the checker) -------------
     if want_parity and world == 1:
@@ -961,7 +1003,10 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
     if world > 1 and rank == 0:
         comm.barrier()
     flags, qnp, out_np = nr.flags, nr.query, nr.share
+    numa = bind_pages_to_gpu_node(out_np, dev) if world > 1 else None
     out_np[:] = 0                                 # first touch by the owner: pages on this rank's NUMA node
+    if world > 1:
+        log(f"[{tag}rank {rank}] response share: {numa}")
     if rank == 0:
         flags[:] = 0
     # the request of a step: nq*m SEAL streams (the same bytes every step; timing does not depend on values);

@@ -20,6 +20,8 @@ struct DevModulus {
     u64 pad2;
     // FP64 NTT constants (pf_ntt_fp.cuh): q, 1/q, centred N^{-1}, centred irp[1]*N^{-1}
     double fq, fqinv, fninv, flast_w;
+    double fpinv; // centred P^{-1} mod q (key-switch finish on the FP64 pipe, pf_keyswitch.cuh)
+    double fpad;
 };
 
 // twiddle tables per modulus: fwd[N] then inv[N], each entry {w, floor(w*2^64/q)}
@@ -100,3 +102,35 @@ __device__ __forceinline__ void stg_once(ulonglong2 *p, ulonglong2 v, u64 pol) {
 __device__ __forceinline__ void stg_stream(ulonglong2 *p, ulonglong2 v) {
     asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y));
 }
+
+// ---- exact modular arithmetic on the FP64 pipe (residues as integer-valued doubles; derivation and
+// bounds in pf_ntt_fp.cuh) ------------------------------------------------------------------------------
+#define PF_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+struct FpConsts {
+    double q, qinv;
+};
+
+__device__ __forceinline__ double fp_mulmod(double a, double w, double q, double qinv) {
+    const double h = __dmul_rn(a, w);
+    const double l = __fma_rn(a, w, -h);
+    const double k = __dadd_rn(__fma_rn(h, qinv, PF_FP_MAGIC), -PF_FP_MAGIC);
+    const double r = __fma_rn(-k, q, h);
+    return __dadd_rn(r, l);
+}
+__device__ __forceinline__ double fp_reduce(double x, double q, double qinv) { // -> [-q/2, q/2]
+    const double k = __dadd_rn(__fma_rn(x, qinv, PF_FP_MAGIC), -PF_FP_MAGIC);
+    return __fma_rn(-k, q, x);
+}
+__device__ __forceinline__ double fp_from_u64(u64 x) { // exact for x < 2^52
+    return __dadd_rn(__longlong_as_double((long long)(x | 0x4330000000000000ull)), -4503599627370496.0);
+}
+__device__ __forceinline__ u64 fp_to_u64(double x) { // exact for integer x in [0, 2^51)
+    return (u64)__double_as_longlong(__dadd_rn(x, 4503599627370496.0)) & 0x000fffffffffffffull;
+}
+__device__ __forceinline__ u64 fp_canonical(double x, double q, double qinv) {
+    double r = fp_reduce(x, q, qinv);
+    r = r < 0.0 ? __dadd_rn(r, q) : r;
+    return fp_to_u64(r);
+}
+

@@ -532,11 +532,13 @@ int build_tables(pf_engine *e) {
         }
         m.split_shift = (u64)((64 - __builtin_clzll(q) + 1) / 2);
         m.p_half_mod = m.p_inv = m.p_inv_sh = m.pad2 = 0;
+        m.fpinv = m.fpad = 0.0;
         if (j < L) {
             const u64 P = e->h_q[k - 1];
             m.p_half_mod = (P >> 1) % q;
             m.p_inv = invmod(P % q, q);
             m.p_inv_sh = shoup(m.p_inv, q);
+            m.fpinv = centred(m.p_inv, q);
         }
     }
     CK(e->d_mods.ensure(mods.size() * sizeof(DevModulus)));
@@ -990,16 +992,27 @@ void launch_mac_occ_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
 int mac_variant(const pf_engine *e) {
     const char *v = getenv("PF_MAC_VARIANT");
     const int env = v ? atoi(v) : -1;
-    if (e->mac_wide || e->K < 4 || e->K > 32) return 0;
-    const bool occ_fits = (size_t)e->K * 2 * 256 * 8 * 3 <= (size_t)227 * 1024;
+    if (e->mac_wide || e->K < 4) return 0;
     if (env == 0) return 0;
+    if (e->K > 16) { // 7 = the one-block-per-lane kernel with the widest slice of which three fit an SM (K = 128: 32 coefficients)
+        const bool fits7 = (size_t)e->K * 2 * 32 * 8 * 3 <= (size_t)227 * 1024;
+        return fits7 ? 7 : 0;
+    }
+    const bool occ_fits = (size_t)e->K * 2 * 256 * 8 * 3 <= (size_t)227 * 1024;
     if (env >= 4 && env <= 6) return occ_fits ? env : 0;
     return occ_fits ? 6 : PF_MAC_DEFAULT_VARIANT;
+}
+
+int mac_tile7(const pf_engine *e) { // variant 7: slice width
+    for (int T : {128, 64, 32})
+        if ((size_t)e->K * 2 * T * 8 * 3 <= (size_t)227 * 1024) return T;
+    return 32;
 }
 
 int mac_tile(const pf_engine *e) {
     const int v = mac_variant(e);
     if (v == 6) return 128;
+    if (v == 7) return mac_tile7(e);
     if (v == 4 || v == 5) return 256;
     const int env_t = getenv("PF_MAC_TILE") ? atoi(getenv("PF_MAC_TILE")) : 0;
     if (env_t == 256 || env_t == 128 || env_t == 64) return env_t;
@@ -1020,6 +1033,12 @@ void launch_mac(pf_engine *e, const MacParams &p, unsigned nchunks) {
     if (v == 4) return launch_mac_occ_t<256, 2>(e, p, nchunks);
     if (v == 5) return (p.K % 8 == 0) ? launch_mac_occ_t<256, 4>(e, p, nchunks) : launch_mac_occ_t<256, 2>(e, p, nchunks);
     if (v == 6) return launch_mac_occ_t<128, 2, 4>(e, p, nchunks);
+    if (v == 7) {
+        const int T7 = mac_tile7(e);
+        if (T7 == 128) return launch_mac_occ_t<128, 2, 3>(e, p, nchunks);
+        if (T7 == 64) return launch_mac_occ_t<64, 2, 3>(e, p, nchunks);
+        return launch_mac_occ_t<32, 2, 3>(e, p, nchunks);
+    }
     const int T = mac_tile(e);
     if (T == 256) launch_mac_tile<256>(e, p, nchunks);
     else if (T == 128) launch_mac_tile<128>(e, p, nchunks);
@@ -1118,11 +1137,25 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     if (rc) return rc;
     HostTick ht2("mac+intt");
     // chunks / pairs of this query range (chunks are ordered by query)
-    size_t c0 = 0, c1 = 0;
-    while (c0 < pl.chunks.size() && (uint64_t)pl.chunks[c0].query < q0) c0++;
-    c1 = c0;
-    while (c1 < pl.chunks.size() && (uint64_t)pl.chunks[c1].query < q0 + nq) c1++;
-    if (c1 == c0) return PF_OK;
+    size_t cb = 0, ce = 0;
+    while (cb < pl.chunks.size() && (uint64_t)pl.chunks[cb].query < q0) cb++;
+    ce = cb;
+    while (ce < pl.chunks.size() && (uint64_t)pl.chunks[ce].query < q0 + nq) ce++;
+    if (ce == cb) return PF_OK;
+    // Sub-batches of whole queries: the full-level results of a sub-batch live in scratch until the
+    // mod-switch has written the response slots, and that scratch is capped (a 256-query batch at
+    // N = 16384 would otherwise hold 35 GiB of it).  One sub-batch in every configuration up to 64 queries.
+    const size_t cap_bytes = getenv("PF_FULL_SCRATCH_MB") ? (size_t)atoll(getenv("PF_FULL_SCRATCH_MB")) << 20 : (size_t)6 << 30; // per call: tests flip it
+    const size_t maxP = std::max<size_t>(1, cap_bytes / (ctw * 8));
+    for (size_t c0 = cb; c0 < ce;) {
+    size_t c1 = c0, np = 0;
+    while (c1 < ce) { // take whole queries while they fit (always at least one)
+        size_t cq = c1, nqp = 0;
+        while (cq < ce && pl.chunks[cq].query == pl.chunks[c1].query) nqp += (size_t)pl.chunks[cq++].pair_count;
+        if (np && e->Lr < L && np + nqp > maxP) break;
+        np += nqp;
+        c1 = cq;
+    }
     const size_t p0 = (size_t)pl.chunks[c0].pair_start;
     const size_t p1 = (size_t)pl.chunks[c1 - 1].pair_start + pl.chunks[c1 - 1].pair_count;
     const size_t P = p1 - p0;
@@ -1208,6 +1241,8 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
             }
         }
     }
+    c0 = c1;
+    } // sub-batches
     CK(cudaGetLastError());
     return PF_OK;
 }

@@ -50,6 +50,15 @@ struct KsParams {
 // LT <= 4: the key words of a thread live in its own shared-memory slots instead of 32 registers
 //          (no barrier: a thread reads back only what it wrote), which brings the kernel to 64
 //          registers and 4 CTAs/SM — it is bound by the latency of the digit gathers and W loads.
+// The NTT-domain Galois permutation maps every aligned pair of positions {2u, 2u+1} onto an aligned pair
+// (possibly swapped): bit 0 of a position is the top bit of its bit-reversed exponent index, and e * N = N
+// (mod 2N) for odd e.  A thread's two coefficients are therefore ONE 16-byte gather (pair perm[2u] >> 1,
+// swap flag perm[2u] & 1) instead of two 8-byte ones, for the hoisted digits and for sigma(c0).
+// FPRED kernels finish on the FP64 pipe (idle here): the lazy sums are reduced to doubles congruent mod q
+// (lazy_reduce_fp_d), the hoisting term, the mod-down correction W, the multiplication by P^{-1} (fp_mulmod,
+// centred constant) and sigma(c0) are applied as exact integer-valued doubles and only the stored word is
+// canonicalised: ~20 FP64 + ~8 integer instructions per output instead of ~50 integer ones (ncu r2: the
+// kernel was issue-bound at 66 %, ALU 48 %, FP64 5 %).
 template <int LT, bool FINISH, bool FPRED>
 __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_accumulate_kernel(const KsParams p, int njobs) {
     constexpr bool SMEMKEY = LT <= 4;
@@ -61,19 +70,20 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_acc
     const DevModulus m = p.mods[ki];
     const int c2 = blockIdx.x * 256 + threadIdx.x; // pair index
     const int sh = (int)m.split_shift;
-    const double qinv = m.fqinv;
+    const double qinv = m.fqinv, fq = m.fq;
     const u64 once = l2_evict_first_policy();
     const int z0 = blockIdx.z * KS_QT, z1 = min(z0 + KS_QT, njobs);
     ulonglong2 k0[SMEMKEY ? 1 : LT], k1[SMEMKEY ? 1 : LT];
     const u64 *cur_key = nullptr;
-    u32 px = 0, py = 0; // NTT-domain permutation of this thread's two coefficients: constant per key
+    u32 pp = 0;       // pair this thread's two coefficients are gathered from: constant per key
+    bool swp = false; // ... in swapped order
     for (int z = z0; z < z1; z++) {
         const RotJob job = p.jobs[z];
         if (job.key != cur_key) { // uniform across the CTA
             cur_key = job.key;
-            const uint2 pp = __ldg(reinterpret_cast<const uint2 *>(job.perm) + c2);
-            px = pp.x;
-            py = pp.y;
+            const u32 p0 = __ldg(job.perm + 2 * c2);
+            pp = p0 >> 1;
+            swp = p0 & 1;
 #pragma unroll
             for (int J = 0; J < LT; J++) {
                 if (J < L) {
@@ -102,9 +112,12 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_acc
             if (J < L) {
                 ulonglong2 dv;
                 if (hoisted) {
-                    const u64 *dj = job.D + ((size_t)J * (L + 1) + I) * N;
-                    dv.x = __ldg(dj + px);
-                    dv.y = __ldg(dj + py);
+                    dv = __ldg(reinterpret_cast<const ulonglong2 *>(job.D + ((size_t)J * (L + 1) + I) * N) + pp);
+                    if (swp) {
+                        const u64 t = dv.x;
+                        dv.x = dv.y;
+                        dv.y = t;
+                    }
                 } else {
                     dv = reinterpret_cast<const ulonglong2 *>(dz + ((size_t)J * (L + 1) + I) * N)[c2];
                 }
@@ -119,11 +132,62 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_acc
             }
         }
         u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
+        if (FPRED) {
+            // everything after the inner product as exact integer-valued doubles (|values| < 2^48)
+            double f00 = lazy_reduce_fp_d(a00, sh, m.q, qinv), f01 = lazy_reduce_fp_d(a01, sh, m.q, qinv);
+            double f10 = lazy_reduce_fp_d(a10, sh, m.q, qinv), f11 = lazy_reduce_fp_d(a11, sh, m.q, qinv);
+            if (hoisted) {
+                const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
+                const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
+                f00 = __dadd_rn(f00, fp_from_u64(m0.x));
+                f01 = __dadd_rn(f01, fp_from_u64(m0.y));
+                f10 = __dadd_rn(f10, fp_from_u64(m1.x));
+                f11 = __dadd_rn(f11, fp_from_u64(m1.y));
+            }
+            if (!FINISH) {
+                ulonglong2 r0, r1;
+                r0.x = fp_canonical(f00, fq, qinv);
+                r0.y = fp_canonical(f01, fq, qinv);
+                r1.x = fp_canonical(f10, fq, qinv);
+                r1.y = fp_canonical(f11, fq, qinv);
+                reinterpret_cast<ulonglong2 *>(Sz + (size_t)I * N)[c2] = r0;
+                reinterpret_cast<ulonglong2 *>(Sz + (size_t)(L + 1 + I) * N)[c2] = r1;
+            } else {
+                const u64 *Wz = p.W + (size_t)z * 2 * L * N;
+                const ulonglong2 w0 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N) + c2, once);
+                const ulonglong2 w1 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N) + c2, once);
+                ulonglong2 c0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.c0_ntt + (size_t)I * N) + pp);
+                if (swp) {
+                    const u64 t = c0.x;
+                    c0.x = c0.y;
+                    c0.y = t;
+                }
+                const double pinv = m.fpinv;
+                const double g00 = __dadd_rn(fp_mulmod(__dadd_rn(f00, -fp_from_u64(w0.x)), pinv, fq, qinv), fp_from_u64(c0.x));
+                const double g01 = __dadd_rn(fp_mulmod(__dadd_rn(f01, -fp_from_u64(w0.y)), pinv, fq, qinv), fp_from_u64(c0.y));
+                const double g10 = fp_mulmod(__dadd_rn(f10, -fp_from_u64(w1.x)), pinv, fq, qinv);
+                const double g11 = fp_mulmod(__dadd_rn(f11, -fp_from_u64(w1.y)), pinv, fq, qinv);
+                ulonglong2 o0, o1;
+                o0.x = fp_canonical(g00, fq, qinv);
+                o0.y = fp_canonical(g01, fq, qinv);
+                o1.x = fp_canonical(g10, fq, qinv);
+                o1.y = fp_canonical(g11, fq, qinv);
+                if (p.out_split) {
+                    o0.x = split_word(o0.x, sh);
+                    o0.y = split_word(o0.y, sh);
+                    o1.x = split_word(o1.x, sh);
+                    o1.y = split_word(o1.y, sh);
+                }
+                stg_once(reinterpret_cast<ulonglong2 *>(job.out + (size_t)I * N) + c2, o0, once);
+                stg_once(reinterpret_cast<ulonglong2 *>(job.out + (size_t)(L + I) * N) + c2, o1, once);
+            }
+            continue;
+        }
         ulonglong2 r0, r1;
-        r0.x = lazy_reduce_sel<FPRED>(a00, sh, m, qinv);
-        r0.y = lazy_reduce_sel<FPRED>(a01, sh, m, qinv);
-        r1.x = lazy_reduce_sel<FPRED>(a10, sh, m, qinv);
-        r1.y = lazy_reduce_sel<FPRED>(a11, sh, m, qinv);
+        r0.x = lazy_reduce(a00, sh, m);
+        r0.y = lazy_reduce(a01, sh, m);
+        r1.x = lazy_reduce(a10, sh, m);
+        r1.y = lazy_reduce(a11, sh, m);
         if (hoisted) {
             const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
             const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);
@@ -139,10 +203,15 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_acc
             const u64 *Wz = p.W + (size_t)z * 2 * L * N;
             const ulonglong2 w0 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)I * N) + c2, once);
             const ulonglong2 w1 = ldg_once(reinterpret_cast<const ulonglong2 *>(Wz + (size_t)(L + I) * N) + c2, once);
-            const u64 *c0 = job.c0_ntt + (size_t)I * N;
+            ulonglong2 c0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.c0_ntt + (size_t)I * N) + pp);
+            if (swp) {
+                const u64 t = c0.x;
+                c0.x = c0.y;
+                c0.y = t;
+            }
             ulonglong2 o0, o1;
-            o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), __ldg(c0 + px), m.q);
-            o0.y = addmod(mul_shoup(submod(r0.y, w0.y, m.q), m.p_inv, m.p_inv_sh, m.q), __ldg(c0 + py), m.q);
+            o0.x = addmod(mul_shoup(submod(r0.x, w0.x, m.q), m.p_inv, m.p_inv_sh, m.q), c0.x, m.q);
+            o0.y = addmod(mul_shoup(submod(r0.y, w0.y, m.q), m.p_inv, m.p_inv_sh, m.q), c0.y, m.q);
             o1.x = mul_shoup(submod(r1.x, w1.x, m.q), m.p_inv, m.p_inv_sh, m.q);
             o1.y = mul_shoup(submod(r1.y, w1.y, m.q), m.p_inv, m.p_inv_sh, m.q);
             if (p.out_split) {

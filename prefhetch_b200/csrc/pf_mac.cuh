@@ -107,6 +107,17 @@ __device__ __forceinline__ u64 lazy_reduce_fp(const LazyAcc &a, int s, u64 q, do
     r = ((long long)r < 0) ? r + q : r;
     return r >= q ? r - q : r;
 }
+// The same reduction left on the FP64 pipe: a double congruent to V mod q with magnitude below 3q (the
+// integer remainder r in [-q, 2q), shifted by +q and converted exactly).  For callers that go on in FP64
+// (key-switch finish): no canonicalisation, no compares.
+__device__ __forceinline__ double lazy_reduce_fp_d(const LazyAcc &a, int s, u64 q, double qinv) {
+    const u64 mid = a.kz - a.lo - a.hi;
+    const double p2s = __longlong_as_double((long long)(1023 + s) << 52);
+    const double v = fma(u52_to_double(a.hi) * p2s, p2s, fma(u52_to_double(mid), p2s, u52_to_double(a.lo)));
+    const u64 qh = (u64)__double2ll_rd(v * qinv);
+    const u64 vlo = a.lo + (mid << s) + (a.hi << (2 * s));
+    return u52_to_double(vlo - qh * q + q);
+}
 template <bool FPRED>
 __device__ __forceinline__ u64 lazy_reduce_sel(const LazyAcc &a, int s, const DevModulus &m, double qinv) {
     return FPRED ? lazy_reduce_fp(a, s, m.q, qinv) : lazy_reduce(a, s, m);

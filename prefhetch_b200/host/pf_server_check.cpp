@@ -1,13 +1,97 @@
 // pf_server_check.cpp — compile-and-run check of the C++ host mirror (prefhetch::Server) against
-// the C ABI: plaintext stages on a tiny synthetic index.  Built by __graft_entry__.build();
-// executed by tests/test_gpu_parity.py::test_cpp_host_mirror on the GPU box.
+// the C ABI.  Built by __graft_entry__.build(); executed on the GPU box by tests/test_gpu_parity.py:
+//   pf_server_check              plaintext stages on a tiny synthetic index (test_cpp_host_mirror)
+//   pf_server_check <dir>        the ENCRYPTED search from C++: index, SEAL GaloisKeys stream, serialized
+//                                query ciphertexts and probe lists are read from files the test wrote;
+//                                the result ciphertext streams are written to <dir>/results.bin, one after
+//                                the other, for a byte comparison with the Python path (and the oracle)
+//                                (test_cpp_encrypted_search_matches_python).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "pf_server.hpp"
 
-int main() {
+namespace {
+
+template <class T>
+std::vector<T> read_file(const std::string &path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    const std::streamsize n = f.tellg();
+    f.seekg(0);
+    std::vector<T> v(static_cast<size_t>(n) / sizeof(T));
+    f.read(reinterpret_cast<char *>(v.data()), static_cast<std::streamsize>(v.size() * sizeof(T)));
+    return v;
+}
+
+int encrypted_check(const std::string &dir) {
+    // params.txt: d n g m result_limbs nprobe nq t k prime_0 .. prime_{k-1}
+    std::ifstream pf(dir + "/params.txt");
+    if (!pf) throw std::runtime_error("cannot open params.txt");
+    uint32_t d, g, m, rl, nprobe;
+    uint64_t n, nq, t, k;
+    pf >> d >> n >> g >> m >> rl >> nprobe >> nq >> t >> k;
+    std::vector<uint64_t> primes(k);
+    for (auto &q : primes) pf >> q;
+    const auto cent = read_file<float>(dir + "/centroids.f32");
+    const auto off = read_file<prefhetch::idx_t>(dir + "/offsets.i64");
+    const auto ids = read_file<prefhetch::idx_t>(dir + "/ids.i64");
+    const auto vec = read_file<float>(dir + "/vectors.f32");
+    const auto keys = read_file<uint8_t>(dir + "/galois_keys.bin");
+    const auto qblob = read_file<uint8_t>(dir + "/queries.bin");
+    const auto qoff = read_file<uint64_t>(dir + "/query_offsets.u64");
+    const auto probes = read_file<prefhetch::idx_t>(dir + "/probes.i64");
+    const uint64_t nlist = off.size() - 1;
+    prefhetch::Server srv(d, n, primes, t, m, g, 0, 0, 1, rl);
+    srv.init_index(nlist, cent.data(), off.data(), ids.data(), vec.data());
+    srv.loadGaloisKeys(keys);
+    // the synchronous call, then the same request twice through submit / collect: all three must agree
+    prefhetch::EncryptedCoarseResult r0, r1, r2;
+    srv.coarseSearchEncrypted(nq, qblob, qoff, probes, nprobe, r0);
+    const uint64_t t1 = srv.submitSearchEncrypted(nq, qblob, qoff, probes, nprobe, r1);
+    const uint64_t t2 = srv.submitSearchEncrypted(nq, qblob, qoff, probes, nprobe, r2);
+    srv.collect(t1, r1);
+    srv.collect(t2, r2);
+    if (r0.ciphertexts != r1.ciphertexts || r0.ciphertexts != r2.ciphertexts || r0.result_offsets != r2.result_offsets ||
+        r0.coarse_vector_indexes != r1.coarse_vector_indexes)
+        return 6;
+    const size_t len = srv.resultSerializedSize();
+    std::ofstream out(dir + "/results.bin", std::ios::binary);
+    for (uint64_t r = 0; r < r0.nresults; r++)
+        out.write(reinterpret_cast<const char *>(r0.ciphertexts.data() + r0.result_offsets[r]), static_cast<std::streamsize>(len));
+    std::ofstream lab(dir + "/labels.i64", std::ios::binary);
+    lab.write(reinterpret_cast<const char *>(r0.coarse_vector_indexes.data()),
+              static_cast<std::streamsize>(r0.coarse_vector_indexes.size() * sizeof(prefhetch::idx_t)));
+    std::printf("pf_server_check encrypted ok: %llu results of %zu bytes, %zu labels\n", (unsigned long long)r0.nresults, len,
+                r0.coarse_vector_indexes.size());
+    // a malformed request is an exception (std::runtime_error, as the reference throws), not a crash
+    try {
+        std::vector<uint64_t> bad(qoff);
+        bad.back() += 64;
+        srv.coarseSearchEncrypted(nq, qblob, bad, probes, nprobe, r1);
+        return 7;
+    } catch (const std::runtime_error &) {
+    }
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc > 1) {
+        try {
+            return encrypted_check(argv[1]);
+        } catch (const std::exception &ex) {
+            std::fprintf(stderr, "pf_server_check (encrypted) failed: %s\n", ex.what());
+            return 1;
+        }
+    }
+
     const uint32_t d = 128;
     const uint64_t nlist = 4, per = 50, nb = nlist * per;
     std::vector<uint64_t> primes = {0x7fffffd8001ULL, 0x7fffffc8001ULL, 0xfffffffc001ULL, 0xffffff6c001ULL,

@@ -433,14 +433,20 @@ def test_cpp_host_mirror():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("n,d,m,g,tbits,rl", [(16384, 128, 1, 16, 24, 0), (8192, 960, 8, 8, 27, 0), (4096, 64, 2, 4, 24, 0),
-                                              (16384, 128, 1, 16, 24, 2), (4096, 64, 2, 4, 24, 1)])
-def test_encrypted_search_other_shapes(pf, oracle, n, d, m, g, tbits, rl):
+@pytest.mark.parametrize("n,d,m,g,tbits,rl,macv", [(16384, 128, 1, 16, 24, 0, None), (8192, 960, 8, 8, 27, 0, None),
+                                                   (8192, 960, 8, 8, 27, 1, "0"), (4096, 64, 2, 4, 24, 0, None),
+                                                   (16384, 128, 1, 16, 24, 2, None), (4096, 64, 2, 4, 24, 1, None),
+                                                   (8192, 256, 1, 8, 24, 1, None)])
+def test_encrypted_search_other_shapes(pf, oracle, monkeypatch, n, d, m, g, tbits, rl, macv):
     """poly degree 16384 (L = 8, 49-bit primes: FP64 NTT with mid-pass reductions), GIST-shaped 960-d
     vectors with 8 query ciphertexts (K = 128 diagonals per block), and a 2-ciphertext small case:
     bytes identical to the oracle's pipeline, decrypted distances exact.  rl > 0: results mod-switched
-    to rl limbs (8 -> 2 on the FP64 kernel with 49-bit primes; 2 -> 1 on the generic integer kernel)."""
+    to rl limbs (8 -> 2 on the FP64 kernel with 49-bit primes; 2 -> 1 on the generic integer kernel).
+    K = 128 runs the narrow-slice one-block-per-lane MAC (32 coefficients, 3 CTAs/SM) by default and the
+    two-blocks-per-lane kernel with PF_MAC_VARIANT=0; d = 256 with one ciphertext gives K = 32 (128-wide)."""
     from oracle.pf_oracle import BATCHING_T, BFV_DEFAULT_PRIMES
+    if macv is not None:
+        monkeypatch.setenv("PF_MAC_VARIANT", macv)
     primes = BFV_DEFAULT_PRIMES[n]
     t = BATCHING_T[(n, tbits)] if (n, tbits) in BATCHING_T else ntt_primes(n, tbits, 1)[0]
     rng = np.random.default_rng(n + d)
@@ -596,7 +602,7 @@ def test_load_galois_keys_stream(pf, oracle):
 
 _VARIANTS = [{"PF_MAC_VARIANT": "0"}, {"PF_MAC_VARIANT": "4"}, {"PF_MAC_VARIANT": "5"}, {"PF_MAC_VARIANT": "6"},
              {"PF_NTT_FP": "0"}, {"PF_MS_INT": "1"}, {"PF_KS_NO_FUSED_PREP": "1"}, {"PF_MAC_NO_FPRED": "1"},
-             {"PF_KS_NO_FPRED": "1"}, {"PF_E2E_GROUPS": "1"}, {"PF_E2E_GROUPS": "7"}]
+             {"PF_KS_NO_FPRED": "1"}, {"PF_E2E_GROUPS": "1"}, {"PF_E2E_GROUPS": "7"}, {"PF_FULL_SCRATCH_MB": "3"}]
 
 
 @pytest.mark.parametrize("n,g,rl", [(8192, 8, 1), (16384, 16, 2)])
@@ -744,3 +750,53 @@ def test_flag_wait_times_out(pf, monkeypatch):
         eng.flag_write(ptr, 5)     # sticky
     eng.ipc_free(ptr)
     eng.close()
+
+
+def test_cpp_encrypted_search_matches_python(pf, oracle, tmp_path):
+    """the reference-side binding in C++ (prefhetch::Server: loadGaloisKeys from a SEAL stream, result_limbs,
+    coarseSearchEncrypted and submit / collect) gives the bytes of the Python path, which is checked against
+    the oracle here as well (the encrypted call was never made from C++)"""
+    import subprocess
+    from pathlib import Path
+    from tests.util import galois_keys_save
+    exe = Path(__file__).resolve().parent.parent / "prefhetch_b200" / "host" / "pf_server_check"
+    assert exe.exists(), "run __graft_entry__.build() first"
+    n, g, d, nprobe, rl = 2048, 16, 128, 3, 1
+    base, query, cent, offsets, ids, vecs = _dataset(41, nb=3000, nlist=12, nq=3)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    cts = np.stack([cl.encrypt_query(q, 700 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    eng, _, _ = _engine(pf, n, g=g, result_limbs=rl)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(keys):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    idx = eng.coarse_quantize(query, nprobe)
+    res = eng.coarseSearchEncrypted(blob, offs, idx)
+    want = b"".join(res.result(r) for r in range(res.stats["nresults"]))
+    # oracle check of the first result
+    rot = oracle.rotate_query_set(cl.ctx, cl.lay, cts[0], keys, False)
+    l = idx[0, 0]
+    xs = vecs[offsets[l]: offsets[l] + min(cl.lay.C, int(offsets[l + 1] - offsets[l]))].astype(np.int32)
+    diag, norm = oracle.encode_block(cl.ctx, cl.lay, xs)
+    first = cl.ctx.ct_save(cl.mod_switch_to(oracle.block_distance(cl.ctx, cl.lay, rot, diag, norm), rl),
+                           parms_id=_parms_id_py(n, primes[:rl], t))
+    assert res.result(0) == first
+    labels = res.labels.copy()
+    eng.close()
+    # the same request from C++
+    (tmp_path / "params.txt").write_text(" ".join(str(x) for x in [d, n, g, 1, rl, nprobe, len(query), t, len(primes), *primes]))
+    cent.astype(np.float32).tofile(tmp_path / "centroids.f32")
+    offsets.astype(np.int64).tofile(tmp_path / "offsets.i64")
+    ids.astype(np.int64).tofile(tmp_path / "ids.i64")
+    vecs.astype(np.float32).tofile(tmp_path / "vectors.f32")
+    (tmp_path / "galois_keys.bin").write_bytes(galois_keys_save(cl.ctx, {cl.ctx.galois_elt(i + 1): k for i, k in enumerate(keys)}))
+    blob.tofile(tmp_path / "queries.bin")
+    offs.astype(np.uint64).tofile(tmp_path / "query_offsets.u64")
+    idx.astype(np.int64).tofile(tmp_path / "probes.i64")
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "results.bin").read_bytes() == want
+    assert np.array_equal(np.fromfile(tmp_path / "labels.i64", dtype=np.int64), labels)
