@@ -1041,7 +1041,7 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
             nr.wait_all(s)
         t_col += time.perf_counter() - ta
 
-    WARM = 2
+    WARM = DEPTH + 2        # every flight's buffers have been allocated (first use) before the clock starts
     for s in range(WARM + e_steps):
         if s == WARM:
             while pend:

@@ -8,7 +8,10 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libprefhetch_b200.so"
+import os
+
+# PF_LIB: an alternative build of the same library (kernel A/B experiments: python -m prefhetch_b200.build --variant NAME -D...)
+LIB_PATH = Path(os.environ["PF_LIB"]) if os.environ.get("PF_LIB") else PKG / "libprefhetch_b200.so"
 
 PF_MAX_PRIMES = 16
 PF_T_COUNT = 8

@@ -47,6 +47,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines) -> Path:
+    """an experiment build next to the product library: libprefhetch_b200.<name>.so compiled with extra -D flags
+    (select it with PF_LIB=<path>); used for kernel A/B measurements recorded in profiles/README.md"""
+    out = PKG / f"libprefhetch_b200.{name}.so"
+    cu, _ = sources()
+    cmd = [NVCC, *FLAGS, *defines, "-o", str(out), *[str(c) for c in cu], "-lz"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    (PKG / f"build.{name}.log").write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed for variant {name}")
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print(LIB)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        build(force="--force" in sys.argv, verbose=True)
+        print(LIB)

@@ -968,19 +968,25 @@ void launch_mac_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
     e->launches++;
 }
 
+template <int T, int UNROLL, int MINCTA, bool FPRED>
+void launch_mac_occ_k(pf_engine *e, const MacParams &p, unsigned nchunks) {
+    const size_t smem = (size_t)p.K * 2 * T * 8;
+    auto kern = mac_kernel_occ<T, UNROLL, FPRED, MINCTA>;
+    // the attribute is a MAXIMUM: raise it when a launch needs more than any launch of this instantiation before
+    // (setting it per launch cost a few microseconds each; lowering it makes a later, larger launch invalid)
+    static size_t attr_max = 48 * 1024;
+    if (smem > attr_max) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_max = smem;
+    }
+    kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
+    e->launches++;
+}
+
 template <int T, int UNROLL, int MINCTA = 3>
 void launch_mac_occ_t(pf_engine *e, const MacParams &p, unsigned nchunks) {
-    const size_t smem = (size_t)p.K * 2 * T * 8;
-    if (e->mac_fpred) {
-        auto kern = mac_kernel_occ<T, UNROLL, true, MINCTA>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
-    } else {
-        auto kern = mac_kernel_occ<T, UNROLL, false, MINCTA>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3(nchunks, p.L * (p.N / T)), 256, smem, e->stream>>>(p);
-    }
-    e->launches++;
+    if (e->mac_fpred) launch_mac_occ_k<T, UNROLL, MINCTA, true>(e, p, nchunks);
+    else launch_mac_occ_k<T, UNROLL, MINCTA, false>(e, p, nchunks);
 }
 
 // MAC variant (PF_MAC_VARIANT, read per call so tests can flip it): 0 = two blocks per lane, 2 CTAs/SM

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256, (LT <= 4 ? 4 : (LT <= 8 ? 2 : 1))) ks_acc
         u64 *Sz = p.S + (size_t)z * 2 * (L + 1) * N;
         if (FPRED) {
             // everything after the inner product as exact integer-valued doubles (|values| < 2^48)
-            double f00 = lazy_reduce_fp_d(a00, sh, m.q, qinv), f01 = lazy_reduce_fp_d(a01, sh, m.q, qinv);
-            double f10 = lazy_reduce_fp_d(a10, sh, m.q, qinv), f11 = lazy_reduce_fp_d(a11, sh, m.q, qinv);
+            double f00 = lazy_reduce_fp_d(a00, sh, fq, qinv), f01 = lazy_reduce_fp_d(a01, sh, fq, qinv);
+            double f10 = lazy_reduce_fp_d(a10, sh, fq, qinv), f11 = lazy_reduce_fp_d(a11, sh, fq, qinv);
             if (hoisted) {
                 const ulonglong2 m0 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)I * N) + c2);
                 const ulonglong2 m1 = __ldg(reinterpret_cast<const ulonglong2 *>(job.KM + (size_t)(L + 1 + I) * N) + c2);

@@ -107,16 +107,24 @@ __device__ __forceinline__ u64 lazy_reduce_fp(const LazyAcc &a, int s, u64 q, do
     r = ((long long)r < 0) ? r + q : r;
     return r >= q ? r - q : r;
 }
-// The same reduction left on the FP64 pipe: a double congruent to V mod q with magnitude below 3q (the
-// integer remainder r in [-q, 2q), shifted by +q and converted exactly).  For callers that go on in FP64
-// (key-switch finish): no canonicalisation, no compares.
-__device__ __forceinline__ double lazy_reduce_fp_d(const LazyAcc &a, int s, u64 q, double qinv) {
+// The reduction done entirely on the FP64 pipe (the integer pipes are the busy ones in the MAC and in the
+// key-switch inner product): V = lo + mid 2^s + hi 2^2s with lo, mid, hi < 2^52 exact in doubles.  A power-of-
+// two scaling is exact, and x - rint(x/q) q is exact for any integer-valued x below 2^94 (the FMA forms
+// k q exactly and the difference is an integer below q), so
+//   V  ==  lo + reduce(mid 2^s) + reduce(hi 2^2s)   (mod q),   |result| < 2^52 + 2q
+// in 11 FP64 operations and no integer multiply, shift or compare.  Returns that double (callers that go
+// on in FP64 use it as it is; lazy_reduce_fp2 canonicalises it).  Valid when 2s + 2 + ceil(log2 K) <= 52.
+__device__ __forceinline__ double fp_reduce_big(double x, double q, double qinv) { // -> about [-q/2, q/2], |x| < 2^94
+    const double k = __dadd_rn(__fma_rn(x, qinv, 6755399441055744.0), -6755399441055744.0);
+    return __fma_rn(-k, q, x);
+}
+__device__ __forceinline__ double lazy_reduce_fp_d(const LazyAcc &a, int s, double q, double qinv) {
     const u64 mid = a.kz - a.lo - a.hi;
     const double p2s = __longlong_as_double((long long)(1023 + s) << 52);
-    const double v = fma(u52_to_double(a.hi) * p2s, p2s, fma(u52_to_double(mid), p2s, u52_to_double(a.lo)));
-    const u64 qh = (u64)__double2ll_rd(v * qinv);
-    const u64 vlo = a.lo + (mid << s) + (a.hi << (2 * s));
-    return u52_to_double(vlo - qh * q + q);
+    const double p22s = __longlong_as_double((long long)(1023 + 2 * s) << 52);
+    const double m = fp_reduce_big(__dmul_rn(u52_to_double(mid), p2s), q, qinv);
+    const double h = fp_reduce_big(__dmul_rn(u52_to_double(a.hi), p22s), q, qinv);
+    return __dadd_rn(__dadd_rn(u52_to_double(a.lo), m), h);
 }
 template <bool FPRED>
 __device__ __forceinline__ u64 lazy_reduce_sel(const LazyAcc &a, int s, const DevModulus &m, double qinv) {
@@ -335,6 +343,10 @@ __global__ void __launch_bounds__(256, MINCTA) mac_kernel_occ(const MacParams p)
     __syncthreads();
     const ulonglong2 *sct = reinterpret_cast<const ulonglong2 *>(smem_ct) + tx;
     const int split = (int)m.split_shift;
+    // (A lane loop that issues the next pair's first loads and norm before the reduction of the current pair,
+    // with the reduction moved to the FP64 pipe, was tried in round 2: 5 % fewer instructions but 0.92 ms
+    // against 0.834 ms — at 64 registers the values held across the epilogue are paid for in local-memory
+    // traffic and long-scoreboard stalls; profiles/README.md.)
     for (int pi = by; pi < ch.pair_count; pi += BY)
         mac_pairs_split<1, UNROLL, TX, FPRED>(p, sct, m, split, coef0, LN, tx, (size_t)ch.pair_start + pi, pol, pol);
 }

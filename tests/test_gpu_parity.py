@@ -647,7 +647,10 @@ def test_kernel_variants_bit_identical(pf, oracle, monkeypatch, n, g, rl):
     for env in _VARIANTS:
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        _, got = run()
+        try:
+            _, got = run()
+        except Exception as ex:
+            raise AssertionError(f"variant {env} failed: {ex}") from ex
         for k in env:
             monkeypatch.delenv(k)
         assert len(got) == len(ref) and all(a == b for a, b in zip(got, ref)), f"variant {env} differs from the default path"
