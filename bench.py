@@ -268,10 +268,14 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        if self.source is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"], "samples": 0}
         if getattr(self, "th", None):
             self.th.join(timeout=2)
+        return self.report(t0, t1)
+
+    def report(self, t0=None, t1=None):
+        """clocks over the samples inside [t0, t1] (host perf_counter); the sampler keeps running"""
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"], "samples": 0}
         rows = list(self.rows)
         win = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
         window = "timed"
@@ -523,6 +527,80 @@ def emit(line):
     print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
+class StageGuard:
+    """No optional stage may cost the run its headline.  After the timed region rank 0 publishes the JSON line as
+    it stands; every later stage (e2e, parity self-check, CPU baseline, the strong-scaling record) runs between
+    enter(stage, limit) and leave().  If a stage hangs (a peer died inside a collective) or a rank reports a
+    failure through the abort file, the watchdog thread of every rank fires: rank 0 emits the published line
+    with `aborted_stage` filled in, and all ranks leave with exit code 0.  The same thread enforces a limit on
+    the whole run."""
+
+    def __init__(self, rank, world, total_limit_s=1500.0):
+        self.rank, self.world = rank, world
+        self.partial, self.stage, self.deadline = None, "setup + timed region", time.monotonic() + total_limit_s
+        self.abort_file = Path(f"/tmp/pf_bench_abort_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
+        self.shm_names = []
+        self.done = threading.Event()
+        try:
+            self.abort_file.unlink()
+        except OSError:
+            pass
+        self.th = threading.Thread(target=self._watch, daemon=True)
+        self.th.start()
+
+    def publish(self, line):
+        self.partial = json.loads(json.dumps(line))     # a deep, serialisable copy
+
+    def enter(self, stage, limit_s):
+        self.stage, self.deadline = stage, time.monotonic() + limit_s
+
+    def leave(self):
+        self.stage, self.deadline = "between stages", time.monotonic() + 600.0
+
+    def abort(self, stage, why):
+        """called by the rank on which an optional stage raised: tells every rank's watchdog to fire"""
+        log(f"[rank {self.rank}] stage '{stage}' failed: {why}")
+        try:
+            self.abort_file.write_text(f"rank {self.rank}: {stage}: {why}"[:2000])
+        except OSError:
+            pass
+        self._fire(f"rank {self.rank}: {why}")
+
+    def finish(self):
+        self.done.set()
+
+    def _watch(self):
+        while not self.done.wait(0.25):
+            if time.monotonic() > self.deadline:
+                self._fire(f"stage exceeded its time limit on rank {self.rank}")
+            if self.abort_file.exists():
+                try:
+                    why = self.abort_file.read_text()
+                except OSError:
+                    why = "abort requested by another rank"
+                time.sleep(0.2 if self.rank == 0 else 1.0)
+                self._fire(why)
+
+    def _fire(self, why):
+        if self.done.is_set():
+            return
+        self.done.set()
+        for name in self.shm_names:
+            try:
+                os.unlink("/dev/shm/" + name)
+            except OSError:
+                pass
+        if self.rank == 0:
+            if self.partial is not None:
+                line = dict(self.partial)
+                line["aborted_stage"] = {"stage": self.stage, "why": str(why)[:1000]}
+                emit(line)
+            else:
+                log(f"[bench] aborted in '{self.stage}' before a result existed: {why}")
+        sys.stderr.flush()
+        os._exit(0 if self.partial is not None or self.rank != 0 else 3)
+
+
 class Comm:
     """torch.distributed plumbing of one job (or of rank 0 alone when `solo`)"""
 
@@ -577,7 +655,7 @@ def split_queries(nq, Qw, qg):
 # one workload on one rank grid
 # ----------------------------------------------------------------------------------------------
 def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=True, want_cpu=False, want_recall=False,
-                 want_parity=False, sampler=None, tag=""):
+                 want_parity=False, sampler=None, tag="", guard=None, on_progress=None):
     """Loads the index, runs the device-resident timed region (`value`), the host-buffer pipeline (`e2e`) and the
     untimed checks.  Returns the record (on rank 0 of `comm`; None elsewhere)."""
     import torch
@@ -787,13 +865,17 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
             mine = (int(st["nresults"]), eng.device_checksum(d_outs[s % NBUF].data_ptr(), nwords, stream.cuda_stream))
             allc = comm.all_gather_object(mine)
             if rank == 0:
-                ok = 0
+                ok, bad = 0, []
                 for r in range(1, world):
                     got = eng.device_checksum(gather_bufs[(s % NBUF, r)], allc[r][0] * res_words, stream.cuda_stream)
                     if got != allc[r][1]:
-                        raise SystemExit(f"gather verification FAILED: rank {r}'s {allc[r][0]} results: checksum {allc[r][1]:#x} computed, {got:#x} landed")
-                    ok += 1
+                        log(f"[{tag}rank 0] gather verification FAILED: rank {r}'s {allc[r][0]} results: checksum {allc[r][1]:#x} computed, {got:#x} landed")
+                        bad.append(r)
+                    else:
+                        ok += 1
                 gather_verified = {"ranks": ok, "results": int(sum(c[0] for c in allc[1:])), "bytes": int(sum(c[0] for c in allc[1:])) * res_bytes}
+                if bad:
+                    gather_verified["mismatch_ranks"] = bad
             comm.barrier()
 
     # distinct blocks per step for the algorithmic-bytes formula (host-side bookkeeping, untimed)
@@ -852,41 +934,64 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
            "gather_verified": gather_verified, "info": info, "L": L, "Lr": eng.Lr, "nprobe": nprobe,
            "db_gib_per_rank": info["db_bytes"] / 2**30}
 
+    if on_progress is not None:
+        on_progress(rec)           # rank 0 publishes the line as it stands: nothing below may cost the headline
+
+    def optional(stage, limit_s, fn):
+        """run one optional stage under the guard; at one rank a failure is recorded, at several it aborts the
+        run through the guard (the collectives of the ranks are out of step after an exception)"""
+        if guard is not None:
+            guard.enter(f"{tag}{stage}", limit_s)
+        try:
+            return fn()
+        except Exception as ex:    # noqa: BLE001 — every failure of an optional stage is handled the same way
+            if world > 1 and guard is not None:
+                guard.abort(f"{tag}{stage}", repr(ex))
+            log(f"[{tag}rank {rank}] {stage} failed: {ex!r}")
+            return {"error": repr(ex)[:500]}
+        finally:
+            if guard is not None:
+                guard.leave()
+
     # ---- recall (BASELINE metric, untimed; single GPU: the whole index is local) ----
     if want_recall and world == 1 and cfg["nb"] < (1 << 21):
-        try:
+        def _recall():
             rm = recall_metrics(eng, data, nprobe, dev)
-            rec["recall"] = rm
             log(f"[{tag}rank {rank}] recall@10 = {rm['recall_at_10']:.4f} (reference definition {rm['reference_recall_10']:.4f}; nprobe {nprobe} of {cfg['nlist']} lists, "
                 f"{rm['queries']} queries, exact brute-force ground truth)")
-        except Exception as ex:  # the metric line must not depend on this bookkeeping
-            log(f"[{tag}rank {rank}] recall@10 not computed: {ex}")
+            return rm
+        rec["recall"] = optional("recall", 300, _recall)
 
     # ---- e2e: host buffers through the public C-ABI calls --------------------------------------
     if want_e2e:
-        # every rank must take the same path: agree first that the flights' buffers fit beside the resident DB
-        free_b, _tot = torch.cuda.mem_get_info(dev)
-        depth = int(os.environ.get("PF_BENCH_E2E_DEPTH", "3"))
-        need = depth * (max_res * eng.slot_bytes + 2 * max(nq_loc, 1) * m * eng.ct_bytes) + (2 << 30)
-        fits = torch.tensor([1.0 if need <= free_b else 0.0], device=dev, dtype=torch.float64)
-        comm.all_reduce(fits)
-        if int(fits.item()) == world:
-            rec["e2e"] = run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag)
-        else:
-            rec["e2e"] = {"value": None, "unit": "distances/s", "skipped": f"{depth} searches in flight need {need / 2**30:.1f} GiB beside the "
-                          f"{info['db_bytes'] / 2**30:.1f} GiB DB; {free_b / 2**30:.1f} GiB free on this GPU (shard the index over more GPUs)"}
-            log(f"[{tag}rank {rank}] e2e skipped: {rec['e2e']['skipped']}")
+        def _e2e():
+            # every rank must take the same path: agree first that the flights' buffers fit beside the resident DB
+            free_b, _tot = torch.cuda.mem_get_info(dev)
+            depth = int(os.environ.get("PF_BENCH_E2E_DEPTH", "3"))
+            need = depth * (max_res * eng.slot_bytes + 2 * max(nq_loc, 1) * m * eng.ct_bytes) + (2 << 30)
+            fits = torch.tensor([1.0 if need <= free_b else 0.0], device=dev, dtype=torch.float64)
+            comm.all_reduce(fits)
+            if int(fits.item()) == world:
+                return run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag, guard)
+            why = (f"{depth} searches in flight need {need / 2**30:.1f} GiB beside the {info['db_bytes'] / 2**30:.1f} GiB DB; "
+                   f"{free_b / 2**30:.1f} GiB free on this GPU (shard the index over more GPUs)")
+            log(f"[{tag}rank {rank}] e2e skipped: {why}")
+            return {"value": None, "unit": "distances/s", "skipped": why}
+        rec["e2e"] = optional("e2e", 300, _e2e)
+        if on_progress is not None:
+            on_progress(rec)
 
     # ---- parity self-check on real encryptions (untimed; the oracle is the checker) -------------
     if want_parity and world == 1:
-        try:
-            rec["parity"] = parity_self_check(eng, cfg, data, nprobe, tag)
-        except AssertionError as ex:
-            raise SystemExit(f"PARITY SELF-CHECK FAILED: {ex}")
+        rec["parity"] = optional("parity self-check", 600, lambda: parity_self_check(eng, cfg, data, nprobe, tag))
+        if rec["parity"].get("error"):
+            rec["parity"]["parity_checked"] = 0
+        if on_progress is not None:
+            on_progress(rec)
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------
     if want_cpu and rank == 0 and world == 1:
-        try:
+        def _cpu():
             from oracle import pf_oracle as O
             O.build()
             nthreads = O.host_cores()
@@ -894,16 +999,17 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
             rl = eng.Lr if eng.Lr < L else 0
             r = cpu_pipeline(cfg, data, nq_s, nthreads, result_limbs=rl)
             r1 = cpu_pipeline(cfg, data, 2, 1, result_limbs=rl)
-            rec["cpu_baseline"] = {
-                "value": r["useful"] / r["seconds"], "unit": "distances/s", "cores": nthreads, "kind": "port",
-                "sample": f"{nq_s} of the {nq} queries of a step / {r['pairs']} (query,block) pairs of the same workload, whole hot path "
-                          f"incl. mod-switch to {eng.Lr} limb(s), {nthreads} OpenMP threads ({r['seconds']:.2f}s: rotations {r['rot_s']:.2f}s, "
-                          f"MAC+INTT {r['mac_s']:.2f}s)",
-                "single_thread_value": r1["useful"] / r1["seconds"], "queries_per_s": nq_s / r["seconds"]}
+            out = {"value": r["useful"] / r["seconds"], "unit": "distances/s", "cores": nthreads, "kind": "port",
+                   "sample": f"{nq_s} of the {nq} queries of a step / {r['pairs']} (query,block) pairs of the same workload, whole hot path "
+                             f"incl. mod-switch to {eng.Lr} limb(s), {nthreads} OpenMP threads ({r['seconds']:.2f}s: rotations {r['rot_s']:.2f}s, "
+                             f"MAC+INTT {r['mac_s']:.2f}s)",
+                   "single_thread_value": r1["useful"] / r1["seconds"], "queries_per_s": nq_s / r["seconds"]}
             if cfg["nb"] <= 200_000:
-                rec["cpu_baseline"]["reference_plaintext_path"] = reference_plaintext_path(data, cfg["nprobe"], min(100, len(data["queries"])))
-        except Exception as ex:  # the baseline is a report, not the product
-            rec["cpu_baseline"] = {"value": None, "error": repr(ex)}
+                out["reference_plaintext_path"] = reference_plaintext_path(data, cfg["nprobe"], min(100, len(data["queries"])))
+            return out
+        rec["cpu_baseline"] = optional("cpu baseline", 600, _cpu)
+        if rec["cpu_baseline"].get("error"):
+            rec["cpu_baseline"]["value"] = None
 
     if world > 1:
         torch.cuda.synchronize()
@@ -925,30 +1031,45 @@ class NodeResponse:
     [share of rank 1]...  With one rank it is a pinned allocation; with several it is a POSIX shared-memory
     segment created by rank 0 and attached by the others (each rank page-locks the parts its GPU touches), so
     every GPU moves its share over its own PCIe link and the handler on rank 0 returns one buffer.
-    flags[r] (int64) = number of steps rank r has completed; rank 0 polls them."""
+    flags[r] (int64) = number of steps rank r has completed; rank 0 polls them.
+    shared_data=False (no room in /dev/shm for the whole buffer): only the flags are shared, every rank keeps
+    its query copy and its share in private pinned memory."""
     FLAGS = 4096
 
-    def __init__(self, rank, world, name, qbytes, shares, pinned_alloc=None):
+    def __init__(self, rank, world, name, qbytes, shares, pinned_alloc=None, shared_data=True):
         self.rank, self.world = rank, world
         self.qbytes = int(qbytes)
         self.qpad = (self.qbytes + 4095) // 4096 * 4096
         self.share_off = np.concatenate([[0], np.cumsum(shares)]).astype(np.int64)
-        self.total = self.FLAGS + self.qpad + int(self.share_off[-1])
+        self.shared_data = bool(shared_data) and world > 1
+        data_bytes = self.qpad + int(self.share_off[-1])
+        self.total = self.FLAGS + (data_bytes if (self.shared_data or world == 1) else 0)
         self.shm = None
+        alloc = pinned_alloc or (lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
+
+        def as_np(x):
+            return x if isinstance(x, np.ndarray) else x.numpy()
         if world > 1:
             from multiprocessing import shared_memory
-            self.shm = shared_memory.SharedMemory(name=name, create=(rank == 0), size=self.total) if rank == 0 else \
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=self.total) if rank == 0 else \
                 shared_memory.SharedMemory(name=name)
             self.whole = np.ndarray((self.total,), dtype=np.uint8, buffer=self.shm.buf)
         else:
-            self._keep = pinned_alloc(self.total) if pinned_alloc else np.zeros(self.total, dtype=np.uint8)
-            self.whole = self._keep if isinstance(self._keep, np.ndarray) else self._keep.numpy()
+            self._keep = alloc(self.total)
+            self.whole = as_np(self._keep)
         self.flags = self.whole[:self.FLAGS].view(np.int64)
-        self.query = self.whole[self.FLAGS:self.FLAGS + self.qbytes]
-        o = self.FLAGS + self.qpad + int(self.share_off[rank])
-        self.share = self.whole[o:o + int(shares[rank])]
+        if self.shared_data or world == 1:
+            self.query = self.whole[self.FLAGS:self.FLAGS + self.qbytes]
+            o = self.FLAGS + self.qpad + int(self.share_off[rank])
+            self.share = self.whole[o:o + int(shares[rank])]
+        else:
+            self._keep = alloc(self.qpad + int(shares[rank]))
+            priv = as_np(self._keep)
+            self.query = priv[:self.qbytes]
+            self.share = priv[self.qpad:self.qpad + int(shares[rank])]
 
     def share_of(self, r):
+        assert self.shared_data or self.world == 1
         o = self.FLAGS + self.qpad + int(self.share_off[r])
         return self.whole[o:o + int(self.share_off[r + 1] - self.share_off[r])]
 
@@ -976,7 +1097,36 @@ class NodeResponse:
                 pass
 
 
-def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag):
+def open_node_response(comm, qbytes, seg, pinned_alloc=None, guard=None):
+    """Collective: every rank calls it with its share size; the SAME sequence of collectives on every rank
+    (all_gather, broadcast, barrier, barrier) — rank 0 creates the segment between the broadcast and the first
+    barrier, the others attach after it."""
+    segs = comm.all_gather_object(int(seg))
+    name, shared = comm.broadcast_object((f"pf_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}",
+                                          shm_has_room(4096 + int(qbytes) + int(sum(segs)))) if comm.rank == 0 else None)
+    if comm.world == 1:
+        return NodeResponse(0, 1, name, qbytes, segs, pinned_alloc=pinned_alloc)
+    if guard is not None:
+        guard.shm_names.append(name)
+    nr = None
+    if comm.rank == 0:
+        nr = NodeResponse(0, comm.world, name, qbytes, segs, pinned_alloc=pinned_alloc, shared_data=shared)
+    comm.barrier()                                # the segment exists
+    if comm.rank != 0:
+        nr = NodeResponse(comm.rank, comm.world, name, qbytes, segs, pinned_alloc=pinned_alloc, shared_data=shared)
+    comm.barrier()                                # everybody is attached
+    return nr
+
+
+def shm_has_room(nbytes):
+    try:
+        st = os.statvfs("/dev/shm")
+        return st.f_bavail * st.f_frsize > nbytes + (256 << 20)
+    except OSError:
+        return False
+
+
+def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag, guard=None):
     """End to end through pf_search_submit / pf_search_collect with HOST buffers.  One response buffer for the
     whole node: at N > 1 it is a POSIX shared-memory segment page-locked by every rank (pf_host_register); the
     query blob of a step is read from it and every rank's GPU writes its share of the response into it over
@@ -995,15 +1145,10 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
     hdr = np.frombuffer(eng.ct_serialize(np.zeros((2, L, n), dtype=np.uint64)), dtype=np.uint8)[:ctb - ctw * 8]
     qbytes = nq * m * ctb
     seg = max_res * eng.slot_bytes
-    segs = comm.all_gather_object(seg)
-    name = comm.broadcast_object(f"pf_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}")
-    if world > 1 and rank != 0:
-        comm.barrier()                            # rank 0 creates the segment first
-    nr = NodeResponse(rank, world, name, qbytes, segs, pinned_alloc=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8).pin_memory())
-    if world > 1 and rank == 0:
-        comm.barrier()
+    nr = open_node_response(comm, qbytes, seg, pinned_alloc=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
+                            guard=guard)
     flags, qnp, out_np = nr.flags, nr.query, nr.share
-    numa = bind_pages_to_gpu_node(out_np, dev) if world > 1 else None
+    numa = bind_pages_to_gpu_node(out_np, dev) if (world > 1 and nr.shared_data) else None
     out_np[:] = 0                                 # first touch by the owner: pages on this rank's NUMA node
     if world > 1:
         log(f"[{tag}rank {rank}] response share: {numa}")
@@ -1011,14 +1156,16 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
         flags[:] = 0
     # the request of a step: nq*m SEAL streams (the same bytes every step; timing does not depend on values);
     # every query group writes the ciphertexts it holds on its GPU into the shared request blob
-    if lr == 0 and nq_loc:
+    if (lr == 0 or not nr.shared_data) and nq_loc:
         mine = ct_pool[0].cpu().numpy().view(np.uint64).reshape(nq_loc * m, -1)
         for c in range(nq_loc * m):
             o = (q_lo * m + c) * ctb
             qnp[o: o + len(hdr)] = hdr
             qnp[o + len(hdr): o + ctb] = mine[c].view(np.uint8)
+    registered = world > 1 and nr.shared_data
     if world > 1:
         comm.barrier()
+    if registered:
         eng.host_register(nr.query_region())
         eng.host_register(out_np)
     my_q = qnp[q_lo * m * ctb: q_hi * m * ctb]
@@ -1087,8 +1234,10 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
     comm.all_reduce(eu)
     if world > 1:
         comm.barrier()
+    if registered:
         eng.host_unregister(nr.query_region())
         eng.host_unregister(out_np)
+    shared_note = nr.shared_data
     del flags, qnp, out_np, my_q
     comm.barrier()
     nr.close()
@@ -1096,7 +1245,8 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
             "h2d_bytes_per_step": int(eu[1].item()) // e_steps, "d2h_bytes_per_step": int(eu[2].item()) // e_steps,
             "ms_per_step": float(et.item()) / e_steps * 1e3, "steps": e_steps, "pipeline_depth": DEPTH,
             "lone_request_ms": lat,
-            "response": "one host buffer per node" + (" (POSIX shm page-locked by every rank; each GPU writes its share over its own PCIe link)" if world > 1 else " (pinned)")}
+            "response": ("one host buffer per node" + (" (POSIX shm page-locked by every rank; each GPU writes its share over its own PCIe link)" if world > 1 else " (pinned)"))
+            if (shared_note or world == 1) else "per-rank pinned buffers, completion flags shared (/dev/shm too small for one node buffer)"}
 
 
 def parity_self_check(eng, cfg, data, nprobe, tag, nsample=32):
@@ -1229,7 +1379,8 @@ def main():
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(minutes=40))   # the StageGuard fires long before
         dist.barrier()
     comm = Comm(world, rank, local_rank, dev)
     grid = parse_grid(args.grid, world)
@@ -1240,35 +1391,11 @@ def main():
     sampler = ClockSampler(local_rank, dev)
     if rank == 0:                          # one poller per job: NVML queries take driver locks
         sampler.start()
-    rec = run_workload(args, cfg_name, cfg, comm, weak, grid, args.steps, args.warmup, want_e2e=not args.no_e2e,
-                       want_cpu=not args.no_cpu_baseline, want_recall=True, want_parity=not args.no_parity, sampler=sampler)
-    clocks = sampler.stop(*rec["timed_window"]) if rank == 0 else None
+    guard = StageGuard(rank, world)
+    state = {"strong": None}
 
-    strong = None
-    if weak and not args.no_strong:
-        # BASELINE configs[2] (fixed 1M index, nlist 4096, nprobe 64): N GPUs, then rank 0 alone (its 1-GPU time)
-        scfg_name = "sift1m_nlist4096_nprobe64"
-        scfg = dict(CONFIGS[scfg_name])
-        ssteps = max(3, min(args.steps, 60))
-        sgrid = parse_grid(os.environ.get("PF_BENCH_STRONG_GRID"), world) if os.environ.get("PF_BENCH_STRONG_GRID") else default_strong_grid(world)
-        rN = run_workload(args, scfg_name, scfg, comm, False, sgrid, ssteps, args.warmup, want_e2e=not args.no_e2e, tag="strong ")
-        r1 = None
-        if rank == 0:
-            r1 = run_workload(args, scfg_name, scfg, Comm(world, rank, local_rank, dev, solo=True), False, (1, 1), ssteps, args.warmup,
-                              want_e2e=not args.no_e2e, tag="strong-1gpu ")
-        comm.barrier()
-        if rank == 0:
-            strong = {"config": bench_config(scfg_name, scfg, rN["L"], rN["Lr"], scfg["nq"], world, False, grid=sgrid),
-                      "scaling": "strong", "n_gpus": world, "value": rN["value"], "ms_per_step": rN["ms_per_step"],
-                      "value_1gpu": r1["value"], "ms_per_step_1gpu": r1["ms_per_step"],
-                      "efficiency": rN["value"] / (world * r1["value"]), "steps": ssteps,
-                      "phases_ms_per_step": rN["phases_ms_per_step"], "phases_ms_per_step_1gpu": r1["phases_ms_per_step"],
-                      "gather_verified": rN["gather_verified"],
-                      "e2e": rN.get("e2e"), "e2e_1gpu": r1.get("e2e"),
-                      "e2e_efficiency": (rN["e2e"]["value"] / (world * r1["e2e"]["value"])) if rN.get("e2e") and r1.get("e2e") else None}
-
-    if rank == 0:
-        info = rec["info"]
+    def make_line(rec):
+        clocks = sampler.report(*rec["timed_window"])
         recall = rec.get("recall") or {}
         line = {
             "metric": "encrypted candidate distances/sec", "value": rec["value"], "unit": "distances/s",
@@ -1283,7 +1410,7 @@ def main():
             "slot_distances_per_s": rec["slot_distances_per_s"],
             "result_cts_per_step": rec["result_cts_per_step"],
             "gpu_launches": rec["gpu_launches"],
-            "clocks": clocks, "roofline": rec["roofline"], "rotate_roofline": rec["rotate_roofline"],
+            "clocks": clocks, "roofline": rec["roofline"], "rotate_roofline": dict(rec["rotate_roofline"]),
             "phases_ms_per_step": rec["phases_ms_per_step"],
             "db_gib_per_rank": rec["db_gib_per_rank"],
             "e2e": rec.get("e2e"), "cpu_baseline": rec.get("cpu_baseline"),
@@ -1296,9 +1423,55 @@ def main():
             floor_ms = max(rr["fp64_ops_per_step"], rr["imad_wide_per_step"]) / per_s * 1e3
             rr.update({"floor_ms_per_step": floor_ms, "frac": floor_ms / rr["ms_per_step"] if rr["ms_per_step"] else None,
                        "sm_mhz": clocks["sm_mhz"]})
-        if strong:
-            line["strong"] = strong
-        emit(line)
+        if state["strong"] is not None:
+            line["strong"] = state["strong"]
+        return line
+
+    def progress(rec):
+        if rank == 0:
+            guard.publish(make_line(rec))
+
+    rec = run_workload(args, cfg_name, cfg, comm, weak, grid, args.steps, args.warmup, want_e2e=not args.no_e2e,
+                       want_cpu=not args.no_cpu_baseline, want_recall=True, want_parity=not args.no_parity, sampler=sampler,
+                       guard=guard, on_progress=progress)
+    if rank == 0:
+        guard.publish(make_line(rec))
+
+    if weak and not args.no_strong:
+        # BASELINE configs[2] (fixed 1M index, nlist 4096, nprobe 64): N GPUs, then rank 0 alone (its 1-GPU time).
+        # An optional stage: a failure or a hang here still leaves the weak-scaling headline (StageGuard).
+        scfg_name = "sift1m_nlist4096_nprobe64"
+        scfg = dict(CONFIGS[scfg_name])
+        ssteps = max(3, min(args.steps, 60))
+        sgrid = parse_grid(os.environ.get("PF_BENCH_STRONG_GRID"), world) if os.environ.get("PF_BENCH_STRONG_GRID") else default_strong_grid(world)
+        guard.enter("strong-scaling record (configs[2])", 600)
+        try:
+            rN = run_workload(args, scfg_name, scfg, comm, False, sgrid, ssteps, args.warmup, want_e2e=not args.no_e2e, tag="strong ",
+                              guard=guard)
+            guard.enter("strong-scaling record (configs[2], 1-GPU reference on rank 0)", 420)
+            r1 = None
+            if rank == 0:
+                r1 = run_workload(args, scfg_name, scfg, Comm(world, rank, local_rank, dev, solo=True), False, (1, 1), ssteps, args.warmup,
+                                  want_e2e=not args.no_e2e, tag="strong-1gpu ", guard=guard)
+            comm.barrier()
+            if rank == 0:
+                e2eN, e2e1 = rN.get("e2e") or {}, r1.get("e2e") or {}
+                state["strong"] = {
+                    "config": bench_config(scfg_name, scfg, rN["L"], rN["Lr"], scfg["nq"], world, False, grid=sgrid),
+                    "scaling": "strong", "n_gpus": world, "value": rN["value"], "ms_per_step": rN["ms_per_step"],
+                    "value_1gpu": r1["value"], "ms_per_step_1gpu": r1["ms_per_step"],
+                    "efficiency": rN["value"] / (world * r1["value"]), "steps": ssteps,
+                    "phases_ms_per_step": rN["phases_ms_per_step"], "phases_ms_per_step_1gpu": r1["phases_ms_per_step"],
+                    "gather_verified": rN["gather_verified"], "e2e": rN.get("e2e"), "e2e_1gpu": r1.get("e2e"),
+                    "e2e_efficiency": (e2eN["value"] / (world * e2e1["value"])) if e2eN.get("value") and e2e1.get("value") else None}
+        except Exception as ex:    # noqa: BLE001
+            guard.abort("strong-scaling record (configs[2])", repr(ex))
+        guard.leave()
+
+    guard.finish()
+    if rank == 0:
+        sampler.stop()
+        emit(make_line(rec))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -1306,7 +1479,11 @@ def main():
 
 
 def default_strong_grid(world):
-    """list shards x query groups for BASELINE configs[2] (chosen by measurement, profiles/README.md)"""
+    """list shards x query groups for BASELINE configs[2].  Two list shards (the lists stay sharded, every rank
+    holds half of the NTT-domain DB) x N/2 query groups: the per-query work (rotations, input NTTs: 0.40 of the
+    4.47 ms 1-GPU step, replicated on every rank of an N x 1 grid — 2.53 ms at 2 GPUs = 0.88) is divided by the
+    query groups.  Derived from the measured 1- and 2-GPU phase times (profiles/README.md); the 8-GPU A/B run
+    of round 2 died on a bench bug before it produced numbers, so `--grid` / PF_BENCH_STRONG_GRID remain."""
     return {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}.get(world, (world, 1))
 
 

@@ -159,3 +159,75 @@ def test_node_response_shared_buffer_gloo(tmp_path):
     out = tmp_path / "result.txt"
     mp.spawn(_response_worker, args=(2, port, f"pf_test_{port}", str(out)), nprocs=2, join=True)
     assert out.read_text() == "ok"
+
+
+def _open_response_worker(rank, world, port, out_path):
+    import bench
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = bench.Comm(world, rank, rank, "cpu")
+    ok = True
+    for round_ in range(2):                  # twice: the segment of the first round is gone before the second
+        nr = bench.open_node_response(comm, qbytes=3000 + round_, seg=2000 + 100 * rank)
+        ok = ok and nr.shared_data and nr.share.size == 2000 + 100 * rank
+        nr.share[:] = rank + 1
+        nr.mark_done(0)
+        if rank == 0:
+            nr.flags[0] = 1
+            nr.wait_all(0, timeout_s=30)
+            ok = ok and all(bool((nr.share_of(r) == r + 1).all()) for r in range(world))
+        dist.barrier()
+        nr.close()
+        dist.barrier()
+    if rank == 0:
+        with open(out_path, "w") as f:
+            f.write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_open_node_response_same_collective_order(tmp_path, world):
+    """bench.open_node_response issues the same collectives in the same order on every rank (a broadcast
+    between two conditional barriers once deadlocked an 8-GPU run): it must complete under gloo"""
+    port = _free_port()
+    out = tmp_path / "result.txt"
+    mp.spawn(_open_response_worker, args=(world, port, str(out)), nprocs=world, join=True)
+    assert out.read_text() == "ok"
+
+
+def test_stage_guard_emits_the_published_line_when_a_stage_hangs(tmp_path):
+    """StageGuard: a hang (or a reported failure) in an optional stage ends the run with exit code 0 and the
+    line published before it, `aborted_stage` filled in"""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "g = bench.StageGuard(0, 1)\n"
+        "g.publish({'metric': 'm', 'value': 1.5})\n"
+        "g.enter('e2e', 0.5)\n"
+        "time.sleep(30)\n" % str(root))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 1.5 and line["aborted_stage"]["stage"] == "e2e"
+    code2 = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "g = bench.StageGuard(0, 1)\n"
+        "g.publish({'metric': 'm', 'value': 2.5})\n"
+        "g.enter('strong', 100)\n"
+        "g.abort('strong', 'boom')\n" % str(root))
+    r = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 2.5 and "boom" in line["aborted_stage"]["why"]
+    # nothing published yet: a non-zero exit code and no line
+    code3 = (
+        "import sys, time; sys.path.insert(0, %r); import bench\n"
+        "g = bench.StageGuard(0, 1, total_limit_s=0.3)\n"
+        "time.sleep(30)\n" % str(root))
+    r = subprocess.run([sys.executable, "-c", code3], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and not r.stdout.strip()
