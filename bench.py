@@ -1314,6 +1314,40 @@ def parity_self_check(eng, cfg, data, nprobe, tag, nsample=32):
             "checker": "oracle/ (CPU restatement; parity unpinned by the reference, DESIGN.md §0)"}
 
 
+def build_line(args, cfg_name, cfg, world, weak, grid, rec, clocks, placement, strong):
+    """the one JSON line of the run from the record run_workload returned (rank 0)"""
+    recall = rec.get("recall") or {}
+    line = {
+        "metric": "encrypted candidate distances/sec", "value": rec["value"], "unit": "distances/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong" if (world > 1 and not weak) else "weak", "vs_baseline": None,
+        "scaling_note": ("N = 1 point of the series: the default run at N GPUs is weak scaling of this workload (N list shards of 1M vectors), "
+                         "`--config X` at N > 1 is strong scaling of X") if world == 1 else None,
+        "dtype": "u64", "data": "synthetic",
+        "config": bench_config(cfg_name, cfg, rec["L"], rec["Lr"], cfg["nq"], world, weak, rec["nprobe"], grid),
+        "queries_per_s": rec["queries_per_s"],
+        "recall_at_10": recall.get("recall_at_10"), "reference_recall_10": recall.get("reference_recall_10"),
+        "slot_distances_per_s": rec["slot_distances_per_s"],
+        "result_cts_per_step": rec["result_cts_per_step"],
+        "gpu_launches": rec["gpu_launches"],
+        "clocks": clocks, "roofline": rec["roofline"], "rotate_roofline": dict(rec["rotate_roofline"]),
+        "phases_ms_per_step": rec["phases_ms_per_step"],
+        "db_gib_per_rank": rec["db_gib_per_rank"],
+        "e2e": rec.get("e2e"), "cpu_baseline": rec.get("cpu_baseline"),
+        "parity_checked": (rec.get("parity") or {}).get("parity_checked"), "parity": rec.get("parity"),
+        "gather_verified": rec.get("gather_verified"), "placement": placement,
+    }
+    if clocks and clocks.get("sm_mhz"):
+        rr = line["rotate_roofline"]
+        per_s = 64.0 * 148 * clocks["sm_mhz"] * 1e6
+        floor_ms = max(rr["fp64_ops_per_step"], rr["imad_wide_per_step"]) / per_s * 1e3
+        rr.update({"floor_ms_per_step": floor_ms, "frac": floor_ms / rr["ms_per_step"] if rr["ms_per_step"] else None,
+                   "sm_mhz": clocks["sm_mhz"]})
+    if strong is not None:
+        line["strong"] = strong
+    return line
+
+
 def main():
     global _JSON_OUT
     ap = argparse.ArgumentParser()
@@ -1395,37 +1429,7 @@ def main():
     state = {"strong": None}
 
     def make_line(rec):
-        clocks = sampler.report(*rec["timed_window"])
-        recall = rec.get("recall") or {}
-        line = {
-            "metric": "encrypted candidate distances/sec", "value": rec["value"], "unit": "distances/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec["ms_per_step"],
-            "higher_is_better": True, "scaling": "strong" if (world > 1 and not weak) else "weak", "vs_baseline": None,
-            "scaling_note": ("N = 1 point of the series: the default run at N GPUs is weak scaling of this workload (N list shards of 1M vectors), "
-                             "`--config X` at N > 1 is strong scaling of X") if world == 1 else None,
-            "dtype": "u64", "data": "synthetic",
-            "config": bench_config(cfg_name, cfg, rec["L"], rec["Lr"], cfg["nq"], world, weak, rec["nprobe"], grid),
-            "queries_per_s": rec["queries_per_s"],
-            "recall_at_10": recall.get("recall_at_10"), "reference_recall_10": recall.get("reference_recall_10"),
-            "slot_distances_per_s": rec["slot_distances_per_s"],
-            "result_cts_per_step": rec["result_cts_per_step"],
-            "gpu_launches": rec["gpu_launches"],
-            "clocks": clocks, "roofline": rec["roofline"], "rotate_roofline": dict(rec["rotate_roofline"]),
-            "phases_ms_per_step": rec["phases_ms_per_step"],
-            "db_gib_per_rank": rec["db_gib_per_rank"],
-            "e2e": rec.get("e2e"), "cpu_baseline": rec.get("cpu_baseline"),
-            "parity_checked": (rec.get("parity") or {}).get("parity_checked"), "parity": rec.get("parity"),
-            "gather_verified": rec.get("gather_verified"), "placement": placement,
-        }
-        if clocks and clocks.get("sm_mhz"):
-            rr = line["rotate_roofline"]
-            per_s = 64.0 * 148 * clocks["sm_mhz"] * 1e6
-            floor_ms = max(rr["fp64_ops_per_step"], rr["imad_wide_per_step"]) / per_s * 1e3
-            rr.update({"floor_ms_per_step": floor_ms, "frac": floor_ms / rr["ms_per_step"] if rr["ms_per_step"] else None,
-                       "sm_mhz": clocks["sm_mhz"]})
-        if state["strong"] is not None:
-            line["strong"] = state["strong"]
-        return line
+        return build_line(args, cfg_name, cfg, world, weak, grid, rec, sampler.report(*rec["timed_window"]), placement, state["strong"])
 
     def progress(rec):
         if rank == 0:

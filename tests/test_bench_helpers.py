@@ -51,3 +51,45 @@ def test_cpu_light_dataset_is_a_valid_ivf():
     lab = ((vec[:, None, :] - cent[None, :, :]) ** 2).sum(-1).argmin(1)
     owner = np.repeat(np.arange(cfg["nlist"]), np.diff(off))
     assert (lab == owner).mean() > 0.999                 # float rounding may flip an exact tie
+
+
+def test_build_line_has_the_contract_keys():
+    """the JSON line is assembled from run_workload's record: every key of the bench contract is there, with an
+    optional stage that failed recorded instead of raising, and it serialises"""
+    import argparse
+    import json
+    args = argparse.Namespace(steps=20, warmup=5)
+    cfg_name = "sift1m_nlist1024_nprobe16"
+    cfg = dict(bench.CONFIGS[cfg_name])
+    rec = {"value": 4.0e8, "ms_per_step": 2.5, "steps": 20, "warmup": 5, "useful_per_step": 1.0e6, "slot_distances_per_s": 4.5e8,
+           "result_cts_per_step": 1100.0, "gpu_launches": 700, "roofline": {"bound": "hbm", "achieved": 4500.0, "peak": 6548.2, "unit": "GB/s",
+                                                                             "frac": 0.69, "traffic": None},
+           "rotate_roofline": {"bound": "fp64+imad pipes", "rotations_per_step": 960, "ms_per_step": 1.0, "fp64_ops_per_step": 4.1e9,
+                               "imad_wide_per_step": 9.4e8, "lanes_per_clk_per_sm": 64, "sms": 148},
+           "phases_ms_per_step": {"mac": 0.83}, "queries_per_s": 25000.0, "timed_window": (0.0, 1.0), "gather_verified": None,
+           "info": {}, "L": 4, "Lr": 1, "nprobe": 16, "db_gib_per_rank": 4.5,
+           "e2e": {"error": "RuntimeError('x')"}, "parity": {"error": "boom", "parity_checked": 0}}
+    clocks = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 3}
+    line = bench.build_line(args, cfg_name, cfg, 1, False, (1, 1), rec, clocks, {"pinned": False}, None)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "roofline", "e2e", "cpu_baseline", "gpu_launches", "parity_checked"):
+        assert key in line, key
+    assert line["config"]["workload"] == cfg_name and "model" not in line["config"]
+    assert line["scaling"] == "weak" and line["parity_checked"] == 0 and line["vs_baseline"] is None
+    assert 0.0 < line["rotate_roofline"]["frac"] < 1.0
+    json.dumps(line)
+    strong = {"scaling": "strong", "efficiency": 0.8}
+    line8 = bench.build_line(args, cfg_name, cfg, 8, True, (8, 1), rec, clocks, {}, strong)
+    assert line8["scaling"] == "weak" and line8["strong"]["efficiency"] == 0.8 and line8["config"]["nlist"] == 8192
+    line_s = bench.build_line(args, "sift1m_nlist4096_nprobe64", dict(bench.CONFIGS["sift1m_nlist4096_nprobe64"]), 8, False, (2, 4), rec, clocks, {}, None)
+    assert line_s["scaling"] == "strong" and "2 list shards x 4 query groups" in line_s["config"]["parallelism"]
+
+
+def test_reference_arm_names_the_same_config_as_the_gpu_arm():
+    """both arms build `config` with the same function and the same arguments -> same_config"""
+    cfg_name = "sift1m_nlist1024_nprobe16"
+    cfg = dict(bench.CONFIGS[cfg_name])
+    a = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"])                       # --impl reference
+    b = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"], 1, False, 16, (1, 1))  # ours, N = 1
+    assert a == b
+    assert bench.cpu_sample_queries(64, 16) == 32 and bench.cpu_sample_queries(64, 1) == 8 and bench.cpu_sample_queries(16, 64) == 16
