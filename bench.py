@@ -900,9 +900,13 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
     if pk.exists():
         peaks = json.loads(pk.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    mac_ms = phases["mac"]["ms"] / max(1, phases["mac"]["launches"])
+    # one MAC launch per step, except when the full-level result scratch is capped and a large batch is cut into
+    # sub-batches of whole queries (pf_engine.cu search_core): bytes and time are both taken PER STEP, which is
+    # bytes per launch / time per launch for equal launches
+    mac_launches_per_step = phases["mac"]["launches"] / max(1, steps)
+    mac_ms = phases["mac"]["ms"] / max(1, steps)
     LN8 = 8.0 * L * n
-    alg_bytes = LN8 * (2.0 * K * nq_loc * steps + (K + 1.0) * blocks_distinct + 2.0 * pairs) / steps  # rank-local
+    alg_bytes = LN8 * (2.0 * K * nq_loc * steps + (K + 1.0) * blocks_distinct + 2.0 * pairs) / steps  # rank-local, per step
     streamed_bytes = LN8 * (2.0 * K * nq_loc * steps + (K + 1.0) * pairs + 2.0 * pairs) / steps
     achieved = alg_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     traffic, mac_name = None, "mac_kernel_occ" if K <= 16 else "mac_kernel"
@@ -912,9 +916,12 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
         traffic, mac_name = tj.get("traffic_bytes_per_launch"), tj.get("kernel", mac_name)
     roofline = {"bound": "hbm", "kernel": mac_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": "measured" if peaks else "fallback",
-                "algorithmic_bytes_per_launch": alg_bytes, "streamed_bytes_per_launch": streamed_bytes,
+                "algorithmic_bytes_per_launch": alg_bytes / max(1.0, mac_launches_per_step),
+                "streamed_bytes_per_launch": streamed_bytes / max(1.0, mac_launches_per_step),
+                "algorithmic_bytes_per_step": alg_bytes,
                 "streamed_gbs": streamed_bytes / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
-                "ms_per_launch": mac_ms}
+                "ms_per_launch": mac_ms / max(1.0, mac_launches_per_step), "launches_per_step": mac_launches_per_step,
+                "ms_per_step": mac_ms}
     # rotate phase (key switch): compute-pipe bound.  Essential work per rotation: 2 + 2L
     # N-point transforms of (N/2) log2 N butterflies at 8 FP64 operations each, and 2 (L+1) L N 64x64
     # multiply-accumulates of 3 IMAD.WIDE each; the two pipes run side by side (64 lanes/clk/SM each), so the

@@ -238,6 +238,15 @@ size_t pf_result_serialized_size(pf_engine *e);
  * PF_ERR_CAPACITY with *written = bytes needed.  (What seal::Serialization::Load does before the members
  * are read; [EXT] SEAL 4.1 serialization.cpp.)  Needs no engine and no GPU. */
 int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t cap, size_t *written, size_t *consumed);
+/* Seeded ciphertexts (seal::Serializable<Ciphertext> of a symmetric-key Encryptor: c1 is replaced by the seed of
+ * the PRNG that drew it; [EXT] SEAL 4.1 Ciphertext::save_members / expand_seed, Blake2xbPRNG,
+ * sample_poly_uniform): writes the equivalent full stream (compr_mode none) of `in` — c1 re-created over the
+ * given data primes — or a copy when `in` is not seeded; zlib input is inflated first.  pf_search_submit /
+ * pf_search_lists_encrypted / pf_ct_deserialize accept seeded streams directly (expanded on the host before
+ * the upload: a slow path like zlib).  PF_ERR_FORMAT for malformed input or a PRNG other than blake2xb;
+ * PF_ERR_CAPACITY with *written = bytes needed.  Needs no engine and no GPU. */
+int pf_seal_ct_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *data_primes, uint32_t nprimes,
+                      uint8_t *out, size_t cap, size_t *written, size_t *consumed);
 /* SEAL parms_id of the BFV parameter set {poly_degree, coeff_primes[0..nprimes), plain_modulus}: BLAKE2b-256
  * of {scheme = 1, N, primes..., t} as 4 little-endian words (replaces EncryptionParameters::parms_id();
  * [EXT] SEAL 4.1 encryptionparams.cpp compute_parms_id).  Needs no engine and no GPU. */

@@ -190,6 +190,17 @@ void pfo_rotate_query_set(const pfo_context *c, const pfo_layout *lay, const uin
 void pfo_block_distance(const pfo_context *c, const pfo_layout *lay, const uint64_t *rot, const uint64_t *diag,
                         const uint64_t *norm, uint64_t *out);
 
+/* ---- SEAL seeded ciphertexts (pf_oracle_seeded.c): BLAKE2b / BLAKE2Xb, Blake2xbPRNG, sample_poly_uniform ---- */
+void pfo_blake2b_param(const uint8_t param[64], const uint8_t *key, size_t keylen, const uint8_t *msg, size_t msglen,
+                       uint8_t *out, size_t outlen);
+void pfo_blake2xb(uint8_t *out, size_t outlen, const uint8_t *in, size_t inlen, const uint8_t *key, size_t keylen);
+void pfo_seal_sample_poly_uniform(const pfo_context *c, int L, const uint8_t seed[64], uint64_t *out);
+void pfo_encrypt_symmetric_seeded(const pfo_context *c, const uint64_t *sk, const uint64_t *plain, uint64_t noise_seed,
+                                  const uint8_t seed[64], uint64_t *ct);
+size_t pfo_ct_save_seeded_size(uint64_t n, int L);
+size_t pfo_ct_save_seeded(const uint64_t *c0, uint64_t n, int L, const uint64_t parms_id[4], const uint8_t seed[64],
+                          uint8_t prng_type, uint8_t *out);
+
 /* ---- whole-step drivers (pf_oracle_pipeline.c), OpenMP over queries / (query, block) pairs ---- */
 int pfo_max_threads(void);
 void pfo_encode_blocks(const pfo_context *c, const pfo_layout *lay, size_t nblocks, const int32_t *xs,

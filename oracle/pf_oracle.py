@@ -32,7 +32,7 @@ BATCHING_T = {(8192, 24): 16760833, (8192, 27): 133857281, (16384, 24): 16580609
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with gcc via oracle/Makefile (outputs only into oracle/_build)."""
-    srcs = [_HERE / "pf_oracle.c", _HERE / "pf_oracle_pipeline.c", _HERE / "pf_oracle.h"]
+    srcs = [_HERE / "pf_oracle.c", _HERE / "pf_oracle_pipeline.c", _HERE / "pf_oracle_seeded.c", _HERE / "pf_oracle.h"]
     if force or not _LIB_PATH.exists() or any(s.stat().st_mtime > _LIB_PATH.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH
@@ -145,6 +145,15 @@ def _declare(l):
     l.pfo_encode_blocks.argtypes = [vp, C.POINTER(Layout), C.c_size_t, i32p, i64p, u32p, u64p, u64p, C.c_int]
     l.pfo_search_pairs.argtypes = [vp, C.POINTER(Layout), C.c_size_t, u64p, C.POINTER(u64p), C.c_int, C.c_size_t,
                                    i32p, i64p, u64p, u64p, u64p, u64p, C.c_int, dp]
+    u8p = C.POINTER(C.c_uint8)
+    l.pfo_blake2b_param.argtypes = [u8p, u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t]
+    l.pfo_blake2xb.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, u8p, C.c_size_t]
+    l.pfo_seal_sample_poly_uniform.argtypes = [vp, C.c_int, u8p, u64p]
+    l.pfo_encrypt_symmetric_seeded.argtypes = [vp, u64p, u64p, C.c_uint64, u8p, u64p]
+    l.pfo_ct_save_seeded_size.argtypes = [C.c_uint64, C.c_int]
+    l.pfo_ct_save_seeded_size.restype = C.c_size_t
+    l.pfo_ct_save_seeded.argtypes = [u64p, C.c_uint64, C.c_int, u64p, u8p, C.c_uint8, u8p]
+    l.pfo_ct_save_seeded.restype = C.c_size_t
     l.pfo_search_pairs_ms.argtypes = [vp, C.POINTER(Layout), C.c_size_t, u64p, C.POINTER(u64p), C.c_int, C.c_size_t,
                                       i32p, i64p, u64p, u64p, u64p, C.c_int, u64p, C.c_int, dp]
 
@@ -236,6 +245,32 @@ class Context:
         plain = np.zeros(self.n, dtype=np.uint64)
         budget = lib().pfo_decrypt(self.h, _p(sk, u64p), _p(c, u64p), _p(plain, u64p))
         return plain, budget
+
+    # --- SEAL seeded ciphertexts (pf_oracle_seeded.c) ---
+    def sample_poly_uniform(self, seed: bytes) -> np.ndarray:
+        """util::sample_poly_uniform over the L data primes from a Blake2xbPRNG with this 64-byte seed"""
+        out = np.zeros((self.L, self.n), dtype=np.uint64)
+        sb = np.frombuffer(seed, dtype=np.uint8).copy()
+        lib().pfo_seal_sample_poly_uniform(self.h, self.L, _p(sb, C.POINTER(C.c_uint8)), _p(out, u64p))
+        return out
+
+    def encrypt_seeded(self, sk: np.ndarray, plain: np.ndarray, noise_seed: int, seed: bytes) -> np.ndarray:
+        """symmetric encryption whose c1 is the expansion of `seed` (what a seeded save / load round-trips)"""
+        p = np.ascontiguousarray(plain, dtype=np.uint64)
+        ct = np.zeros((2, self.L, self.n), dtype=np.uint64)
+        sb = np.frombuffer(seed, dtype=np.uint8).copy()
+        lib().pfo_encrypt_symmetric_seeded(self.h, _p(sk, u64p), _p(p, u64p), noise_seed, _p(sb, C.POINTER(C.c_uint8)), _p(ct, u64p))
+        return ct
+
+    def ct_save_seeded(self, ct: np.ndarray, seed: bytes, parms_id=(0, 0, 0, 0), prng_type: int = 1) -> bytes:
+        """Serializable<Ciphertext>::save of a seeded ciphertext: c0 and the PRNG seed instead of c1"""
+        buf = np.zeros(lib().pfo_ct_save_seeded_size(self.n, self.L), dtype=np.uint8)
+        pid = (C.c_uint64 * 4)(*parms_id)
+        sb = np.frombuffer(seed, dtype=np.uint8).copy()
+        c0 = np.ascontiguousarray(ct[0], dtype=np.uint64)
+        w = lib().pfo_ct_save_seeded(_p(c0, u64p), self.n, self.L, pid, _p(sb, C.POINTER(C.c_uint8)), prng_type,
+                                     _p(buf, C.POINTER(C.c_uint8)))
+        return buf[:w].tobytes()
 
     # --- evaluator ---
     def ct_to_ntt(self, ct: np.ndarray) -> np.ndarray:
@@ -496,3 +531,19 @@ def vecs_read(path: str, dtype=np.float32) -> np.ndarray:
     arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_uint32)), shape=(n.value * d.value,)).copy()
     C.CDLL(None).free(data)
     return arr.view(dtype).reshape(n.value, d.value)
+
+
+def blake2b_param(param: bytes, key: bytes, msg: bytes, outlen: int) -> bytes:
+    pb, kb, mb = (np.frombuffer(x, dtype=np.uint8).copy() if len(x) else np.zeros(1, dtype=np.uint8) for x in (param, key, msg))
+    out = np.zeros(outlen, dtype=np.uint8)
+    u8 = C.POINTER(C.c_uint8)
+    lib().pfo_blake2b_param(_p(pb, u8), _p(kb, u8), len(key), _p(mb, u8), len(msg), _p(out, u8), outlen)
+    return out.tobytes()
+
+
+def blake2xb(outlen: int, msg: bytes, key: bytes) -> bytes:
+    kb, mb = (np.frombuffer(x, dtype=np.uint8).copy() if len(x) else np.zeros(1, dtype=np.uint8) for x in (key, msg))
+    out = np.zeros(outlen, dtype=np.uint8)
+    u8 = C.POINTER(C.c_uint8)
+    lib().pfo_blake2xb(_p(out, u8), outlen, _p(mb, u8), len(msg), _p(kb, u8), len(key))
+    return out.tobytes()

@@ -22,6 +22,7 @@
 #include "pf_encode.cuh"
 #include "pf_blake2b.h"
 #include "pf_host_math.h"
+#include "pf_seal_prng.h"
 #include <zlib.h>
 #include "pf_keyswitch.cuh"
 #include "pf_mac.cuh"
@@ -1376,6 +1377,47 @@ int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_nt
     return 0;
 }
 
+// SEAL seeded ciphertext (Serializable<Ciphertext> of a symmetric-key encryption): Ciphertext::save_members
+// writes the members, the DynArray of the FIRST polynomial only (L*N words) and then the
+// UniformRandomGeneratorInfo of the PRNG that drew c1 as a nested stream {SEALHeader, uint8 type, 64-byte seed}
+// [EXT: SEAL 4.1 ciphertext.cpp save_members / load_members / expand_seed].  `p` is an uncompressed stream.
+// Returns 1 when the stream is not seeded (untouched), 0 when `out` holds the equivalent full stream (c1 =
+// sample_poly_uniform of a Blake2xb PRNG with that seed, coefficient form), < 0 on malformed input
+// (-8: a PRNG type other than blake2xb, e.g. shake256).
+constexpr size_t SEAL_PRNG_INFO_BYTES = 16 + 1 + 64;
+int expand_seeded_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_t *primes, uint32_t L, std::vector<uint8_t> &out) {
+    if (len < SEAL_CT_HEADER) return -1;
+    if (p[0] != 0x5E || p[1] != 0xA1 || p[2] != 0x10 || p[3] != 4 || p[5] != 0) return -2;
+    uint64_t total, size, n, cms, words;
+    memcpy(&total, p + 8, 8);
+    if (total > len) return -1;
+    memcpy(&size, p + 49, 8);
+    memcpy(&n, p + 57, 8);
+    memcpy(&cms, p + 65, 8);
+    const uint8_t *in = p + 89;
+    if (in[0] != 0x5E || in[1] != 0xA1 || in[5] != 0) return -2;
+    memcpy(&words, in + 16, 8);
+    if (size != 2 || n != N || cms != (uint64_t)L) return -4;
+    if (words == 2 * n * cms) return 1; // both polynomials present
+    if (words != n * cms) return -4;
+    const size_t half = (size_t)words * 8;
+    if (total != SEAL_CT_HEADER + half + SEAL_PRNG_INFO_BYTES) return -4;
+    const uint8_t *info = p + SEAL_CT_HEADER + half;
+    uint64_t info_total;
+    memcpy(&info_total, info + 8, 8);
+    if (info[0] != 0x5E || info[1] != 0xA1 || info[5] != 0 || info_total != SEAL_PRNG_INFO_BYTES) return -4;
+    if (info[16] != 1) return -8; // prng_type::blake2xb = 1 (shake256 = 2)
+    out.resize(SEAL_CT_HEADER + 2 * half);
+    memcpy(out.data(), p, SEAL_CT_HEADER + half);
+    const uint64_t new_total = SEAL_CT_HEADER + 2 * half, arr_total = 16 + 8 + 2 * half, new_words = 2 * words;
+    memcpy(out.data() + 8, &new_total, 8);
+    memcpy(out.data() + 89 + 8, &arr_total, 8);
+    memcpy(out.data() + 89 + 16, &new_words, 8);
+    pfh::SealBlake2xbPrng prng(info + 17);
+    pfh::seal_sample_poly_uniform(prng, primes, L, N, reinterpret_cast<uint64_t *>(out.data() + SEAL_CT_HEADER + half));
+    return 0;
+}
+
 } // namespace
 
 // =============================================================================================
@@ -1415,6 +1457,42 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
     if (consumed) *consumed = used;
     if (!out || cap < plain.size()) return PF_ERR_CAPACITY;
     memcpy(out, plain.data(), plain.size());
+    return PF_OK;
+}
+
+int pf_seal_ct_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *data_primes, uint32_t nprimes,
+                      uint8_t *out, size_t cap, size_t *written, size_t *consumed) {
+    if (!in || !written || !data_primes || !nprimes || nprimes > PF_MAX_PRIMES) return PF_ERR_INVALID;
+    if (poly_degree < 2 || poly_degree > 32768 || (poly_degree & (poly_degree - 1))) return PF_ERR_INVALID;
+    for (uint32_t j = 0; j < nprimes; j++)
+        if (data_primes[j] < 2 || data_primes[j] >> 61) return PF_ERR_INVALID;
+    if (len < 16 || in[0] != 0x5E || in[1] != 0xA1) return PF_ERR_FORMAT;
+    const size_t full = SEAL_CT_HEADER + (size_t)2 * nprimes * poly_degree * 8;
+    std::vector<uint8_t> plain, expanded;
+    size_t used = 0;
+    const uint8_t *src = in;
+    size_t slen = len;
+    const int zr = inflate_seal_stream(in, len, plain, &used, full);
+    if (zr < 0) return PF_ERR_FORMAT;
+    if (zr == 0) {
+        src = plain.data();
+        slen = plain.size();
+    } else {
+        uint64_t total;
+        memcpy(&total, in + 8, 8);
+        if (total > len || total < 16) return PF_ERR_FORMAT;
+        used = (size_t)total;
+    }
+    const int er = expand_seeded_stream(src, slen, poly_degree, data_primes, nprimes, expanded);
+    if (er < 0) return PF_ERR_FORMAT;
+    const uint8_t *res = er == 0 ? expanded.data() : src;
+    uint64_t res_len;
+    if (er == 0) res_len = expanded.size();
+    else memcpy(&res_len, src + 8, 8);
+    *written = (size_t)res_len;
+    if (consumed) *consumed = used;
+    if (!out || cap < res_len) return PF_ERR_CAPACITY;
+    memcpy(out, res, (size_t)res_len);
     return PF_OK;
 }
 
@@ -2191,6 +2269,16 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
                 src = inflated.back().data();
                 len = inflated.back().size();
             }
+            if (len >= SEAL_CT_HEADER && src[5] == 0) { // seeded stream: c1 re-created from its PRNG seed (host, slow path)
+                std::vector<uint8_t> full;
+                const int er = expand_seeded_stream(src, len, (uint64_t)N, reinterpret_cast<const uint64_t *>(e->h_q.data()), (uint32_t)L, full);
+                if (er == -8) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is seeded with a PRNG other than blake2xb (unsupported)", c);
+                if (er == 0) {
+                    inflated.emplace_back(std::move(full));
+                    src = inflated.back().data();
+                    len = inflated.back().size();
+                }
+            }
             ct_src[c] = src;
             int is_ntt;
             uint64_t cms;
@@ -2653,13 +2741,27 @@ int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct,
         in = plain.data();
         len = plain.size();
     }
+    // a seeded stream (top level only: that is where symmetric encryptions are made) is expanded first
+    std::vector<uint8_t> full;
+    size_t seeded_consumed = 0;
+    if (len >= SEAL_CT_HEADER && in[5] == 0) {
+        uint64_t stream_total;
+        memcpy(&stream_total, in + 8, 8);
+        const int er = expand_seeded_stream(in, len, (uint64_t)e->N, reinterpret_cast<const uint64_t *>(e->h_q.data()), (uint32_t)e->L, full);
+        if (er == -8) return e->fail(PF_ERR_FORMAT, "ciphertext is seeded with a PRNG other than blake2xb (unsupported)");
+        if (er == 0) {
+            seeded_consumed = (size_t)stream_total;
+            in = full.data();
+            len = full.size();
+        }
+    }
     const int pr = parse_ct_prefix(e, in, len, &ntt, pid, &cms, &total);
     if (pr || cms < 1 || cms > (uint64_t)e->L) return e->fail(PF_ERR_FORMAT, "malformed ciphertext (code %d)", pr);
     if ((total - SEAL_CT_HEADER) / 8 > cap_words) return e->fail(PF_ERR_CAPACITY, "need %zu words", (total - SEAL_CT_HEADER) / 8);
     memcpy(ct, in + SEAL_CT_HEADER, total - SEAL_CT_HEADER);
     if (limbs) *limbs = (int)cms;
     if (is_ntt) *is_ntt = ntt;
-    if (consumed) *consumed = zr == 0 ? zconsumed : total;
+    if (consumed) *consumed = zr == 0 ? zconsumed : (seeded_consumed ? seeded_consumed : total);
     return PF_OK;
 }
 

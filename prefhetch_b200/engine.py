@@ -56,6 +56,25 @@ def seal_stream_inflate(blob) -> bytes:
     return out.tobytes()
 
 
+def seal_ct_expand(blob, poly_degree: int, data_primes) -> bytes:
+    """a SEAL ciphertext stream (seeded and / or zlib) -> the equivalent full compr_mode none stream; needs no GPU
+    (pf_seal_ct_expand)"""
+    lib = _capi.load()
+    b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+    pr = (C.c_uint64 * len(data_primes))(*data_primes)
+    need, used = C.c_size_t(), C.c_size_t()
+    rc = lib.pf_seal_ct_expand(b.ctypes.data_as(C.c_void_p), b.size, poly_degree, pr, len(data_primes), None, 0,
+                               C.byref(need), C.byref(used))
+    if rc != _capi.PF_ERR_CAPACITY:
+        raise PfError(rc, "malformed or unsupported SEAL ciphertext stream")
+    out = np.empty(need.value, dtype=np.uint8)
+    rc = lib.pf_seal_ct_expand(b.ctypes.data_as(C.c_void_p), b.size, poly_degree, pr, len(data_primes),
+                               out.ctypes.data_as(C.c_void_p), out.size, C.byref(need), C.byref(used))
+    if rc:
+        raise PfError(rc, "malformed or unsupported SEAL ciphertext stream")
+    return out.tobytes()
+
+
 def batching_plain_modulus(n: int, bits: int) -> int:
     return _BATCHING[(n, bits)]
 
