@@ -38,6 +38,11 @@ class IVFPQFile:
     by_residual: bool = True
     metric_type: int = 1                       # METRIC_L2
     is_trained: bool = True
+    # what the reference's dynamic_cast<IndexIVFPQ*> also accepts and a re-write must keep:
+    direct_map_type: int = 0                   # DirectMap::NoMap / Array (1) / Hashtable (2)
+    direct_map_array: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))
+    direct_map_pairs: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int64))
+    refine: bytes | None = None                # IndexIVFPQR ("IwQR"): refine_pq + refine_codes + k_factor, kept verbatim
 
     def csr(self, base_vectors: np.ndarray):
         """-> (list_offsets[nlist+1], ids, vectors in list order) for Engine.load_index"""
@@ -53,13 +58,19 @@ class _R:
         self.b, self.o = b, 0
 
     def take(self, fmt):
+        size = struct.calcsize("<" + fmt)
+        if self.o + size > len(self.b):
+            raise ValueError("truncated index file")
         v = struct.unpack_from("<" + fmt, self.b, self.o)
-        self.o += struct.calcsize("<" + fmt)
+        self.o += size
         return v if len(v) > 1 else v[0]
 
     def arr(self, dtype, n):
-        a = np.frombuffer(self.b, dtype=dtype, count=n, offset=self.o).copy()
-        self.o += a.nbytes
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        if n < 0 or self.o + nbytes > len(self.b):
+            raise ValueError("truncated index file")
+        a = np.frombuffer(self.b, dtype=dtype, count=int(n), offset=self.o).copy()
+        self.o += nbytes
         return a
 
     def vec(self, dtype):
@@ -81,28 +92,42 @@ def _read_header(r: _R):
 def read_ivfpq(path: str) -> IVFPQFile:
     r = _R(open(path, "rb").read())
     h = r.take("I")
-    if h != _fourcc("IwPQ"):
+    # IndexIVFPQR ("IwQR") derives from IndexIVFPQ: the reference's dynamic_cast accepts it (ref:
+    # src/server/server_lib.cpp:92-95); its refine section follows the inverted lists and is carried verbatim.
+    # "IvPQ" / "IvQR" are the pre-2018 layouts (lists stored per list with their own headers): refused by name.
+    if h in (_fourcc("IvPQ"), _fourcc("IvQR")):
+        raise ValueError("legacy IndexIVFPQ file layout (IvPQ / IvQR): re-save it with a current FAISS")
+    if h not in (_fourcc("IwPQ"), _fourcc("IwQR")):
         raise ValueError("Loaded index is not of type IndexIVFPQ")  # ref: src/server/server_lib.cpp:92-95
+    is_pqr = h == _fourcc("IwQR")
     d, ntotal, is_trained, metric = _read_header(r)
     nlist, nprobe = r.take("Q"), r.take("Q")
+    if d <= 0 or ntotal < 0 or nlist == 0 or nlist > (1 << 32):
+        raise ValueError("implausible index header")
     hq = r.take("I")
-    if hq not in (_fourcc("IxF2"), _fourcc("IxFI")):
+    if hq not in (_fourcc("IxF2"), _fourcc("IxFI"), _fourcc("IxFl")):
         raise ValueError("coarse quantizer is not an IndexFlat")
     dq, nq, _, _ = _read_header(r)
     cent = r.vec(np.float32)
     if dq != d or nq != nlist or cent.size != nlist * d:
         raise ValueError("quantizer shape does not match the IVF header")
     dm_type = r.take("B")
-    r.vec(np.int64)
-    if dm_type == 2:                                   # DirectMap::Hashtable
+    if dm_type > 2:
+        raise ValueError("unknown direct-map type")
+    dm_array = r.vec(np.int64)
+    dm_pairs = np.zeros((0, 2), np.int64)
+    if dm_type == 2:                                   # DirectMap::Hashtable: vector of (id, list/offset) pairs
         n = r.take("Q")
-        r.arr(np.int64, 2 * n)
+        dm_pairs = r.arr(np.int64, 2 * n).reshape(-1, 2)
     by_residual = bool(r.take("B"))
     code_size = r.take("Q")
     pq_d, pq_M, pq_nbits = r.take("Q"), r.take("Q"), r.take("Q")
     pq_cent = r.vec(np.float32)
-    if r.take("I") != _fourcc("ilar"):
-        raise ValueError("unsupported inverted-list container")
+    il = r.take("I")
+    if il == _fourcc("il00"):
+        raise ValueError("index file holds no inverted lists (il00)")
+    if il != _fourcc("ilar"):
+        raise ValueError("unsupported inverted-list container (only in-memory ArrayInvertedLists, 'ilar')")
     il_nlist, il_cs = r.take("Q"), r.take("Q")
     if il_nlist != nlist or il_cs != code_size or pq_d != d:
         raise ValueError("inverted lists do not match the index header")
@@ -114,7 +139,12 @@ def read_ivfpq(path: str) -> IVFPQFile:
             raise ValueError("bad list size table")
         sizes[:] = s
     elif kind == _fourcc("sprs"):
-        s = r.vec(np.uint64).reshape(-1, 2)
+        s = r.vec(np.uint64)
+        if s.size % 2:
+            raise ValueError("bad list size table")
+        s = s.reshape(-1, 2)
+        if s.size and int(s[:, 0].max()) >= nlist:
+            raise ValueError("bad list size table")
         sizes[s[:, 0].astype(np.int64)] = s[:, 1]
     else:
         raise ValueError("unknown list size encoding")
@@ -125,8 +155,15 @@ def read_ivfpq(path: str) -> IVFPQFile:
         ids.append(r.arr(np.int64, n))
     if sum(len(x) for x in ids) != ntotal:
         raise ValueError("ntotal does not match the inverted lists")
+    refine = None
+    if is_pqr:
+        refine = bytes(r.b[r.o:])
+        if len(refine) < 24 + 8 + 8 + 4:
+            raise ValueError("truncated index file")
+    elif r.o != len(r.b):
+        raise ValueError("trailing bytes after the inverted lists")
     return IVFPQFile(d, ntotal, nlist, nprobe, cent.reshape(nlist, d), ids, codes, code_size, pq_M, pq_nbits, pq_cent,
-                     by_residual, metric, is_trained)
+                     by_residual, metric, is_trained, dm_type, dm_array, dm_pairs, refine)
 
 
 def write_ivfpq(path: str, f: IVFPQFile):
@@ -135,12 +172,16 @@ def write_ivfpq(path: str, f: IVFPQFile):
     def header(d, ntotal, trained, metric):
         return struct.pack("<iqqqBi", d, ntotal, 1 << 20, 1 << 20, int(trained), metric)
 
-    out += struct.pack("<I", _fourcc("IwPQ")) + header(f.d, f.ntotal, f.is_trained, f.metric_type)
+    out += struct.pack("<I", _fourcc("IwQR" if f.refine is not None else "IwPQ")) + header(f.d, f.ntotal, f.is_trained, f.metric_type)
     out += struct.pack("<QQ", f.nlist, f.nprobe)
     cent = np.ascontiguousarray(f.centroids, dtype=np.float32)
     out += struct.pack("<I", _fourcc("IxF2")) + header(f.d, f.nlist, True, f.metric_type)
     out += struct.pack("<Q", cent.size) + cent.tobytes()
-    out += struct.pack("<B", 0) + struct.pack("<Q", 0)                      # DirectMap::NoMap, empty array
+    dma = np.ascontiguousarray(f.direct_map_array, dtype=np.int64)
+    out += struct.pack("<B", f.direct_map_type) + struct.pack("<Q", dma.size) + dma.tobytes()
+    if f.direct_map_type == 2:
+        dmp = np.ascontiguousarray(f.direct_map_pairs, dtype=np.int64)
+        out += struct.pack("<Q", dmp.shape[0]) + dmp.tobytes()
     out += struct.pack("<BQ", int(f.by_residual), f.code_size)
     pqc = np.ascontiguousarray(f.pq_centroids, dtype=np.float32)
     out += struct.pack("<QQQ", f.d, f.pq_M, f.pq_nbits) + struct.pack("<Q", pqc.size) + pqc.tobytes()
@@ -156,4 +197,6 @@ def write_ivfpq(path: str, f: IVFPQFile):
         if len(f.list_ids[l]):
             out += np.ascontiguousarray(f.list_codes[l], dtype=np.uint8).tobytes()
             out += np.ascontiguousarray(f.list_ids[l], dtype=np.int64).tobytes()
+    if f.refine is not None:
+        out += f.refine
     open(path, "wb").write(bytes(out))

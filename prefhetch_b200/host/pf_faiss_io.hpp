@@ -44,6 +44,11 @@ class Cursor {
         m_Pos += n;
     }
     void skip(size_t n) { copy(nullptr, n); }
+    void skip_items(uint64_t count, uint64_t item_bytes) { // count * item_bytes without overflow
+        if (item_bytes && count > (m_Buf.size() - m_Pos) / item_bytes) throw std::runtime_error("truncated index file");
+        skip(static_cast<size_t>(count * item_bytes));
+    }
+    bool at_end() const { return m_Pos == m_Buf.size(); }
 
   private:
     std::vector<uint8_t> m_Buf;
@@ -66,28 +71,39 @@ inline IvfFile read_ivfpq_file(const std::string &path) {
     using namespace detail;
     Cursor c(path);
     IvfFile out;
-    if (c.get<uint32_t>() != fourcc("IwPQ")) throw std::runtime_error("Loaded index is not of type IndexIVFPQ");
+    // "IwQR" = IndexIVFPQR, a subclass the reference's dynamic_cast<IndexIVFPQ*> accepts (its refine section after
+    // the inverted lists is not needed here); "IvPQ" / "IvQR" = the legacy per-list layout, refused by name
+    const uint32_t top = c.get<uint32_t>();
+    if (top == fourcc("IvPQ") || top == fourcc("IvQR"))
+        throw std::runtime_error("legacy IndexIVFPQ file layout (IvPQ / IvQR): re-save it with a current FAISS");
+    if (top != fourcc("IwPQ") && top != fourcc("IwQR")) throw std::runtime_error("Loaded index is not of type IndexIVFPQ");
     index_header(c, out.d, out.ntotal);
     out.nlist = c.get<uint64_t>();
     out.nprobe = c.get<uint64_t>();
+    if (out.d == 0 || out.nlist == 0 || out.nlist > (1ull << 32)) throw std::runtime_error("implausible index header");
     const uint32_t qcc = c.get<uint32_t>();
-    if (qcc != fourcc("IxF2") && qcc != fourcc("IxFI")) throw std::runtime_error("coarse quantizer is not an IndexFlat");
+    if (qcc != fourcc("IxF2") && qcc != fourcc("IxFI") && qcc != fourcc("IxFl"))
+        throw std::runtime_error("coarse quantizer is not an IndexFlat");
     uint32_t qd;
     uint64_t qn;
     index_header(c, qd, qn);
     const uint64_t nfloats = c.get<uint64_t>();
     if (qd != out.d || qn != out.nlist || nfloats != out.nlist * out.d)
         throw std::runtime_error("quantizer shape does not match the IVF header");
+    if (nfloats > (1ull << 40)) throw std::runtime_error("truncated index file");
     out.centroids.resize(nfloats);
     c.copy(out.centroids.data(), nfloats * sizeof(float));
-    const uint8_t dm = c.get<uint8_t>();
-    c.skip(c.get<uint64_t>() * 8);
-    if (dm == 2) c.skip(c.get<uint64_t>() * 16);
+    const uint8_t dm = c.get<uint8_t>(); // DirectMap::NoMap / Array / Hashtable
+    if (dm > 2) throw std::runtime_error("unknown direct-map type");
+    c.skip_items(c.get<uint64_t>(), 8);
+    if (dm == 2) c.skip_items(c.get<uint64_t>(), 16);
     c.skip(1); // by_residual
     out.code_size = c.get<uint64_t>();
     c.skip(24); // pq.d, pq.M, pq.nbits
-    c.skip(c.get<uint64_t>() * sizeof(float));
-    if (c.get<uint32_t>() != fourcc("ilar")) throw std::runtime_error("unsupported inverted-list container");
+    c.skip_items(c.get<uint64_t>(), sizeof(float));
+    const uint32_t il = c.get<uint32_t>();
+    if (il == fourcc("il00")) throw std::runtime_error("index file holds no inverted lists (il00)");
+    if (il != fourcc("ilar")) throw std::runtime_error("unsupported inverted-list container (only in-memory ArrayInvertedLists, 'ilar')");
     if (c.get<uint64_t>() != out.nlist || c.get<uint64_t>() != out.code_size)
         throw std::runtime_error("inverted lists do not match the index header");
     std::vector<uint64_t> sizes(out.nlist, 0);
@@ -97,6 +113,7 @@ inline IvfFile read_ivfpq_file(const std::string &path) {
         if (nsz != out.nlist) throw std::runtime_error("bad list size table");
         c.copy(sizes.data(), nsz * 8);
     } else if (kind == fourcc("sprs")) {
+        if (nsz % 2) throw std::runtime_error("bad list size table");
         for (uint64_t i = 0; i < nsz / 2; i++) {
             const uint64_t l = c.get<uint64_t>(), n = c.get<uint64_t>();
             if (l >= out.nlist) throw std::runtime_error("bad list size table");
@@ -106,14 +123,18 @@ inline IvfFile read_ivfpq_file(const std::string &path) {
         throw std::runtime_error("unknown list size encoding");
     }
     out.list_offsets.assign(out.nlist + 1, 0);
-    for (uint64_t l = 0; l < out.nlist; l++) out.list_offsets[l + 1] = out.list_offsets[l] + static_cast<int64_t>(sizes[l]);
+    for (uint64_t l = 0; l < out.nlist; l++) {
+        if (sizes[l] > out.ntotal) throw std::runtime_error("ntotal does not match the inverted lists");
+        out.list_offsets[l + 1] = out.list_offsets[l] + static_cast<int64_t>(sizes[l]);
+    }
     if (static_cast<uint64_t>(out.list_offsets[out.nlist]) != out.ntotal)
         throw std::runtime_error("ntotal does not match the inverted lists");
     out.ids.resize(out.ntotal);
     for (uint64_t l = 0; l < out.nlist; l++) {
-        c.skip(sizes[l] * out.code_size);
+        c.skip_items(sizes[l], out.code_size);
         c.copy(out.ids.data() + out.list_offsets[l], sizes[l] * 8);
     }
+    if (top == fourcc("IwPQ") && !c.at_end()) throw std::runtime_error("trailing bytes after the inverted lists");
     return out;
 }
 
