@@ -93,3 +93,16 @@ def test_reference_arm_names_the_same_config_as_the_gpu_arm():
     b = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"], 1, False, 16, (1, 1))  # ours, N = 1
     assert a == b
     assert bench.cpu_sample_queries(64, 16) == 32 and bench.cpu_sample_queries(64, 1) == 8 and bench.cpu_sample_queries(16, 64) == 16
+
+
+def test_overlapping_mixture_has_recall_below_one(oracle):
+    """bench.py reports recall@10 on SURVEY's well-separated mixture (1.0) AND on an overlapping one, where probing
+    a few lists misses true neighbours; the reference definition (|GT100 ∩ top10| / 10) is never below the standard one"""
+    cfg = dict(nb=20000, d=32, nlist=64)
+    hard = bench.make_dataset(cfg, "cpu", seed=777, sigma=48.0, spread=128.0, lloyd=2, offset=64.0)
+    off = hard["offsets"]
+    assert off[-1] == cfg["nb"] and hard["vectors"].min() >= 0 and hard["vectors"].max() <= 255
+    rm = bench.recall_metrics(_StubEngine(oracle, hard), hard, nprobe=2, dev="cpu", nq_r=32)
+    assert 0.3 < rm["recall_at_10"] < 0.98 and rm["reference_recall_10"] >= rm["recall_at_10"]
+    full = bench.recall_metrics(_StubEngine(oracle, hard), hard, nprobe=64, dev="cpu", nq_r=8)
+    assert full["recall_at_10"] == 1.0
