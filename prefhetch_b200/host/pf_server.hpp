@@ -178,6 +178,8 @@ class Server {
 
     size_t resultSerializedSize() const { return pf_result_serialized_size(m_Engine.get()); }
 
+    uint32_t dim() const { return m_Dim; }
+    uint64_t nlist() const { return m_Nlist; }
     pf_engine *handle() const { return m_Engine.get(); }
     const pf_index_info &info() const { return m_Info; }
 

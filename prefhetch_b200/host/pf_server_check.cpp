@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "pf_query_handlers.hpp"
 #include "pf_server.hpp"
 
 namespace {
@@ -80,9 +81,102 @@ int encrypted_check(const std::string &dir) {
     return 0;
 }
 
+// `--handlers <dir>`: the handler bodies of pf_query_handlers.hpp end to end — JSON request bodies in the
+// reference's shape in, JSON responses out — against direct calls on the same Server (files as in encrypted_check).
+int handlers_check(const std::string &dir) {
+    namespace h = prefhetch::handlers;
+    std::ifstream pf(dir + "/params.txt");
+    if (!pf) throw std::runtime_error("cannot open params.txt");
+    uint32_t d, g, m, rl, nprobe;
+    uint64_t n, nq, t, k;
+    pf >> d >> n >> g >> m >> rl >> nprobe >> nq >> t >> k;
+    std::vector<uint64_t> primes(k);
+    for (auto &q : primes) pf >> q;
+    const auto cent = read_file<float>(dir + "/centroids.f32");
+    const auto off = read_file<prefhetch::idx_t>(dir + "/offsets.i64");
+    const auto ids = read_file<prefhetch::idx_t>(dir + "/ids.i64");
+    const auto vec = read_file<float>(dir + "/vectors.f32");
+    const auto keys = read_file<uint8_t>(dir + "/galois_keys.bin");
+    const auto qblob = read_file<uint8_t>(dir + "/queries.bin");
+    const auto qoff = read_file<uint64_t>(dir + "/query_offsets.u64");
+    const auto probes = read_file<prefhetch::idx_t>(dir + "/probes.i64");
+    const auto queries = read_file<float>(dir + "/queries.f32");
+    const uint64_t nlist = off.size() - 1;
+    prefhetch::Server srv(d, n, primes, t, m, g, 0, 0, 1, rl);
+    srv.init_index(nlist, cent.data(), off.data(), ids.data(), vec.data());
+    srv.loadGaloisKeys(keys);
+    // GET /query
+    size_t r = 0, c = 0;
+    const auto cent2 = h::json::matrix<float>(h::query(srv), r, c);
+    if (r != nlist || c != d || cent2 != cent) return 10;
+    // POST /coarsesearch
+    std::string body = "{\"preciseQuery\":";
+    h::json::put_matrix(body, queries.data(), nq, d);
+    body += ",\"nearestCentroidIndexes\":";
+    h::json::put_matrix(body, probes.data(), nq, nprobe);
+    body += "}";
+    const auto resp = h::json::object(h::coarse_search(srv, body));
+    std::vector<float> dist;
+    std::vector<prefhetch::idx_t> labels;
+    std::vector<size_t> sizes;
+    srv.coarseSearch(queries, probes, nprobe, dist, labels, sizes);
+    if (h::json::vector<float>(h::json::at(resp, "coarseDistanceScores")) != dist) return 11;
+    if (h::json::vector<prefhetch::idx_t>(h::json::at(resp, "coarseVectorIndexes")) != labels) return 12;
+    if (h::json::vector<size_t>(h::json::at(resp, "listSizesPerQuery")) != sizes) return 13;
+    // POST /precisesearch on the first candidates of every query
+    const size_t probe = 4;
+    std::vector<prefhetch::idx_t> cand(nq * probe);
+    size_t o = 0;
+    for (uint64_t i = 0; i < nq; i++) {
+        for (size_t j = 0; j < probe; j++) cand[i * probe + j] = labels[o + j];
+        o += sizes[i];
+    }
+    std::string pbody = "{\"preciseQuery\":";
+    h::json::put_matrix(pbody, queries.data(), nq, d);
+    pbody += ",\"nearestCoarseVectorIndexes\":";
+    h::json::put_matrix(pbody, cand.data(), nq, probe);
+    pbody += "}";
+    const auto presp = h::json::object(h::precise_search(srv, pbody));
+    std::vector<float> pd;
+    srv.preciseSearch(queries, cand, probe, pd);
+    if (h::json::matrix<float>(h::json::at(presp, "preciseDistanceScores"), r, c) != pd || r != nq || c != probe) return 14;
+    o = 0;
+    for (uint64_t i = 0; i < nq; i++) { // plaintext stage 2 and the exact re-rank agree on integer data
+        for (size_t j = 0; j < probe; j++)
+            if (pd[i * probe + j] != dist[o + j]) return 15;
+        o += sizes[i];
+    }
+    // POST /coarsesearch-encrypted
+    std::string ebody = "{\"queryCiphertexts\":\"" + h::json::base64_encode(qblob.data(), qblob.size()) + "\",\"ctOffsets\":";
+    h::json::put_vector(ebody, qoff.data(), qoff.size());
+    ebody += ",\"nearestCentroidIndexes\":";
+    h::json::put_matrix(ebody, probes.data(), nq, nprobe);
+    ebody += "}";
+    const auto eresp = h::json::object(h::coarse_search_encrypted(srv, ebody));
+    prefhetch::EncryptedCoarseResult direct;
+    srv.coarseSearchEncrypted(nq, qblob, qoff, probes, nprobe, direct);
+    if (h::json::base64_decode(h::json::string(h::json::at(eresp, "resultCiphertexts"))) != direct.ciphertexts) return 16;
+    if (h::json::vector<uint64_t>(h::json::at(eresp, "resultOffsets")) != direct.result_offsets) return 17;
+    if (h::json::vector<prefhetch::idx_t>(h::json::at(eresp, "coarseVectorIndexes")) != direct.coarse_vector_indexes) return 18;
+    if (h::json::number<uint64_t>(h::json::at(eresp, "resultBytes")) != srv.resultSerializedSize()) return 19;
+    size_t pr = 0, pc = 0;
+    if (h::json::matrix<uint64_t>(h::json::at(eresp, "probedListSizes"), pr, pc) != direct.probed_sizes || pr != nq || pc != nprobe) return 20;
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char **argv) {
+    if (argc > 2 && std::string(argv[1]) == "--handlers") {
+        try {
+            const int rc = handlers_check(argv[2]);
+            if (rc == 0) std::printf("pf_server_check handlers ok\n");
+            return rc;
+        } catch (const std::exception &ex) {
+            std::fprintf(stderr, "pf_server_check (handlers) failed: %s\n", ex.what());
+            return 1;
+        }
+    }
     if (argc > 1) {
         try {
             return encrypted_check(argv[1]);

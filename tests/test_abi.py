@@ -113,3 +113,16 @@ def test_seal_stream_inflate_is_bounded():
                                     C.byref(need), C.byref(used))
     assert rc == _capi.PF_OK and need.value == exact.size and used.value == len(z)
     assert exact[5] == 0 and not exact[16:].any()
+
+
+def test_handler_json_envelope_cpp():
+    """the JSON codec of the handler bodies (prefhetch_b200/host/pf_query_handlers.hpp) on the reference's request
+    shapes (ref: src/server/controllers/Query.cc:34-42): compiled and run on the CPU; the handler bodies with an
+    engine behind them run on the GPU box (tests/test_gpu_parity.py::test_cpp_handlers_end_to_end)"""
+    import subprocess
+    exe = ROOT / "prefhetch_b200" / "host" / "pf_handlers_check"
+    if not exe.exists():
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -755,6 +755,21 @@ def test_flag_wait_times_out(pf, monkeypatch):
     eng.close()
 
 
+def _write_cpp_case(tmp_path, cl, keys, d, n, g, rl, nprobe, query, t, primes, cent, offsets, ids, vecs, blob, offs, idx):
+    """the files host/pf_server_check.cpp reads (its header lists them)"""
+    from tests.util import galois_keys_save
+    (tmp_path / "params.txt").write_text(" ".join(str(x) for x in [d, n, g, 1, rl, nprobe, len(query), t, len(primes), *primes]))
+    cent.astype(np.float32).tofile(tmp_path / "centroids.f32")
+    offsets.astype(np.int64).tofile(tmp_path / "offsets.i64")
+    ids.astype(np.int64).tofile(tmp_path / "ids.i64")
+    vecs.astype(np.float32).tofile(tmp_path / "vectors.f32")
+    (tmp_path / "galois_keys.bin").write_bytes(galois_keys_save(cl.ctx, {cl.ctx.galois_elt(i + 1): k for i, k in enumerate(keys)}))
+    blob.tofile(tmp_path / "queries.bin")
+    offs.astype(np.uint64).tofile(tmp_path / "query_offsets.u64")
+    idx.astype(np.int64).tofile(tmp_path / "probes.i64")
+    np.ascontiguousarray(query, dtype=np.float32).tofile(tmp_path / "queries.f32")
+
+
 def test_cpp_encrypted_search_matches_python(pf, oracle, tmp_path):
     """the reference-side binding in C++ (prefhetch::Server: loadGaloisKeys from a SEAL stream, result_limbs,
     coarseSearchEncrypted and submit / collect) gives the bytes of the Python path, which is checked against
@@ -790,15 +805,7 @@ def test_cpp_encrypted_search_matches_python(pf, oracle, tmp_path):
     labels = res.labels.copy()
     eng.close()
     # the same request from C++
-    (tmp_path / "params.txt").write_text(" ".join(str(x) for x in [d, n, g, 1, rl, nprobe, len(query), t, len(primes), *primes]))
-    cent.astype(np.float32).tofile(tmp_path / "centroids.f32")
-    offsets.astype(np.int64).tofile(tmp_path / "offsets.i64")
-    ids.astype(np.int64).tofile(tmp_path / "ids.i64")
-    vecs.astype(np.float32).tofile(tmp_path / "vectors.f32")
-    (tmp_path / "galois_keys.bin").write_bytes(galois_keys_save(cl.ctx, {cl.ctx.galois_elt(i + 1): k for i, k in enumerate(keys)}))
-    blob.tofile(tmp_path / "queries.bin")
-    offs.astype(np.uint64).tofile(tmp_path / "query_offsets.u64")
-    idx.astype(np.int64).tofile(tmp_path / "probes.i64")
+    _write_cpp_case(tmp_path, cl, keys, d, n, g, rl, nprobe, query, t, primes, cent, offsets, ids, vecs, blob, offs, idx)
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "results.bin").read_bytes() == want
@@ -848,3 +855,24 @@ def test_seeded_query_ciphertexts(pf, oracle):
         eng.coarseSearchEncrypted(*blob_of([cl.ctx.ct_save_seeded(cts[0], seeds[0], prng_type=2), full[1], full[2]]), idx)
     assert ei.value.code == 5
     eng.close()
+
+
+def test_cpp_handlers_end_to_end(pf, oracle, tmp_path):
+    """the handler bodies of host/pf_query_handlers.hpp (ref: src/server/controllers/Query.cc:10-98 + the additive
+    encrypted endpoint): JSON request bodies in the reference's shape in, JSON out, equal to direct calls on the
+    same prefhetch::Server; run by `pf_server_check --handlers` on files written here"""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "prefhetch_b200" / "host" / "pf_server_check"
+    assert exe.exists(), "run __graft_entry__.build() first"
+    n, g, d, nprobe, rl = 2048, 16, 128, 3, 1
+    base, query, cent, offsets, ids, vecs = _dataset(61, nb=3000, nlist=12, nq=3, frac_centroids=False)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    cts = np.stack([cl.encrypt_query(q, 800 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    oidx, _ = oracle.coarse_quantize(query, cent, nprobe)
+    _write_cpp_case(tmp_path, cl, keys, d, n, g, rl, nprobe, query, t, primes, cent, offsets, ids, vecs, blob, offs, oidx)
+    r = subprocess.run([str(exe), "--handlers", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "handlers ok" in r.stdout, r.stdout + r.stderr
