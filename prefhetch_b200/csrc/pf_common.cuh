@@ -107,10 +107,6 @@ __device__ __forceinline__ void stg_stream(ulonglong2 *p, ulonglong2 v) {
 // bounds in pf_ntt_fp.cuh) ------------------------------------------------------------------------------
 #define PF_FP_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
 
-struct FpConsts {
-    double q, qinv;
-};
-
 __device__ __forceinline__ double fp_mulmod(double a, double w, double q, double qinv) {
     const double h = __dmul_rn(a, w);
     const double l = __fma_rn(a, w, -h);

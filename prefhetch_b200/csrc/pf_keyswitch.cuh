@@ -262,26 +262,6 @@ __global__ void __launch_bounds__(256) ks_moddown_prep_kernel(const KsParams p) 
     }
 }
 
-// out_c[j] = (S_c[j] - Wntt_c[j]) * P^{-1} (+ c0_ntt[j][perm] for c = 0).  grid (N/256, 2*L, z)
-__global__ void __launch_bounds__(256) ks_finish_kernel(const KsParams p) {
-    const int c = blockIdx.y / p.L, j = blockIdx.y % p.L, z = blockIdx.z, L = p.L, N = p.N;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const RotJob job = p.jobs[z];
-    const u64 q = p.mods[j].q;
-    const u64 s = p.S[((size_t)z * 2 + c) * (L + 1) * N + (size_t)j * N + i];
-    const u64 w = p.W[(((size_t)z * 2 + c) * L + j) * N + i];
-    u64 r = mul_shoup(submod(s, w, q), p.p_inv_mod_q[j], p.p_inv_mod_q_sh[j], q);
-    if (c == 0) r = addmod(r, job.c0_ntt[(size_t)j * N + job.perm[i]], q);
-    if (p.out_split) r = split_word(r, (int)p.mods[j].split_shift);
-    job.out[((size_t)c * L + j) * N + i] = r;
-}
-
-// NTT-domain Galois permutation of whole polynomials: out[y][i] = in[y][perm[i]].  grid (N/256, npoly)
-__global__ void __launch_bounds__(256) galois_ntt_perm_kernel(const u64 *in, const u32 *perm, u64 *out, int N) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    out[(size_t)blockIdx.y * N + i] = in[(size_t)blockIdx.y * N + perm[i]];
-}
-
 // element-wise ciphertext add: limb of polynomial y is y % L.  grid (N/256, 2*L)
 __global__ void __launch_bounds__(256) ct_add_kernel(const u64 *a, const u64 *b, u64 *out, const DevModulus *mods,
                                                      int L, int N) {

@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(128) stamp_headers_kernel(unsigned char *blob,
     if (r >= nresults) return;
     unsigned char *dst = blob + r * slot + pad;
     for (int i = 0; i < 113; i++) dst[i] = hd.b[i];
+    for (size_t i = 0; i < pad; i++) blob[r * slot + i] = 0; // the alignment pad travels with the response: keep it deterministic
 }
 
 // Query ciphertexts arrive as SEAL streams: 113 header bytes, then 2*L*N little-endian words — at a byte offset
