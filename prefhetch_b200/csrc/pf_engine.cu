@@ -68,27 +68,6 @@ struct DevBuf {
     }
 };
 
-struct PinBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    ~PinBuf() {
-        if (p) cudaFreeHost(p);
-    }
-    cudaError_t ensure(size_t n) {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMallocHost(&p, n);
-        if (e == cudaSuccess) bytes = n;
-        return e;
-    }
-    template <class T>
-    T *as() const {
-        return reinterpret_cast<T *>(p);
-    }
-};
-
 // host memory the GPU reads / writes in place (zero-copy): small results that must not queue behind a
 // large response download on the device-to-host copy engine
 struct MappedBuf {
@@ -193,7 +172,6 @@ struct pf_engine {
     DevBuf s_x, s_cx, s_dist, s_keys, s_jobs, s_pl_dist, s_pl_labels, s_ids;
     DevBuf s_rot, s_cqntt, s_hoistD, s_flags, s_ks_d, s_ks_S, s_ks_W, s_rotjobs, s_c1coef, s_chunks, s_pairblock, s_pairout, s_qcts, s_tmp, s_plain,
         s_encblocks;
-    PinBuf h_stage, h_stage2;
     MappedBuf m_cx, m_cidx, m_cdist; // stage 1: query vectors in, probe ids / distances out (zero-copy)
     // pinned upload arena: pageable cudaMemcpyAsync would synchronise the stream (and the host) on every
     // small table upload; 4 call slots, a slot is reused only after the call that used it has finished
@@ -1202,7 +1180,6 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
     {
         PhaseTimer pt(e, PF_T_INTT);
         u64 *base = full + full_base * full_stride;
-        const int nd = L - e->Lr;
         // (an inverse NTT with the mod-switch folded into its store was bit-exact but 2-6x slower than the
         // pair INTT + modswitch kernel — register pressure in the 32-point pass — and was removed)
         for (size_t off = 0; off < P; off += 32768) {
