@@ -11,69 +11,7 @@ import pytest
 
 from tests.util import is_prime, ntt_primes, zlib_stream
 
-IV = [0x6a09e667f3bcc908, 0xbb67ae8584caa73b, 0x3c6ef372fe94f82b, 0xa54ff53a5f1d36f1,
-      0x510e527fade682d1, 0x9b05688c2b3e6c1f, 0x1f83d9abfb41bd6b, 0x5be0cd19137e2179]
-SIGMA = [[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15], [14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3],
-         [11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4], [7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8],
-         [9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13], [2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9],
-         [12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11], [13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10],
-         [6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5], [10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0]]
-M64 = (1 << 64) - 1
-
-
-def _py_blake2b(param: bytes, key: bytes, msg: bytes, outlen: int) -> bytes:
-    """RFC 7693 BLAKE2b with an explicit 64-byte parameter block (pure Python, big integers)"""
-    h = [IV[i] ^ struct.unpack_from("<Q", param, 8 * i)[0] for i in range(8)]
-    data = (key.ljust(128, b"\0") if key else b"") + msg
-    total = len(data)
-    blocks = [data[i:i + 128].ljust(128, b"\0") for i in range(0, max(total, 1), 128)]
-    rotr = lambda x, n: ((x >> n) | (x << (64 - n))) & M64
-    for bi, blk in enumerate(blocks):
-        last = bi == len(blocks) - 1
-        t = total if last else (bi + 1) * 128
-        m = struct.unpack("<16Q", blk)
-        v = h + IV[:]
-        v[12] ^= t
-        if last:
-            v[14] ^= M64
-
-        def G(a, b, c, d, x, y):
-            v[a] = (v[a] + v[b] + x) & M64
-            v[d] = rotr(v[d] ^ v[a], 32)
-            v[c] = (v[c] + v[d]) & M64
-            v[b] = rotr(v[b] ^ v[c], 24)
-            v[a] = (v[a] + v[b] + y) & M64
-            v[d] = rotr(v[d] ^ v[a], 16)
-            v[c] = (v[c] + v[d]) & M64
-            v[b] = rotr(v[b] ^ v[c], 63)
-        for r in range(12):
-            s = SIGMA[r % 10]
-            G(0, 4, 8, 12, m[s[0]], m[s[1]])
-            G(1, 5, 9, 13, m[s[2]], m[s[3]])
-            G(2, 6, 10, 14, m[s[4]], m[s[5]])
-            G(3, 7, 11, 15, m[s[6]], m[s[7]])
-            G(0, 5, 10, 15, m[s[8]], m[s[9]])
-            G(1, 6, 11, 12, m[s[10]], m[s[11]])
-            G(2, 7, 8, 13, m[s[12]], m[s[13]])
-            G(3, 4, 9, 14, m[s[14]], m[s[15]])
-        h = [h[i] ^ v[i] ^ v[i + 8] for i in range(8)]
-    return struct.pack("<8Q", *h)[:outlen]
-
-
-def _param(digest, keylen=0, fanout=1, depth=1, leaf=0, node_offset=0, xof=0, node_depth=0, inner=0) -> bytes:
-    return struct.pack("<BBBBIIIBB", digest, keylen, fanout, depth, leaf, node_offset, xof, node_depth, inner) + bytes(46)
-
-
-def _py_blake2xb(outlen: int, msg: bytes, key: bytes) -> bytes:
-    """BLAKE2X paper section 2 / reference blake2xb.c"""
-    h0 = _py_blake2b(_param(64, len(key), 1, 1, 0, 0, outlen), key, msg, 64)
-    out = b""
-    i = 0
-    while len(out) < outlen:
-        want = min(64, outlen - len(out))
-        out += _py_blake2b(_param(want, 0, 0, 0, 64, i, outlen, 0, 64), b"", h0, want)
-        i += 1
-    return out
+from tests.golden.make_golden_seeded import M64, param_block as _param, py_blake2b as _py_blake2b, py_blake2xb as _py_blake2xb
 
 
 def test_blake2b_three_way(oracle):
@@ -99,14 +37,7 @@ def test_blake2xb_oracle_matches_python(oracle):
     assert oracle.blake2xb(128, b"m", b"")[:64] != oracle.blake2xb(64, b"m", b"")
 
 
-def _seal_prng_words(seed: bytes, count: int):
-    """seal::Blake2xbPRNG as a word stream (pure Python): 4096-byte blocks blake2xb(., 4096, counter_le64, seed)"""
-    out, ctr = [], 0
-    while len(out) < count:
-        blk = _py_blake2xb(4096, struct.pack("<Q", ctr), seed)
-        out += list(struct.unpack("<512Q", blk))
-        ctr += 1
-    return out
+from tests.golden.make_golden_seeded import seal_prng_words as _seal_prng_words  # noqa: E402
 
 
 @pytest.mark.parametrize("bits", [40, 60])
@@ -208,3 +139,39 @@ def test_product_expansion_rejects_malformed(oracle):
         pf.seal_ct_expand(good, 2 * n, data_primes)                              # another poly degree
     with pytest.raises(pf.PfError):
         pf.seal_ct_expand(good, n, data_primes[:-1])                             # another limb count
+
+
+def test_committed_golden_vectors(oracle):
+    """tests/golden/kat_seeded_v1.json (made by tests/golden/make_golden_seeded.py, pure Python): the oracle's BLAKE2Xb,
+    PRNG stream and sampler reproduce the committed vectors; so does the product's expansion (through a stream)"""
+    import json
+    from pathlib import Path
+    import prefhetch_b200 as pf
+    kat = json.loads((Path(__file__).resolve().parent / "golden" / "kat_seeded_v1.json").read_text())
+    for v in kat["blake2xb"]:
+        assert oracle.blake2xb(v["outlen"], bytes.fromhex(v["msg"]), bytes.fromhex(v["key"])).hex() == v["out"]
+    for v in kat["prng_words"]:
+        seed = bytes.fromhex(v["seed"])
+        blk0 = oracle.blake2xb(4096, struct.pack("<Q", 0), seed)
+        blk1 = oracle.blake2xb(4096, struct.pack("<Q", 1), seed)
+        w = list(struct.unpack("<1024Q", blk0 + blk1))
+        assert w[:4] == v["first4"] and w[511:514] == v["word511_512_513"]
+        assert hashlib.sha256(struct.pack("<1024Q", *w)).hexdigest() == v["sha256_first_1024"]
+    for v in kat["sample_poly_uniform"]:
+        n, primes, seed = v["n"], v["primes"], bytes.fromhex(v["seed"])
+        # the product: a seeded stream with c0 = 0 over these primes -> c1 of the expanded stream
+        L = len(primes)
+        hdr = bytearray(113)
+        hdr[0:8] = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0])
+        struct.pack_into("<Q", hdr, 8, 113 + L * n * 8 + 81)
+        struct.pack_into("<QQQ", hdr, 49, 2, n, L)
+        struct.pack_into("<d", hdr, 73, 1.0)
+        struct.pack_into("<Q", hdr, 81, 1)
+        hdr[89:97] = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0])
+        struct.pack_into("<QQ", hdr, 97, 16 + 8 + L * n * 8, L * n)
+        info = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0]) + struct.pack("<Q", 81) + b"\x01" + seed
+        full = pf.seal_ct_expand(bytes(hdr) + bytes(L * n * 8) + info, n, primes)
+        c1 = np.frombuffer(full[113 + L * n * 8:], dtype=np.uint64)
+        assert c1[:4].tolist() == v["first4"]
+        assert hashlib.sha256(c1.tobytes()).hexdigest() == v["sha256"]
+    assert kat["sample_poly_uniform"][1]["redraws"] > 10
