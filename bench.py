@@ -552,6 +552,7 @@ class StageGuard:
         self.partial = json.loads(json.dumps(line))     # a deep, serialisable copy
 
     def enter(self, stage, limit_s):
+        limit_s = float(os.environ.get("PF_BENCH_STAGE_LIMIT_S", limit_s))   # tests shorten it
         self.stage, self.deadline = stage, time.monotonic() + limit_s
 
     def leave(self):
@@ -1428,14 +1429,25 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import prefhetch_b200 as pf   # noqa: F401
-    from prefhetch_b200.build import build as build_lib
-    if rank == 0:
-        build_lib()
+    # PF_BENCH_DRYRUN=1 (tests/test_bench_dryrun.py): the control flow of this file on the CPU — gloo, a stub engine,
+    # no-op streams — to prove that every rank takes the same path through the collectives.  Measures nothing.
+    dry = os.environ.get("PF_BENCH_DRYRUN") == "1"
+    if dry:
+        from tests import bench_stub
+        sys.modules["prefhetch_b200"] = bench_stub.install(torch)
+        if os.environ.get("PF_BENCH_DRYRUN_NB"):
+            for c in CONFIGS.values():
+                c["nb"] = min(c["nb"], int(os.environ["PF_BENCH_DRYRUN_NB"]))
+            cfg["nb"] = min(cfg["nb"], int(os.environ["PF_BENCH_DRYRUN_NB"]))
+    else:
+        import prefhetch_b200 as pf   # noqa: F401
+        from prefhetch_b200.build import build as build_lib
+        if rank == 0:
+            build_lib()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev = torch.device("cpu") if dry else torch.device("cuda", local_rank)
     placement = pin_to_gpu_numa_node(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -1443,7 +1455,10 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         from datetime import timedelta
-        dist.init_process_group("nccl", device_id=dev, timeout=timedelta(minutes=40))   # the StageGuard fires long before
+        if dry:
+            dist.init_process_group("gloo", timeout=timedelta(minutes=5))
+        else:
+            dist.init_process_group("nccl", device_id=dev, timeout=timedelta(minutes=40))   # the StageGuard fires long before
         dist.barrier()
     comm = Comm(world, rank, local_rank, dev)
     grid = parse_grid(args.grid, world)
