@@ -1470,10 +1470,13 @@ def main():
     if rank == 0:                          # one poller per job: NVML queries take driver locks
         sampler.start()
     guard = StageGuard(rank, world)
-    state = {"strong": None}
+    state = {"strong": None, "configs4": None}
 
     def make_line(rec):
-        return build_line(args, cfg_name, cfg, world, weak, grid, rec, sampler.report(*rec["timed_window"]), placement, state["strong"])
+        line = build_line(args, cfg_name, cfg, world, weak, grid, rec, sampler.report(*rec["timed_window"]), placement, state["strong"])
+        if state["configs4"] is not None:
+            line["configs4"] = state["configs4"]
+        return line
 
     def progress(rec):
         if rank == 0:
@@ -1514,6 +1517,34 @@ def main():
                     "e2e_efficiency": (e2eN["value"] / (world * e2e1["value"])) if e2eN.get("value") and e2e1.get("value") else None}
         except Exception as ex:    # noqa: BLE001
             guard.abort("strong-scaling record (configs[2])", repr(ex))
+        guard.leave()
+
+    # BASELINE configs[4] (10M x 128, nlist 16384, batch of 256 encrypted queries) is specified on 8 GPUs: the default
+    # 8-GPU run records it as one more optional stage (N = 8192; the N = 16384 point of the sweep is a 1-GPU number in
+    # profiles/).  Last, bounded and guarded: whatever happens here, the headline and the strong record are already
+    # published.  PF_BENCH_EXTRAS=0 skips it.
+    if weak and world >= int(os.environ.get("PF_BENCH_EXTRAS_MIN_GPUS", "8")) and os.environ.get("PF_BENCH_EXTRAS", "1") != "0":
+        if rank == 0:
+            guard.publish(make_line(rec))
+        xname = "synth10m_nlist16384"
+        xcfg = dict(CONFIGS[xname])
+        xsteps = max(3, min(args.steps, 6))
+        xgrid = default_strong_grid(world)
+        guard.enter("configs[4] record (10M x 128, 256-query batches)", 480)
+        try:
+            rX = run_workload(args, xname, xcfg, comm, False, xgrid, xsteps, args.warmup, want_e2e=not args.no_e2e, tag="configs4 ",
+                              guard=guard)
+            if rank == 0:
+                state["configs4"] = {
+                    "config": bench_config(xname, xcfg, rX["L"], rX["Lr"], xcfg["nq"], world, False, grid=xgrid),
+                    "scaling": "strong (fixed 10M index)", "n_gpus": world, "value": rX["value"], "ms_per_step": rX["ms_per_step"],
+                    "steps": xsteps, "queries_per_s": rX["queries_per_s"], "slot_distances_per_s": rX["slot_distances_per_s"],
+                    "result_cts_per_step": rX["result_cts_per_step"], "phases_ms_per_step": rX["phases_ms_per_step"],
+                    "roofline": rX["roofline"], "db_gib_per_rank": rX["db_gib_per_rank"], "gather_verified": rX["gather_verified"],
+                    "e2e": rX.get("e2e"),
+                    "one_gpu_reference": "profiles/r2_bench_synth10m_n8192_1gpu.json: 25.4 ms/step, 394 M distances/s on one B200"}
+        except Exception as ex:    # noqa: BLE001
+            guard.abort("configs[4] record", repr(ex))
         guard.leave()
 
     guard.finish()

@@ -70,3 +70,12 @@ def test_optional_stage_failure_keeps_the_headline(inject):
     assert r.returncode == 0, r.stderr[-3000:]
     assert line is not None and line["value"] > 0 and line["n_gpus"] == 2
     assert line["aborted_stage"] is not None and "e2e" in line["aborted_stage"]["stage"]
+
+
+def test_configs4_record_stage():
+    """the 8-GPU default run records BASELINE configs[4] as a last optional stage (here triggered at 2 ranks)"""
+    r, line = _run(2, ["--no-strong"], {"PF_BENCH_EXTRAS_MIN_GPUS": "2"})
+    assert r.returncode == 0 and line is not None, r.stderr[-3000:]
+    c4 = line["configs4"]
+    assert c4["value"] > 0 and c4["config"]["workload"] == "synth10m_nlist16384" and c4["config"]["queries_per_step"] == 256
+    assert c4["gather_verified"]["ranks"] == 1 and line.get("aborted_stage") is None
