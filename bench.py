@@ -547,6 +547,11 @@ class StageGuard:
             pass
         self.th = threading.Thread(target=self._watch, daemon=True)
         self.th.start()
+        try:   # torchrun ends the surviving workers with SIGTERM when one of them dies (e.g. killed for memory)
+            import signal
+            signal.signal(signal.SIGTERM, lambda signum, frame: self._fire("SIGTERM (another worker of the job died?)"))
+        except ValueError:
+            pass   # not the main thread
 
     def publish(self, line):
         self.partial = json.loads(json.dumps(line))     # a deep, serialisable copy

@@ -224,6 +224,18 @@ def test_stage_guard_emits_the_published_line_when_a_stage_hangs(tmp_path):
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["value"] == 2.5 and "boom" in line["aborted_stage"]["why"]
+    # SIGTERM (torchrun tearing the job down): the published line still goes out
+    code4 = (
+        "import os, signal, sys, time; sys.path.insert(0, %r); import bench\n"
+        "g = bench.StageGuard(0, 1)\n"
+        "g.publish({'metric': 'm', 'value': 3.5})\n"
+        "g.enter('strong', 100)\n"
+        "os.kill(os.getpid(), signal.SIGTERM)\n"
+        "time.sleep(30)\n" % str(root))
+    r = subprocess.run([sys.executable, "-c", code4], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["value"] == 3.5 and "SIGTERM" in line["aborted_stage"]["why"]
     # nothing published yet: a non-zero exit code and no line
     code3 = (
         "import sys, time; sys.path.insert(0, %r); import bench\n"
