@@ -545,13 +545,22 @@ class StageGuard:
             self.abort_file.unlink()
         except OSError:
             pass
+        # torchrun ends the surviving workers with SIGTERM when one of them dies (e.g. killed for memory).  A Python
+        # signal handler only runs when the MAIN thread returns to the interpreter — not while it waits inside a
+        # collective — so the signal number is also written to a wake-up pipe that the watchdog thread polls.
+        self.sig_r = None
+        try:
+            import signal
+            r, w = os.pipe()
+            os.set_blocking(r, False)
+            os.set_blocking(w, False)
+            signal.set_wakeup_fd(w, warn_on_full_buffer=False)
+            signal.signal(signal.SIGTERM, lambda signum, frame: self._fire("SIGTERM (another worker of the job died?)"))
+            self.sig_r, self.sigterm = r, int(signal.SIGTERM)
+        except (ValueError, OSError):
+            pass   # not the main thread
         self.th = threading.Thread(target=self._watch, daemon=True)
         self.th.start()
-        try:   # torchrun ends the surviving workers with SIGTERM when one of them dies (e.g. killed for memory)
-            import signal
-            signal.signal(signal.SIGTERM, lambda signum, frame: self._fire("SIGTERM (another worker of the job died?)"))
-        except ValueError:
-            pass   # not the main thread
 
     def publish(self, line):
         self.partial = json.loads(json.dumps(line))     # a deep, serialisable copy
@@ -577,6 +586,12 @@ class StageGuard:
 
     def _watch(self):
         while not self.done.wait(0.25):
+            if self.sig_r is not None:
+                try:
+                    if self.sigterm in os.read(self.sig_r, 64):
+                        self._fire("SIGTERM (another worker of the job died?)")
+                except (BlockingIOError, OSError):
+                    pass
             if time.monotonic() > self.deadline:
                 self._fire(f"stage exceeded its time limit on rank {self.rank}")
             if self.abort_file.exists():

@@ -230,8 +230,9 @@ def test_stage_guard_emits_the_published_line_when_a_stage_hangs(tmp_path):
         "g = bench.StageGuard(0, 1)\n"
         "g.publish({'metric': 'm', 'value': 3.5})\n"
         "g.enter('strong', 100)\n"
-        "os.kill(os.getpid(), signal.SIGTERM)\n"
-        "time.sleep(30)\n" % str(root))
+        "import ctypes, threading\n"
+        "threading.Timer(0.5, lambda: os.kill(os.getpid(), signal.SIGTERM)).start()\n"
+        "ctypes.CDLL(None).sleep(30)\n" % str(root))   # the main thread sits in C, as it does inside a collective
     r = subprocess.run([sys.executable, "-c", code4], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stderr
     line = json.loads(r.stdout.strip().splitlines()[-1])
