@@ -1112,6 +1112,7 @@ int search_core(pf_engine *e, uint64_t q0, uint64_t nq, const u64 *d_cts, const 
                 size_t out_stride) {
     const int L = e->L, N = e->N;
     const size_t ctw = (size_t)2 * L * N;
+    if (!nq) return PF_OK; // an empty query range (a rank whose query group is empty): nothing to launch
     CK(e->s_rot.ensure_grow(nq * e->K * ctw * 8));
     u64 *rot = e->s_rot.as<u64>();
     int rc;

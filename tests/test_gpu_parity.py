@@ -602,14 +602,16 @@ def test_load_galois_keys_stream(pf, oracle):
 
 _VARIANTS = [{"PF_MAC_VARIANT": "0"}, {"PF_MAC_VARIANT": "4"}, {"PF_MAC_VARIANT": "5"}, {"PF_MAC_VARIANT": "6"},
              {"PF_NTT_FP": "0"}, {"PF_MS_INT": "1"}, {"PF_KS_NO_FUSED_PREP": "1"}, {"PF_MAC_NO_FPRED": "1"},
-             {"PF_KS_NO_FPRED": "1"}, {"PF_E2E_GROUPS": "1"}, {"PF_E2E_GROUPS": "7"}, {"PF_FULL_SCRATCH_MB": "3"}]
+             {"PF_KS_NO_FPRED": "1"}, {"PF_FULL_SCRATCH_MB": "3"}]
+# (the query-group count of a search — PF_E2E_GROUPS is read once per process — is exercised through
+# pf_search_set_groups in test_submit_collect_pipelined)
 
 
 @pytest.mark.parametrize("n,g,rl", [(8192, 8, 1), (16384, 16, 2)])
 def test_kernel_variants_bit_identical(pf, oracle, monkeypatch, n, g, rl):
     """every kept non-default kernel (environment switches of DESIGN.md) gives the bytes of the default path,
     which is itself checked against the oracle: MAC variants 0/4/5/6, integer NTT at N >= 8192, integer
-    mod-switch, un-fused mod-down prep, Barrett instead of FP64-assisted reductions, other group counts."""
+    mod-switch, un-fused mod-down prep, Barrett instead of FP64-assisted reductions, sub-batched result scratch."""
     d, nprobe, nq = 128, 3, 5
     primes, t = _params(n)
     lay = oracle.LayoutPlan(n, d, 1, g)
