@@ -234,15 +234,16 @@ size_t pf_ct_serialized_size(pf_engine *e);
  * result's SEAL stream (results have result_limbs limbs) */
 size_t pf_result_slot_size(pf_engine *e);
 size_t pf_result_serialized_size(pf_engine *e);
-/* Normalises one SEAL stream (16-byte SEALHeader + body) to compr_mode none: zlib-compressed streams are
- * inflated, uncompressed ones copied; zstd or corrupt input -> PF_ERR_FORMAT; too small a buffer ->
+/* Normalises one SEAL stream (16-byte SEALHeader + body) to compr_mode none: zlib- and zstd-compressed streams
+ * are inflated (zstd through libzstd.so.1, bound at run time: without it such a stream is a format error),
+ * uncompressed ones copied; corrupt input or an unknown compr_mode -> PF_ERR_FORMAT; too small a buffer ->
  * PF_ERR_CAPACITY with *written = bytes needed.  (What seal::Serialization::Load does before the members
  * are read; [EXT] SEAL 4.1 serialization.cpp.)  Needs no engine and no GPU. */
 int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t cap, size_t *written, size_t *consumed);
 /* Seeded ciphertexts (seal::Serializable<Ciphertext> of a symmetric-key Encryptor: c1 is replaced by the seed of
  * the PRNG that drew it; [EXT] SEAL 4.1 Ciphertext::save_members / expand_seed, Blake2xbPRNG,
  * sample_poly_uniform): writes the equivalent full stream (compr_mode none) of `in` — c1 re-created over the
- * given data primes — or a copy when `in` is not seeded; zlib input is inflated first.  pf_search_submit /
+ * given data primes — or a copy when `in` is not seeded; zlib / zstd input is inflated first.  pf_search_submit /
  * pf_search_lists_encrypted / pf_ct_deserialize accept seeded streams directly (expanded on the host before
  * the upload: a slow path like zlib).  PF_ERR_FORMAT for malformed input or a PRNG other than blake2xb;
  * PF_ERR_CAPACITY with *written = bytes needed.  Needs no engine and no GPU. */

@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     cu, _ = sources()
-    cmd = [NVCC, *FLAGS, "-o", str(LIB), *[str(c) for c in cu], "-lz"]  # zlib: SEAL compr_mode zlib streams
+    cmd = [NVCC, *FLAGS, "-o", str(LIB), *[str(c) for c in cu], "-lz", "-ldl"]  # zlib: SEAL compr_mode zlib streams; dl: libzstd.so.1 bound at run time
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = PKG / "build.log"
     log.write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -52,7 +52,7 @@ def build_variant(name: str, defines) -> Path:
     (select it with PF_LIB=<path>); used for kernel A/B measurements recorded in profiles/README.md"""
     out = PKG / f"libprefhetch_b200.{name}.so"
     cu, _ = sources()
-    cmd = [NVCC, *FLAGS, *defines, "-o", str(out), *[str(c) for c in cu], "-lz"]
+    cmd = [NVCC, *FLAGS, *defines, "-o", str(out), *[str(c) for c in cu], "-lz", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     (PKG / f"build.{name}.log").write_text(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode:

@@ -23,6 +23,7 @@
 #include "pf_blake2b.h"
 #include "pf_host_math.h"
 #include "pf_seal_prng.h"
+#include <dlfcn.h>
 #include <zlib.h>
 #include "pf_keyswitch.cuh"
 #include "pf_mac.cuh"
@@ -1272,21 +1273,106 @@ void write_ct_prefix(const pf_engine *e, uint8_t *p, int is_ntt, const uint64_t 
 }
 
 // returns 0 on success; data_off = offset of the words, nlimbs = coeff_modulus_size
-// SEAL streams saved with compr_mode_type::zlib: the 16-byte SEALHeader is followed by one zlib
-// (RFC 1950) stream holding what an uncompressed save would have written after its header; nested
-// objects inside are saved uncompressed [EXT: SEAL 4.1 serialization.cpp / util/ztools.cpp].  Inflates
-// into `out` as the equivalent compr_mode none stream.  Returns 0, 1 (not zlib-compressed, untouched), <0 error.
+// SEAL streams saved with compr_mode_type::zlib or ::zstd: the 16-byte SEALHeader is followed by one zlib
+// (RFC 1950) stream / one Zstandard frame holding what an uncompressed save would have written after its
+// header; nested objects inside are saved uncompressed [EXT: SEAL 4.1 serialization.cpp / util/ztools.cpp].
+// Inflates into `out` as the equivalent compr_mode none stream.  Returns 0, 1 (compr_mode none, untouched),
+// <0 error (-3: unknown mode, or zstd without libzstd.so.1 on this host).
 // `max_out` bounds the inflated size (header included): the streams come from clients, and a few KB of
 // deflate can expand a thousandfold — callers pass the size the object can legitimately have (-7 beyond
 // it).  Input and output are fed to zlib in chunks below its 32-bit avail_in / avail_out.
+// compr_mode_type::zstd (SEAL's default when built with it): the body is one Zstandard frame written by
+// ZSTD_compressStream2 [EXT: SEAL 4.1 util/ztools.cpp zstd_deflate_array_inplace].  The image ships the
+// runtime library without its header, so the five stable entry points of the streaming decoder (zstd.h,
+// stable since v1.3) are declared here and bound with dlopen on first use; without the library a zstd
+// stream is refused (-3) like any other unsupported mode.
+struct ZstdInBuffer {
+    const void *src;
+    size_t size, pos;
+};
+struct ZstdOutBuffer {
+    void *dst;
+    size_t size, pos;
+};
+struct ZstdApi {
+    void *(*create)() = nullptr;
+    size_t (*release)(void *) = nullptr;
+    size_t (*init)(void *) = nullptr;
+    size_t (*run)(void *, ZstdOutBuffer *, ZstdInBuffer *) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool ok = false;
+    ZstdApi() {
+        const char *forced = getenv("PF_ZSTD_LIB"); // tests: point at a missing file to exercise the refusal
+        void *lib = forced ? dlopen(forced, RTLD_NOW | RTLD_LOCAL) : nullptr;
+        if (!forced)
+            for (const char *name : {"libzstd.so.1", "libzstd.so"})
+                if ((lib = dlopen(name, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!lib) return;
+        create = reinterpret_cast<void *(*)()>(dlsym(lib, "ZSTD_createDStream"));
+        release = reinterpret_cast<size_t (*)(void *)>(dlsym(lib, "ZSTD_freeDStream"));
+        init = reinterpret_cast<size_t (*)(void *)>(dlsym(lib, "ZSTD_initDStream"));
+        run = reinterpret_cast<size_t (*)(void *, ZstdOutBuffer *, ZstdInBuffer *)>(dlsym(lib, "ZSTD_decompressStream"));
+        is_error = reinterpret_cast<unsigned (*)(size_t)>(dlsym(lib, "ZSTD_isError"));
+        ok = create && release && init && run && is_error;
+    }
+};
+const ZstdApi &zstd_api() {
+    static const ZstdApi api;
+    return api;
+}
+
+// body of a compr_mode zstd stream -> out (which already holds the 16 header bytes); same contract and
+// the same output ceiling as the zlib loop below
+int inflate_zstd_body(const uint8_t *body, size_t body_len, std::vector<uint8_t> &out, size_t max_out) {
+    const ZstdApi &z = zstd_api();
+    if (!z.ok) return -3;
+    struct DGuard {
+        const ZstdApi &z;
+        void *ds;
+        ~DGuard() {
+            if (ds) z.release(ds);
+        }
+    } g{z, z.create()};
+    if (!g.ds || z.is_error(z.init(g.ds))) return -5;
+    ZstdInBuffer in{body, body_len, 0};
+    constexpr size_t ZCHUNK = (size_t)1 << 30;
+    for (;;) {
+        const size_t have = out.size();
+        uint8_t probe = 0;
+        const bool at_cap = have >= max_out; // the object cannot be larger: one probe byte tells "ended" from "more"
+        const size_t grow = at_cap ? 1 : std::min(std::min(max_out - have, ZCHUNK), std::max<size_t>(1 << 16, body_len * 4));
+        if (!at_cap) out.resize(have + grow);
+        ZstdOutBuffer o{at_cap ? static_cast<void *>(&probe) : static_cast<void *>(out.data() + have), grow, 0};
+        const size_t r = z.run(g.ds, &o, &in);
+        if (z.is_error(r)) return -6;
+        if (at_cap && o.pos) return -7;
+        if (!at_cap) out.resize(have + o.pos);
+        if (r == 0) return 0;                                  // the frame is decoded and flushed
+        if (in.pos == in.size && o.pos < o.size) return -1;    // truncated: input exhausted, output not full
+    }
+}
+
 int inflate_seal_stream(const uint8_t *p, size_t len, std::vector<uint8_t> &out, size_t *consumed, size_t max_out) {
     if (len < 16 || p[0] != 0x5E || p[1] != 0xA1) return -2;
-    if (p[5] != 1) return 1;
+    if (p[5] == 0) return 1;
+    if (p[5] != 1 && p[5] != 2) return -3; // compr_mode_type: 0 none, 1 zlib, 2 zstd
     uint64_t total;
     memcpy(&total, p + 8, 8);
     if (total > len || total < 16) return -1;
     if (max_out < 16) return -7;
     out.assign(16, 0);
+    auto finish = [&]() {
+        memcpy(out.data(), p, 16);
+        out[5] = 0;
+        const uint64_t new_total = out.size();
+        memcpy(out.data() + 8, &new_total, 8);
+        if (consumed) *consumed = (size_t)total;
+        return 0;
+    };
+    if (p[5] == 2) {
+        const int zr = inflate_zstd_body(p + 16, (size_t)(total - 16), out, max_out);
+        return zr ? zr : finish();
+    }
     struct ZGuard {
         z_stream zs{};
         bool live = false;
@@ -1323,19 +1409,14 @@ int inflate_seal_stream(const uint8_t *p, size_t len, std::vector<uint8_t> &out,
         if (zr != Z_OK && zr != Z_BUF_ERROR) return -6;
         if (zs.avail_in == 0 && in_left == 0 && zs.avail_out != 0) return -1; // truncated
     }
-    memcpy(out.data(), p, 16);
-    out[5] = 0;
-    const uint64_t new_total = out.size();
-    memcpy(out.data() + 8, &new_total, 8);
-    if (consumed) *consumed = (size_t)total;
-    return 0;
+    return finish();
 }
 
 int parse_ct_prefix(const pf_engine *e, const uint8_t *p, size_t len, int *is_ntt, uint64_t parms_id[4],
                     uint64_t *nlimbs, size_t *total_out) {
     if (len < SEAL_CT_HEADER) return -1;
     if (p[0] != 0x5E || p[1] != 0xA1 || p[2] != 0x10 || p[3] != 4) return -2;
-    if (p[5] != 0) return -3; // zlib streams are inflated by the callers first; zstd is not available here
+    if (p[5] != 0) return -3; // compressed streams are inflated by the callers first
     uint64_t total, size, n, cms, words;
     memcpy(&total, p + 8, 8);
     if (total > len) return -1;
@@ -2087,7 +2168,7 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
         }
     }
     if (len < 16 + 32 + 8 || bytes[0] != 0x5E || bytes[1] != 0xA1 || bytes[5] != 0)
-        return e->fail(PF_ERR_FORMAT, "not a SEAL stream with compr_mode none or zlib");
+        return e->fail(PF_ERR_FORMAT, "not a SEAL stream (compr_mode none, zlib or zstd)");
     uint64_t total;
     memcpy(&total, bytes + 8, 8);
     if (total > len) return e->fail(PF_ERR_FORMAT, "truncated GaloisKeys stream");
@@ -2240,10 +2321,11 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
         for (size_t c = 0; c < ncts; c++) {
             const uint8_t *src = query_cts + ct_offsets[c];
             size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
-            if (len >= 16 && src[5] == 1) {
+            if (len >= 16 && src[5] != 0) {
                 inflated.emplace_back();
                 const int zr = inflate_seal_stream(src, len, inflated.back(), nullptr, SEAL_CT_HEADER + ctw * 8);
-                if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed zlib stream (code %d)", c, zr);
+                if (zr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: compr_mode %d is not supported on this host (none, zlib; zstd needs libzstd.so.1)", c, (int)src[5]);
+                if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed compressed stream (code %d)", c, zr);
                 src = inflated.back().data();
                 len = inflated.back().size();
             }
@@ -2262,7 +2344,6 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
             uint64_t cms;
             size_t total;
             const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
-            if (pr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu uses an unsupported compression (zstd); save with compr_mode_type::none or zlib", c);
             if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
             if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
         }

@@ -41,7 +41,7 @@ def parms_id(poly_degree: int, primes, plain_modulus: int):
 
 
 def seal_stream_inflate(blob) -> bytes:
-    """one SEAL stream -> its compr_mode none form (zlib streams inflated); needs no GPU"""
+    """one SEAL stream -> its compr_mode none form (zlib and zstd streams inflated); needs no GPU"""
     lib = _capi.load()
     b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
     need, used = C.c_size_t(), C.c_size_t()
@@ -57,7 +57,7 @@ def seal_stream_inflate(blob) -> bytes:
 
 
 def seal_ct_expand(blob, poly_degree: int, data_primes) -> bytes:
-    """a SEAL ciphertext stream (seeded and / or zlib) -> the equivalent full compr_mode none stream; needs no GPU
+    """a SEAL ciphertext stream (seeded and / or zlib / zstd) -> the equivalent full compr_mode none stream; needs no GPU
     (pf_seal_ct_expand)"""
     lib = _capi.load()
     b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))

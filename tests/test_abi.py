@@ -85,9 +85,80 @@ def test_seal_stream_inflate_matches_python_zlib(oracle):
     assert pf.seal_stream_inflate(z) == raw          # inflated, header rewritten to compr none + new size
     assert pf.seal_stream_inflate(raw) == raw        # uncompressed streams pass through
     assert pf.seal_stream_inflate(z + b"tail") == raw  # trailing bytes of a longer buffer are not consumed
-    for bad in (z[:-9], z[:5] + b"\x02" + z[6:], z[:40] + bytes(8) + z[48:], b"\x00" * 32):
-        with pytest.raises(pf.PfError):
+    for bad in (z[:-9], z[:5] + b"\x02" + z[6:], z[:5] + b"\x03" + z[6:], z[:40] + bytes(8) + z[48:], b"\x00" * 32):
+        with pytest.raises(pf.PfError):      # truncated; a zlib body labelled zstd; an unknown mode; corrupt; not a stream
             pf.seal_stream_inflate(bad)
+
+
+def test_seal_stream_inflate_zstd(oracle):
+    """compr_mode zstd (SEAL's default when built with it): the product binds libzstd.so.1 at run time and decodes
+    one-shot frames (content size in the header) and streamed frames (none, what SEAL's ZSTD_compressStream2 loop
+    writes); the frames come from pyarrow's own bundled libzstd.  Truncated, corrupt and over-long streams are
+    refused; the ceiling holds."""
+    import ctypes as C
+    import struct
+    import prefhetch_b200 as pf
+    from prefhetch_b200 import _capi
+    from tests.util import have_zstd, toy_params, zstd_stream
+    if not have_zstd():
+        pytest.skip("pyarrow without the zstd codec: no independent encoder to make vectors with")
+    n, primes, t = toy_params()
+    ctx = oracle.Context(n, primes, t)
+    rng = np.random.default_rng(2)
+    ct = np.stack([[rng.integers(0, q, size=n, dtype=np.uint64) for q in primes[:-1]] for _ in range(2)])
+    raw = ctx.ct_save(ct)
+    for streaming in (False, True):
+        z = zstd_stream(raw, streaming)
+        assert z[5] == 2 and z[16:20] == bytes([0x28, 0xB5, 0x2F, 0xFD])       # Zstandard frame magic
+        assert pf.seal_stream_inflate(z) == raw
+        assert pf.seal_stream_inflate(z + b"tail") == raw
+        # truncated; a broken frame magic; a block header claiming a reserved block type.  (Flipped payload bytes of a
+        # raw block go unnoticed, as in SEAL: it writes frames without the optional content checksum.)
+        hdr = 16 + (6 if streaming else 4 + 1 + {0: 1, 1: 2, 2: 4, 3: 8}[z[20] >> 6] + (0 if z[20] & 0x20 else 1))
+        for bad in (z[:-5], z[:16] + b"\x00" + z[17:], z[:hdr] + bytes([z[hdr] | 0x06]) + z[hdr + 1:]):
+            with pytest.raises(pf.PfError):
+                pf.seal_stream_inflate(bad)
+    # a zstd bomb: 8 MiB of zeros in a few hundred bytes
+    lib = _capi.load()
+    payload = bytes(8 << 20)
+    z = zstd_stream(bytes(16) + payload, streaming=True)
+    z = bytes([0x5E, 0xA1, 0x10, 4, 1, 2, 0, 0]) + z[8:]
+    assert len(z) < 4096
+    zin = np.frombuffer(z, dtype=np.uint8)
+    need, used = C.c_size_t(), C.c_size_t()
+    small = np.full(4096 + 64, 0xAB, dtype=np.uint8)
+    rc = lib.pf_seal_stream_inflate(zin.ctypes.data_as(C.c_void_p), zin.size, small.ctypes.data_as(C.c_void_p), 4096,
+                                    C.byref(need), C.byref(used))
+    assert rc == _capi.PF_ERR_CAPACITY and need.value == 16 + len(payload) and (small == 0xAB).all()
+    exact = np.zeros(16 + len(payload), dtype=np.uint8)
+    rc = lib.pf_seal_stream_inflate(zin.ctypes.data_as(C.c_void_p), zin.size, exact.ctypes.data_as(C.c_void_p), exact.size,
+                                    C.byref(need), C.byref(used))
+    assert rc == _capi.PF_OK and need.value == exact.size and used.value == len(z) and exact[5] == 0 and not exact[16:].any()
+
+
+def test_zstd_without_the_library_is_refused():
+    """no libzstd on the host (PF_ZSTD_LIB points at nothing): a zstd stream is a format error, not a crash, and
+    zlib / uncompressed streams still work.  Separate process: the binding is resolved once per process."""
+    import subprocess
+    import sys
+    from tests.util import have_zstd
+    if not have_zstd():
+        pytest.skip("pyarrow without the zstd codec")
+    code = (
+        "import struct, zlib\n"
+        "import prefhetch_b200 as pf\n"
+        "from tests.util import zstd_stream, zlib_stream\n"
+        "raw = bytes([0x5E, 0xA1, 0x10, 4, 1, 0, 0, 0]) + struct.pack('<Q', 16 + 4096) + bytes(range(256)) * 16\n"
+        "assert pf.seal_stream_inflate(zlib_stream(raw)) == raw\n"
+        "try:\n"
+        "    pf.seal_stream_inflate(zstd_stream(raw))\n"
+        "    print('accepted')\n"
+        "except pf.PfError as e:\n"
+        "    print('refused', e.code)\n")
+    import os
+    env = dict(os.environ, PF_ZSTD_LIB="/nonexistent/libzstd.so.1", PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env, cwd=str(ROOT))
+    assert r.returncode == 0 and r.stdout.strip().startswith("refused"), r.stdout + r.stderr
 
 
 def test_seal_stream_inflate_is_bounded():

@@ -353,7 +353,18 @@ def test_zlib_compressed_streams(pf, oracle):
     with pytest.raises(pf.PfError):
         eng.ct_deserialize(zparts[0][:-20])          # truncated deflate stream
     with pytest.raises(pf.PfError):
-        eng.ct_deserialize(zparts[0][:5] + b"\x02" + zparts[0][6:])   # zstd: not available
+        eng.ct_deserialize(zparts[0][:5] + b"\x02" + zparts[0][6:])   # a deflate body labelled zstd
+    from tests.util import have_zstd, zstd_stream
+    if have_zstd():     # compr_mode zstd, SEAL's default when built with it (libzstd.so.1 bound at run time)
+        sparts = [zstd_stream(bytes(blob[offs[i]:offs[i + 1]]), streaming=bool(i & 1)) for i in range(len(cts))]
+        sblob = np.frombuffer(b"".join(sparts), dtype=np.uint8)
+        soffs = np.concatenate([[0], np.cumsum([len(z) for z in sparts])]).astype(np.uint64)
+        comp = eng.coarseSearchEncrypted(sblob, soffs, idx)
+        assert comp.stats["nresults"] == len(want) and all(comp.result(r) == want[r] for r in range(len(want)))
+        got, is_ntt = eng.ct_deserialize(sparts[1])
+        assert np.array_equal(got, cts[1][0]) and not is_ntt
+        with pytest.raises(pf.PfError):
+            eng.ct_deserialize(sparts[0][:-20])      # truncated frame
     eng.close()
 
 
@@ -568,7 +579,7 @@ def test_encrypted_search_bench_shape(pf, oracle, rl):
 
 
 def test_load_galois_keys_stream(pf, oracle):
-    """pf_load_galois_keys: a SEAL GaloisKeys stream (compr_mode none and zlib) gives the same rotated query
+    """pf_load_galois_keys: a SEAL GaloisKeys stream (compr_mode none, zlib and zstd) gives the same rotated query
     set as the raw-word setter and the oracle; malformed streams are refused."""
     from tests.util import galois_keys_save, zlib_stream
     n, d, g = 2048, 128, 16
@@ -580,7 +591,8 @@ def test_load_galois_keys_stream(pf, oracle):
     q = np.random.default_rng(2).integers(0, 256, size=d)
     cts = cl.encrypt_query(q, 9)
     want = oracle.rotate_query_set(cl.ctx, cl.lay, cts, keys, False)
-    for stream in (blob, zlib_stream(blob)):
+    from tests.util import have_zstd, zstd_stream
+    for stream in (blob, zlib_stream(blob)) + ((zstd_stream(blob, streaming=True),) if have_zstd() else ()):
         eng, _, _ = _engine(pf, n, g=g)
         eng.load_galois_keys(stream)
         assert np.array_equal(eng.rotate_query_set(cts, False), want)

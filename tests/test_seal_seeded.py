@@ -9,7 +9,7 @@ import struct
 import numpy as np
 import pytest
 
-from tests.util import is_prime, ntt_primes, zlib_stream
+from tests.util import have_zstd, is_prime, ntt_primes, zlib_stream, zstd_stream
 
 from tests.golden.make_golden_seeded import M64, param_block as _param, py_blake2b as _py_blake2b, py_blake2xb as _py_blake2xb
 
@@ -116,6 +116,9 @@ def test_product_expansion_matches_oracle(oracle, n, bits):
     assert pf.seal_ct_expand(zlib_stream(seeded), n, data_primes) == full
     assert pf.seal_ct_expand(full, n, data_primes) == full                       # not seeded: passes through
     assert pf.seal_ct_expand(zlib_stream(full), n, data_primes) == full
+    if have_zstd():     # SEAL's default compr_mode when built with zstd
+        assert pf.seal_ct_expand(zstd_stream(seeded, streaming=True), n, data_primes) == full
+        assert pf.seal_ct_expand(zstd_stream(full), n, data_primes) == full
     assert pf.seal_ct_expand(seeded + b"next stream", n, data_primes) == full    # only its own bytes are consumed
 
 

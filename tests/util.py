@@ -160,3 +160,27 @@ def zlib_stream(raw: bytes) -> bytes:
     import zlib
     body = zlib.compress(raw[16:], 6)
     return raw[:5] + b"\x01" + raw[6:8] + struct.pack("<Q", 16 + len(body)) + body
+
+
+def have_zstd() -> bool:
+    try:
+        import pyarrow as pa
+        return bool(pa.Codec.is_available("zstd"))
+    except Exception:       # noqa: BLE001
+        return False
+
+
+def zstd_stream(raw: bytes, streaming: bool = False) -> bytes:
+    """what SEAL writes with compr_mode_type::zstd: header (compr_mode 2, new size) + one Zstandard frame of the
+    body.  The frames come from pyarrow's bundled libzstd: one-shot (content size in the frame header) or, like
+    SEAL's ZSTD_compressStream2 loop, streamed (no content size)."""
+    import struct
+    import pyarrow as pa
+    if streaming:
+        sink = pa.BufferOutputStream()
+        with pa.CompressedOutputStream(sink, "zstd") as z:
+            z.write(raw[16:])
+        body = sink.getvalue().to_pybytes()
+    else:
+        body = pa.compress(raw[16:], codec="zstd", asbytes=True)
+    return raw[:5] + b"\x02" + raw[6:8] + struct.pack("<Q", 16 + len(body)) + body
