@@ -354,17 +354,6 @@ def test_zlib_compressed_streams(pf, oracle):
         eng.ct_deserialize(zparts[0][:-20])          # truncated deflate stream
     with pytest.raises(pf.PfError):
         eng.ct_deserialize(zparts[0][:5] + b"\x02" + zparts[0][6:])   # a deflate body labelled zstd
-    from tests.util import have_zstd, zstd_stream
-    if have_zstd():     # compr_mode zstd, SEAL's default when built with it (libzstd.so.1 bound at run time)
-        sparts = [zstd_stream(bytes(blob[offs[i]:offs[i + 1]]), streaming=bool(i & 1)) for i in range(len(cts))]
-        sblob = np.frombuffer(b"".join(sparts), dtype=np.uint8)
-        soffs = np.concatenate([[0], np.cumsum([len(z) for z in sparts])]).astype(np.uint64)
-        comp = eng.coarseSearchEncrypted(sblob, soffs, idx)
-        assert comp.stats["nresults"] == len(want) and all(comp.result(r) == want[r] for r in range(len(want)))
-        got, is_ntt = eng.ct_deserialize(sparts[1])
-        assert np.array_equal(got, cts[1][0]) and not is_ntt
-        with pytest.raises(pf.PfError):
-            eng.ct_deserialize(sparts[0][:-20])      # truncated frame
     eng.close()
 
 
@@ -579,7 +568,7 @@ def test_encrypted_search_bench_shape(pf, oracle, rl):
 
 
 def test_load_galois_keys_stream(pf, oracle):
-    """pf_load_galois_keys: a SEAL GaloisKeys stream (compr_mode none, zlib and zstd) gives the same rotated query
+    """pf_load_galois_keys: a SEAL GaloisKeys stream (compr_mode none and zlib) gives the same rotated query
     set as the raw-word setter and the oracle; malformed streams are refused."""
     from tests.util import galois_keys_save, zlib_stream
     n, d, g = 2048, 128, 16
@@ -591,8 +580,7 @@ def test_load_galois_keys_stream(pf, oracle):
     q = np.random.default_rng(2).integers(0, 256, size=d)
     cts = cl.encrypt_query(q, 9)
     want = oracle.rotate_query_set(cl.ctx, cl.lay, cts, keys, False)
-    from tests.util import have_zstd, zstd_stream
-    for stream in (blob, zlib_stream(blob)) + ((zstd_stream(blob, streaming=True),) if have_zstd() else ()):
+    for stream in (blob, zlib_stream(blob)):
         eng, _, _ = _engine(pf, n, g=g)
         eng.load_galois_keys(stream)
         assert np.array_equal(eng.rotate_query_set(cts, False), want)
@@ -890,3 +878,42 @@ def test_cpp_handlers_end_to_end(pf, oracle, tmp_path):
     _write_cpp_case(tmp_path, cl, keys, d, n, g, rl, nprobe, query, t, primes, cent, offsets, ids, vecs, blob, offs, oidx)
     r = subprocess.run([str(exe), "--handlers", str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "handlers ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_zstd_compressed_streams(pf, oracle):
+    """SEAL compr_mode zstd on the request side (f-3; SEAL's default when built with zstd): query ciphertexts, single
+    ciphertexts and GaloisKeys saved as Zstandard frames (one-shot and streamed, made by pyarrow's bundled libzstd)
+    give the same bytes out as their uncompressed form.  The decoder itself is covered on the CPU (tests/test_abi.py)."""
+    from tests.util import galois_keys_save, have_zstd, zstd_stream
+    if not have_zstd():
+        pytest.skip("pyarrow without the zstd codec: no independent encoder to make vectors with")
+    n, g, d, nprobe = 2048, 16, 128, 3
+    base, query, cent, offsets, ids, vecs = _dataset(23, nb=3000, nlist=16, nq=3)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    keys = cl.step_keys()
+    cts = np.stack([cl.encrypt_query(q, 400 + i) for i, q in enumerate(query)])
+    blob, offs = cl.serialize_queries(cts)
+    sparts = [zstd_stream(bytes(blob[offs[i]:offs[i + 1]]), streaming=bool(i & 1)) for i in range(len(cts))]
+    sblob = np.frombuffer(b"".join(sparts), dtype=np.uint8)
+    soffs = np.concatenate([[0], np.cumsum([len(z) for z in sparts])]).astype(np.uint64)
+    eng, _, _ = _engine(pf, n, g=g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    kblob = galois_keys_save(cl.ctx, {cl.ctx.galois_elt(i + 1): k for i, k in enumerate(keys)})
+    eng.load_galois_keys(zstd_stream(kblob, streaming=True))
+    idx = eng.coarse_quantize(query, nprobe)
+    plain = eng.coarseSearchEncrypted(blob, offs, idx)
+    want = [plain.result(r) for r in range(plain.stats["nresults"])]
+    assert want
+    comp = eng.coarseSearchEncrypted(sblob, soffs, idx)
+    assert comp.stats["nresults"] == len(want) and all(comp.result(r) == want[r] for r in range(len(want)))
+    # the keys that came in as a zstd stream rotate like the raw-word ones
+    assert np.array_equal(eng.rotate_query_set(cts[0], False), oracle.rotate_query_set(cl.ctx, cl.lay, cts[0], keys, False))
+    got, is_ntt = eng.ct_deserialize(sparts[1])
+    assert np.array_equal(got, cts[1][0]) and not is_ntt
+    with pytest.raises(pf.PfError):
+        eng.ct_deserialize(sparts[0][:-20])          # truncated frame
+    with pytest.raises(pf.PfError):
+        eng.load_galois_keys(zstd_stream(kblob)[:-9])
+    eng.close()
