@@ -1,0 +1,114 @@
+// pf_client_check.cpp — drives prefhetch::Client (pf_client.hpp) on files, for tests/test_client.py (CPU: the
+// oracle plays the server) and tests/test_gpu_parity.py (the engine is the server).  No CUDA, no SEAL.
+//   pf_client_check keygen  <dir>   params.txt, seed.bin, queries.i64 -> sk.i8, galois_keys.bin,
+//                                   queries_seeded.bin/.off, queries_full.bin/.off, encode_probe.u64
+//   pf_client_check decrypt <dir>   + results.bin/.off, probed_sizes.u64, results_per_query.u64, labels.i64
+//                                   -> scores.f32, list_sizes.u64, nearest.i64, budget.txt
+// params.txt: dim N t m g nq nprobe coarse_probe k p_0 ... p_{k-1}
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <string>
+
+#include "pf_client.hpp"
+
+namespace {
+template <class T>
+std::vector<T> read_file(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<T> out(raw.size() / sizeof(T));
+    memcpy(out.data(), raw.data(), out.size() * sizeof(T));
+    return out;
+}
+template <class T>
+void write_file(const std::string &path, const std::vector<T> &v) {
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char *>(v.data()), (std::streamsize)(v.size() * sizeof(T)));
+    if (!f) throw std::runtime_error("cannot write " + path);
+}
+} // namespace
+
+int main(int argc, char **argv) {
+    if (argc != 3) {
+        fprintf(stderr, "usage: pf_client_check keygen|decrypt <dir>\n");
+        return 2;
+    }
+    try {
+        const std::string mode = argv[1], dir = std::string(argv[2]) + "/";
+        std::ifstream pf(dir + "params.txt");
+        uint64_t dim, N, t, m, g, nq, nprobe, coarse_probe, k;
+        if (!(pf >> dim >> N >> t >> m >> g >> nq >> nprobe >> coarse_probe >> k)) throw std::runtime_error("params.txt");
+        std::vector<prefhetch::u64> primes(k);
+        for (auto &p : primes)
+            if (!(pf >> p)) throw std::runtime_error("params.txt: primes");
+        const std::vector<uint8_t> seed_v = read_file<uint8_t>(dir + "seed.bin");
+        const std::vector<int64_t> queries = read_file<int64_t>(dir + "queries.i64");
+        if (seed_v.size() != 64 || queries.size() != nq * dim) throw std::runtime_error("seed.bin / queries.i64 size");
+        std::array<uint8_t, 64> seed;
+        memcpy(seed.data(), seed_v.data(), 64);
+        prefhetch::Client cl((uint32_t)dim, N, primes, t, (uint32_t)m, (uint32_t)g);
+        cl.generateKeys(seed);
+        if (mode == "keygen") {
+            write_file(dir + "sk.i8", std::vector<int8_t>(cl.secretKeyCoefficients()));
+            write_file(dir + "galois_keys.bin", cl.galoisKeys());
+            for (int seeded = 1; seeded >= 0; seeded--) {
+                std::vector<uint8_t> blob;
+                std::vector<uint64_t> offs{0};
+                for (uint64_t i = 0; i < nq; i++) {
+                    std::vector<prefhetch::u64> o;
+                    const std::vector<uint8_t> b = cl.compute_encrypted_coarse_query(queries.data() + i * dim, &o, seeded != 0);
+                    for (size_t a = 1; a < o.size(); a++) offs.push_back(blob.size() + o[a]);
+                    blob.insert(blob.end(), b.begin(), b.end());
+                }
+                const std::string stem = dir + (seeded ? "queries_seeded" : "queries_full");
+                write_file(stem + ".bin", blob);
+                write_file(stem + ".off", offs);
+            }
+            // BatchEncoder probe: encode(0, 1, 2, ...) so the test can compare the plaintext polynomial itself
+            std::vector<prefhetch::u64> ramp(N);
+            for (uint64_t i = 0; i < N; i++) ramp[i] = (i * 2654435761ULL + 17) % t;
+            const std::vector<prefhetch::u64> plain = cl.encode(ramp);
+            if (cl.decode(plain) != ramp) throw std::runtime_error("encode / decode do not invert each other");
+            write_file(dir + "encode_probe.u64", std::vector<uint64_t>(plain.begin(), plain.end()));
+            printf("ok keygen: %llu queries x %u ciphertexts, %u rotation keys, %u candidates per result\n", (unsigned long long)nq,
+                   cl.queryCiphertexts(), cl.rotations() - 1, cl.candidatesPerResult());
+            return 0;
+        }
+        if (mode == "decrypt") {
+            const std::vector<uint8_t> results = read_file<uint8_t>(dir + "results.bin");
+            const std::vector<uint64_t> roff = read_file<uint64_t>(dir + "results.off");
+            const std::vector<uint64_t> probed = read_file<uint64_t>(dir + "probed_sizes.u64");
+            const std::vector<uint64_t> rpq = read_file<uint64_t>(dir + "results_per_query.u64");
+            const std::vector<int64_t> labels = read_file<int64_t>(dir + "labels.i64");
+            if (probed.size() != nq * nprobe || rpq.size() != nq || roff.empty()) throw std::runtime_error("response envelope sizes");
+            std::vector<uint64_t> list_sizes;
+            int budget = 0;
+            const std::vector<float> scores = cl.decrypt_coarse_scores(
+                nq, (uint32_t)nprobe, queries.data(), probed.data(), rpq.data(),
+                [&](uint64_t r) {
+                    if (r + 1 >= roff.size() || roff[r + 1] > results.size() || roff[r] > roff[r + 1]) throw std::runtime_error("result index beyond the response");
+                    return std::pair<const uint8_t *, size_t>(results.data() + roff[r], (size_t)(roff[r + 1] - roff[r]));
+                },
+                &list_sizes, &budget);
+            if (labels.size() != scores.size()) throw std::runtime_error("labels and scores differ in length");
+            const auto nearest = prefhetch::Client::compute_nearest_coarse_vectors(scores, labels, list_sizes, coarse_probe);
+            std::vector<int64_t> top;
+            for (const auto &q : nearest)
+                for (uint64_t j = 0; j < coarse_probe; j++) top.push_back(q[j].idx);
+            write_file(dir + "scores.f32", scores);
+            write_file(dir + "list_sizes.u64", list_sizes);
+            write_file(dir + "nearest.i64", top);
+            std::ofstream(dir + "budget.txt") << budget << "\n";
+            printf("ok decrypt: %zu scores, min noise budget %d bits\n", scores.size(), budget);
+            return 0;
+        }
+        fprintf(stderr, "unknown mode %s\n", mode.c_str());
+        return 2;
+    } catch (const std::exception &ex) {
+        fprintf(stderr, "pf_client_check: %s\n", ex.what());
+        return 1;
+    }
+}

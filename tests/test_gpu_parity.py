@@ -917,3 +917,61 @@ def test_zstd_compressed_streams(pf, oracle):
     with pytest.raises(pf.PfError):
         eng.load_galois_keys(zstd_stream(kblob)[:-9])
     eng.close()
+
+
+@pytest.mark.parametrize("n,m,g,rl", [(2048, 1, 16, 1), (8192, 1, 8, 1), (2048, 2, 8, 0)])
+def test_cpp_client_round_trip(pf, tmp_path, n, m, g, rl):
+    """f-4, no oracle in the loop: the C++ client (host/pf_client.hpp) makes the secret key, the GaloisKeys stream and
+    seeded query ciphertexts; the engine loads them as any SEAL client's and answers; the client decrypts the response
+    into the reference's packed coarse scores — the exact squared L2 of every candidate of every probed list — and
+    ranks them like client_lib.cpp:122-156.  (The same client against the oracle as the server: tests/test_client.py.)"""
+    import subprocess
+    from pathlib import Path
+    from tests.test_client import write_case
+    exe = Path(__file__).resolve().parent.parent / "prefhetch_b200" / "host" / "pf_client_check"
+    assert exe.exists(), "run __graft_entry__.build() first"
+    d, nprobe, coarse_probe = 128, 3, 10
+    base, query, cent, offsets, ids, vecs = _dataset(61 + n, nb=2500, nlist=10, nq=3)
+    primes, t = _params(n)
+    write_case(tmp_path, n, primes, t, d, m, g, query.astype(np.int64), nprobe, coarse_probe, np.random.default_rng(n).bytes(64))
+    r = subprocess.run([str(exe), "keygen", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok keygen"), r.stdout + r.stderr
+    eng = pf.Engine(d, n, primes, t, m, g, result_limbs=rl)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    eng.load_galois_keys((tmp_path / "galois_keys.bin").read_bytes())
+    idx = eng.coarse_quantize(query, nprobe)
+    blob = np.fromfile(tmp_path / "queries_seeded.bin", dtype=np.uint8)
+    offs = np.fromfile(tmp_path / "queries_seeded.off", dtype=np.uint64)
+    res = eng.coarseSearchEncrypted(blob, offs, idx)
+    nres = res.stats["nresults"]
+    assert nres == int(res.results_per_query.sum()) and nres > 0
+    streams = [res.result(i) for i in range(nres)]
+    (tmp_path / "results.bin").write_bytes(b"".join(streams))
+    np.concatenate([[0], np.cumsum([len(s) for s in streams])]).astype(np.uint64).tofile(tmp_path / "results.off")
+    res.probed_sizes.astype(np.uint64).tofile(tmp_path / "probed_sizes.u64")
+    res.results_per_query.astype(np.uint64).tofile(tmp_path / "results_per_query.u64")
+    np.ascontiguousarray(res.labels, dtype=np.int64).tofile(tmp_path / "labels.i64")
+    r = subprocess.run([str(exe), "decrypt", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok decrypt"), r.stdout + r.stderr
+    scores = np.fromfile(tmp_path / "scores.f32", dtype=np.float32)
+    sizes = np.fromfile(tmp_path / "list_sizes.u64", dtype=np.uint64)
+    assert np.array_equal(sizes.astype(np.int64), res.list_sizes)
+    want, labels = [], []
+    for qi in range(len(query)):
+        for l in idx[qi]:
+            xs = vecs[offsets[l]:offsets[l + 1]].astype(np.int64)
+            want.append(((xs - query[qi].astype(np.int64)) ** 2).sum(1))
+            labels.append(ids[offsets[l]:offsets[l + 1]])
+    want, labels = np.concatenate(want), np.concatenate(labels)
+    assert np.array_equal(np.asarray(res.labels), labels)
+    assert np.array_equal(scores.astype(np.int64), want)
+    assert int((tmp_path / "budget.txt").read_text()) > 0
+    nearest = np.fromfile(tmp_path / "nearest.i64", dtype=np.int64).reshape(len(query), coarse_probe)
+    for qi in range(len(query)):
+        a, b = int(sizes[:qi].sum()), int(sizes[:qi + 1].sum())
+        assert np.array_equal(nearest[qi], labels[a:b][np.argsort(want[a:b], kind="stable")[:coarse_probe]])
+    # the same scores through the plaintext endpoint of the reference (Server::coarseSearch)
+    pdist, plabels, psizes = eng.coarseSearch(query, idx)
+    assert np.array_equal(np.asarray(pdist, dtype=np.float32), scores) and np.array_equal(plabels, labels)
+    eng.close()
