@@ -512,6 +512,28 @@ class Client {
         return scores;
     }
 
+    // ref: src/client/client_lib.cpp:49-81 — stage 1 on the client: squared L2 of every query to every centroid in
+    // the reference's arithmetic (float difference, squared in double by std::pow, accumulated into a float with a
+    // rounding per step), sorted ascending.  The reference's std::ranges::sort leaves the order of equal distances
+    // open; here ties keep centroid order, which is also what the engine's pf_coarse_quantize returns.
+    static std::vector<std::vector<DistanceIndexData>> sort_nearest_centroids(const float *precise_query, uint64_t nq, const float *centroids,
+                                                                             uint64_t nlist, uint32_t dim) {
+        std::vector<std::vector<DistanceIndexData>> nearest(nq);
+        for (uint64_t i = 0; i < nq; i++) {
+            nearest[i].reserve(nlist);
+            for (uint64_t j = 0; j < nlist; j++) {
+                float distance = 0.0f;
+                for (uint32_t k = 0; k < dim; k++) {
+                    const float diff = precise_query[i * dim + k] - centroids[j * dim + k];
+                    distance = (float)((double)distance + (double)diff * (double)diff);
+                }
+                nearest[i].push_back({distance, (int64_t)j});
+            }
+            std::stable_sort(nearest[i].begin(), nearest[i].end(), [](const DistanceIndexData &x, const DistanceIndexData &y) { return x.distance < y.distance; });
+        }
+        return nearest;
+    }
+
     // ref: src/client/client_lib.cpp:122-156 — unpack per query, sort ascending by distance; a query with fewer than
     // coarse_probe candidates is an error, as there
     static std::vector<std::vector<DistanceIndexData>> compute_nearest_coarse_vectors(const std::vector<float> &coarse_distance_scores,

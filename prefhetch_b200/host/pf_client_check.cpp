@@ -2,6 +2,7 @@
 // oracle plays the server) and tests/test_gpu_parity.py (the engine is the server).  No CUDA, no SEAL.
 //   pf_client_check keygen  <dir>   params.txt, seed.bin, queries.i64 -> sk.i8, galois_keys.bin,
 //                                   queries_seeded.bin/.off, queries_full.bin/.off, encode_probe.u64
+//   pf_client_check nearest <dir>   params.txt, queries.f32, centroids.f32 -> nearest_centroids.i64/.f32 [nq][nprobe]
 //   pf_client_check decrypt <dir>   + results.bin/.off, probed_sizes.u64, results_per_query.u64, labels.i64
 //                                   -> scores.f32, list_sizes.u64, nearest.i64, budget.txt
 // params.txt: dim N t m g nq nprobe coarse_probe k p_0 ... p_{k-1}
@@ -33,7 +34,7 @@ void write_file(const std::string &path, const std::vector<T> &v) {
 
 int main(int argc, char **argv) {
     if (argc != 3) {
-        fprintf(stderr, "usage: pf_client_check keygen|decrypt <dir>\n");
+        fprintf(stderr, "usage: pf_client_check keygen|nearest|decrypt <dir>\n");
         return 2;
     }
     try {
@@ -44,6 +45,22 @@ int main(int argc, char **argv) {
         std::vector<prefhetch::u64> primes(k);
         for (auto &p : primes)
             if (!(pf >> p)) throw std::runtime_error("params.txt: primes");
+        if (mode == "nearest") { // stage 1 needs no keys
+            const std::vector<float> qf = read_file<float>(dir + "queries.f32"), cf = read_file<float>(dir + "centroids.f32");
+            if (qf.size() != nq * dim || cf.size() % dim || cf.size() / dim < nprobe) throw std::runtime_error("queries.f32 / centroids.f32 size");
+            const auto nearest = prefhetch::Client::sort_nearest_centroids(qf.data(), nq, cf.data(), cf.size() / dim, (uint32_t)dim);
+            std::vector<int64_t> idx;
+            std::vector<float> dist;
+            for (const auto &q : nearest)
+                for (uint64_t j = 0; j < nprobe; j++) {
+                    idx.push_back(q[j].idx);
+                    dist.push_back(q[j].distance);
+                }
+            write_file(dir + "nearest_centroids.i64", idx);
+            write_file(dir + "nearest_centroids.f32", dist);
+            printf("ok nearest: %llu queries x %llu of %zu centroids\n", (unsigned long long)nq, (unsigned long long)nprobe, cf.size() / dim);
+            return 0;
+        }
         const std::vector<uint8_t> seed_v = read_file<uint8_t>(dir + "seed.bin");
         const std::vector<int64_t> queries = read_file<int64_t>(dir + "queries.i64");
         if (seed_v.size() != 64 || queries.size() != nq * dim) throw std::runtime_error("seed.bin / queries.i64 size");

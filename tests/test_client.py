@@ -224,6 +224,27 @@ def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d,
     assert r.returncode == 1
 
 
+def test_client_stage1_matches_reference_semantics(oracle, exe, tmp_path):
+    """sort_nearest_centroids (ref: client_lib.cpp:49-81) in the client library: the same probed lists and the same
+    float bits as the oracle's restatement (and hence as the engine's pf_coarse_quantize), ties by centroid order"""
+    rng = np.random.default_rng(4)
+    d, nlist, nq, nprobe = 128, 300, 9, 17
+    base, query, cent = sift_like(rng, 10, d, nlist, nq)
+    cent = (cent + rng.normal(0, 0.37, size=cent.shape)).astype(np.float32)
+    cent[7] = cent[3]                                   # an exact tie
+    query[0] = cent[3] + 1.0
+    write_case(tmp_path, 2048, [12289, 40961], 65537, d, 1, 16, np.zeros((nq, d), dtype=np.int64), nprobe, 1, bytes(64))
+    query.astype(np.float32).tofile(tmp_path / "queries.f32")
+    cent.tofile(tmp_path / "centroids.f32")
+    r = subprocess.run([str(exe), "nearest", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok nearest"), r.stdout + r.stderr
+    idx = np.fromfile(tmp_path / "nearest_centroids.i64", dtype=np.int64).reshape(nq, nprobe)
+    dist = np.fromfile(tmp_path / "nearest_centroids.f32", dtype=np.float32).reshape(nq, nprobe)
+    oidx, odist = oracle.coarse_quantize(query, cent, nprobe)
+    assert np.array_equal(idx, oidx) and np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
+    assert list(idx[0, :2]) == [3, 7]
+
+
 def test_client_rejects_bad_parameters(exe, tmp_path):
     n = 2048
     primes, t = ntt_primes(n, 40, 3) + ntt_primes(n, 41, 1), ntt_primes(n, 24, 1)[0]
