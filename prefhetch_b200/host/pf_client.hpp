@@ -554,6 +554,49 @@ class Client {
         return nearest;
     }
 
+    // ref: src/client/client_lib.cpp:189-209 — pair the precise scores with the ids they were asked for (the first
+    // coarse_probe of the sorted coarse vectors), sort ascending
+    static std::vector<std::vector<DistanceIndexData>> compute_nearest_precise_vectors(const float *precise_scores /*[nq][coarse_probe]*/,
+                                                                                      const std::vector<std::vector<DistanceIndexData>> &sorted_coarse_vectors,
+                                                                                      uint64_t coarse_probe) {
+        std::vector<std::vector<DistanceIndexData>> nearest(sorted_coarse_vectors.size());
+        for (size_t i = 0; i < nearest.size(); i++) {
+            if (sorted_coarse_vectors[i].size() < coarse_probe) throw std::runtime_error("fewer coarse vectors than COARSE_PROBE");
+            for (uint64_t j = 0; j < coarse_probe; j++) nearest[i].push_back({precise_scores[i * coarse_probe + j], sorted_coarse_vectors[i][j].idx});
+            std::stable_sort(nearest[i].begin(), nearest[i].end(), [](const DistanceIndexData &x, const DistanceIndexData &y) { return x.distance < y.distance; });
+        }
+        return nearest;
+    }
+
+    // ref: src/client/client_lib.cpp:246-330 benchmark_results — recall and MRR as the reference counts them: for each
+    // of the first K ground-truth neighbours, its rank k among the K returned ids counts towards recall@1/10/100 when
+    // k < 1/10/100 (divided by 1/10/100 * nq); MRR takes the first ground-truth neighbour only
+    struct BenchmarkResults {
+        float recall_1, recall_10, recall_100, mrr_1, mrr_10, mrr_100;
+    };
+    static BenchmarkResults benchmark_results(const int64_t *observed /*[nq][K]*/, uint64_t nq, uint64_t K, const int32_t *ground_truth /*[nq][gt_k]*/,
+                                              uint64_t gt_k) {
+        if (K > gt_k) throw std::runtime_error("K greater than nearest neigbours per query in ground truth dataset");
+        float mrr_1 = 0, mrr_10 = 0, mrr_100 = 0;
+        int r1 = 0, r10 = 0, r100 = 0;
+        for (uint64_t i = 0; i < nq; i++)
+            for (uint64_t j = 0; j < K; j++)
+                for (uint64_t k = 0; k < K; k++)
+                    if ((int64_t)ground_truth[i * gt_k + j] == observed[i * K + k]) {
+                        r1 += k < 1;
+                        r10 += k < 10;
+                        r100 += k < 100;
+                        if (j == 0) {
+                            if (k < 1) mrr_1 += 1.0f / static_cast<float>(k + 1);
+                            if (k < 10) mrr_10 += 1.0f / static_cast<float>(k + 1);
+                            if (k < 100) mrr_100 += 1.0f / static_cast<float>(k + 1);
+                        }
+                        break;
+                    }
+        const float n = (float)nq;
+        return {(float)r1 / (1 * n), (float)r10 / (10 * n), (float)r100 / (100 * n), mrr_1 / n, mrr_10 / n, mrr_100 / n};
+    }
+
   private:
     struct Level {                     // the data level with l primes
         detail::Big q_big, q_half;     // Q_l, floor(Q_l / 2)

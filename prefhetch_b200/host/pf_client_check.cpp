@@ -3,6 +3,8 @@
 //   pf_client_check keygen  <dir>   params.txt, seed.bin, queries.i64 -> sk.i8, galois_keys.bin,
 //                                   queries_seeded.bin/.off, queries_full.bin/.off, encode_probe.u64
 //   pf_client_check nearest <dir>   params.txt, queries.f32, centroids.f32 -> nearest_centroids.i64/.f32 [nq][nprobe]
+//   pf_client_check rank    <dir>   params.txt (K = coarse_probe field), precise_scores.f32 [nq][K], coarse_ids.i64 [nq][K],
+//                                   groundtruth.i32 [nq][gt_k] -> ranked.i64 [nq][K], benchmark.txt
 //   pf_client_check decrypt <dir>   + results.bin/.off, probed_sizes.u64, results_per_query.u64, labels.i64
 //                                   -> scores.f32, list_sizes.u64, nearest.i64, budget.txt
 // params.txt: dim N t m g nq nprobe coarse_probe k p_0 ... p_{k-1}
@@ -34,7 +36,7 @@ void write_file(const std::string &path, const std::vector<T> &v) {
 
 int main(int argc, char **argv) {
     if (argc != 3) {
-        fprintf(stderr, "usage: pf_client_check keygen|nearest|decrypt <dir>\n");
+        fprintf(stderr, "usage: pf_client_check keygen|nearest|rank|decrypt <dir>\n");
         return 2;
     }
     try {
@@ -59,6 +61,26 @@ int main(int argc, char **argv) {
             write_file(dir + "nearest_centroids.i64", idx);
             write_file(dir + "nearest_centroids.f32", dist);
             printf("ok nearest: %llu queries x %llu of %zu centroids\n", (unsigned long long)nq, (unsigned long long)nprobe, cf.size() / dim);
+            return 0;
+        }
+        if (mode == "rank") { // stage 3 + the reference's recall bookkeeping
+            const std::vector<float> ps = read_file<float>(dir + "precise_scores.f32");
+            const std::vector<int64_t> cid = read_file<int64_t>(dir + "coarse_ids.i64");
+            const std::vector<int32_t> gt = read_file<int32_t>(dir + "groundtruth.i32");
+            const uint64_t K = coarse_probe;
+            if (ps.size() != nq * K || cid.size() != nq * K || gt.size() % nq) throw std::runtime_error("rank inputs");
+            std::vector<std::vector<prefhetch::DistanceIndexData>> coarse(nq);
+            for (uint64_t i = 0; i < nq; i++)
+                for (uint64_t j = 0; j < K; j++) coarse[i].push_back({0.0f, cid[i * K + j]});
+            const auto ranked = prefhetch::Client::compute_nearest_precise_vectors(ps.data(), coarse, K);
+            std::vector<int64_t> out;
+            for (const auto &q : ranked)
+                for (const auto &e : q) out.push_back(e.idx);
+            write_file(dir + "ranked.i64", out);
+            const auto b = prefhetch::Client::benchmark_results(out.data(), nq, K, gt.data(), gt.size() / nq);
+            std::ofstream(dir + "benchmark.txt") << b.recall_1 << " " << b.recall_10 << " " << b.recall_100 << " " << b.mrr_1 << " " << b.mrr_10 << " "
+                                                 << b.mrr_100 << "\n";
+            printf("ok rank\n");
             return 0;
         }
         const std::vector<uint8_t> seed_v = read_file<uint8_t>(dir + "seed.bin");

@@ -245,6 +245,30 @@ def test_client_stage1_matches_reference_semantics(oracle, exe, tmp_path):
     assert list(idx[0, :2]) == [3, 7]
 
 
+def test_client_ranking_and_benchmark_bookkeeping(oracle, exe, tmp_path):
+    """compute_nearest_precise_vectors + benchmark_results (ref: client_lib.cpp:189-209, 246-330) against numpy and
+    the oracle's restatement of the reference's recall definition"""
+    rng = np.random.default_rng(12)
+    nq, K, gt_k = 7, 20, 100
+    gt = np.stack([rng.permutation(5000)[:gt_k] for _ in range(nq)]).astype(np.int32)
+    cid = np.stack([np.concatenate([rng.permutation(gt[i, :K])[:K - 6], 6000 + np.arange(6)]) for i in range(nq)]).astype(np.int64)
+    cid = np.stack([rng.permutation(row) for row in cid])
+    scores = rng.integers(0, 50, size=(nq, K)).astype(np.float32)      # many ties: order among equals is the input order
+    write_case(tmp_path, 2048, [12289, 40961], 65537, 128, 1, 16, np.zeros((nq, 128), dtype=np.int64), 1, K, bytes(64))
+    scores.tofile(tmp_path / "precise_scores.f32")
+    cid.tofile(tmp_path / "coarse_ids.i64")
+    gt.tofile(tmp_path / "groundtruth.i32")
+    r = subprocess.run([str(exe), "rank", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok rank"), r.stdout + r.stderr
+    ranked = np.fromfile(tmp_path / "ranked.i64", dtype=np.int64).reshape(nq, K)
+    want = np.stack([cid[i][np.argsort(scores[i], kind="stable")] for i in range(nq)])
+    assert np.array_equal(ranked, want)
+    got = [float(v) for v in (tmp_path / "benchmark.txt").read_text().split()]
+    ref = oracle.recall(ranked, gt)
+    assert abs(got[0] - ref["ref_recall_1"]) < 1e-6 and abs(got[1] - ref["ref_recall_10"]) < 1e-6 and abs(got[2] - ref["ref_recall_100"]) < 1e-6
+    assert abs(got[4] - ref["mrr_10"]) < 1e-6 and got[3] <= got[4] <= got[5]
+
+
 def test_client_rejects_bad_parameters(exe, tmp_path):
     n = 2048
     primes, t = ntt_primes(n, 40, 3) + ntt_primes(n, 41, 1), ntt_primes(n, 24, 1)[0]
