@@ -35,6 +35,7 @@
 #include "../csrc/pf_blake2b.h"
 #include "../csrc/pf_host_math.h"
 #include "../csrc/pf_seal_prng.h"
+#include "pf_json.hpp"
 
 namespace prefhetch {
 
@@ -178,6 +179,18 @@ inline void put_seal_header(std::vector<uint8_t> &o, u64 total) {
 
 constexpr size_t SEAL_CT_PREFIX = 113; // bytes before the words of a serialized ciphertext
 constexpr size_t SEAL_SEED_INFO = 81;  // UniformRandomGeneratorInfo stream: header 16 + type 1 + seed 64
+
+// The response of POST /coarsesearch-encrypted (pf_query_handlers.hpp) as the client holds it after parsing
+struct EncryptedCoarseResponse {
+    std::vector<uint8_t> ciphertexts;             // result streams in the server's aligned slots
+    std::vector<uint64_t> result_offsets;         // [nresults + 1]: start of every stream
+    uint64_t result_bytes = 0;                    // length of every stream
+    std::vector<uint64_t> results_per_query;      // [nq]
+    std::vector<int64_t> coarse_vector_indexes;   // labels, packed per query (as in Query.cc:53-61)
+    std::vector<uint64_t> list_sizes_per_query;   // [nq]
+    std::vector<uint64_t> probed_sizes;           // [nq][nprobe]
+    size_t nq = 0, nprobe = 0;
+};
 
 class Client {
   public:
@@ -510,6 +523,54 @@ class Client {
             if (results_per_query && r - r_begin != results_per_query[i]) throw std::runtime_error("response envelope does not match its result count");
         }
         return scores;
+    }
+
+    // ref: src/client/client_lib.cpp:83-120 get_coarse_scores, for the encrypted endpoint: the JSON request body
+    // (ciphertexts base64, as nlohmann would dump a string) ...
+    static std::string coarse_search_encrypted_request(const std::vector<uint8_t> &query_ciphertexts, const std::vector<u64> &ct_offsets,
+                                                       const int64_t *nearest_centroids_id, size_t nq, size_t nprobe) {
+        namespace json = handlers::json;
+        std::string out = "{\"queryCiphertexts\":\"";
+        out += json::base64_encode(query_ciphertexts.data(), query_ciphertexts.size());
+        out += "\",\"ctOffsets\":";
+        json::put_vector(out, ct_offsets.data(), ct_offsets.size());
+        out += ",\"nearestCentroidIndexes\":";
+        json::put_matrix(out, nearest_centroids_id, nq, nprobe);
+        out.push_back('}');
+        return out;
+    }
+    // ... and the response body
+    static EncryptedCoarseResponse parse_coarse_search_encrypted_response(std::string_view body) {
+        namespace json = handlers::json;
+        const auto resp = json::object(body);
+        EncryptedCoarseResponse r;
+        r.ciphertexts = json::base64_decode(json::string(json::at(resp, "resultCiphertexts")));
+        r.result_offsets = json::vector<uint64_t>(json::at(resp, "resultOffsets"));
+        r.result_bytes = json::number<uint64_t>(json::at(resp, "resultBytes"));
+        r.results_per_query = json::vector<uint64_t>(json::at(resp, "resultsPerQuery"));
+        r.coarse_vector_indexes = json::vector<int64_t>(json::at(resp, "coarseVectorIndexes"));
+        r.list_sizes_per_query = json::vector<uint64_t>(json::at(resp, "listSizesPerQuery"));
+        r.probed_sizes = json::matrix<uint64_t>(json::at(resp, "probedListSizes"), r.nq, r.nprobe);
+        if (r.results_per_query.size() != r.nq || r.list_sizes_per_query.size() != r.nq || r.result_offsets.empty())
+            throw std::runtime_error("coarsesearch-encrypted response: array lengths disagree");
+        for (size_t i = 0; i + 1 < r.result_offsets.size(); i++)
+            if (r.result_offsets[i] > r.ciphertexts.size() || r.result_bytes > r.ciphertexts.size() - r.result_offsets[i])
+                throw std::runtime_error("coarsesearch-encrypted response: result offsets beyond the ciphertext body");
+        return r;
+    }
+    // get_coarse_scores after the round trip: the three outputs of the reference's function, decrypted
+    void get_coarse_scores(const EncryptedCoarseResponse &r, const int64_t *queries /*[nq][dim]*/, std::vector<float> &coarse_scores,
+                           std::vector<int64_t> &coarse_vectors_idx, std::vector<uint64_t> &list_sizes_per_query, int *min_noise_budget = nullptr) const {
+        coarse_scores = decrypt_coarse_scores(
+            r.nq, (uint32_t)r.nprobe, queries, r.probed_sizes.data(), r.results_per_query.data(),
+            [&](uint64_t i) {
+                if (i + 1 >= r.result_offsets.size()) throw std::runtime_error("response holds fewer results than its envelope describes");
+                return std::pair<const uint8_t *, size_t>(r.ciphertexts.data() + r.result_offsets[i], (size_t)r.result_bytes);
+            },
+            &list_sizes_per_query, min_noise_budget);
+        coarse_vectors_idx = r.coarse_vector_indexes;
+        if (coarse_vectors_idx.size() != coarse_scores.size() || list_sizes_per_query != r.list_sizes_per_query)
+            throw std::runtime_error("response envelope disagrees with the decrypted candidates");
     }
 
     // ref: src/client/client_lib.cpp:49-81 — stage 1 on the client: squared L2 of every query to every centroid in

@@ -5,6 +5,8 @@
 //   pf_client_check nearest <dir>   params.txt, queries.f32, centroids.f32 -> nearest_centroids.i64/.f32 [nq][nprobe]
 //   pf_client_check rank    <dir>   params.txt (K = coarse_probe field), precise_scores.f32 [nq][K], coarse_ids.i64 [nq][K],
 //                                   groundtruth.i32 [nq][gt_k] -> ranked.i64 [nq][K], benchmark.txt
+//   pf_client_check request <dir>   queries_seeded.bin/.off, nearest_idx.i64 [nq][nprobe] -> request.json (the POST body)
+//   pf_client_check respond <dir>   response.json (the endpoint's answer) -> scores.f32, list_sizes.u64, labels_out.i64, budget.txt
 //   pf_client_check decrypt <dir>   + results.bin/.off, probed_sizes.u64, results_per_query.u64, labels.i64
 //                                   -> scores.f32, list_sizes.u64, nearest.i64, budget.txt
 // params.txt: dim N t m g nq nprobe coarse_probe k p_0 ... p_{k-1}
@@ -36,7 +38,7 @@ void write_file(const std::string &path, const std::vector<T> &v) {
 
 int main(int argc, char **argv) {
     if (argc != 3) {
-        fprintf(stderr, "usage: pf_client_check keygen|nearest|rank|decrypt <dir>\n");
+        fprintf(stderr, "usage: pf_client_check keygen|nearest|rank|request|respond|decrypt <dir>\n");
         return 2;
     }
     try {
@@ -114,6 +116,33 @@ int main(int argc, char **argv) {
             write_file(dir + "encode_probe.u64", std::vector<uint64_t>(plain.begin(), plain.end()));
             printf("ok keygen: %llu queries x %u ciphertexts, %u rotation keys, %u candidates per result\n", (unsigned long long)nq,
                    cl.queryCiphertexts(), cl.rotations() - 1, cl.candidatesPerResult());
+            return 0;
+        }
+        if (mode == "request") {
+            const std::vector<uint8_t> blob = read_file<uint8_t>(dir + "queries_seeded.bin");
+            const std::vector<uint64_t> offs64 = read_file<uint64_t>(dir + "queries_seeded.off");
+            const std::vector<int64_t> nearest = read_file<int64_t>(dir + "nearest_idx.i64");
+            if (nearest.size() != nq * nprobe) throw std::runtime_error("nearest_idx.i64 size");
+            const std::string body = prefhetch::Client::coarse_search_encrypted_request(blob, std::vector<prefhetch::u64>(offs64.begin(), offs64.end()),
+                                                                                       nearest.data(), nq, nprobe);
+            std::ofstream(dir + "request.json", std::ios::binary) << body;
+            printf("ok request: %zu bytes\n", body.size());
+            return 0;
+        }
+        if (mode == "respond") {
+            std::ifstream f(dir + "response.json", std::ios::binary);
+            const std::string body((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            const prefhetch::EncryptedCoarseResponse resp = prefhetch::Client::parse_coarse_search_encrypted_response(body);
+            std::vector<float> scores;
+            std::vector<int64_t> labels;
+            std::vector<uint64_t> list_sizes;
+            int budget = 0;
+            cl.get_coarse_scores(resp, queries.data(), scores, labels, list_sizes, &budget);
+            write_file(dir + "scores.f32", scores);
+            write_file(dir + "list_sizes.u64", list_sizes);
+            write_file(dir + "labels_out.i64", labels);
+            std::ofstream(dir + "budget.txt") << budget << "\n";
+            printf("ok respond: %zu scores, min noise budget %d bits\n", scores.size(), budget);
             return 0;
         }
         if (mode == "decrypt") {

@@ -213,6 +213,39 @@ def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d,
         assert np.array_equal(nearest[qi], lab[a:b][order])
         pos = b
 
+    # the same exchange through the JSON envelope of POST /coarsesearch-encrypted (pf_query_handlers.hpp): the request
+    # body the client writes is read back with Python's json, the response is written by Python's json in the
+    # engine's slot layout (128-byte aligned words: 15 pad bytes before every stream)
+    import base64
+    import json
+    idx.astype(np.int64).tofile(tmp_path / "nearest_idx.i64")
+    r = subprocess.run([str(exe), "request", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok request"), r.stdout + r.stderr
+    req = json.loads((tmp_path / "request.json").read_text())
+    assert sorted(req) == ["ctOffsets", "nearestCentroidIndexes", "queryCiphertexts"]
+    assert base64.b64decode(req["queryCiphertexts"]) == (tmp_path / "queries_seeded.bin").read_bytes()
+    assert req["ctOffsets"] == [int(v) for v in np.fromfile(tmp_path / "queries_seeded.off", dtype=np.uint64)]
+    assert req["nearestCentroidIndexes"] == idx.tolist()
+    slot = (15 + len(streams[0]) + 127) // 128 * 128
+    body = bytearray(slot * len(streams))
+    for i, st in enumerate(streams):
+        body[i * slot + 15:i * slot + 15 + len(st)] = st
+    resp = {"resultCiphertexts": base64.b64encode(bytes(body)).decode(), "resultOffsets": [i * slot + 15 for i in range(len(streams))] + [slot * len(streams)],
+            "resultBytes": len(streams[0]), "resultsPerQuery": [int(v) for v in rpq], "coarseVectorIndexes": [int(v) for v in lab],
+            "listSizesPerQuery": [int(v) for v in sizes], "probedListSizes": probed.astype(np.int64).tolist()}
+    (tmp_path / "response.json").write_text(json.dumps(resp, indent=1))      # whitespace the codec has to skip
+    for f in ("scores.f32", "list_sizes.u64", "budget.txt"):
+        (tmp_path / f).unlink()
+    r = subprocess.run([str(exe), "respond", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok respond"), r.stdout + r.stderr
+    assert np.array_equal(np.fromfile(tmp_path / "scores.f32", dtype=np.float32).astype(np.int64), want)
+    assert np.array_equal(np.fromfile(tmp_path / "labels_out.i64", dtype=np.int64), lab)
+    assert np.array_equal(np.fromfile(tmp_path / "list_sizes.u64", dtype=np.uint64), sizes)
+    resp["resultsPerQuery"][0] += 1                                          # an envelope that does not add up
+    (tmp_path / "response.json").write_text(json.dumps(resp))
+    r = subprocess.run([str(exe), "respond", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 1 and "pf_client_check:" in r.stderr
+
     # a response of another parameter set, a truncated one and a short envelope are refused
     bad = bytearray(streams[0])
     bad[16] ^= 1
