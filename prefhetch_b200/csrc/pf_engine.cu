@@ -1457,7 +1457,7 @@ int expand_seeded_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_
     if (in[0] != 0x5E || in[1] != 0xA1 || in[5] != 0) return -2;
     memcpy(&words, in + 16, 8);
     if (size != 2 || n != N || cms != (uint64_t)L) return -4;
-    if (words == 2 * n * cms) return 1; // both polynomials present
+    if (words == 2 * n * cms) return total == SEAL_CT_HEADER + words * 8 ? 1 : -4; // both polynomials present
     if (words != n * cms) return -4;
     const size_t half = (size_t)words * 8;
     if (total != SEAL_CT_HEADER + half + SEAL_PRNG_INFO_BYTES) return -4;
