@@ -537,7 +537,11 @@ class StageGuard:
 
     def __init__(self, rank, world, total_limit_s=1500.0):
         self.rank, self.world = rank, world
-        self.partial, self.stage, self.deadline = None, "setup + timed region", time.monotonic() + total_limit_s
+        # the driver gives one bench run 870 s (SCALE_r01.json: per_n_timeout_s) and then kills it: whatever the stages
+        # do, the line that exists by then is emitted BEFORE that (PF_BENCH_RUN_LIMIT_S, counted from here)
+        total_limit_s = min(total_limit_s, float(os.environ.get("PF_BENCH_RUN_LIMIT_S", 780.0)))
+        self.run_deadline = time.monotonic() + total_limit_s
+        self.partial, self.stage, self.deadline = None, "setup + timed region", self.run_deadline
         self.abort_file = Path(f"/tmp/pf_bench_abort_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}")
         self.shm_names = []
         self.done = threading.Event()
@@ -572,6 +576,10 @@ class StageGuard:
     def leave(self):
         self.stage, self.deadline = "between stages", time.monotonic() + 600.0
 
+    def remaining(self):
+        """seconds left of the whole run's allowance"""
+        return self.run_deadline - time.monotonic()
+
     def abort(self, stage, why):
         """called by the rank on which an optional stage raised: tells every rank's watchdog to fire"""
         log(f"[rank {self.rank}] stage '{stage}' failed: {why}")
@@ -592,8 +600,9 @@ class StageGuard:
                         self._fire("SIGTERM (another worker of the job died?)")
                 except (BlockingIOError, OSError):
                     pass
-            if time.monotonic() > self.deadline:
-                self._fire(f"stage exceeded its time limit on rank {self.rank}")
+            if time.monotonic() > min(self.deadline, self.run_deadline):
+                self._fire(f"stage exceeded its time limit on rank {self.rank}" if time.monotonic() <= self.run_deadline
+                           else f"the run reached its overall time allowance on rank {self.rank}")
             if self.abort_file.exists():
                 try:
                     why = self.abort_file.read_text()
@@ -1508,7 +1517,16 @@ def main():
     if rank == 0:
         guard.publish(make_line(rec))
 
-    if weak and not args.no_strong:
+    def time_for(stage, need_s):
+        """optional extras start only with enough of the run's allowance left; rank 0 decides for everybody"""
+        ok = comm.broadcast_object(guard.remaining() > need_s) if world > 1 else guard.remaining() > need_s
+        if not ok:
+            log(f"[rank {rank}] skipping {stage}: {guard.remaining():.0f}s of the run's allowance left, {need_s}s wanted")
+        return ok
+
+    if weak and not args.no_strong and not time_for("the strong-scaling record", 240):
+        state["strong"] = {"skipped": "not enough of the run's time allowance left (PF_BENCH_RUN_LIMIT_S)"}
+    elif weak and not args.no_strong:
         # BASELINE configs[2] (fixed 1M index, nlist 4096, nprobe 64): N GPUs, then rank 0 alone (its 1-GPU time).
         # An optional stage: a failure or a hang here still leaves the weak-scaling headline (StageGuard).
         scfg_name = "sift1m_nlist4096_nprobe64"
@@ -1543,7 +1561,10 @@ def main():
     # 8-GPU run records it as one more optional stage (N = 8192; the N = 16384 point of the sweep is a 1-GPU number in
     # profiles/).  Last, bounded and guarded: whatever happens here, the headline and the strong record are already
     # published.  PF_BENCH_EXTRAS=0 skips it.
-    if weak and world >= int(os.environ.get("PF_BENCH_EXTRAS_MIN_GPUS", "8")) and os.environ.get("PF_BENCH_EXTRAS", "1") != "0":
+    want_configs4 = weak and world >= int(os.environ.get("PF_BENCH_EXTRAS_MIN_GPUS", "8")) and os.environ.get("PF_BENCH_EXTRAS", "1") != "0"
+    if want_configs4 and not time_for("the configs[4] record", 300):
+        state["configs4"] = {"skipped": "not enough of the run's time allowance left (PF_BENCH_RUN_LIMIT_S)"}
+    elif want_configs4:
         if rank == 0:
             guard.publish(make_line(rec))
         xname = "synth10m_nlist16384"

@@ -79,3 +79,20 @@ def test_configs4_record_stage():
     c4 = line["configs4"]
     assert c4["value"] > 0 and c4["config"]["workload"] == "synth10m_nlist16384" and c4["config"]["queries_per_step"] == 256
     assert c4["gather_verified"]["ranks"] == 1 and line.get("aborted_stage") is None
+
+
+def test_extras_are_skipped_when_the_run_allowance_is_short():
+    """the driver kills a run after its per-N limit: with little of the allowance left the strong record and the
+    configs[4] record are skipped (rank 0 decides, every rank agrees) and the headline is emitted as usual"""
+    r, line = _run(2, [], {"PF_BENCH_EXTRAS_MIN_GPUS": "2", "PF_BENCH_RUN_LIMIT_S": "200"})
+    assert r.returncode == 0 and line is not None, r.stderr[-3000:]
+    assert line["value"] > 0 and line.get("aborted_stage") is None
+    assert "skipped" in line["strong"] and "skipped" in line["configs4"]
+
+
+def test_run_allowance_fires_the_guard():
+    """the overall allowance ends while an optional stage is still running: the published headline goes out"""
+    r, line = _run(2, ["--no-strong"], {"PF_BENCH_DRYRUN_INJECT": "hang:1", "PF_BENCH_STAGE_LIMIT_S": "600", "PF_BENCH_RUN_LIMIT_S": "60"},
+                   timeout=300)
+    assert r.returncode == 0 and line is not None, r.stderr[-3000:]
+    assert line["value"] > 0 and "allowance" in line["aborted_stage"]["why"]
