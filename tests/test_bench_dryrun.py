@@ -92,7 +92,7 @@ def test_extras_are_skipped_when_the_run_allowance_is_short():
 
 def test_run_allowance_fires_the_guard():
     """the overall allowance ends while an optional stage is still running: the published headline goes out"""
-    r, line = _run(2, ["--no-strong"], {"PF_BENCH_DRYRUN_INJECT": "hang:1", "PF_BENCH_STAGE_LIMIT_S": "600", "PF_BENCH_RUN_LIMIT_S": "60"},
+    r, line = _run(2, ["--no-strong"], {"PF_BENCH_DRYRUN_INJECT": "hang:1", "PF_BENCH_STAGE_LIMIT_S": "600", "PF_BENCH_RUN_LIMIT_S": "35"},
                    timeout=300)
     assert r.returncode == 0 and line is not None, r.stderr[-3000:]
     assert line["value"] > 0 and "allowance" in line["aborted_stage"]["why"]
