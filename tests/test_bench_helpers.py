@@ -106,3 +106,47 @@ def test_overlapping_mixture_has_recall_below_one(oracle):
     assert 0.3 < rm["recall_at_10"] < 0.98 and rm["reference_recall_10"] >= rm["recall_at_10"]
     full = bench.recall_metrics(_StubEngine(oracle, hard), hard, nprobe=64, dev="cpu", nq_r=8)
     assert full["recall_at_10"] == 1.0
+
+
+def test_bench_calls_bind_to_the_real_engine():
+    """bench.py's multi-GPU flow is dry-run on the CPU against tests/bench_stub.py; this keeps the stub honest: every
+    `eng.<method>(...)` call in bench.py binds to the signature of the REAL prefhetch_b200.Engine method (count and
+    keyword names), every attribute bench.py reads exists on the real class or is set in its __init__, and every stub
+    method has the real one's arity."""
+    import ast
+    import inspect
+    from pathlib import Path
+    from prefhetch_b200.engine import Engine
+    from tests import bench_stub
+    root = Path(__file__).resolve().parent.parent
+    tree = ast.parse((root / "bench.py").read_text())
+    init_src = inspect.getsource(Engine.__init__) + inspect.getsource(Engine.set_list_sizes)
+    calls, attrs = [], set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == "eng":
+            attrs.add(node.attr)
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and isinstance(node.func.value, ast.Name) \
+                and node.func.value.id == "eng":
+            calls.append((node.lineno, node.func.attr, len(node.args), [k.arg for k in node.keywords if k.arg]))
+    assert len(calls) > 40
+    for lineno, name, npos, kws in calls:
+        assert hasattr(Engine, name), f"bench.py:{lineno}: Engine has no method {name}"
+        inspect.signature(getattr(Engine, name)).bind(None, *([0] * npos), **{k: 0 for k in kws})
+    for a in attrs:
+        assert hasattr(Engine, a) or f"self.{a}" in init_src, f"bench.py reads eng.{a}, which the real Engine does not have"
+    stub = bench_stub.Engine
+    for name, fn in inspect.getmembers(stub, inspect.isfunction):
+        if name.startswith("_"):
+            continue
+        assert hasattr(Engine, name), f"stub method {name} does not exist on the real Engine"
+        def arity(f):
+            ps = [q for q in inspect.signature(f).parameters.values() if q.name != "self" and q.kind == q.POSITIONAL_OR_KEYWORD]
+            return sum(q.default is q.empty for q in ps), len(ps)
+        req_s, max_s = arity(fn)
+        req_r, max_r = arity(getattr(Engine, name))
+        assert req_s == req_r and max_s <= max_r, f"stub {name}: takes {req_s}..{max_s} arguments, the real method {req_r}..{max_r}"
+    # the constructor call of bench.py binds too
+    ctor = [n for n in ast.walk(tree) if isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr == "Engine"]
+    assert ctor
+    for n in ctor:
+        inspect.signature(Engine.__init__).bind(None, *([0] * len(n.args)), **{k.arg: 0 for k in n.keywords if k.arg})
