@@ -249,6 +249,13 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
  * PF_ERR_CAPACITY with *written = bytes needed.  Needs no engine and no GPU. */
 int pf_seal_ct_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *data_primes, uint32_t nprimes,
                       uint8_t *out, size_t cap, size_t *written, size_t *consumed);
+/* The same for keys: a SEAL GaloisKeys stream as seal::Serializable<GaloisKeys> saves it (every key ciphertext seeded:
+ * c1 replaced by its PRNG seed — what KeyGenerator::create_galois_keys returns without a destination; [EXT] SEAL 4.1
+ * keygenerator.cpp, kswitchkeys.h) -> the equivalent full compr_mode none stream over the k = L + 1 key primes;
+ * full streams are copied, zlib / zstd inflated.  pf_load_galois_keys accepts seeded streams directly; this entry
+ * point needs no engine and no GPU.  PF_ERR_CAPACITY with *written = bytes needed when out is too small. */
+int pf_seal_galois_keys_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *key_primes, uint32_t nprimes,
+                               uint8_t *out, size_t cap, size_t *written);
 /* SEAL parms_id of the BFV parameter set {poly_degree, coeff_primes[0..nprimes), plain_modulus}: BLAKE2b-256
  * of {scheme = 1, N, primes..., t} as 4 little-endian words (replaces EncryptionParameters::parms_id();
  * [EXT] SEAL 4.1 encryptionparams.cpp compute_parms_id).  Needs no engine and no GPU. */

@@ -1477,6 +1477,52 @@ int expand_seeded_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_
     return 0;
 }
 
+// Serializable<GaloisKeys> (what KeyGenerator::create_galois_keys returns without a destination, the usual way
+// keys travel): every key ciphertext — NTT form, all k primes — is saved seeded like a symmetric ciphertext, c1
+// replaced by the seed it expands from [EXT: SEAL 4.1 keygenerator.cpp generate_one_kswitch_key with save_seed,
+// kswitchkeys.h save_members].  `p` is an uncompressed KSwitchKeys stream; returns 1 when no key inside is seeded
+// (untouched), 0 when `out` holds the equivalent full stream, < 0 on malformed input (-8: a PRNG other than
+// blake2xb).  Output is bounded by twice the input.
+int expand_galois_keys_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_t *primes, uint32_t k, std::vector<uint8_t> &out) {
+    if (len < 16 + 32 + 8 || p[0] != 0x5E || p[1] != 0xA1 || p[5] != 0) return -2;
+    uint64_t total, dim1;
+    memcpy(&total, p + 8, 8);
+    if (total > len || total < 16 + 32 + 8) return -1;
+    memcpy(&dim1, p + 48, 8);
+    if (dim1 > N) return -4;
+    out.assign(p, p + 56);
+    size_t off = 56;
+    bool any = false;
+    std::vector<uint8_t> full;
+    for (uint64_t index = 0; index < dim1; index++) {
+        if (off + 8 > total) return -1;
+        uint64_t dim2;
+        memcpy(&dim2, p + off, 8);
+        out.insert(out.end(), p + off, p + off + 8);
+        off += 8;
+        if (dim2 > PF_MAX_PRIMES) return -4;
+        for (uint64_t j = 0; j < dim2; j++) {
+            if (off + 16 > total) return -1;
+            uint64_t ctotal;
+            memcpy(&ctotal, p + off + 8, 8);
+            if (ctotal < SEAL_CT_HEADER || ctotal > total - off) return -1;
+            const int er = expand_seeded_stream(p + off, (size_t)ctotal, N, primes, k, full);
+            if (er == -8) return -8;
+            if (er == 0) {
+                any = true;
+                out.insert(out.end(), full.begin(), full.end());
+            } else { // full already, or something the strict parser of the caller will name
+                out.insert(out.end(), p + off, p + off + ctotal);
+            }
+            off += (size_t)ctotal;
+        }
+    }
+    if (!any) return 1;
+    const uint64_t new_total = out.size();
+    memcpy(out.data() + 8, &new_total, 8);
+    return 0;
+}
+
 } // namespace
 
 // =============================================================================================
@@ -1516,6 +1562,40 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
     if (consumed) *consumed = used;
     if (!out || cap < plain.size()) return PF_ERR_CAPACITY;
     memcpy(out, plain.data(), plain.size());
+    return PF_OK;
+}
+
+int pf_seal_galois_keys_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *key_primes, uint32_t nprimes,
+                               uint8_t *out, size_t cap, size_t *written) {
+    if (!in || !written || !key_primes || nprimes < 2 || nprimes > PF_MAX_PRIMES) return PF_ERR_INVALID;
+    if (poly_degree < 2 || poly_degree > 32768 || (poly_degree & (poly_degree - 1))) return PF_ERR_INVALID;
+    for (uint32_t j = 0; j < nprimes; j++)
+        if (key_primes[j] < 2 || key_primes[j] >> 61) return PF_ERR_INVALID;
+    if (len < 16 || in[0] != 0x5E || in[1] != 0xA1) return PF_ERR_FORMAT;
+    const size_t key_bytes = (size_t)(nprimes - 1) * (SEAL_CT_HEADER + (size_t)2 * nprimes * poly_degree * 8);
+    const size_t bound = 16 + 32 + 8 + (size_t)poly_degree * 8 + (size_t)PF_MAX_GALOIS_KEYS * key_bytes;
+    std::vector<uint8_t> plain, expanded;
+    const uint8_t *src = in;
+    size_t slen = len;
+    const int zr = inflate_seal_stream(in, len, plain, nullptr, bound);
+    if (zr < 0) return PF_ERR_FORMAT;
+    if (zr == 0) {
+        src = plain.data();
+        slen = plain.size();
+    }
+    const int er = expand_galois_keys_stream(src, slen, poly_degree, key_primes, nprimes, expanded);
+    if (er < 0) return PF_ERR_FORMAT;
+    if (er == 0) {
+        src = expanded.data();
+        slen = expanded.size();
+    } else {
+        uint64_t total;
+        memcpy(&total, src + 8, 8);
+        slen = (size_t)total;
+    }
+    *written = slen;
+    if (!out || cap < slen) return PF_ERR_CAPACITY;
+    memcpy(out, src, slen);
     return PF_OK;
 }
 
@@ -2169,6 +2249,16 @@ int pf_load_galois_keys(pf_engine *e, const uint8_t *bytes, size_t len) {
     }
     if (len < 16 + 32 + 8 || bytes[0] != 0x5E || bytes[1] != 0xA1 || bytes[5] != 0)
         return e->fail(PF_ERR_FORMAT, "not a SEAL stream (compr_mode none, zlib or zstd)");
+    // Serializable<GaloisKeys>: seeded key ciphertexts are expanded first (host); a stream without any is parsed as it is
+    std::vector<uint8_t> expanded;
+    {
+        const int xr = expand_galois_keys_stream(bytes, len, (uint64_t)e->N, reinterpret_cast<const uint64_t *>(e->h_q.data()), (uint32_t)e->k, expanded);
+        if (xr == -8) return e->fail(PF_ERR_FORMAT, "GaloisKeys seeded with a PRNG other than blake2xb (unsupported)");
+        if (xr == 0) {
+            bytes = expanded.data();
+            len = expanded.size();
+        }
+    }
     uint64_t total;
     memcpy(&total, bytes + 8, 8);
     if (total > len) return e->fail(PF_ERR_FORMAT, "truncated GaloisKeys stream");

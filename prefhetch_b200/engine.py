@@ -75,6 +75,24 @@ def seal_ct_expand(blob, poly_degree: int, data_primes) -> bytes:
     return out.tobytes()
 
 
+def seal_galois_keys_expand(blob, poly_degree: int, key_primes) -> bytes:
+    """a SEAL GaloisKeys stream (Serializable<GaloisKeys>: seeded key ciphertexts; and / or zlib / zstd) -> the
+    equivalent full compr_mode none stream over the k key primes; needs no GPU (pf_seal_galois_keys_expand)"""
+    lib = _capi.load()
+    b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+    pr = (C.c_uint64 * len(key_primes))(*key_primes)
+    need = C.c_size_t()
+    rc = lib.pf_seal_galois_keys_expand(b.ctypes.data_as(C.c_void_p), b.size, poly_degree, pr, len(key_primes), None, 0, C.byref(need))
+    if rc != _capi.PF_ERR_CAPACITY:
+        raise PfError(rc, "malformed or unsupported SEAL GaloisKeys stream")
+    out = np.empty(need.value, dtype=np.uint8)
+    rc = lib.pf_seal_galois_keys_expand(b.ctypes.data_as(C.c_void_p), b.size, poly_degree, pr, len(key_primes),
+                                        out.ctypes.data_as(C.c_void_p), out.size, C.byref(need))
+    if rc:
+        raise PfError(rc, "malformed or unsupported SEAL GaloisKeys stream")
+    return out.tobytes()
+
+
 def batching_plain_modulus(n: int, bits: int) -> int:
     return _BATCHING[(n, bits)]
 

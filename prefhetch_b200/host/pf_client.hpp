@@ -371,17 +371,22 @@ class Client {
 
     // KeyGenerator::create_galois_keys(steps 1..R-1).save(): the keys the server's hoisted rotations use
     // (pf_load_galois_keys / Server::setGaloisKeys).  Slot of element e is (e - 1) / 2; N slots in the stream.
-    std::vector<uint8_t> galoisKeys() {
+    // seeded (the default, like Serializable<GaloisKeys>): every key ciphertext carries c0 and the seed of c1 — half
+    // the bytes; the draws are the same either way, so both forms of one key set describe the same keys.
+    std::vector<uint8_t> galoisKeys(bool seeded = true) {
         need_keys();
         const std::array<u64, 4> key_id = parmsId(k_);
-        const u64 key_words = (u64)2 * k_ * N_, key_stream = SEAL_CT_PREFIX + key_words * 8;
+        const u64 key_words = seeded ? (u64)k_ * N_ : (u64)2 * k_ * N_;
+        const u64 key_stream = SEAL_CT_PREFIX + key_words * 8 + (seeded ? SEAL_SEED_INFO : 0);
         std::vector<std::vector<uint8_t>> slot(N_);
         for (uint32_t step = 1; step < R_; step++) {
             const u64 elt = pfh::powmod(3, step, 2 * N_);
             std::vector<uint8_t> &o = slot[(elt - 1) >> 1];
             const std::vector<u64> rot = rotated_secret_key(elt);
             for (uint32_t J = 0; J < L_; J++) {
-                std::vector<u64> kw = encrypt_zero_key_level();
+                uint8_t seed[64];
+                prng_->generate(64, seed);
+                std::vector<u64> kw = encrypt_zero_key_level(seed);
                 // c0 limb J += (P mod q_J) * sigma_elt(s)
                 const u64 q = q_[J];
                 u64 *dst = kw.data() + (size_t)J * N_;
@@ -390,6 +395,11 @@ class Client {
                 put_ct_prefix(o, key_stream, key_id, true, k_, key_words);
                 const uint8_t *w = reinterpret_cast<const uint8_t *>(kw.data());
                 o.insert(o.end(), w, w + key_words * 8);
+                if (seeded) {
+                    detail::put_seal_header(o, SEAL_SEED_INFO);
+                    o.push_back(1); // prng_type::blake2xb
+                    o.insert(o.end(), seed, seed + 64);
+                }
             }
         }
         u64 total = 16 + 32 + 8;
@@ -693,11 +703,13 @@ class Client {
                    __builtin_popcount(x[4]) - __builtin_popcount(x[5]);
         }
     }
-    // encrypt_zero_symmetric at the key level: [2][k][N] NTT form, c1 = a uniform, c0 = -(a*s + e)
-    std::vector<u64> encrypt_zero_key_level() {
+    // encrypt_zero_symmetric at the key level: [2][k][N] NTT form, c1 = a = the expansion of `ct_seed` read as NTT
+    // form (what Ciphertext::expand_seed re-creates on the server), c0 = -(a*s + e)
+    std::vector<u64> encrypt_zero_key_level(const uint8_t ct_seed[64]) {
         std::vector<u64> out((size_t)2 * k_ * N_);
         u64 *c0 = out.data(), *c1 = c0 + (size_t)k_ * N_;
-        pfh::seal_sample_poly_uniform(*prng_, reinterpret_cast<const uint64_t *>(q_.data()), k_, N_, reinterpret_cast<uint64_t *>(c1));
+        pfh::SealBlake2xbPrng a_prng(ct_seed);
+        pfh::seal_sample_poly_uniform(a_prng, reinterpret_cast<const uint64_t *>(q_.data()), k_, N_, reinterpret_cast<uint64_t *>(c1));
         std::vector<int64_t> e(N_);
         sample_noise(e.data());
         for (uint32_t j = 0; j < k_; j++) {

@@ -1,6 +1,6 @@
 // pf_client_check.cpp — drives prefhetch::Client (pf_client.hpp) on files, for tests/test_client.py (CPU: the
 // oracle plays the server) and tests/test_gpu_parity.py (the engine is the server).  No CUDA, no SEAL.
-//   pf_client_check keygen  <dir>   params.txt, seed.bin, queries.i64 -> sk.i8, galois_keys.bin,
+//   pf_client_check keygen  <dir>   params.txt, seed.bin, queries.i64 -> sk.i8, galois_keys.bin (seeded), galois_keys_full.bin,
 //                                   queries_seeded.bin/.off, queries_full.bin/.off, encode_probe.u64
 //   pf_client_check nearest <dir>   params.txt, queries.f32, centroids.f32 -> nearest_centroids.i64/.f32 [nq][nprobe]
 //   pf_client_check rank    <dir>   params.txt (K = coarse_probe field), precise_scores.f32 [nq][K], coarse_ids.i64 [nq][K],
@@ -94,7 +94,12 @@ int main(int argc, char **argv) {
         cl.generateKeys(seed);
         if (mode == "keygen") {
             write_file(dir + "sk.i8", std::vector<int8_t>(cl.secretKeyCoefficients()));
-            write_file(dir + "galois_keys.bin", cl.galoisKeys());
+            {   // the same key set twice: seeded (what travels) and full, from two clients with the same seed
+                prefhetch::Client twin((uint32_t)dim, N, primes, t, (uint32_t)m, (uint32_t)g);
+                twin.generateKeys(seed);
+                write_file(dir + "galois_keys_full.bin", twin.galoisKeys(false));
+            }
+            write_file(dir + "galois_keys.bin", cl.galoisKeys(true));
             for (int seeded = 1; seeded >= 0; seeded--) {
                 std::vector<uint8_t> blob;
                 std::vector<uint64_t> offs{0};

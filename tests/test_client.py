@@ -169,8 +169,27 @@ def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d,
         fresh = ctx.decrypt(sk, ctx.encrypt(sk, ctx.encode(want), 5))[1]
         assert abs(min(budgets) - fresh) <= 2 and max(budgets) - min(budgets) <= 2, (budgets, fresh)
 
-    # GaloisKeys stream: the R-1 rotation keys, at the key level
-    keys_by_elt, pid = parse_galois_keys((tmp_path / "galois_keys.bin").read_bytes(), n, ctx.k, ctx.L)
+    # GaloisKeys: the stream that travels is seeded like Serializable<GaloisKeys> (every key ciphertext = c0 + the
+    # seed of c1); the product expands it (pf_seal_galois_keys_expand, also inside pf_load_galois_keys) to exactly the
+    # full stream a twin client with the same seed writes; compressed forms too
+    gk_seeded, gk_full = (tmp_path / "galois_keys.bin").read_bytes(), (tmp_path / "galois_keys_full.bin").read_bytes()
+    nkeys = lay.R - 1
+    assert len(gk_full) == 56 + 8 * n + nkeys * ctx.L * (113 + 2 * ctx.k * n * 8)
+    assert len(gk_seeded) == 56 + 8 * n + nkeys * ctx.L * (113 + ctx.k * n * 8 + 81)
+    assert pf.seal_galois_keys_expand(gk_seeded, n, primes) == gk_full
+    assert pf.seal_galois_keys_expand(gk_full, n, primes) == gk_full
+    from tests.util import have_zstd, zlib_stream, zstd_stream
+    assert pf.seal_galois_keys_expand(zlib_stream(gk_seeded), n, primes) == gk_full
+    if have_zstd():
+        assert pf.seal_galois_keys_expand(zstd_stream(gk_seeded, streaming=True), n, primes) == gk_full
+    if nkeys:
+        first = 56 + 8 * ((ctx.galois_elt(1) - 1) // 2 + 1)          # the first key ciphertext of step 1
+        with pytest.raises(pf.PfError):
+            pf.seal_galois_keys_expand(gk_seeded[:first + 113 + ctx.k * n * 8 + 16] + b"\x02" + gk_seeded[first + 113 + ctx.k * n * 8 + 17:], n, primes)  # shake256
+        with pytest.raises(pf.PfError):
+            pf.seal_galois_keys_expand(gk_seeded[:-40], n, primes)
+    # the R-1 rotation keys, at the key level
+    keys_by_elt, pid = parse_galois_keys(gk_full, n, ctx.k, ctx.L)
     assert pid == key_id and sorted(keys_by_elt) == sorted(ctx.galois_elt(r) for r in range(1, lay.R))
     keys = [keys_by_elt[ctx.galois_elt(r)] for r in range(1, lay.R)]
     # one key on its own: rotate_rows with it moves the slots by one

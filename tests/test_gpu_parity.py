@@ -939,7 +939,8 @@ def test_cpp_client_round_trip(pf, tmp_path, n, m, g, rl):
     eng = pf.Engine(d, n, primes, t, m, g, result_limbs=rl)
     eng.load_index(cent, offsets, ids, vecs)
     eng.set_list_sizes(offsets)
-    eng.load_galois_keys((tmp_path / "galois_keys.bin").read_bytes())
+    # the keys travel seeded (Serializable<GaloisKeys>); one case loads the full stream of the same key set instead
+    eng.load_galois_keys((tmp_path / ("galois_keys_full.bin" if m == 2 else "galois_keys.bin")).read_bytes())
     idx = eng.coarse_quantize(query, nprobe)
     blob = np.fromfile(tmp_path / "queries_seeded.bin", dtype=np.uint8)
     offs = np.fromfile(tmp_path / "queries_seeded.off", dtype=np.uint64)

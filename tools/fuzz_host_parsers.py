@@ -6,10 +6,10 @@ CPU only.  What it builds and runs (all outputs under /tmp):
                            and the Python reader (prefhetch_b200/faiss_io.py) must agree on accept / reject
   * host/pf_json.hpp + pf_client.hpp (pf_client_check): mutated response bodies of POST /coarsesearch-encrypted
   * the SEAL stream parsers of the engine library (pf_seal_stream_inflate, pf_seal_ct_expand: none / zlib / zstd /
-    seeded) through ctypes, the library rebuilt with -fsanitize=address and loaded via PF_LIB
+    seeded; pf_seal_galois_keys_expand: full / seeded GaloisKeys) through ctypes, the library rebuilt with -fsanitize=address and loaded via PF_LIB
 
     python tools/fuzz_host_parsers.py            # ~6 min, most of it the ASAN build of the library
-Round 2 result: 600 + 300 + 4000 mutants, no sanitizer report, no disagreement between the two FAISS readers."""
+Round 2 result: 600 + 300 + 4000 + 1000 mutants, no sanitizer report, no disagreement between the two FAISS readers."""
 from __future__ import annotations
 
 import json
@@ -134,6 +134,26 @@ def fuzz_seal_streams(n=4000) -> int:
             except pf.PfError:
                 pass
     print(f"seal streams: {n} mutants x 2 parsers clean under ASAN ({acc} accepted)")
+    # GaloisKeys streams (full and seeded, as the C++ client writes them) through pf_seal_galois_keys_expand
+    import tests.test_client as T
+    exe = HOST / "pf_client_check"
+    tmp = Path("/tmp/fuzz_gk_case")
+    shutil.rmtree(tmp, ignore_errors=True)
+    kn, kprimes, kt = 1024, T.ntt_primes(1024, 40, 2) + T.ntt_primes(1024, 41, 1), T.ntt_primes(1024, 20, 1)[0]
+    T.write_case(tmp, kn, kprimes, kt, 64, 1, 16, np.zeros((1, 64), dtype=np.int64), 1, 1, bytes(range(64)))
+    subprocess.run([str(exe), "keygen", str(tmp)], check=True, capture_output=True)
+    gks = [(tmp / "galois_keys.bin").read_bytes(), (tmp / "galois_keys_full.bin").read_bytes()]
+    gks += [zlib_stream(gks[0]), zstd_stream(gks[0], True)]
+    want, acc = gks[1], 0
+    for _ in range(n // 4):
+        b = mutate(R, R.choice(gks), 80 + 8 * kn)
+        try:
+            out = pf.seal_galois_keys_expand(b, kn, kprimes)
+            acc += 1
+            assert len(out) <= 2 * len(want) + 4096
+        except pf.PfError:
+            pass
+    print(f"galois keys: {n // 4} mutants clean under ASAN ({acc} accepted)")
     return 0
 
 
