@@ -249,6 +249,14 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
  * PF_ERR_CAPACITY with *written = bytes needed.  Needs no engine and no GPU. */
 int pf_seal_ct_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *data_primes, uint32_t nprimes,
                       uint8_t *out, size_t cap, size_t *written, size_t *consumed);
+/* pf_seal_ct_expand for a whole request: the ncts streams in[offsets[c], offsets[c+1]) -> their full compr_mode none
+ * forms back to back in out (out_offsets[ncts + 1]; PF_ERR_CAPACITY with out_offsets filled when out is too small).
+ * This is the slow path pf_search_submit runs on compressed / seeded queries: the streams are independent and are
+ * handled by up to `threads` host threads (0 = the engine's default: hardware threads, at most 16, env
+ * PF_HOST_THREADS).  Needs no engine and no GPU. */
+int pf_seal_ct_expand_batch(const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint64_t ncts, uint64_t poly_degree,
+                            const uint64_t *data_primes, uint32_t nprimes, uint8_t *out, size_t cap, uint64_t *out_offsets,
+                            uint32_t threads);
 /* The same for keys: a SEAL GaloisKeys stream as seal::Serializable<GaloisKeys> saves it (every key ciphertext seeded:
  * c1 replaced by its PRNG seed — what KeyGenerator::create_galois_keys returns without a destination; [EXT] SEAL 4.1
  * keygenerator.cpp, kswitchkeys.h) -> the equivalent full compr_mode none stream over the k = L + 1 key primes;

@@ -4,6 +4,6 @@ Host-side mirror of the reference's `Server` surface (ref: include/server/server
 the C ABI in include/prefhetch_b200.h.  All arithmetic runs in hand-written sm_100a CUDA kernels
 (prefhetch_b200/csrc); nothing here falls back to the CPU or touches oracle/.
 """
-from .engine import Engine, PfError, SearchResult, bfv_default_primes, batching_plain_modulus, parms_id, seal_stream_inflate, seal_ct_expand, seal_galois_keys_expand  # noqa: F401
+from .engine import Engine, PfError, SearchResult, bfv_default_primes, batching_plain_modulus, parms_id, seal_stream_inflate, seal_ct_expand, seal_galois_keys_expand, seal_ct_expand_batch  # noqa: F401
 
-__all__ = ["Engine", "PfError", "SearchResult", "bfv_default_primes", "batching_plain_modulus", "parms_id", "seal_stream_inflate", "seal_ct_expand", "seal_galois_keys_expand"]
+__all__ = ["Engine", "PfError", "SearchResult", "bfv_default_primes", "batching_plain_modulus", "parms_id", "seal_stream_inflate", "seal_ct_expand", "seal_galois_keys_expand", "seal_ct_expand_batch"]

@@ -15,6 +15,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/prefhetch_b200.h"
@@ -1477,6 +1478,84 @@ int expand_seeded_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_
     return 0;
 }
 
+// The request's slow path, for a whole batch: ciphertext c needs host work when its stream is compressed (zlib /
+// zstd) or seeded; out[c] receives its full compr_mode none form and stays EMPTY for streams that are already
+// that (the fast path uploads those straight from the caller's blob).  `out` is left empty altogether when no
+// stream needs work.  Streams are independent: the work is spread over up to `threads` host threads (Blake2xb
+// expansion of one N = 8192 ciphertext is ~0.3 ms of one core; a batch of 64 would otherwise cost more than the
+// GPU step).  Returns 0, or the error of the lowest failing index (codes of inflate_seal_stream /
+// expand_seeded_stream) in *err_index, *err_mode (the stream's compr_mode byte).
+int normalize_ct_streams(const uint8_t *blob, const uint64_t *offs, size_t ncts, uint64_t N, const uint64_t *primes, uint32_t L,
+                         std::vector<std::vector<uint8_t>> &out, unsigned threads, size_t *err_index, int *err_mode) {
+    const size_t full_bytes = SEAL_CT_HEADER + (size_t)2 * L * N * 8;
+    std::vector<size_t> work;
+    for (size_t c = 0; c < ncts; c++) {
+        const uint8_t *src = blob + offs[c];
+        const size_t len = (size_t)(offs[c + 1] - offs[c]);
+        bool slow = len >= 16 && src[5] != 0;
+        if (!slow && len >= SEAL_CT_HEADER) { // seeded: the DynArray holds one polynomial
+            uint64_t words;
+            memcpy(&words, src + 105, 8);
+            slow = words == N * L;
+        }
+        if (slow) work.push_back(c);
+    }
+    out.clear();
+    if (work.empty()) return 0;
+    out.resize(ncts);
+    std::vector<int> code(work.size(), 0);
+    auto run = [&](size_t first, size_t step) {
+        for (size_t w = first; w < work.size(); w += step) {
+            const size_t c = work[w];
+            const uint8_t *src = blob + offs[c];
+            size_t len = (size_t)(offs[c + 1] - offs[c]);
+            std::vector<uint8_t> plain, full;
+            if (src[5] != 0) {
+                const int zr = inflate_seal_stream(src, len, plain, nullptr, full_bytes);
+                if (zr) {
+                    code[w] = zr;
+                    continue;
+                }
+                src = plain.data();
+                len = plain.size();
+            }
+            const int er = len >= SEAL_CT_HEADER ? expand_seeded_stream(src, len, N, primes, L, full) : 1;
+            if (er == -8) {
+                code[w] = -8;
+                continue;
+            }
+            if (er == 0) out[c] = std::move(full);
+            else if (!plain.empty()) out[c] = std::move(plain); // inflated, not seeded (or malformed: the strict parser names it)
+            // else: looked seeded but is not expandable — left to the strict parser on the original bytes
+        }
+    };
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(threads ? threads : 1, work.size()));
+    if (nt == 1) {
+        run(0, 1);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < nt; t++) pool.emplace_back(run, t, nt);
+        run(0, nt);
+        for (auto &th : pool) th.join();
+    }
+    for (size_t w = 0; w < work.size(); w++)
+        if (code[w]) {
+            if (err_index) *err_index = work[w];
+            if (err_mode) *err_mode = (int)blob[offs[work[w]] + 5];
+            return code[w];
+        }
+    return 0;
+}
+
+unsigned host_threads() {
+    static const unsigned n = [] {
+        const char *env = getenv("PF_HOST_THREADS");
+        unsigned v = env ? (unsigned)atoi(env) : std::thread::hardware_concurrency();
+        return std::max(1u, std::min(v ? v : 1u, 16u));
+    }();
+    return n;
+}
+
 // Serializable<GaloisKeys> (what KeyGenerator::create_galois_keys returns without a destination, the usual way
 // keys travel): every key ciphertext — NTT form, all k primes — is saved seeded like a symmetric ciphertext, c1
 // replaced by the seed it expands from [EXT: SEAL 4.1 keygenerator.cpp generate_one_kswitch_key with save_seed,
@@ -1563,6 +1642,38 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
     if (!out || cap < plain.size()) return PF_ERR_CAPACITY;
     memcpy(out, plain.data(), plain.size());
     return PF_OK;
+}
+
+int pf_seal_ct_expand_batch(const uint8_t *in, size_t in_bytes, const uint64_t *offsets, uint64_t ncts, uint64_t poly_degree,
+                            const uint64_t *data_primes, uint32_t nprimes, uint8_t *out, size_t cap, uint64_t *out_offsets,
+                            uint32_t threads) {
+    if (!in || !offsets || !out_offsets || !data_primes || !nprimes || nprimes > PF_MAX_PRIMES) return PF_ERR_INVALID;
+    if (poly_degree < 2 || poly_degree > 32768 || (poly_degree & (poly_degree - 1))) return PF_ERR_INVALID;
+    for (uint32_t j = 0; j < nprimes; j++)
+        if (data_primes[j] < 2 || data_primes[j] >> 61) return PF_ERR_INVALID;
+    for (uint64_t c = 0; c < ncts; c++)
+        if (offsets[c] > offsets[c + 1] || offsets[c + 1] > in_bytes) return PF_ERR_INVALID;
+    std::vector<std::vector<uint8_t>> norm;
+    const int nr = normalize_ct_streams(in, offsets, (size_t)ncts, poly_degree, data_primes, nprimes, norm, threads ? threads : host_threads(), nullptr, nullptr);
+    if (nr) return PF_ERR_FORMAT;
+    size_t pos = 0;
+    out_offsets[0] = 0;
+    for (uint64_t c = 0; c < ncts; c++) {
+        const bool n = !norm.empty() && !norm[c].empty();
+        const uint8_t *src = n ? norm[c].data() : in + offsets[c];
+        size_t len = n ? norm[c].size() : (size_t)(offsets[c + 1] - offsets[c]);
+        if (!n) { // an untouched stream: only its own bytes
+            uint64_t total;
+            if (len < 16 || src[0] != 0x5E || src[1] != 0xA1) return PF_ERR_FORMAT;
+            memcpy(&total, src + 8, 8);
+            if (total > len || total < 16) return PF_ERR_FORMAT;
+            len = (size_t)total;
+        }
+        if (out && pos + len <= cap) memcpy(out + pos, src, len);
+        pos += len;
+        out_offsets[c + 1] = pos;
+    }
+    return (!out || pos > cap) ? PF_ERR_CAPACITY : PF_OK;
 }
 
 int pf_seal_galois_keys_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *key_primes, uint32_t nprimes,
@@ -2405,30 +2516,20 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
     CK(fl.qcts.ensure_grow(std::max<size_t>(8, ncts * ctw * 8)));
     uint64_t parms_id[4] = {0, 0, 0, 0};
     std::vector<const uint8_t *> ct_src(ncts);
-    std::vector<std::vector<uint8_t>> inflated; // zlib-compressed queries (slow path: inflated on the host)
+    std::vector<std::vector<uint8_t>> inflated; // full form of compressed / seeded queries (slow path, host threads); empty = none
     {
         HostTick ht("parse_queries");
+        size_t bad = 0;
+        int bad_mode = 0;
+        const int nr = normalize_ct_streams(query_cts, ct_offsets, ncts, (uint64_t)N, reinterpret_cast<const uint64_t *>(e->h_q.data()), (uint32_t)L,
+                                            inflated, host_threads(), &bad, &bad_mode);
+        if (nr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: compr_mode %d is not supported on this host (none, zlib; zstd needs libzstd.so.1)", bad, bad_mode);
+        if (nr == -8) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is seeded with a PRNG other than blake2xb (unsupported)", bad);
+        if (nr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed compressed stream (code %d)", bad, nr);
         for (size_t c = 0; c < ncts; c++) {
-            const uint8_t *src = query_cts + ct_offsets[c];
-            size_t len = (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
-            if (len >= 16 && src[5] != 0) {
-                inflated.emplace_back();
-                const int zr = inflate_seal_stream(src, len, inflated.back(), nullptr, SEAL_CT_HEADER + ctw * 8);
-                if (zr == -3) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: compr_mode %d is not supported on this host (none, zlib; zstd needs libzstd.so.1)", c, (int)src[5]);
-                if (zr) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu: malformed compressed stream (code %d)", c, zr);
-                src = inflated.back().data();
-                len = inflated.back().size();
-            }
-            if (len >= SEAL_CT_HEADER && src[5] == 0) { // seeded stream: c1 re-created from its PRNG seed (host, slow path)
-                std::vector<uint8_t> full;
-                const int er = expand_seeded_stream(src, len, (uint64_t)N, reinterpret_cast<const uint64_t *>(e->h_q.data()), (uint32_t)L, full);
-                if (er == -8) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is seeded with a PRNG other than blake2xb (unsupported)", c);
-                if (er == 0) {
-                    inflated.emplace_back(std::move(full));
-                    src = inflated.back().data();
-                    len = inflated.back().size();
-                }
-            }
+            const bool norm = !inflated.empty() && !inflated[c].empty();
+            const uint8_t *src = norm ? inflated[c].data() : query_cts + ct_offsets[c];
+            const size_t len = norm ? inflated[c].size() : (size_t)(ct_offsets[c + 1] - ct_offsets[c]);
             ct_src[c] = src;
             int is_ntt;
             uint64_t cms;

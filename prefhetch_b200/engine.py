@@ -75,6 +75,27 @@ def seal_ct_expand(blob, poly_degree: int, data_primes) -> bytes:
     return out.tobytes()
 
 
+def seal_ct_expand_batch(blob, offsets, poly_degree: int, data_primes, threads: int = 0):
+    """every stream of a request (seeded and / or compressed) -> (full compr_mode none streams back to back, offsets);
+    the host slow path of the search calls, multi-threaded; needs no GPU (pf_seal_ct_expand_batch)"""
+    lib = _capi.load()
+    b = np.ascontiguousarray(np.frombuffer(blob, dtype=np.uint8))
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ncts = len(offs) - 1
+    pr = (C.c_uint64 * len(data_primes))(*data_primes)
+    out_offs = np.zeros(ncts + 1, dtype=np.uint64)
+    rc = lib.pf_seal_ct_expand_batch(b.ctypes.data_as(C.c_void_p), b.size, _ptr(offs, U64P), ncts, poly_degree, pr, len(data_primes),
+                                     None, 0, _ptr(out_offs, U64P), threads)
+    if rc not in (_capi.PF_OK, _capi.PF_ERR_CAPACITY):
+        raise PfError(rc, "malformed or unsupported SEAL ciphertext stream in the batch")
+    out = np.empty(max(1, int(out_offs[-1])), dtype=np.uint8)
+    rc = lib.pf_seal_ct_expand_batch(b.ctypes.data_as(C.c_void_p), b.size, _ptr(offs, U64P), ncts, poly_degree, pr, len(data_primes),
+                                     out.ctypes.data_as(C.c_void_p), out.size, _ptr(out_offs, U64P), threads)
+    if rc:
+        raise PfError(rc, "malformed or unsupported SEAL ciphertext stream in the batch")
+    return out[:int(out_offs[-1])].tobytes(), out_offs
+
+
 def seal_galois_keys_expand(blob, poly_degree: int, key_primes) -> bytes:
     """a SEAL GaloisKeys stream (Serializable<GaloisKeys>: seeded key ciphertexts; and / or zlib / zstd) -> the
     equivalent full compr_mode none stream over the k key primes; needs no GPU (pf_seal_galois_keys_expand)"""

@@ -178,3 +178,57 @@ def test_committed_golden_vectors(oracle):
         assert c1[:4].tolist() == v["first4"]
         assert hashlib.sha256(c1.tobytes()).hexdigest() == v["sha256"]
     assert kat["sample_poly_uniform"][1]["redraws"] > 10
+
+
+def test_batch_expansion_is_the_per_stream_expansion(oracle):
+    """pf_seal_ct_expand_batch — the slow path of the search calls for a whole request, spread over host threads —
+    returns exactly what pf_seal_ct_expand returns stream by stream, for any mix of full / seeded / zlib / zstd streams
+    and any thread count; untouched streams are copied; one bad stream fails the batch"""
+    import time
+    import prefhetch_b200 as pf
+    n = 4096
+    primes, t = ntt_primes(n, 40, 3) + ntt_primes(n, 41, 1), ntt_primes(n, 24, 1)[0]
+    ctx = oracle.Context(n, primes, t)
+    rng = np.random.default_rng(77)
+    sk = ctx.keygen(1)
+    data_primes = primes[:-1]
+    parts, want = [], []
+    for i in range(24):
+        seed = rng.bytes(64)
+        ct = ctx.encrypt_seeded(sk, ctx.encode(rng.integers(0, t, size=n, dtype=np.uint64)), 100 + i, seed)
+        full, seeded = ctx.ct_save(ct), ctx.ct_save_seeded(ct, seed)
+        kind = i % 6
+        s = [full, seeded, zlib_stream(seeded), zlib_stream(full), seeded, full][kind]
+        if have_zstd() and kind >= 4:
+            s = zstd_stream(seeded if kind == 4 else full, streaming=bool(i & 8))
+        parts.append(s)
+        want.append(full)
+    blob = b"".join(parts)
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint64)
+    woffs = np.concatenate([[0], np.cumsum([len(p) for p in want])]).astype(np.uint64)
+    for threads in (1, 3, 8, 0):
+        t0 = time.perf_counter()
+        out, ooffs = pf.seal_ct_expand_batch(blob, offs, n, data_primes, threads)
+        dt = time.perf_counter() - t0
+        assert out == b"".join(want) and np.array_equal(ooffs, woffs), threads
+        print(f"batch of {len(parts)} streams, threads={threads}: {dt * 1e3:.1f} ms")
+    # all-full batch: nothing to do, streams copied; empty batch
+    fblob = b"".join(want)
+    out, ooffs = pf.seal_ct_expand_batch(fblob, woffs, n, data_primes, 4)
+    assert out == fblob and np.array_equal(ooffs, woffs)
+    out, ooffs = pf.seal_ct_expand_batch(b"\0", np.zeros(1, dtype=np.uint64), n, data_primes, 4)
+    assert out == b"" and list(ooffs) == [0]
+    # one stream seeded with shake256, one truncated, offsets out of range
+    bad = list(parts)
+    bad[7] = parts[7][:-65] + b"\x02" + parts[7][-64:]
+    assert len(parts[7]) == 113 + len(data_primes) * n * 8 + 81        # index 7 is an uncompressed seeded stream
+    boffs = np.concatenate([[0], np.cumsum([len(p) for p in bad])]).astype(np.uint64)
+    with pytest.raises(pf.PfError):
+        pf.seal_ct_expand_batch(b"".join(bad), boffs, n, data_primes, 4)
+    bad = list(parts)
+    bad[2] = parts[2][:-30]
+    boffs = np.concatenate([[0], np.cumsum([len(p) for p in bad])]).astype(np.uint64)
+    with pytest.raises(pf.PfError):
+        pf.seal_ct_expand_batch(b"".join(bad), boffs, n, data_primes, 4)
+    with pytest.raises(pf.PfError):
+        pf.seal_ct_expand_batch(blob[:-5], offs, n, data_primes, 4)
