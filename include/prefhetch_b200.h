@@ -125,7 +125,9 @@ typedef struct {
 
 /* The encrypted variant of Server::coarseSearch (additive to ref: src/server/controllers/Query.cc:29-63):
  * query_cts[0, query_bytes) holds nq*m SEAL-serialized BFV ciphertexts (coefficient form, top level),
- * ct_offsets[nq*m+1] their byte offsets (ascending, all <= query_bytes, else PF_ERR_INVALID).  For query i
+ * ct_offsets[nq*m+1] their byte offsets (ascending, all <= query_bytes, else PF_ERR_INVALID).  A ciphertext whose
+ * parms_id is neither this engine's top data level (pf_parms_id over the L data primes) nor all zero ("not
+ * stamped") is refused with PF_ERR_FORMAT, as seal::Ciphertext::load(context, ...) refuses it.  For query i
  * and each of its lists idx[i][p] (in order, lists not owned by this rank are skipped) one result
  * ciphertext per block of the list is written to out_cts in SEAL format (coefficient form).  Result r is
  * the pf_result_serialized_size() bytes starting at result_offsets[r]; results sit in slots of

@@ -2537,6 +2537,10 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
             const int pr = parse_ct_prefix(e, src, len, &is_ntt, parms_id, &cms, &total);
             if (pr || cms != (uint64_t)L) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu malformed (code %d)", c, pr);
             if (is_ntt) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
+            // seal::Ciphertext::load(context, ...) refuses a ciphertext of another parameter set; so does this (an
+            // all-zero parms_id = "not stamped", as hand-packed test streams have it)
+            if ((parms_id[0] | parms_id[1] | parms_id[2] | parms_id[3]) && memcmp(parms_id, e->level_pid[L], 32) != 0)
+                return e->fail(PF_ERR_FORMAT, "query ciphertext %zu was made for other encryption parameters (parms_id differs from this engine's top data level)", c);
         }
     }
     // Query groups: the H2D of group i+1 (upload stream) and the D2H of group i-1 (copy stream) overlap

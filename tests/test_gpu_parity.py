@@ -975,4 +975,10 @@ def test_cpp_client_round_trip(pf, tmp_path, n, m, g, rl):
     # the same scores through the plaintext endpoint of the reference (Server::coarseSearch)
     pdist, plabels, psizes = eng.coarseSearch(query, idx)
     assert np.array_equal(np.asarray(pdist, dtype=np.float32), scores) and np.array_equal(plabels, labels)
+    # a ciphertext stamped for other encryption parameters is refused, as seal::Ciphertext::load(context, ...) would
+    other = blob.copy()
+    other[int(offs[1]) + 16] ^= 0x40
+    with pytest.raises(pf.PfError) as ei:
+        eng.coarseSearchEncrypted(other, offs, idx)
+    assert ei.value.code == 5 and "parameters" in str(ei.value)
     eng.close()
