@@ -113,6 +113,7 @@ CASES = [
     pytest.param(2048, None, 128, 2, 8, 0, id="n2048-m2-g8-full"),
     pytest.param(2048, None, 96, 1, 32, 2, id="n2048-d96-g32-rl2"),
     pytest.param(8192, "bfv", 128, 1, 8, 1, id="n8192-bfvdefault-rl1"),
+    pytest.param(16384, "bfv", 128, 1, 16, 2, id="n16384-bfvdefault-rl2"),     # L = 8, 9 key primes (configs[4] sweep)
 ]
 
 
