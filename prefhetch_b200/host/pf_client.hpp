@@ -62,7 +62,16 @@ inline u64 signed_mod(int64_t v, u64 q) { return v >= 0 ? (u64)v % q : q - 1 - (
 struct NttPlan {
     u64 q = 0, n = 0, ninv = 0;
     int logn = 0;
-    std::vector<u64> w, winv; // psi^bitrev(i), psi^-bitrev(i)
+    std::vector<u64> w, winv;     // psi^bitrev(i), psi^-bitrev(i)
+    std::vector<u64> wsh, winvsh; // floor(w * 2^64 / q): Shoup quotients, one high multiply instead of a division
+    u64 ninvsh = 0;
+
+    // x * w mod q for x < q, with wq = floor(w * 2^64 / q); q < 2^63
+    static u64 mul_shoup(u64 x, u64 w_, u64 wq, u64 q_) {
+        const u64 hi = (u64)(((u128)x * wq) >> 64);
+        const u64 r = x * w_ - hi * q_;
+        return r >= q_ ? r - q_ : r;
+    }
 
     NttPlan() = default;
     NttPlan(u64 n_, u64 q_) : q(q_), n(n_) {
@@ -81,16 +90,23 @@ struct NttPlan {
             ip = pfh::mulmod(ip, ipsi, q);
         }
         ninv = pfh::invmod(n % q, q);
+        wsh.resize(n);
+        winvsh.resize(n);
+        for (u64 i = 0; i < n; i++) {
+            wsh[i] = pfh::shoup(w[i], q);
+            winvsh[i] = pfh::shoup(winv[i], q);
+        }
+        ninvsh = pfh::shoup(ninv, q);
     }
     void forward(u64 *a) const {
         u64 t = n;
         for (u64 m = 1; m < n; m <<= 1) {
             t >>= 1;
             for (u64 i = 0; i < m; i++) {
-                const u64 W = w[m + i];
+                const u64 W = w[m + i], Wq = wsh[m + i];
                 u64 *x = a + 2 * i * t, *y = x + t;
                 for (u64 j = 0; j < t; j++) {
-                    const u64 u = x[j], v = pfh::mulmod(y[j], W, q);
+                    const u64 u = x[j], v = mul_shoup(y[j], W, Wq, q);
                     x[j] = add_mod(u, v, q);
                     y[j] = sub_mod(u, v, q);
                 }
@@ -102,17 +118,17 @@ struct NttPlan {
         for (u64 m = n; m > 1; m >>= 1) {
             const u64 h = m >> 1;
             for (u64 i = 0; i < h; i++) {
-                const u64 W = winv[h + i];
+                const u64 W = winv[h + i], Wq = winvsh[h + i];
                 u64 *x = a + 2 * i * t, *y = x + t;
                 for (u64 j = 0; j < t; j++) {
                     const u64 u = x[j], v = y[j];
                     x[j] = add_mod(u, v, q);
-                    y[j] = pfh::mulmod(sub_mod(u, v, q), W, q);
+                    y[j] = mul_shoup(sub_mod(u, v, q), W, Wq, q);
                 }
             }
             t <<= 1;
         }
-        for (u64 i = 0; i < n; i++) a[i] = pfh::mulmod(a[i], ninv, q);
+        for (u64 i = 0; i < n; i++) a[i] = mul_shoup(a[i], ninv, ninvsh, q);
     }
 };
 
@@ -209,7 +225,10 @@ class Client {
         if (dc_ % g_ || dc_ > N_ / 2) throw std::invalid_argument("bad layout (g does not divide the chunk, or chunk > N/2)");
         R_ = dc_ / g_;
         C_ = (uint32_t)(N_ / g_);
-        for (u64 q : q_) ntt_.emplace_back(N_, q);
+        for (u64 q : q_) {
+            if (q >> 61) throw std::invalid_argument("coefficient primes above 61 bits are not supported (SEAL's own limit)");
+            ntt_.emplace_back(N_, q);
+        }
         ntt_t_ = detail::NttPlan(N_, t_);
         // BatchEncoder: slot i of row 0 is the evaluation at zeta^(3^i), of row 1 at zeta^(-3^i)
         slot_to_coeff_.resize(N_);
