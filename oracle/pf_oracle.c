@@ -1,6 +1,8 @@
 /*
  * pf_oracle.c — CPU oracle for the PreFHEtch server-side search hot path.  See pf_oracle.h.
- * TEST INFRASTRUCTURE ONLY; PARITY UNPINNED by the reference (no HE code / tests / vectors there).
+ * TEST INFRASTRUCTURE ONLY.  The plaintext functions (pfo_l2sqr_ref, pfo_coarse_quantize, pfo_search_lists_plain,
+ * pfo_recall) are PINNED to outputs of the reference's own code (oracle/_ref, tests/golden/ref_plain_v1.json,
+ * tests/test_ref_pin.py); the HE part is PARITY UNPINNED by the reference (no HE code / tests / vectors there).
  *
  * Citation convention: "ref:" paths are relative to /root/reference (in-tree reference code);
  * "SEAL:" paths name files of Microsoft SEAL 4.1 (native/src/seal/...), the third-party

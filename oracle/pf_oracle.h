@@ -5,9 +5,11 @@
  * code; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs do, and there only as the checker or the CPU baseline.
  *
- * PARITY UNPINNED by the reference: the reference snapshot holds no HE code, no tests and no
+ * HE half: PARITY UNPINNED by the reference — the reference snapshot holds no HE code, no tests and no
  * golden vectors.  The plaintext half of this file restates in-tree
- * reference code (cited per function, paths relative to /root/reference).  The HE half
+ * reference code (cited per function, paths relative to /root/reference) and IS pinned: the reference's
+ * own functions, compiled from its sources (oracle/ref_build -> oracle/_ref), produce
+ * tests/golden/ref_plain_v1.json, which tests/test_ref_pin.py holds this file to bit for bit.  The HE half
  * restates the published algorithms of Microsoft SEAL 4.1 (pinned by the reference at
  * commit 7a931d55ba84a40b85938f6ca3ac206f18654093, CMakeLists.txt:33-38; source NOT in the
  * reference tree) — BFV evaluator semantics, negacyclic Harvey NTT with the numerically

@@ -5,6 +5,7 @@
 //   pf_client_check nearest <dir>   params.txt, queries.f32, centroids.f32 -> nearest_centroids.i64/.f32 [nq][nprobe]
 //   pf_client_check rank    <dir>   params.txt (K = coarse_probe field), precise_scores.f32 [nq][K], coarse_ids.i64 [nq][K],
 //                                   groundtruth.i32 [nq][gt_k] -> ranked.i64 [nq][K], benchmark.txt
+//   pf_client_check coarse-rank <dir>  scores.f32, labels.i64, list_sizes.u64 -> coarse_ranked.i64 / .f32 (packed per query)
 //   pf_client_check request <dir>   queries_seeded.bin/.off, nearest_idx.i64 [nq][nprobe] -> request.json (the POST body)
 //   pf_client_check respond <dir>   response.json (the endpoint's answer) -> scores.f32, list_sizes.u64, labels_out.i64, budget.txt
 //   pf_client_check decrypt <dir>   + results.bin/.off, probed_sizes.u64, results_per_query.u64, labels.i64
@@ -38,7 +39,7 @@ void write_file(const std::string &path, const std::vector<T> &v) {
 
 int main(int argc, char **argv) {
     if (argc != 3) {
-        fprintf(stderr, "usage: pf_client_check keygen|nearest|rank|request|respond|decrypt <dir>\n");
+        fprintf(stderr, "usage: pf_client_check keygen|nearest|coarse-rank|rank|request|respond|decrypt <dir>\n");
         return 2;
     }
     try {
@@ -65,10 +66,28 @@ int main(int argc, char **argv) {
             printf("ok nearest: %llu queries x %llu of %zu centroids\n", (unsigned long long)nq, (unsigned long long)nprobe, cf.size() / dim);
             return 0;
         }
+        if (mode == "coarse-rank") { // compute_nearest_coarse_vectors on a plaintext response
+            const std::vector<float> sc = read_file<float>(dir + "scores.f32");
+            const std::vector<int64_t> lb = read_file<int64_t>(dir + "labels.i64");
+            const std::vector<uint64_t> ls = read_file<uint64_t>(dir + "list_sizes.u64");
+            const auto nearest = prefhetch::Client::compute_nearest_coarse_vectors(sc, lb, ls, coarse_probe);
+            std::vector<int64_t> oi;
+            std::vector<float> od;
+            for (const auto &q : nearest)
+                for (const auto &e : q) {
+                    oi.push_back(e.idx);
+                    od.push_back(e.distance);
+                }
+            write_file(dir + "coarse_ranked.i64", oi);
+            write_file(dir + "coarse_ranked.f32", od);
+            printf("ok coarse-rank\n");
+            return 0;
+        }
         if (mode == "rank") { // stage 3 + the reference's recall bookkeeping
             const std::vector<float> ps = read_file<float>(dir + "precise_scores.f32");
             const std::vector<int64_t> cid = read_file<int64_t>(dir + "coarse_ids.i64");
-            const std::vector<int32_t> gt = read_file<int32_t>(dir + "groundtruth.i32");
+            const bool have_gt = std::ifstream(dir + "groundtruth.i32").good();     // without it: the ranking only
+            const std::vector<int32_t> gt = have_gt ? read_file<int32_t>(dir + "groundtruth.i32") : std::vector<int32_t>();
             const uint64_t K = coarse_probe;
             if (ps.size() != nq * K || cid.size() != nq * K || gt.size() % nq) throw std::runtime_error("rank inputs");
             std::vector<std::vector<prefhetch::DistanceIndexData>> coarse(nq);
@@ -79,9 +98,15 @@ int main(int argc, char **argv) {
             for (const auto &q : ranked)
                 for (const auto &e : q) out.push_back(e.idx);
             write_file(dir + "ranked.i64", out);
-            const auto b = prefhetch::Client::benchmark_results(out.data(), nq, K, gt.data(), gt.size() / nq);
-            std::ofstream(dir + "benchmark.txt") << b.recall_1 << " " << b.recall_10 << " " << b.recall_100 << " " << b.mrr_1 << " " << b.mrr_10 << " "
-                                                 << b.mrr_100 << "\n";
+            std::vector<float> outd;
+            for (const auto &q : ranked)
+                for (const auto &e : q) outd.push_back(e.distance);
+            write_file(dir + "ranked.f32", outd);
+            if (have_gt) {
+                const auto b = prefhetch::Client::benchmark_results(out.data(), nq, K, gt.data(), gt.size() / nq);
+                std::ofstream(dir + "benchmark.txt") << b.recall_1 << " " << b.recall_10 << " " << b.recall_100 << " " << b.mrr_1 << " " << b.mrr_10
+                                                     << " " << b.mrr_100 << "\n";
+            }
             printf("ok rank\n");
             return 0;
         }

@@ -982,3 +982,32 @@ def test_cpp_client_round_trip(pf, tmp_path, n, m, g, rl):
         eng.coarseSearchEncrypted(other, offs, idx)
     assert ei.value.code == 5 and "parameters" in str(ei.value)
     eng.close()
+
+
+def test_plain_stages_against_reference_golden(pf):
+    """The CUDA plaintext stages against outputs of the REFERENCE ITSELF (tests/golden/ref_plain_v1.json: the
+    reference's sort_nearest_centroids and Server::preciseSearch compiled from its own sources and run on these
+    inputs — tests/test_ref_pin.py has the CPU side): pf_coarse_quantize returns the reference's order and the
+    reference's float bits for all centroids, pf_precise_search the reference's float bits, on integer and on
+    fractional data (where the float / double accumulation order shows in the low bits)."""
+    from tests.golden.make_golden_ref import ref_inputs
+    from tests.test_ref_pin import GOLD, NQ, CP, f32, same_up_to_ties
+    x = ref_inputs()
+    cent = x["cent"]
+    nlist = len(cent)
+    for tag in ("int", "frac"):
+        base, query = x[f"base_{tag}"], x[f"query_{tag}"]
+        offsets, ids, vecs = build_ivf(base, cent)
+        eng, _, _ = _engine(pf, 2048)
+        eng.load_index(cent, offsets, ids, vecs)        # fractional data: plaintext stages only (no encrypted index)
+        g = GOLD[f"sort_nearest_centroids_{tag}"]
+        want_idx, want_dist = np.array(g["idx"]).reshape(NQ, nlist), f32(g["dist_bits"]).reshape(NQ, nlist)
+        idx, dist = eng.coarse_quantize(query, nlist, return_dist=True)
+        assert np.array_equal(dist.view(np.uint32), want_dist.view(np.uint32)), tag
+        assert all(same_up_to_ties(idx[i], want_idx[i], want_dist[i]) for i in range(NQ)) and np.array_equal(idx, want_idx), tag
+        idx20 = eng.coarse_quantize(query, 20)          # the reference's NPROBE
+        assert np.array_equal(idx20, want_idx[:, :20]), tag
+        want = np.array(GOLD[f"precise_search_{tag}"]["score_bits"], dtype=np.uint32).reshape(NQ, CP)
+        got = eng.preciseSearch(query, x["ids"])
+        assert np.array_equal(got.view(np.uint32), want), tag
+        eng.close()
