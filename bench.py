@@ -430,6 +430,29 @@ def reference_plaintext_path(data, nprobe, nq, repeats=3):
             "plaintext_distances_per_s": best[3] / best[0], "queries_per_s": nq / best[0]}
 
 
+def reference_functions_timed(data):
+    """The reference's OWN plaintext functions — sort_nearest_centroids (src/client/client_lib.cpp:49-81) and
+    Server::preciseSearch (src/server/server_lib.cpp:140-167), compiled from its sources into oracle/_ref (recipe:
+    oracle/ref_build/Makefile; prebuilt .so on the GPU box) — timed on this host, one thread, in the reference's
+    compile-time shape (5 queries, 200 candidates).  kind "reference": no restatement involved."""
+    try:
+        from oracle import pf_ref as R
+        if not R.build():
+            return {"unavailable": "oracle/_ref not built and the reference sources are not on this machine"}
+        d = data["vectors"].shape[1]
+        if d != R.D:
+            return {"unavailable": f"the reference is compiled for d = {R.D}"}
+        q = np.ascontiguousarray(data["queries"][:R.NQUERY], dtype=np.float32)
+        ids = (np.arange(R.NQUERY * R.COARSE_PROBE, dtype=np.int64) * 7919 % len(data["vectors"])).reshape(R.NQUERY, R.COARSE_PROBE)
+        t = R.time_reference_functions(q, data["centroids"], ids, data["vectors"])
+        t.update({"kind": "reference", "cores": 1,
+                  "centroid_distances_per_s": R.NQUERY * len(data["centroids"]) / t["sort_nearest_centroids_s"],
+                  "exact_distances_per_s": R.NQUERY * R.COARSE_PROBE / t["precise_search_s"]})
+        return t
+    except Exception as ex:    # noqa: BLE001 — a record, not a gate
+        return {"unavailable": repr(ex)[:300]}
+
+
 def bench_config(cfg_name, cfg, L, result_limbs, nq, world=1, weak=False, nprobe=None, grid=None, db_gib=None):
     """the `config` object of the JSON line — built by ONE function for both arms so that they name the same
     workload key for key (the CPU arm's bounded sample is described under cpu_baseline.sample)"""
@@ -470,6 +493,7 @@ def run_reference(args, cfg, cfg_name):
     }
     if cfg["nb"] <= 200_000:   # BASELINE configs[0]: also what the reference computes today, in plaintext
         line["reference_plaintext_path"] = reference_plaintext_path(data, cfg["nprobe"], min(100, len(data["queries"])))
+        line["reference_functions"] = reference_functions_timed(data)
     emit(line)
     return 0
 

@@ -150,3 +150,25 @@ def precise_search(query: np.ndarray, ids: np.ndarray, base: np.ndarray) -> np.n
     if rc:
         raise RuntimeError("the reference threw")
     return out
+
+
+def time_reference_functions(query, centroids, ids, base, reps: int = 200):
+    """seconds per call of the reference's own sort_nearest_centroids (NQUERY queries x len(centroids)) and
+    Server::preciseSearch (NQUERY x COARSE_PROBE exact distances), single thread, as compiled here with -O2"""
+    q = np.ascontiguousarray(query, dtype=np.float32).reshape(NQUERY, D)
+    c = np.ascontiguousarray(centroids, dtype=np.float32).reshape(-1, D)
+    ix = np.ascontiguousarray(ids, dtype=np.int64).reshape(NQUERY, COARSE_PROBE)
+    b = np.ascontiguousarray(base, dtype=np.float32).reshape(-1, D)
+    f1 = _lib("client").ref_sort_nearest_centroids_timed
+    f1.restype = C.c_double
+    t_sort = f1(_p(q, C.c_float), _p(c, C.c_float), C.c_int64(len(c)), C.c_int(reps))
+    f2 = _lib("server").ref_precise_search_timed
+    f2.restype = C.c_double
+    with _Tree() as t:
+        _vecs_write(t.data / "siftsmall_base.fvecs", b)
+        _vecs_write(t.data / "siftsmall_learn.fvecs", b[:16])
+        t_precise = f2(_p(q, C.c_float), _p(ix, C.c_int64), C.c_int(reps))
+    if t_precise < 0:
+        raise RuntimeError("the reference threw")
+    return {"sort_nearest_centroids_s": t_sort, "precise_search_s": t_precise, "queries": NQUERY, "centroids": len(c),
+            "coarse_probe": COARSE_PROBE, "reps": reps}

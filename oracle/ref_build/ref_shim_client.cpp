@@ -3,6 +3,7 @@
 // oracle's restatements of these functions are pinned against what this library returns (tests/golden/).
 // Shapes are the reference's compile-time constants (include/common/client_server_utils.h:10-20).
 #include <array>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,24 @@ void ref_sort_nearest_centroids(const float *query /*[NQUERY][128]*/, const floa
             idx_out[i * nlist + j] = nearest[i][j].idx;
             dist_out[i * nlist + j] = nearest[i][j].distance;
         }
+}
+
+// the same call `reps` times on the same inputs; returns seconds per call (bench.py --impl reference, configs[0])
+double ref_sort_nearest_centroids_timed(const float *query, const float *centroids, int64_t nlist, int reps) {
+    std::array<std::array<float, PRECISE_VECTOR_DIMENSIONS>, NQUERY> q;
+    for (int i = 0; i < NQUERY; i++)
+        for (int k = 0; k < PRECISE_VECTOR_DIMENSIONS; k++) q[i][k] = query[i * PRECISE_VECTOR_DIMENSIONS + k];
+    std::vector<std::array<float, PRECISE_VECTOR_DIMENSIONS>> cent(nlist);
+    for (int64_t j = 0; j < nlist; j++)
+        for (int k = 0; k < PRECISE_VECTOR_DIMENSIONS; k++) cent[j][k] = centroids[j * PRECISE_VECTOR_DIMENSIONS + k];
+    const auto t0 = std::chrono::steady_clock::now();
+    volatile float sink = 0;
+    for (int r = 0; r < reps; r++) {
+        std::array<std::vector<DistanceIndexData>, NQUERY> nearest;
+        sort_nearest_centroids(q, cent, nearest);
+        sink = sink + nearest[0][0].distance;
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
 }
 
 // ref: src/client/client_lib.cpp:122-156.  Returns 0, or 1 when the reference throws (fewer than COARSE_PROBE

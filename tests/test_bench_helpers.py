@@ -150,3 +150,19 @@ def test_bench_calls_bind_to_the_real_engine():
     assert ctor
     for n in ctor:
         inspect.signature(Engine.__init__).bind(None, *([0] * len(n.args)), **{k.arg: 0 for k in n.keywords if k.arg})
+
+
+def test_reference_functions_timed_uses_the_reference_itself():
+    """the configs[0] reference arm times the reference's own compiled functions (oracle/_ref) when they exist"""
+    import bench
+    from oracle import pf_ref as R
+    rng = np.random.default_rng(0)
+    data = {"vectors": rng.integers(0, 256, size=(3000, 128)).astype(np.float32), "queries": rng.integers(0, 256, size=(8, 128)).astype(np.float32),
+            "centroids": rng.uniform(0, 200, size=(50, 128)).astype(np.float32)}
+    r = bench.reference_functions_timed(data)
+    if R.build():
+        assert r["kind"] == "reference" and r["cores"] == 1 and r["exact_distances_per_s"] > 1e4 and r["centroid_distances_per_s"] > 1e4
+    else:
+        assert "unavailable" in r
+    data["vectors"] = data["vectors"][:, :64]
+    assert "unavailable" in bench.reference_functions_timed(data)
