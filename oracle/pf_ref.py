@@ -39,8 +39,10 @@ def buildable() -> bool:
 def build(force: bool = False) -> bool:
     """compile from the reference's sources when they are present; returns whether the libraries exist afterwards"""
     if buildable() and (force or not available()):
-        subprocess.run(["make", "-C", str(HERE / "ref_build"), f"REF={REF}"] + (["-B"] if force else []), check=True,
-                       capture_output=True)
+        r = subprocess.run(["make", "-C", str(HERE / "ref_build"), f"REF={REF}"] + (["-B"] if force else []), capture_output=True, text=True)
+        if r.returncode:     # test infrastructure: a failure here must not fail the product build
+            import sys
+            sys.stderr.write("oracle/_ref could not be built from the reference sources:\n" + r.stdout[-2000:] + r.stderr[-2000:])
     return available()
 
 

@@ -216,7 +216,7 @@ def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d,
     sizes = np.fromfile(tmp_path / "list_sizes.u64", dtype=np.uint64)
     assert np.array_equal(sizes, probed.sum(1))
     # exact squared L2 of every candidate of every probed list, packed per query like Server::coarseSearch
-    want, pos = [], 0
+    want = []
     for qi in range(nq):
         for l in idx[qi]:
             xs = vecs[offsets[l]:offsets[l + 1]].astype(np.int64)
@@ -231,7 +231,7 @@ def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d,
         a, b = int(sizes[:qi].sum()), int(sizes[:qi + 1].sum())
         order = np.argsort(want[a:b], kind="stable")[:coarse_probe]
         assert np.array_equal(nearest[qi], lab[a:b][order])
-        pos = b
+    
 
     # the same exchange through the JSON envelope of POST /coarsesearch-encrypted (pf_query_handlers.hpp): the request
     # body the client writes is read back with Python's json, the response is written by Python's json in the
