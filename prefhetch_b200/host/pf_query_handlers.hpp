@@ -15,6 +15,7 @@
 //   POST /coarsesearch        {preciseQuery:[[..]], nearestCentroidIndexes:[[..]]}
 //                             -> {coarseDistanceScores, coarseVectorIndexes, listSizesPerQuery}   (Query.cc:29-63)
 //   POST /precisesearch       {preciseQuery, nearestCoarseVectorIndexes} -> {preciseDistanceScores:[[..]]}  (Query.cc:65-98)
+//   POST /galoiskeys          (additive)  {galoisKeys: base64 of the client's SEAL GaloisKeys stream} -> {galoisKeysBytes}
 //   POST /coarsesearch-encrypted (additive)  {queryCiphertexts: base64 of the SEAL streams back to back,
 //                             ctOffsets:[..], nearestCentroidIndexes:[[..]]}
 //                             -> {resultCiphertexts: base64, resultOffsets, resultsPerQuery, coarseVectorIndexes,
@@ -78,6 +79,19 @@ inline std::string precise_search(const Server &srv, std::string_view body) {
     srv.preciseSearch(precise_query, ids, (uint32_t)probe, scores);
     std::string out = "{\"preciseDistanceScores\":";
     json::put_matrix(out, scores.data(), nq, probe);
+    out.push_back('}');
+    return out;
+}
+
+// POST /galoiskeys (additive): the client's SEAL GaloisKeys stream (full or seeded, any compr_mode the engine reads),
+// base64 in {"galoisKeys": "..."} — once per client session, before the first encrypted search.  The engine holds one
+// key set at a time (one client); multi-tenant key management is the server application's business.
+inline std::string galois_keys(Server &srv, std::string_view body) {
+    const auto req = json::object(body);
+    const std::vector<uint8_t> blob = json::base64_decode(json::string(json::at(req, "galoisKeys")));
+    srv.loadGaloisKeys(blob);
+    std::string out = "{\"galoisKeysBytes\":";
+    json::put_number(out, (uint64_t)blob.size());
     out.push_back('}');
     return out;
 }

@@ -119,7 +119,7 @@ class Server {
                                 coarse_probe, precise_distance_scores.data()));
     }
 
-    // SEAL-serialized GaloisKeys of the client (compr_mode none)
+    // SEAL-serialized GaloisKeys of the client: full or seeded (Serializable<GaloisKeys>), compr_mode none / zlib / zstd
     void loadGaloisKeys(std::span<const uint8_t> blob) { check(pf_load_galois_keys(m_Engine.get(), blob.data(), blob.size())); }
 
     // one Galois key from raw words [L][2][k][N] (GaloisKeys::key(galois_elt) data, NTT form)

@@ -146,6 +146,12 @@ int handlers_check(const std::string &dir) {
             if (pd[i * probe + j] != dist[o + j]) return 15;
         o += sizes[i];
     }
+    // POST /galoiskeys: the same key stream through the handler (replaces the set loaded above with itself)
+    {
+        const std::string kbody = "{\"galoisKeys\":\"" + h::json::base64_encode(keys.data(), keys.size()) + "\"}";
+        const auto kresp = h::json::object(h::galois_keys(srv, kbody));
+        if (h::json::number<uint64_t>(h::json::at(kresp, "galoisKeysBytes")) != keys.size()) return 21;
+    }
     // POST /coarsesearch-encrypted
     std::string ebody = "{\"queryCiphertexts\":\"" + h::json::base64_encode(qblob.data(), qblob.size()) + "\",\"ctOffsets\":";
     h::json::put_vector(ebody, qoff.data(), qoff.size());
