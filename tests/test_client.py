@@ -114,14 +114,15 @@ CASES = [
     pytest.param(2048, None, 96, 1, 32, 2, id="n2048-d96-g32-rl2"),
     pytest.param(8192, "bfv", 128, 1, 8, 1, id="n8192-bfvdefault-rl1"),
     pytest.param(16384, "bfv", 128, 1, 16, 2, id="n16384-bfvdefault-rl2"),     # L = 8, 9 key primes (configs[4] sweep)
+    pytest.param(8192, "bfv27", 960, 8, 8, 1, id="n8192-gist960-m8-rl1"),      # configs[3]: 8 query ciphertexts, 27-bit t
 ]
 
 
 @pytest.mark.parametrize("n,pset,d,m,g,rl", CASES)
 def test_client_round_trip_against_the_oracle(oracle, exe, tmp_path, n, pset, d, m, g, rl):
     import prefhetch_b200 as pf
-    if pset == "bfv":
-        primes, t = oracle.BFV_DEFAULT_PRIMES[n], oracle.BATCHING_T[(n, 24)]
+    if pset in ("bfv", "bfv27"):
+        primes, t = oracle.BFV_DEFAULT_PRIMES[n], oracle.BATCHING_T[(n, 27 if pset == "bfv27" else 24)]
     else:
         primes, t = ntt_primes(n, 40, 3) + ntt_primes(n, 41, 1), ntt_primes(n, 24, 1)[0]
     ctx = oracle.Context(n, primes, t)
