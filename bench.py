@@ -337,8 +337,10 @@ def bind_pages_to_gpu_node(arr, torch_device):
         mask = (ctypes.c_ulong * 16)()
         mask[node // 64] = 1 << (node % 64)
         libc = ctypes.CDLL(None, use_errno=True)
-        MPOL_BIND, SYS_mbind = 2, 237
-        rc = libc.syscall(SYS_mbind, ctypes.c_void_p(start), ctypes.c_ulong(length), ctypes.c_int(MPOL_BIND), mask,
+        # MPOL_PREFERRED, not MPOL_BIND: if the node cannot supply the pages the kernel falls back to another node
+        # instead of failing the first touch
+        MPOL_PREFERRED, SYS_mbind = 1, 237
+        rc = libc.syscall(SYS_mbind, ctypes.c_void_p(start), ctypes.c_ulong(length), ctypes.c_int(MPOL_PREFERRED), mask,
                           ctypes.c_ulong(16 * 64), ctypes.c_uint(0))
         if rc != 0:
             return {"bound": False, "node": node, "why": f"mbind errno {ctypes.get_errno()}"}
