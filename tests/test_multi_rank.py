@@ -180,6 +180,22 @@ def _open_response_worker(rank, world, port, out_path):
         dist.barrier()
         nr.close()
         dist.barrier()
+    # /dev/shm too small for the whole buffer (rank 0 decides, everybody follows): only the flags are shared, every
+    # rank keeps its query copy and its share in private memory; completion still reaches rank 0 through the flags
+    bench.shm_has_room = lambda nbytes: False
+    nr = bench.open_node_response(comm, qbytes=3000, seg=2000 + 100 * rank)
+    ok = ok and not nr.shared_data and nr.share.size == 2000 + 100 * rank and nr.query.size == 3000 and nr.whole.size == nr.FLAGS
+    nr.share[:] = rank + 1
+    if rank == 0:
+        nr.flags[:] = 0
+    dist.barrier()
+    nr.mark_done(4)
+    if rank == 0:
+        nr.wait_all(4, timeout_s=30)
+        ok = ok and [int(v) for v in nr.flags[:world]] == [5] * world
+    dist.barrier()
+    nr.close()
+    dist.barrier()
     if rank == 0:
         with open(out_path, "w") as f:
             f.write("ok" if ok else "mismatch")
