@@ -1203,6 +1203,8 @@ def open_node_response(comm, qbytes, seg, pinned_alloc=None, guard=None):
 
 
 def shm_has_room(nbytes):
+    if os.environ.get("PF_BENCH_PRIVATE_RESPONSE") == "1":      # tests: take the fallback
+        return False
     try:
         st = os.statvfs("/dev/shm")
         return st.f_bavail * st.f_frsize > nbytes + (256 << 20)
