@@ -212,7 +212,8 @@ class Client {
   public:
     // primes: the k = L + 1 coefficient primes, special prime last (what the server was created with);
     // dim, m, g: the layout parameters of the index (prefhetch::Server / pf_create)
-    Client(uint32_t dim, u64 poly_degree, const std::vector<u64> &primes, u64 plain_modulus, uint32_t m = 1, uint32_t g = 16)
+    // (public signatures use uint64_t like prefhetch::Server; u64 inside is the same width)
+    Client(uint32_t dim, uint64_t poly_degree, const std::vector<uint64_t> &primes, uint64_t plain_modulus, uint32_t m = 1, uint32_t g = 16)
         : d_(dim), N_(poly_degree), q_(primes.begin(), primes.end()), t_(plain_modulus), m_(m), g_(g) {
         if (q_.size() < 2) throw std::invalid_argument("need at least one data prime and the special prime");
         if (N_ < 8 || (N_ & (N_ - 1))) throw std::invalid_argument("poly_degree must be a power of two");
@@ -373,7 +374,7 @@ class Client {
 
     // The encrypted query of the additive endpoint (the prototype of client_lib.h:33-35): the m ciphertexts of one
     // query vector as SEAL streams, back to back; offsets gets m + 1 entries relative to the start of the blob.
-    std::vector<uint8_t> compute_encrypted_coarse_query(const int64_t *query, std::vector<u64> *offsets, bool seeded = true) {
+    std::vector<uint8_t> compute_encrypted_coarse_query(const int64_t *query, std::vector<uint64_t> *offsets, bool seeded = true) {
         need_keys();
         std::vector<uint8_t> blob;
         if (offsets) offsets->assign(1, 0);
@@ -556,7 +557,7 @@ class Client {
 
     // ref: src/client/client_lib.cpp:83-120 get_coarse_scores, for the encrypted endpoint: the JSON request body
     // (ciphertexts base64, as nlohmann would dump a string) ...
-    static std::string coarse_search_encrypted_request(const std::vector<uint8_t> &query_ciphertexts, const std::vector<u64> &ct_offsets,
+    static std::string coarse_search_encrypted_request(const std::vector<uint8_t> &query_ciphertexts, const std::vector<uint64_t> &ct_offsets,
                                                        const int64_t *nearest_centroids_id, size_t nq, size_t nprobe) {
         namespace json = handlers::json;
         std::string out = "{\"queryCiphertexts\":\"";

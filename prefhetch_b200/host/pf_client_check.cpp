@@ -47,7 +47,7 @@ int main(int argc, char **argv) {
         std::ifstream pf(dir + "params.txt");
         uint64_t dim, N, t, m, g, nq, nprobe, coarse_probe, k;
         if (!(pf >> dim >> N >> t >> m >> g >> nq >> nprobe >> coarse_probe >> k)) throw std::runtime_error("params.txt");
-        std::vector<prefhetch::u64> primes(k);
+        std::vector<uint64_t> primes(k);
         for (auto &p : primes)
             if (!(pf >> p)) throw std::runtime_error("params.txt: primes");
         if (mode == "nearest") { // stage 1 needs no keys
@@ -129,7 +129,7 @@ int main(int argc, char **argv) {
                 std::vector<uint8_t> blob;
                 std::vector<uint64_t> offs{0};
                 for (uint64_t i = 0; i < nq; i++) {
-                    std::vector<prefhetch::u64> o;
+                    std::vector<uint64_t> o;
                     const std::vector<uint8_t> b = cl.compute_encrypted_coarse_query(queries.data() + i * dim, &o, seeded != 0);
                     for (size_t a = 1; a < o.size(); a++) offs.push_back(blob.size() + o[a]);
                     blob.insert(blob.end(), b.begin(), b.end());
@@ -153,8 +153,7 @@ int main(int argc, char **argv) {
             const std::vector<uint64_t> offs64 = read_file<uint64_t>(dir + "queries_seeded.off");
             const std::vector<int64_t> nearest = read_file<int64_t>(dir + "nearest_idx.i64");
             if (nearest.size() != nq * nprobe) throw std::runtime_error("nearest_idx.i64 size");
-            const std::string body = prefhetch::Client::coarse_search_encrypted_request(blob, std::vector<prefhetch::u64>(offs64.begin(), offs64.end()),
-                                                                                       nearest.data(), nq, nprobe);
+            const std::string body = prefhetch::Client::coarse_search_encrypted_request(blob, offs64, nearest.data(), nq, nprobe);
             std::ofstream(dir + "request.json", std::ios::binary) << body;
             printf("ok request: %zu bytes\n", body.size());
             return 0;

@@ -1011,3 +1011,16 @@ def test_plain_stages_against_reference_golden(pf):
         got = eng.preciseSearch(query, x["ids"])
         assert np.array_equal(got.view(np.uint32), want), tag
         eng.close()
+
+
+def test_cpp_roundtrip_example():
+    """host/pf_roundtrip_example.cpp: the reference's client main (src/client/client.cpp) with the coarse step
+    encrypted — C++ client, handler bodies with their JSON, prefhetch::Server over the C ABI — in one process, no
+    oracle and no Python in the loop: decrypted scores equal the plaintext endpoint's, the re-ranked distances equal
+    exact brute force"""
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "prefhetch_b200" / "host" / "pf_roundtrip_example"
+    assert exe.exists(), "run __graft_entry__.build() first"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "pf_roundtrip_example ok" in r.stdout, r.stdout + r.stderr
