@@ -197,3 +197,15 @@ def test_handler_json_envelope_cpp():
         __graft_entry__.build()
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md §1 maps every function the header declares to the reference interface it replaces (or says that
+    nothing in the reference corresponds); a new entry point has to be added there"""
+    import re
+    hdr = (ROOT / "include" / "prefhetch_b200.h").read_text()
+    funcs = sorted(set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", hdr)))
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    families = [p[:-1] for p in re.findall(r"`(pf_[a-z_]+\*)`", doc)]
+    missing = [f for f in funcs if f not in doc and not any(f.startswith(p) for p in families)]
+    assert len(funcs) > 50 and not missing, missing
