@@ -92,6 +92,10 @@ def test_reference_arm_names_the_same_config_as_the_gpu_arm():
     a = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"])                       # --impl reference
     b = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"], 1, False, 16, (1, 1))  # ours, N = 1
     assert a == b
+    # N = 4 default run: the GPU arm weak-scales (4 list shards, nprobe 64); run_reference builds the same object
+    ours = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"], 4, True, 64, (4, 1))
+    ref = bench.bench_config(cfg_name, cfg, 4, 1, cfg["nq"], 4, True, min(cfg["nprobe"] * 4, cfg["nlist"]), (4, 1))
+    assert ours == ref and ours["nprobe"] == 64 and ours["nb"] == 4 * cfg["nb"]
     assert bench.cpu_sample_queries(64, 16) == 32 and bench.cpu_sample_queries(64, 1) == 8 and bench.cpu_sample_queries(16, 64) == 16
 
 
