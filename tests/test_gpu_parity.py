@@ -1,6 +1,12 @@
 """GPU parity: every C-ABI entry point of libprefhetch_b200.so against the CPU oracle on the same
 seeded inputs — bit-exact for all integer / ciphertext work, bit-exact float bits for the
-plaintext distances (the kernels restate the reference's float/double arithmetic)."""
+plaintext distances (the kernels restate the reference's float/double arithmetic).
+
+TOLERANCE (BASELINE north star: "decrypted distances and recall@10 must match within a stated tolerance"): ZERO.
+Result ciphertexts are compared byte for byte, probed lists index for index, decrypted distances are integers and
+must be EQUAL to the exact squared L2 (and hence recall@10 identical to the plaintext pipeline's: the two pipelines
+rank the same numbers), and the floating-point outputs of the plaintext stages are compared as float32 BIT PATTERNS.
+No assertion in this file uses an epsilon."""
 import hashlib
 
 import numpy as np
