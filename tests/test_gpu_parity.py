@@ -925,7 +925,7 @@ def test_zstd_compressed_streams(pf, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("n,m,g,rl", [(2048, 1, 16, 1), (8192, 1, 8, 1), (2048, 2, 8, 0)])
+@pytest.mark.parametrize("n,m,g,rl", [(2048, 1, 16, 1), (8192, 1, 8, 1), (2048, 2, 16, 0)])
 def test_cpp_client_round_trip(pf, tmp_path, n, m, g, rl):
     """f-4, no oracle in the loop: the C++ client (host/pf_client.hpp) makes the secret key, the GaloisKeys stream and
     seeded query ciphertexts; the engine loads them as any SEAL client's and answers; the client decrypts the response
