@@ -11,6 +11,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <type_traits>
 #include <vector>
 
 namespace prefhetch::handlers {
@@ -80,6 +81,10 @@ inline std::map<std::string, std::string_view> object(std::string_view body) {
         throw std::runtime_error("json: ',' or '}' expected");
     }
 }
+
+// the views point INTO the body: a temporary string must not be parsed (object(handler(...)) would leave them dangling)
+template <class S, std::enable_if_t<std::is_same_v<std::remove_cv_t<S>, std::string>, int> = 0>
+std::map<std::string, std::string_view> object(S &&) = delete;
 
 inline std::string_view at(const std::map<std::string, std::string_view> &o, const char *key) {
     auto it = o.find(key);

@@ -98,7 +98,8 @@ int main(int argc, char **argv) {
         preq += ",\"nearestCentroidIndexes\":";
         h::json::put_matrix(preq, probe_ids.data(), nq, nprobe);
         preq += "}";
-        const auto presp = h::json::object(h::coarse_search(srv, preq));
+        const std::string presp_body = h::coarse_search(srv, preq); // the parsed views point into it
+        const auto presp = h::json::object(presp_body);
         if (h::json::vector<float>(h::json::at(presp, "coarseDistanceScores")) != coarse_scores) throw std::runtime_error("decrypted scores differ from the plaintext endpoint");
         if (h::json::vector<int64_t>(h::json::at(presp, "coarseVectorIndexes")) != coarse_idx) throw std::runtime_error("labels differ from the plaintext endpoint");
         // rank, re-rank, compare with brute force over the probed candidates
@@ -111,7 +112,8 @@ int main(int argc, char **argv) {
         sreq += ",\"nearestCoarseVectorIndexes\":";
         h::json::put_matrix(sreq, cand.data(), nq, coarse_probe);
         sreq += "}";
-        const auto sresp = h::json::object(h::precise_search(srv, sreq));
+        const std::string sresp_body = h::precise_search(srv, sreq);
+        const auto sresp = h::json::object(sresp_body);
         const std::vector<float> pscores = h::json::matrix<float>(h::json::at(sresp, "preciseDistanceScores"), r, c);
         const auto precise = prefhetch::Client::compute_nearest_precise_vectors(pscores.data(), coarse, coarse_probe);
         uint64_t hits = 0;

@@ -115,7 +115,8 @@ int handlers_check(const std::string &dir) {
     body += ",\"nearestCentroidIndexes\":";
     h::json::put_matrix(body, probes.data(), nq, nprobe);
     body += "}";
-    const auto resp = h::json::object(h::coarse_search(srv, body));
+    const std::string resp_body = h::coarse_search(srv, body); // the parsed views point into it
+    const auto resp = h::json::object(resp_body);
     std::vector<float> dist;
     std::vector<prefhetch::idx_t> labels;
     std::vector<size_t> sizes;
@@ -136,7 +137,8 @@ int handlers_check(const std::string &dir) {
     pbody += ",\"nearestCoarseVectorIndexes\":";
     h::json::put_matrix(pbody, cand.data(), nq, probe);
     pbody += "}";
-    const auto presp = h::json::object(h::precise_search(srv, pbody));
+    const std::string presp_body = h::precise_search(srv, pbody);
+    const auto presp = h::json::object(presp_body);
     std::vector<float> pd;
     srv.preciseSearch(queries, cand, probe, pd);
     if (h::json::matrix<float>(h::json::at(presp, "preciseDistanceScores"), r, c) != pd || r != nq || c != probe) return 14;
@@ -149,7 +151,8 @@ int handlers_check(const std::string &dir) {
     // POST /galoiskeys: the same key stream through the handler (replaces the set loaded above with itself)
     {
         const std::string kbody = "{\"galoisKeys\":\"" + h::json::base64_encode(keys.data(), keys.size()) + "\"}";
-        const auto kresp = h::json::object(h::galois_keys(srv, kbody));
+        const std::string kresp_body = h::galois_keys(srv, kbody);
+        const auto kresp = h::json::object(kresp_body);
         if (h::json::number<uint64_t>(h::json::at(kresp, "galoisKeysBytes")) != keys.size()) return 21;
     }
     // POST /coarsesearch-encrypted
@@ -158,7 +161,8 @@ int handlers_check(const std::string &dir) {
     ebody += ",\"nearestCentroidIndexes\":";
     h::json::put_matrix(ebody, probes.data(), nq, nprobe);
     ebody += "}";
-    const auto eresp = h::json::object(h::coarse_search_encrypted(srv, ebody));
+    const std::string eresp_body = h::coarse_search_encrypted(srv, ebody);
+    const auto eresp = h::json::object(eresp_body);
     prefhetch::EncryptedCoarseResult direct;
     srv.coarseSearchEncrypted(nq, qblob, qoff, probes, nprobe, direct);
     if (h::json::base64_decode(h::json::string(h::json::at(eresp, "resultCiphertexts"))) != direct.ciphertexts) return 16;
