@@ -105,8 +105,8 @@ def make_dataset(cfg, device, seed=1234, sigma=24.0, spread=160.0, lloyd=0, npoo
     qa = torch.randint(0, nlist, (npool,), generator=g, device=device)
     queries = torch.clamp(torch.round(centres[qa] + torch.randn((npool, d), generator=g, device=device) * sigma), 0, 255)
     return dict(centroids=cent.cpu().numpy().astype(np.float32), offsets=offsets.cpu().numpy().astype(np.int64),
-                ids=order.cpu().numpy().astype(np.int64), vectors=vecs.cpu().numpy().astype(np.float32),
-                queries=queries.cpu().numpy().astype(np.float32))
+                ids=order.cpu().numpy().astype(np.int64, copy=False), vectors=vecs.cpu().numpy().astype(np.float32, copy=False),
+                queries=queries.cpu().numpy().astype(np.float32, copy=False))
 
 
 def make_dataset_shard(cfg, device, rank, world, seed=1234):
@@ -1599,8 +1599,16 @@ def main():
     # profiles/).  Last, bounded and guarded: whatever happens here, the headline and the strong record are already
     # published.  PF_BENCH_EXTRAS=0 skips it.
     want_configs4 = weak and world >= int(os.environ.get("PF_BENCH_EXTRAS_MIN_GPUS", "8")) and os.environ.get("PF_BENCH_EXTRAS", "1") != "0"
+    c4_mem = (True, 0, None)
+    if want_configs4:
+        c4_mem = host_memory_fits(CONFIGS["synth10m_nlist16384"], world)
+        c4_mem = comm.broadcast_object(c4_mem) if world > 1 else c4_mem      # rank 0 decides for everybody
     if want_configs4 and not time_for("the configs[4] record", 300):
         state["configs4"] = {"skipped": "not enough of the run's time allowance left (PF_BENCH_RUN_LIMIT_S)"}
+    elif want_configs4 and not c4_mem[0]:
+        state["configs4"] = {"skipped": f"host memory: building the 10M-vector data set on {world} ranks needs about {c4_mem[1] / 2**30:.0f} GiB, "
+                                        f"{(c4_mem[2] or 0) / 2**30:.0f} GiB available on this host"}
+        log(f"[rank {rank}] skipping the configs[4] record: {state['configs4']['skipped']}")
     elif want_configs4:
         if rank == 0:
             guard.publish(make_line(rec))
@@ -1633,6 +1641,35 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def host_memory_available():
+    """bytes of host memory this job can still take: MemAvailable, capped by the cgroup limit of the container"""
+    avail = None
+    try:
+        for ln in Path("/proc/meminfo").read_text().splitlines():
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except (OSError, ValueError):
+        pass
+    for lim_f, use_f in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = Path(lim_f).read_text().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                room = int(lim) - int(Path(use_f).read_text().strip())
+                avail = room if avail is None else min(avail, room)
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
+def host_memory_fits(cfg, world):
+    """every rank of a fixed-index run builds the WHOLE synthetic data set on the host before it keeps its shard
+    (make_dataset): nb x d float32 + ids + slack per rank.  A job that the kernel's OOM killer ends loses its line."""
+    need = world * (int(cfg["nb"]) * (cfg["d"] * 4 + 8) * 1.25 + (1 << 30)) + (8 << 30)
+    avail = host_memory_available()
+    return (avail is None or avail > need), need, avail
 
 
 def default_strong_grid(world):
