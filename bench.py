@@ -1497,10 +1497,18 @@ def main():
     import torch.distributed as dist
     # PF_BENCH_DRYRUN=1 (tests/test_bench_dryrun.py): the control flow of this file on the CPU — gloo, a stub engine,
     # no-op streams — to prove that every rank takes the same path through the collectives.  Measures nothing.
-    dry = os.environ.get("PF_BENCH_DRYRUN") == "1"
+    # PF_BENCH_DRYRUN=emul (tests/test_cuda_emulated.py): the same no-op streams, but the REAL prefhetch_b200.Engine over the
+    # CPU-emulated build of the CUDA sources (PF_LIB = tests/cuda_emul's library; one rank): the whole N = 1 flow — timed
+    # loops, e2e submit / collect, recall, parity self-check, CPU baseline — with real arithmetic.  Measures nothing either.
+    dry_mode = os.environ.get("PF_BENCH_DRYRUN", "")
+    dry = dry_mode in ("1", "emul")
     if dry:
         from tests import bench_stub
-        sys.modules["prefhetch_b200"] = bench_stub.install(torch)
+        stub = bench_stub.install(torch)
+        if dry_mode == "1":
+            sys.modules["prefhetch_b200"] = stub
+        elif not os.environ.get("PF_LIB") or world > 1:
+            raise SystemExit("PF_BENCH_DRYRUN=emul needs PF_LIB (the emulated build) and runs one rank")
         if os.environ.get("PF_BENCH_DRYRUN_NB"):
             for c in CONFIGS.values():
                 c["nb"] = min(c["nb"], int(os.environ["PF_BENCH_DRYRUN_NB"]))

@@ -179,7 +179,12 @@ def rewrite(text: str, name: str) -> str:
     return text
 
 
-def build(out_dir: Path, opt: str = "-O2", verbose: bool = False) -> Path:
+def asan_runtime() -> str:
+    """libasan.so to LD_PRELOAD into the python that loads an --asan build"""
+    return subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+
+
+def build(out_dir: Path, opt: str = "-O2", verbose: bool = False, asan: bool = False) -> Path:
     out_dir = Path(out_dir)
     gen = out_dir / "gen" / "prefhetch_b200" / "csrc"
     gen.mkdir(parents=True, exist_ok=True)
@@ -194,8 +199,11 @@ def build(out_dir: Path, opt: str = "-O2", verbose: bool = False) -> Path:
         dst.write_text(rewrite(p.read_text(), p.name))
         if p.suffix == ".cu":
             units.append(dst)
-    so = out_dir / "libprefhetch_b200_emul.so"
-    cmd = ["/usr/bin/g++", "-std=c++17", opt, "-g1", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-pthread",
+    so = out_dir / ("libprefhetch_b200_emul_asan.so" if asan else "libprefhetch_b200_emul.so")
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
+    if asan:
+        opt = "-O1"
+    cmd = ["/usr/bin/g++", "-std=c++17", opt, *san, "-g1", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-pthread",
            "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-attributes",
            "-I" + str(HERE / "include"), "-o", str(so), *[str(u) for u in units], "-lz", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -208,5 +216,6 @@ def build(out_dir: Path, opt: str = "-O2", verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    d = Path(sys.argv[1] if len(sys.argv) > 1 else os.environ.get("PF_EMUL_DIR", "/tmp/pf_cuda_emul"))
-    print(build(d, verbose=True))
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    d = Path(argv[0] if argv else os.environ.get("PF_EMUL_DIR", "/tmp/pf_cuda_emul"))
+    print(build(d, verbose=True, asan="--asan" in sys.argv))

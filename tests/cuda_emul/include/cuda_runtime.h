@@ -139,7 +139,25 @@ pf_emul_switch:
 #error "tests/cuda_emul needs x86-64"
 #endif
 
+// AddressSanitizer build (build_emul.py --asan): a memcheck of every kernel — device allocations are exact-size
+// heap blocks, the dynamic shared memory of a block is an exact-size heap block, and the fiber switches are
+// announced to the sanitizer so that its stack bookkeeping follows them.
+#if defined(__SANITIZE_ADDRESS__)
+#define PF_EMUL_ASAN 1
+extern "C" void __sanitizer_start_switch_fiber(void **fake_stack_save, const void *bottom, size_t size);
+extern "C" void __sanitizer_finish_switch_fiber(void *fake_stack_save, const void **bottom_old, size_t *size_old);
+#define PF_ASAN_START(save, bottom, size) __sanitizer_start_switch_fiber(save, bottom, size)
+#define PF_ASAN_FINISH(save, bo, so) __sanitizer_finish_switch_fiber(save, bo, so)
+#else
+#define PF_ASAN_START(save, bottom, size) ((void)0)
+#define PF_ASAN_FINISH(save, bo, so) ((void)0)
+#endif
+
+#if defined(PF_EMUL_ASAN)
+constexpr size_t kStack = 128 * 1024;   // instrumented frames are larger
+#else
 constexpr size_t kStack = 96 * 1024;
+#endif
 constexpr int kMaxThreads = 1024;
 constexpr size_t kMaxDynSmem = 232 * 1024;
 
@@ -161,11 +179,20 @@ struct Block {
     void *sched_sp = nullptr;
     int cur = 0;
     dim3 bdim;
+    // sanitizer bookkeeping
+    void *fake[kMaxThreads];
+    void *sched_fake = nullptr;
+    const void *sched_bottom = nullptr;
+    size_t sched_size = 0;
 };
+
+inline std::atomic<unsigned long long> g_launch_id{0};
 
 struct Worker {
     char *stacks = nullptr;       // kMaxThreads fiber stacks
     char *dyn = nullptr;          // dynamic shared memory of the running block
+    char *exact = nullptr;        // sanitizer build: exact-size dynamic shared memory of the current launch
+    unsigned long long exact_launch = ~0ull;
     Block blk;
     void ensure() {
         if (stacks) return;
@@ -185,7 +212,9 @@ inline thread_local dim3 tl_blockDim, tl_gridDim;
 inline void yield_to_scheduler() {
     Block &b = tl_worker.blk;
     const int me = b.cur;
+    PF_ASAN_START(&b.fake[me], b.sched_bottom, b.sched_size);
     pf_emul_switch(&b.sp[me], b.sched_sp);
+    PF_ASAN_FINISH(tl_worker.blk.fake[me], nullptr, nullptr);
 }
 
 inline void release_if_complete(Barrier &bar, int live) {
@@ -205,19 +234,36 @@ inline void barrier_wait(Barrier &bar, const int &live) {
 extern "C" inline void pf_emul_fiber_entry() {
     Block &b = tl_worker.blk;
     const int me = b.cur;
+    PF_ASAN_FINISH(nullptr, &b.sched_bottom, &b.sched_size);
     (*b.body)();
     b.done[me] = true;
     b.live--;
     b.wlive[me / 32]--;
     release_if_complete(b.bar, b.live);           // threads that exited count as arrived
     release_if_complete(b.wbar[me / 32], b.wlive[me / 32]);
+    PF_ASAN_START(nullptr, b.sched_bottom, b.sched_size);    // nullptr: this fiber's fake stack is released
     pf_emul_switch(&b.sp[me], b.sched_sp);
     abort();                                       // a finished fiber is never resumed
 }
 
-inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, unsigned bx, unsigned by, unsigned bz) {
+inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, size_t smem, unsigned bx, unsigned by, unsigned bz) {
     Worker &w = tl_worker;
     w.ensure();
+#if defined(PF_EMUL_ASAN)
+    // an exact-size block per (worker, launch): a kernel that indexes past the dynamic shared memory it was
+    // launched with is reported.  Not per CTA: freed blocks sit in the sanitizer's quarantine, and thousands of
+    // 100 KB blocks per launch turn into page-fault time.
+    if (w.exact_launch != g_launch_id.load() || !w.exact) {
+        free(w.exact);
+        w.exact = nullptr;
+        if (posix_memalign((void **)&w.exact, 16, smem ? smem : 16)) abort();   // 16: what the kernels may assume
+        w.exact_launch = g_launch_id.load();
+    }
+    char *const pool_dyn = w.dyn;
+    w.dyn = w.exact;
+#else
+    (void)smem;
+#endif
     Block &b = w.blk;
     const int T = (int)(block.x * block.y * block.z);
     b.body = &body;
@@ -250,7 +296,9 @@ inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, 
             b.cur = t;
             const unsigned tx = (unsigned)t % block.x, ty = ((unsigned)t / block.x) % block.y, tz = (unsigned)t / (block.x * block.y);
             tl_threadIdx = uint3{tx, ty, tz};
+            PF_ASAN_START(&b.sched_fake, w.stacks + (size_t)t * kStack, kStack);
             pf_emul_switch(&b.sched_sp, b.sp[t]);
+            PF_ASAN_FINISH(b.sched_fake, nullptr, nullptr);
             if (b.done[t]) {
                 remaining--;
                 progressed++;
@@ -262,6 +310,9 @@ inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, 
         }
         (void)progressed;
     }
+#if defined(PF_EMUL_ASAN)
+    w.dyn = pool_dyn;
+#endif
 }
 
 // ---- the block pool ---------------------------------------------------------------------------------------
@@ -272,6 +323,7 @@ struct Pool {
     std::vector<std::thread> workers;
     const std::function<void()> *body = nullptr;
     dim3 grid, block;
+    size_t smem_bytes = 0;
     std::atomic<unsigned long long> next{0};
     unsigned long long total = 0;
     unsigned long long epoch = 0;
@@ -283,7 +335,7 @@ struct Pool {
             const unsigned long long i = next.fetch_add(1);
             if (i >= total) break;
             const unsigned bx = (unsigned)(i % grid.x), by = (unsigned)((i / grid.x) % grid.y), bz = (unsigned)(i / ((unsigned long long)grid.x * grid.y));
-            run_block(*body, grid, block, bx, by, bz);
+            run_block(*body, grid, block, smem_bytes, bx, by, bz);
         }
     }
     void loop() {
@@ -325,6 +377,8 @@ struct Pool {
         body = &fn;
         grid = g;
         block = b;
+        smem_bytes = smem;
+        g_launch_id++;
         total = nblocks;
         next.store(0);
         const bool fan_out = nblocks > 1 && !workers.empty();
@@ -373,6 +427,13 @@ struct AllocHdr {
     size_t bytes;
     unsigned long long magic;
 };
+#if defined(PF_EMUL_ASAN)
+inline void *dev_alloc(size_t bytes) {
+    void *p = nullptr;
+    return posix_memalign(&p, 256, bytes ? bytes : 1) ? nullptr : p;
+}
+inline void dev_free(void *p) { free(p); }
+#else
 inline void *dev_alloc(size_t bytes) {
     char *raw = nullptr;
     const size_t total = kRed + bytes + kRed;
@@ -404,6 +465,7 @@ inline void dev_free(void *p) {
         }
     free(raw);
 }
+#endif
 
 }  // namespace pf_emul
 

@@ -78,3 +78,44 @@ def test_smoke_on_the_emulated_device(emul):
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True,
                        timeout=900, env=env, cwd=str(ROOT))
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
+
+
+def test_bench_on_the_emulated_device(emul):
+    """bench.py's whole N = 1 flow — setup, timed loops, recall, the pipelined e2e submit / collect, the parity
+    self-check on real encryptions, the CPU baseline, the JSON line — through the REAL Engine over the emulated
+    device (PF_BENCH_DRYRUN=emul: no-op torch streams; tests/test_bench_dryrun.py covers the multi-rank control flow
+    with a stub engine).  The numbers mean nothing; the line's structure and the parity count do."""
+    import json
+    so, env = emul
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--config", "siftsmall_nlist100_nprobe8", "--nq", "4", "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=900, env=dict(env, PF_BENCH_DRYRUN="emul"), cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line.get("aborted_stage") is None
+    assert line["parity_checked"] == 32 and line["parity"]["results_in_batch"] == 32
+    assert line["gpu_launches"] > 0 and line["value"] > 0 and line["roofline"]["achieved"] > 0
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 4 * (113 + 2 * 4 * 8192 * 8) and e2e["d2h_bytes_per_step"] >= 32 * 2 * 8192 * 8
+    assert line["cpu_baseline"]["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["recall_at_10"] is not None and line["config"]["queries_per_step"] == 4
+    assert set(line["phases_ms_per_step"]) == {"coarse", "to_ntt", "rotate", "mac", "intt"}
+
+
+@pytest.mark.skipif(os.environ.get("PF_EMUL_ASAN") != "1", reason="8.5 minutes: PF_EMUL_ASAN=1 runs the memcheck (result recorded in profiles/README.md)")
+def test_gpu_suite_memcheck_under_asan(tmp_path):
+    """the whole -m gpu suite with the emulated device built under AddressSanitizer: device allocations and the
+    dynamic shared memory of a launch are exact-size heap blocks, so any kernel (or host) access outside them
+    aborts the run with a report — compute-sanitizer memcheck's job, on the CPU"""
+    sys.path.insert(0, str(ROOT / "tests" / "cuda_emul"))
+    import build_emul
+    so = build_emul.build(tmp_path, asan=True)
+    ld = tmp_path / "ld"
+    ld.mkdir()
+    (ld / "libprefhetch_b200.so").symlink_to(so)
+    env = dict(os.environ, PF_LIB=str(so), LD_PRELOAD=build_emul.asan_runtime(), LD_LIBRARY_PATH=str(ld),
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
+                       capture_output=True, text=True, timeout=3000, env=env, cwd=str(ROOT))
+    assert r.returncode == 0 and "AddressSanitizer" not in (r.stdout + r.stderr), (r.stdout + r.stderr)[-6000:]
