@@ -1498,7 +1498,7 @@ def main():
     # PF_BENCH_DRYRUN=1 (tests/test_bench_dryrun.py): the control flow of this file on the CPU — gloo, a stub engine,
     # no-op streams — to prove that every rank takes the same path through the collectives.  Measures nothing.
     # PF_BENCH_DRYRUN=emul (tests/test_cuda_emulated.py): the same no-op streams, but the REAL prefhetch_b200.Engine over the
-    # CPU-emulated build of the CUDA sources (PF_LIB = tests/cuda_emul's library; one rank): the whole N = 1 flow — timed
+    # CPU-emulated build of the CUDA sources (PF_LIB = tests/cuda_emul's library; several ranks with PF_EMUL_IPC=1): the whole flow — timed
     # loops, e2e submit / collect, recall, parity self-check, CPU baseline — with real arithmetic.  Measures nothing either.
     dry_mode = os.environ.get("PF_BENCH_DRYRUN", "")
     dry = dry_mode in ("1", "emul")
@@ -1507,8 +1507,12 @@ def main():
         stub = bench_stub.install(torch)
         if dry_mode == "1":
             sys.modules["prefhetch_b200"] = stub
-        elif not os.environ.get("PF_LIB") or world > 1:
-            raise SystemExit("PF_BENCH_DRYRUN=emul needs PF_LIB (the emulated build) and runs one rank")
+        elif not os.environ.get("PF_LIB"):
+            raise SystemExit("PF_BENCH_DRYRUN=emul needs PF_LIB (the emulated build of tests/cuda_emul)")
+        for key, env in (("nq", "PF_BENCH_DRYRUN_NQ"), ("nprobe", "PF_BENCH_DRYRUN_NPROBE"), ("nlist", "PF_BENCH_DRYRUN_NLIST")):
+            if os.environ.get(env):       # emulated runs: every workload of the job (strong record, configs[4]) shrinks with it
+                for c in list(CONFIGS.values()) + [cfg]:
+                    c[key] = min(c[key], int(os.environ[env]))
         if os.environ.get("PF_BENCH_DRYRUN_NB"):
             for c in CONFIGS.values():
                 c["nb"] = min(c["nb"], int(os.environ["PF_BENCH_DRYRUN_NB"]))

@@ -18,13 +18,18 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <time.h>
 
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <map>
+#include <string>
 #include <mutex>
 #include <thread>
 #include <type_traits>
@@ -289,9 +294,32 @@ inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, 
     }
     int remaining = T;
     long passes = 0;
+    // PF_EMUL_ORDER: the order in which the threads of a block are resumed in a scheduling pass — "forward"
+    // (default), "reverse", or "random[:seed]" (a fresh permutation every pass).  Results must not depend on it:
+    // a kernel that does is missing a barrier (the racecheck of this emulation).
+    static const int order_mode = [] {
+        const char *e = getenv("PF_EMUL_ORDER");
+        return !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+    }();
+    static const unsigned long long order_seed = [] {
+        const char *e = getenv("PF_EMUL_ORDER");
+        const char *c = e ? strchr(e, ':') : nullptr;
+        return c ? strtoull(c + 1, nullptr, 10) : 12345ull;
+    }();
+    unsigned long long rng = order_seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)bx << 40) + ((unsigned long long)by << 20) + bz + 1;
+    static thread_local int perm[kMaxThreads];
+    for (int t = 0; t < T; t++) perm[t] = order_mode == 1 ? T - 1 - t : t;
     while (remaining > 0) {
         int progressed = 0;
-        for (int t = 0; t < T; t++) {
+        if (order_mode == 2)
+            for (int t = T - 1; t > 0; t--) {     // Fisher-Yates with a xorshift generator
+                rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+                const int j = (int)(rng % (unsigned long long)(t + 1));
+                const int tmp = perm[t];
+                perm[t] = perm[j], perm[j] = tmp;
+            }
+        for (int ti = 0; ti < T; ti++) {
+            const int t = perm[ti];
             if (b.done[t]) continue;
             b.cur = t;
             const unsigned tx = (unsigned)t % block.x, ty = ((unsigned)t / block.x) % block.y, tz = (unsigned)t / (block.x * block.y);
@@ -421,6 +449,68 @@ inline unsigned long long globaltimer() {
     return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
 }
 
+// ---- PF_EMUL_IPC=1: allocations up to PF_EMUL_IPC_MAX_MB (default 256) live in POSIX shared memory, so that
+// cudaIpcGetMemHandle / cudaIpcOpenMemHandle work ACROSS PROCESSES (the multi-rank gather protocol of bench.py:
+// peer buffers, arrival / ack flags) --------------------------------------------------------------------
+struct ShmRec {
+    std::string name;
+    size_t bytes;
+    bool owner;
+};
+struct ShmTable {
+    std::mutex mu;
+    std::map<void *, ShmRec> recs;
+    unsigned long long seq = 0;
+    ~ShmTable() {
+        for (auto &kv : recs)
+            if (kv.second.owner) shm_unlink(kv.second.name.c_str());
+    }
+};
+inline ShmTable &shm_table() {
+    static ShmTable t;
+    return t;
+}
+inline bool ipc_enabled() {
+    static const bool on = getenv("PF_EMUL_IPC") && atoi(getenv("PF_EMUL_IPC")) != 0;
+    return on;
+}
+inline size_t ipc_max_bytes() {
+    static const size_t mb = getenv("PF_EMUL_IPC_MAX_MB") ? (size_t)atoll(getenv("PF_EMUL_IPC_MAX_MB")) : 256;
+    return mb << 20;
+}
+inline void *shm_alloc(size_t bytes) {
+    ShmTable &t = shm_table();
+    std::lock_guard<std::mutex> lk(t.mu);
+    char name[64];
+    snprintf(name, sizeof name, "/pf_emul_%d_%llu", (int)getpid(), t.seq++);
+    const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    const size_t len = (bytes + 4095) & ~(size_t)4095;
+    if (ftruncate(fd, (off_t)len)) {
+        close(fd);
+        shm_unlink(name);
+        return nullptr;
+    }
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        shm_unlink(name);
+        return nullptr;
+    }
+    t.recs[p] = ShmRec{name, len, true};
+    return p;
+}
+inline bool shm_release(void *p) {
+    ShmTable &t = shm_table();
+    std::lock_guard<std::mutex> lk(t.mu);
+    auto it = t.recs.find(p);
+    if (it == t.recs.end()) return false;
+    munmap(p, it->second.bytes);
+    if (it->second.owner) shm_unlink(it->second.name.c_str());
+    t.recs.erase(it);
+    return true;
+}
+
 // ---- device allocations with red zones (a write past either end aborts at cudaFree) -------------------
 constexpr size_t kRed = 256;
 struct AllocHdr {
@@ -429,12 +519,16 @@ struct AllocHdr {
 };
 #if defined(PF_EMUL_ASAN)
 inline void *dev_alloc(size_t bytes) {
+    if (ipc_enabled() && bytes <= ipc_max_bytes()) return shm_alloc(bytes ? bytes : 1);
     void *p = nullptr;
     return posix_memalign(&p, 256, bytes ? bytes : 1) ? nullptr : p;
 }
-inline void dev_free(void *p) { free(p); }
+inline void dev_free(void *p) {
+    if (p && !shm_release(p)) free(p);
+}
 #else
 inline void *dev_alloc(size_t bytes) {
+    if (ipc_enabled() && bytes <= ipc_max_bytes()) return shm_alloc(bytes ? bytes : 1);
     char *raw = nullptr;
     const size_t total = kRed + bytes + kRed;
     if (posix_memalign((void **)&raw, 256, total ? total : 256)) return nullptr;
@@ -445,7 +539,7 @@ inline void *dev_alloc(size_t bytes) {
     return raw + kRed;
 }
 inline void dev_free(void *p) {
-    if (!p) return;
+    if (!p || shm_release(p)) return;
     char *raw = (char *)p - kRed;
     AllocHdr h;
     memcpy(&h, raw, sizeof h);
@@ -674,11 +768,17 @@ static inline typename std::common_type<A, B>::type max(A a, B b) {
 }
 
 // ---- runtime API: synchronous streams, host memory is device memory ---------------------------------------
+namespace pf_emul {
+inline int device_count() {
+    static const int n = getenv("PF_EMUL_DEVICES") ? atoi(getenv("PF_EMUL_DEVICES")) : 1;   // all of them are this host
+    return n < 1 ? 1 : n;
+}
+}  // namespace pf_emul
 static inline cudaError_t cudaGetDeviceCount(int *n) {
-    *n = 1;
+    *n = pf_emul::device_count();
     return cudaSuccess;
 }
-static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < pf_emul::device_count() ? cudaSuccess : cudaErrorInvalidValue; }
 static inline cudaError_t cudaGetDevice(int *d) {
     *d = 0;
     return cudaSuccess;
@@ -774,15 +874,45 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEve
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 template <class F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
-// CUDA IPC, same process only: the handle carries the pointer (cross-process mapping needs a device; the multi-rank
-// protocol is covered under gloo by tests/test_multi_rank.py and tests/test_bench_dryrun.py)
+// CUDA IPC.  PF_EMUL_IPC=1: the handle names the POSIX shared-memory segment behind the allocation and another
+// process maps it; otherwise same-process only (the handle carries the pointer).
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
     memset(h, 0, sizeof *h);
-    memcpy(h->reserved, &p, sizeof p);
+    if (pf_emul::ipc_enabled()) {
+        pf_emul::ShmTable &t = pf_emul::shm_table();
+        std::lock_guard<std::mutex> lk(t.mu);
+        auto it = t.recs.find(p);
+        if (it == t.recs.end() || it->second.name.size() > 47) return cudaErrorInvalidValue;
+        h->reserved[0] = 'S';
+        memcpy(h->reserved + 1, it->second.name.c_str(), it->second.name.size() + 1);
+        memcpy(h->reserved + 56, &it->second.bytes, 8);
+        return cudaSuccess;
+    }
+    h->reserved[0] = 'P';
+    memcpy(h->reserved + 8, &p, sizeof p);
     return cudaSuccess;
 }
 static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
-    memcpy(p, h.reserved, sizeof *p);
-    return *p ? cudaSuccess : cudaErrorInvalidValue;
+    if (h.reserved[0] == 'P') {
+        memcpy(p, h.reserved + 8, sizeof *p);
+        return *p ? cudaSuccess : cudaErrorInvalidValue;
+    }
+    if (h.reserved[0] != 'S') return cudaErrorInvalidValue;
+    h.reserved[55] = 0;
+    size_t bytes = 0;
+    memcpy(&bytes, h.reserved + 56, 8);
+    const int fd = shm_open(h.reserved + 1, O_RDWR, 0600);
+    if (fd < 0) return cudaErrorInvalidValue;
+    void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return cudaErrorMemoryAllocation;
+    pf_emul::ShmTable &t = pf_emul::shm_table();
+    std::lock_guard<std::mutex> lk(t.mu);
+    t.recs[m] = pf_emul::ShmRec{std::string(h.reserved + 1), bytes, false};
+    *p = m;
+    return cudaSuccess;
 }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *p) {
+    if (pf_emul::ipc_enabled()) return pf_emul::shm_release(p) ? cudaSuccess : cudaErrorInvalidValue;
+    return cudaSuccess;
+}

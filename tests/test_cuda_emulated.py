@@ -75,8 +75,9 @@ def test_gpu_suite_on_the_emulated_device(emul):
 def test_smoke_on_the_emulated_device(emul):
     """__graft_entry__.smoke() — the driver's first call on the GPU box — end to end on the emulated device"""
     so, env = emul
+    # threads of a block resumed in a random order every scheduling pass: results must not depend on it
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], capture_output=True, text=True,
-                       timeout=900, env=env, cwd=str(ROOT))
+                       timeout=900, env=dict(env, PF_EMUL_ORDER="random:3"), cwd=str(ROOT))
     assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
 
 
@@ -119,3 +120,41 @@ def test_gpu_suite_memcheck_under_asan(tmp_path):
     r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-q", "-m", "gpu", "-x", "-p", "no:cacheprovider"],
                        capture_output=True, text=True, timeout=3000, env=env, cwd=str(ROOT))
     assert r.returncode == 0 and "AddressSanitizer" not in (r.stdout + r.stderr), (r.stdout + r.stderr)[-6000:]
+
+
+def _torchrun_bench(env, n, port, extra_env=None):
+    import json
+    e = dict(env, PF_BENCH_DRYRUN="emul", PF_EMUL_IPC="1", PF_EMUL_DEVICES="8", PF_EMUL_THREADS=str(max(1, 8 // n)),
+             PF_BENCH_DRYRUN_NB="6000", PF_BENCH_DRYRUN_NQ="8", PF_BENCH_DRYRUN_NPROBE="2", PF_BENCH_DRYRUN_NLIST="24")
+    e.update(extra_env or {})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(ROOT / "bench.py"), "--gpus", str(n), "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=1500, env=e, cwd=str(ROOT))
+    assert r.returncode == 0, r.stderr[-4000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("n", [2] + ([4, 8] if os.environ.get("PF_EMUL_FULL") == "1" else []))
+def test_multi_rank_bench_on_emulated_devices(emul, n):
+    """the driver's `bench.py --gpus N` default run with the REAL engine on every rank: emulated devices whose
+    allocations live in POSIX shared memory (PF_EMUL_IPC=1), so the peer-buffer gather (IPC handles, copy into rank
+    0's buffer, arrival / ack flag kernels) moves real result ciphertexts between processes and `gather_verified`
+    compares real checksums; then the e2e pass through the one shared response buffer, the strong-scaling record on
+    its L x Q rank grid with its 1-GPU reference, and at 8 ranks the configs[4] stage.  gloo instead of NCCL,
+    synchronous streams: the protocol and the bookkeeping are what is checked."""
+    so, env = emul
+    line = _torchrun_bench(env, n, 29700 + n)
+    assert line.get("aborted_stage") is None and line["n_gpus"] == n and line["scaling"] == "weak"
+    gv = line["gather_verified"]
+    assert gv["ranks"] == n - 1 and gv["results"] > 0 and "mismatch_ranks" not in gv
+    assert line["e2e"]["value"] > 0 and "one host buffer per node" in line["e2e"]["response"]
+    st = line["strong"]
+    assert st["scaling"] == "strong" and st["value"] > 0 and st["value_1gpu"] > 0 and st["e2e"]["value"] > 0
+    assert st["gather_verified"]["ranks"] == n - 1 and "mismatch_ranks" not in st["gather_verified"]
+    assert st["config"]["parallelism"].startswith({2: "grid 2 list shards x 1", 4: "grid 2 list shards x 2", 8: "grid 2 list shards x 4"}[n])
+    if n == 8:
+        c4 = line["configs4"]
+        assert c4["value"] > 0 and c4["gather_verified"]["ranks"] == 7 and c4["e2e"]["value"] > 0
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("pf_emul_") or f.startswith("pf_bench_297")]
