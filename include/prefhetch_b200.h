@@ -104,6 +104,18 @@ int pf_coarse_quantize(pf_engine *e, uint64_t nq, const float *x, uint32_t nprob
  * nothing past cap is written and PF_ERR_CAPACITY is returned with *total = required entries. */
 int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64_t *idx, uint32_t nprobe,
                           float *dist, int64_t *labels, uint64_t cap, uint64_t *list_sizes, uint64_t *total);
+/* The same call with the distance the reference's FAISS fork computes TODAY: product-quantizer ADC
+ * (replaces: faiss::IndexIVFPQ::search_encrypted as called at ref: src/server/server_lib.cpp:126-130 on the index
+ * built at :34-36 with SUB_QUANTIZERS x SUB_QUANTIZER_SIZE bits, include/common/client_server_utils.h:19-20).
+ * pf_load_pq gives the engine the product quantizer of the loaded index: M sub-quantizers of nbits = 8 bits,
+ * pq_centroids [M][256][d/M] (FAISS ProductQuantizer::centroids as stored in the .faiss file) and codes
+ * [ntotal][M], one row per vector in the order of pf_load_index's `ids` (the invlists' code arrays back to back).
+ * pf_search_lists_pq packs (distance, id) exactly like pf_search_lists_plain; distance = sum over sub-quantizers of
+ * ||(x - centroid[l])_m - pq[m][code_m]||^2 in float (by_residual, METRIC_L2).  [EXT]: restated from the published
+ * FAISS algorithm (the fork's source is absent); equal to a FAISS build up to float rounding, not bit for bit. */
+int pf_load_pq(pf_engine *e, uint32_t M, uint32_t nbits, const float *pq_centroids, const uint8_t *codes);
+int pf_search_lists_pq(pf_engine *e, uint64_t nq, const float *x, const int64_t *idx, uint32_t nprobe,
+                       float *dist, int64_t *labels, uint64_t cap, uint64_t *list_sizes, uint64_t *total);
 /* replaces: Server::preciseSearch (ref: src/server/server_lib.cpp:140-167): ids [nq][nids] are
  * base-file row numbers, out [nq][nids]. */
 int pf_precise_search(pf_engine *e, uint64_t nq, const float *x, const int64_t *ids, uint32_t nids, float *out);

@@ -918,7 +918,7 @@ void pfo_coarse_quantize(size_t nq, size_t d, size_t nlist, const float *x, cons
  * one (distance, id) per stored vector, packed back to back, list_sizes[i] = sum of list lengths
  * (consumer contract: src/client/client_lib.cpp:129-148).  The distance is the exact squared L2
  * of src/server/server_lib.cpp:140-167 (the semantics the HE evaluation reproduces); the fork's
- * PQ-ADC approximation is not restated (source absent). */
+ * PQ-ADC approximation is restated separately: pfo_search_lists_pq below. */
 size_t pfo_search_lists_plain(size_t nq, size_t d, const float *x, const int64_t *idx, size_t nprobe,
                               const int64_t *list_offsets, const int64_t *ids, const float *vectors, float *dist,
                               int64_t *labels, size_t cap, size_t *list_sizes) {
@@ -940,6 +940,93 @@ size_t pfo_search_lists_plain(size_t nq, size_t d, const float *x, const int64_t
         list_sizes[i] = cnt;
     }
     return w;
+}
+
+/* What m_Index->search_encrypted computes in the reference TODAY (ref: src/server/server_lib.cpp:126-130 on the
+ * faiss::IndexIVFPQ built at :34-36 with SUB_QUANTIZERS sub-quantizers of SUB_QUANTIZER_SIZE bits,
+ * include/common/client_server_utils.h:19-20): the product-quantizer asymmetric distance (ADC) of the query to every
+ * stored code of every given list, all of them returned (no top-k), packed like pfo_search_lists_plain.
+ * [EXT] The fork's source is absent (PES-Innovation-Lab/PreFHEtch-faiss @ 49c5b57c); this restates the
+ * published FAISS algorithm for IndexIVFPQ with by_residual = true and METRIC_L2 in its defining form
+ * (faiss/IndexIVFPQ.cpp, IVFPQScannerT::precompute_list_tables with use_precomputed_table = 0 and scan_list_with_table;
+ * faiss/impl/ProductQuantizer.cpp compute_distance_table; faiss/utils/distances_simd.cpp fvec_L2sqr_ref):
+ *     r        = x - centroid[l]                                   (float)
+ *     tab[m][j] = sum_k (r[m dsub + k] - pq[m][j][k])^2            (float, k ascending, multiply then add)
+ *     dis(code) = sum_m tab[m][code[m]]                            (float, m ascending, from 0)
+ * FAISS's default build evaluates the same sums with SIMD partial sums (and, when the table fits, through its
+ * precomputed ||c||^2 + 2<c, pq> tables), which rounds differently: equality with a FAISS build is to float rounding,
+ * not bit for bit.  PARITY UNPINNED by the reference.  nbits = 8 (one byte per sub-quantizer), as the reference builds it.
+ * pq_centroids [M][256][dsub] (FAISS ProductQuantizer::centroids layout), codes [ntotal][M] in list order. */
+__attribute__((optimize("fp-contract=off")))
+size_t pfo_search_lists_pq(size_t nq, size_t d, const float *x, const int64_t *idx, size_t nprobe, const float *centroids,
+                           const int64_t *list_offsets, const int64_t *ids, size_t M, const float *pq_centroids,
+                           const uint8_t *codes, float *dist, int64_t *labels, size_t cap, size_t *list_sizes) {
+    const size_t ksub = 256, dsub = d / M;
+    float *r = (float *)malloc(d * sizeof(float));
+    float *tab = (float *)malloc(M * ksub * sizeof(float));
+    size_t w = 0;
+    for (size_t i = 0; i < nq; i++) {
+        size_t cnt = 0;
+        for (size_t p = 0; p < nprobe; p++) {
+            int64_t l = idx[i * nprobe + p];
+            if (l < 0) continue;
+            if (list_offsets[l + 1] > list_offsets[l]) {
+                for (size_t k = 0; k < d; k++) r[k] = x[i * d + k] - centroids[(size_t)l * d + k];
+                for (size_t m = 0; m < M; m++)
+                    for (size_t j = 0; j < ksub; j++) {
+                        const float *c = pq_centroids + (m * ksub + j) * dsub;
+                        float acc = 0.0f;
+                        for (size_t k = 0; k < dsub; k++) {
+                            const float t = r[m * dsub + k] - c[k];
+                            const float t2 = t * t;
+                            acc = acc + t2;
+                        }
+                        tab[m * ksub + j] = acc;
+                    }
+            }
+            for (int64_t o = list_offsets[l]; o < list_offsets[l + 1]; o++) {
+                if (w < cap) {
+                    const uint8_t *code = codes + (size_t)o * M;
+                    float acc = 0.0f;
+                    for (size_t m = 0; m < M; m++) acc = acc + tab[m * ksub + code[m]];
+                    dist[w] = acc;
+                    labels[w] = ids[o];
+                }
+                w++;
+                cnt++;
+            }
+        }
+        list_sizes[i] = cnt;
+    }
+    free(r);
+    free(tab);
+    return w;
+}
+
+/* FAISS ProductQuantizer::compute_code for nbits = 8 (faiss/impl/ProductQuantizer.cpp: nearest sub-centroid per
+ * sub-vector by fvec_L2sqr, first minimum wins) applied to the residual of a vector to the centroid of its list —
+ * what IndexIVFPQ::add stores (ref: src/server/server_lib.cpp:80).  Test / bench data generation only. */
+__attribute__((optimize("fp-contract=off")))
+void pfo_pq_encode_residuals(size_t n, size_t d, const float *vectors, const int64_t *list_of, const float *centroids, size_t M,
+                             const float *pq_centroids, uint8_t *codes) {
+    const size_t ksub = 256, dsub = d / M;
+    for (size_t v = 0; v < n; v++)
+        for (size_t m = 0; m < M; m++) {
+            float best = 0.0f;
+            size_t bj = 0;
+            for (size_t j = 0; j < ksub; j++) {
+                const float *c = pq_centroids + (m * ksub + j) * dsub;
+                float acc = 0.0f;
+                for (size_t k = 0; k < dsub; k++) {
+                    const float rk = vectors[v * d + m * dsub + k] - centroids[(size_t)list_of[v] * d + m * dsub + k];
+                    const float t = rk - c[k];
+                    const float t2 = t * t;
+                    acc = acc + t2;
+                }
+                if (j == 0 || acc < best) best = acc, bj = j;
+            }
+            codes[v * M + m] = (uint8_t)bj;
+        }
 }
 
 /* ref: src/client/client_lib.cpp:272-291,325-330.  returned[nq][k_ret], gt[nq][gt_k].  The

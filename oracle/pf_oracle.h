@@ -155,6 +155,12 @@ float pfo_l2sqr_ref(const float *base_vec, const float *query, size_t d);
 size_t pfo_search_lists_plain(size_t nq, size_t d, const float *x, const int64_t *idx, size_t nprobe,
                               const int64_t *list_offsets, const int64_t *ids, const float *vectors, float *dist,
                               int64_t *labels, size_t cap, size_t *list_sizes);
+/* PQ-ADC restatement of the FAISS fork's search_encrypted (see pf_oracle.c) and the matching encoder */
+size_t pfo_search_lists_pq(size_t nq, size_t d, const float *x, const int64_t *idx, size_t nprobe, const float *centroids,
+                           const int64_t *list_offsets, const int64_t *ids, size_t M, const float *pq_centroids,
+                           const uint8_t *codes, float *dist, int64_t *labels, size_t cap, size_t *list_sizes);
+void pfo_pq_encode_residuals(size_t n, size_t d, const float *vectors, const int64_t *list_of, const float *centroids, size_t M,
+                             const float *pq_centroids, uint8_t *codes);
 /* recall as the reference counts it (client_lib.cpp:272-281,325-328) and the standard definition */
 void pfo_recall(size_t nq, size_t k_ret, const int64_t *returned, size_t gt_k, const int32_t *gt, double *ref_recall_1,
                 double *ref_recall_10, double *ref_recall_100, double *std_recall_10, double *mrr_10);

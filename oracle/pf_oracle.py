@@ -129,6 +129,12 @@ def _declare(l):
     l.pfo_search_lists_plain.argtypes = [C.c_size_t, C.c_size_t, f32p, i64p, C.c_size_t, i64p, i64p, f32p, f32p,
                                          i64p, C.c_size_t, C.POINTER(C.c_size_t)]
     l.pfo_search_lists_plain.restype = C.c_size_t
+    u8p_ = C.POINTER(C.c_uint8)
+    l.pfo_search_lists_pq.argtypes = [C.c_size_t, C.c_size_t, f32p, i64p, C.c_size_t, f32p, i64p, i64p, C.c_size_t, f32p, u8p_,
+                                      f32p, i64p, C.c_size_t, C.POINTER(C.c_size_t)]
+    l.pfo_search_lists_pq.restype = C.c_size_t
+    l.pfo_pq_encode_residuals.argtypes = [C.c_size_t, C.c_size_t, f32p, i64p, f32p, C.c_size_t, f32p, u8p_]
+    l.pfo_pq_encode_residuals.restype = None
     dp = C.POINTER(C.c_double)
     l.pfo_recall.argtypes = [C.c_size_t, C.c_size_t, i64p, C.c_size_t, i32p, dp, dp, dp, dp, dp]
     l.pfo_layout_init.argtypes = [C.POINTER(Layout), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
@@ -512,6 +518,41 @@ def search_lists_plain(x, idx, list_offsets, ids, vectors):
                                      _p(v, f32p), _p(dist, f32p), _p(labels, i64p), cap, ls)
     assert w == cap
     return dist[:cap], labels[:cap], np.array(list(ls), dtype=np.int64)
+
+
+def search_lists_pq(x, idx, centroids, list_offsets, ids, pq_M, pq_centroids, codes):
+    """PQ-ADC restatement of the FAISS fork's search_encrypted (pf_oracle.c: pfo_search_lists_pq)"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    cent = np.ascontiguousarray(centroids, dtype=np.float32)
+    lo = np.ascontiguousarray(list_offsets, dtype=np.int64)
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    pqc = np.ascontiguousarray(pq_centroids, dtype=np.float32).reshape(-1)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    nq, d = x.shape
+    assert d % pq_M == 0 and pqc.size == 256 * d and codes.shape == (int(lo[-1]), pq_M)
+    sizes = (lo[1:] - lo[:-1])
+    cap = int(sum(int(sizes[l]) for l in idx.reshape(-1) if l >= 0))
+    dist = np.zeros(max(cap, 1), dtype=np.float32)
+    labels = np.zeros(max(cap, 1), dtype=np.int64)
+    ls = (C.c_size_t * nq)()
+    w = lib().pfo_search_lists_pq(nq, d, _p(x, f32p), _p(idx, i64p), idx.shape[1], _p(cent, f32p), _p(lo, i64p), _p(ids, i64p), pq_M,
+                                  _p(pqc, f32p), codes.ctypes.data_as(C.POINTER(C.c_uint8)), _p(dist, f32p), _p(labels, i64p), cap, ls)
+    assert w == cap
+    return dist[:cap], labels[:cap], np.array(list(ls), dtype=np.int64)
+
+
+def pq_encode_residuals(vectors, list_offsets, centroids, pq_M, pq_centroids):
+    """codes [ntotal][M] of list-ordered vectors (FAISS compute_code on the residual to the list's centroid)"""
+    v = np.ascontiguousarray(vectors, dtype=np.float32)
+    lo = np.ascontiguousarray(list_offsets, dtype=np.int64)
+    cent = np.ascontiguousarray(centroids, dtype=np.float32)
+    pqc = np.ascontiguousarray(pq_centroids, dtype=np.float32).reshape(-1)
+    list_of = np.repeat(np.arange(len(lo) - 1, dtype=np.int64), np.diff(lo))
+    codes = np.zeros((len(v), pq_M), dtype=np.uint8)
+    lib().pfo_pq_encode_residuals(len(v), v.shape[1], _p(v, f32p), _p(list_of, i64p), _p(cent, f32p), pq_M, _p(pqc, f32p),
+                                  codes.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return codes
 
 
 def recall(returned: np.ndarray, gt: np.ndarray):

@@ -22,7 +22,7 @@ PHASES = {"coarse": 0, "to_ntt": 1, "rotate": 2, "mac": 3, "intt": 4}
 EXPORTS = [
     "pf_abi_version", "pf_engine_create", "pf_engine_destroy", "pf_last_error", "pf_engine_stream",
     "pf_engine_set_stream", "pf_engine_synchronize", "pf_load_index", "pf_get_index_info", "pf_retrieve_centroids",
-    "pf_coarse_quantize", "pf_search_lists_plain", "pf_precise_search", "pf_set_galois_key", "pf_load_galois_keys",
+    "pf_coarse_quantize", "pf_search_lists_plain", "pf_load_pq", "pf_search_lists_pq", "pf_precise_search", "pf_set_galois_key", "pf_load_galois_keys",
     "pf_galois_elt_from_step", "pf_search_lists_encrypted", "pf_search_device", "pf_timing_enable", "pf_timing_read",
     "pf_launch_count", "pf_ipc_alloc", "pf_ipc_open", "pf_ipc_close", "pf_ipc_free", "pf_copy_async", "pf_flag_write", "pf_flag_wait", "pf_ntt_forward", "pf_ntt_inverse", "pf_ct_pt_mac", "pf_ct_add", "pf_ct_to_ntt",
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
@@ -78,6 +78,8 @@ def load() -> C.CDLL:
         "pf_retrieve_centroids": ([vp, f32p, C.c_uint64], C.c_int),
         "pf_coarse_quantize": ([vp, C.c_uint64, f32p, C.c_uint32, i64p, f32p], C.c_int),
         "pf_search_lists_plain": ([vp, C.c_uint64, f32p, i64p, C.c_uint32, f32p, i64p, C.c_uint64, u64p, u64p], C.c_int),
+        "pf_load_pq": ([vp, C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_uint8)], C.c_int),
+        "pf_search_lists_pq": ([vp, C.c_uint64, f32p, i64p, C.c_uint32, f32p, i64p, C.c_uint64, u64p, u64p], C.c_int),
         "pf_precise_search": ([vp, C.c_uint64, f32p, i64p, C.c_uint32, f32p], C.c_int),
         "pf_set_galois_key": ([vp, C.c_uint32, u64p], C.c_int),
         "pf_load_galois_keys": ([vp, u8p, C.c_size_t], C.c_int),

@@ -164,6 +164,8 @@ struct pf_engine {
     std::vector<long long> h_list_offsets;
     std::vector<long long> h_ids;
     DevBuf d_centroids, d_ids, d_base_f32, d_base_u8, d_pos_of_id;
+    DevBuf d_pq_cent, d_pq_codes; // product quantizer of the loaded index (pf_load_pq): [M][256][d/M] floats, [ntotal][M] bytes
+    u32 pq_M = 0;                 // 0 = none loaded
     bool ids_are_rows = false;
     std::vector<BlockInfo> blocks;            // local blocks
     std::vector<long long> list_block_start;  // [nlist+1] into blocks (0 length for lists not owned)
@@ -2045,6 +2047,7 @@ int pf_load_index(pf_engine *e, uint64_t nlist, const float *centroids, const in
     e->h_centroids.assign(centroids, centroids + nlist * d);
     e->h_list_offsets.assign(list_offsets, list_offsets + nlist + 1);
     e->h_ids.assign(ids, ids + ntotal);
+    e->pq_M = 0; // a product quantizer belongs to the index it was trained on
     CK(e->d_centroids.ensure(nlist * d * sizeof(float)));
     CK(cudaMemcpyAsync(e->d_centroids.p, centroids, nlist * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CK(e->d_ids.ensure(std::max<size_t>(8, ntotal * 8)));
@@ -2297,6 +2300,85 @@ int pf_search_lists_plain(pf_engine *e, uint64_t nq, const float *x, const int64
         e->s_x.as<float>(), e->d_base_f32.as<float>(), e->d_ids.as<long long>(), e->s_jobs.as<ListJob>(),
         e->s_pl_dist.as<float>(), e->s_pl_labels.as<long long>(), (int)d, w);
     e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dist, e->s_pl_dist.p, w * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(labels, e->s_pl_labels.p, w * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return PF_OK;
+}
+
+// ---- stage 2 as the reference's FAISS fork computes it today: PQ-ADC --------------------------------
+int pf_load_pq(pf_engine *e, uint32_t M, uint32_t nbits, const float *pq_centroids, const uint8_t *codes) {
+    if (!e || !pq_centroids || !codes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    if (nbits != 8) return e->fail(PF_ERR_INVALID, "product quantizer with %u bits per sub-quantizer (only 8, as the reference builds it)", nbits);
+    if (!M || e->d % M) return e->fail(PF_ERR_INVALID, "%u sub-quantizers do not divide the dimension %u", M, e->d);
+    if (((size_t)e->d + (size_t)M * 256) * sizeof(float) > 200 * 1024)
+        return e->fail(PF_ERR_INVALID, "distance table of %u sub-quantizers does not fit shared memory", M);
+    CK(cudaSetDevice(e->prm.device));
+    const size_t ntotal = (size_t)e->h_list_offsets[e->nlist];
+    CK(e->d_pq_cent.ensure((size_t)256 * e->d * sizeof(float)));
+    CK(e->d_pq_codes.ensure(std::max<size_t>(16, ntotal * M + 16))); // + 16: the 16-byte code loads of the last row stay inside
+    CK(cudaMemcpyAsync(e->d_pq_cent.p, pq_centroids, (size_t)256 * e->d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    if (ntotal) CK(cudaMemcpyAsync(e->d_pq_codes.p, codes, ntotal * M, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->pq_M = M;
+    return PF_OK;
+}
+
+int pf_search_lists_pq(pf_engine *e, uint64_t nq, const float *x, const int64_t *idx, uint32_t nprobe, float *dist,
+                       int64_t *labels, uint64_t cap, uint64_t *list_sizes, uint64_t *total) {
+    if (!e || !x || !idx || !list_sizes) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->has_index) return e->fail(PF_ERR_STATE, "no index loaded");
+    if (!e->pq_M) return e->fail(PF_ERR_STATE, "no product quantizer loaded (pf_load_pq)");
+    CK(cudaSetDevice(e->prm.device));
+    std::vector<ListJob> jobs;
+    std::vector<int> job_list;
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < nq; i++) {
+        uint64_t cnt = 0;
+        for (uint32_t p = 0; p < nprobe; p++) {
+            const int64_t l = idx[i * nprobe + p];
+            if (l < 0 || (uint64_t)l >= e->nlist)
+                return e->fail(PF_ERR_INVALID, "list id %lld out of range", (long long)l);
+            const long long n = e->h_list_offsets[l + 1] - e->h_list_offsets[l];
+            if (n > 0) {
+                jobs.push_back(ListJob{e->h_list_offsets[l], (long long)w, (int)n, (int)i});
+                job_list.push_back((int)l);
+            }
+            w += (uint64_t)n;
+            cnt += (uint64_t)n;
+        }
+        list_sizes[i] = cnt;
+    }
+    if (total) *total = w;
+    if (w > cap || (w && (!dist || !labels))) return e->fail(PF_ERR_CAPACITY, "output needs %llu entries, capacity %llu", (unsigned long long)w, (unsigned long long)cap);
+    if (!w) return PF_OK;
+    const u32 d = e->d, M = e->pq_M;
+    const size_t jobs_bytes = (jobs.size() * sizeof(ListJob) + 15) & ~(size_t)15;
+    CK(e->s_x.ensure_grow(nq * d * sizeof(float)));
+    CK(e->s_jobs.ensure_grow(jobs_bytes + job_list.size() * sizeof(int)));
+    CK(e->s_pl_dist.ensure_grow(w * sizeof(float)));
+    CK(e->s_pl_labels.ensure_grow(w * sizeof(long long)));
+    CK(cudaMemcpyAsync(e->s_x.p, x, nq * d * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->s_jobs.p, jobs.data(), jobs.size() * sizeof(ListJob), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->s_jobs.as<char>() + jobs_bytes, job_list.data(), job_list.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    const size_t smem = ((size_t)d + (size_t)M * 256) * sizeof(float);
+    static size_t attr_max = 48 * 1024;
+    if (smem > attr_max) {
+        CK(cudaFuncSetAttribute(list_pq_adc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_max = smem;
+    }
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += 1u << 30) { // grid.x limit is 2^31 - 1; one launch in practice
+        const size_t nj = std::min<size_t>(jobs.size() - j0, 1u << 30);
+        list_pq_adc_kernel<<<(unsigned)nj, 256, smem, e->stream>>>(
+            e->s_x.as<float>(), e->d_centroids.as<float>(), e->d_pq_cent.as<float>(), e->d_pq_codes.as<unsigned char>(),
+            e->d_ids.as<long long>(), e->s_jobs.as<ListJob>() + j0, reinterpret_cast<const int *>(e->s_jobs.as<char>() + jobs_bytes) + j0,
+            e->s_pl_dist.as<float>(), e->s_pl_labels.as<long long>(), (int)d, (int)M, w);
+        e->launches++;
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dist, e->s_pl_dist.p, w * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(labels, e->s_pl_labels.p, w * sizeof(long long), cudaMemcpyDeviceToHost, e->stream));

@@ -213,6 +213,58 @@ __global__ void __launch_bounds__(128) list_l2_kernel(const float *__restrict__ 
     }
 }
 
+// Product-quantizer ADC over every code of every probed list (what the reference's FAISS fork computes in
+// search_encrypted today; restated by the CPU checker (pfo_search_lists_pq), same float operations in the same
+// order: r = x - centroid, tab[m][j] = sum_k (r - pq)^2, dis = sum_m tab[m][code[m]]; multiply and add are separate
+// roundings, as in FAISS's reference fvec_L2sqr).  One CTA per (query, list) job: the residual and the M x 256
+// distance table live in shared memory (M = 32: 32 KiB), then every thread scores codes of the list — M table
+// look-ups per code, the code bytes read 16 at a time when M allows.
+__global__ void __launch_bounds__(256) list_pq_adc_kernel(const float *__restrict__ x, const float *__restrict__ cent,
+                                                          const float *__restrict__ pqc, const unsigned char *__restrict__ codes,
+                                                          const long long *__restrict__ ids, const ListJob *jobs,
+                                                          const int *__restrict__ job_list, float *__restrict__ dist,
+                                                          long long *__restrict__ labels, int d, int M,
+                                                          unsigned long long cap) {
+    extern __shared__ float pq_sm[]; // [d] residual, then [M][256] table
+    float *r = pq_sm, *tab = pq_sm + d;
+    const ListJob job = jobs[blockIdx.x];
+    const int l = job_list[blockIdx.x];
+    const int dsub = d / M;
+    for (int k = threadIdx.x; k < d; k += 256) r[k] = __fsub_rn(x[(size_t)job.query * d + k], __ldg(cent + (size_t)l * d + k));
+    __syncthreads();
+    for (int e = threadIdx.x; e < M * 256; e += 256) { // e = m * 256 + j: consecutive threads read consecutive sub-centroids
+        const int m = e >> 8;
+        const float *c = pqc + (size_t)e * dsub;
+        const float *rm = r + m * dsub;
+        float acc = 0.0f;
+        for (int k = 0; k < dsub; k++) {
+            const float t = __fsub_rn(rm[k], __ldg(c + k));
+            acc = __fadd_rn(acc, __fmul_rn(t, t));
+        }
+        tab[e] = acc;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < job.count; v += 256) {
+        const unsigned char *code = codes + (size_t)(job.vec_begin + v) * M;
+        float acc = 0.0f;
+        int m = 0;
+        if ((M & 15) == 0) {
+            for (; m < M; m += 16) {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(code + m));
+                const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int b = 0; b < 16; b++) acc = __fadd_rn(acc, tab[((m + b) << 8) + ((ws[b >> 2] >> (8 * (b & 3))) & 255u)]);
+            }
+        }
+        for (; m < M; m++) acc = __fadd_rn(acc, tab[(m << 8) + code[m]]);
+        const unsigned long long o = (unsigned long long)(job.out_begin + v);
+        if (o < cap) {
+            dist[o] = acc;
+            labels[o] = ids[job.vec_begin + v];
+        }
+    }
+}
+
 // Server::preciseSearch: ids are base row numbers; pos_of_id maps them to list-ordered positions
 __global__ void __launch_bounds__(128) precise_l2_kernel(const float *__restrict__ x, const float *__restrict__ base,
                                                          const long long *__restrict__ pos_of_id,

@@ -225,7 +225,13 @@ class Engine:
         if f.d != self.dim:
             raise PfError(1, f"index dimension {f.d} does not match the engine ({self.dim})")
         offsets, ids, vecs = f.csr(np.asarray(base_vectors))
-        return self.load_index(f.centroids, offsets, ids, vecs)
+        info = self.load_index(f.centroids, offsets, ids, vecs)
+        # the file's product quantizer (what the reference's search_encrypted scores with today), when it holds one
+        if f.pq_nbits == 8 and f.pq_M and f.pq_centroids.size == 256 * f.d and len(f.list_codes) == f.nlist:
+            codes = np.concatenate([np.asarray(c, dtype=np.uint8).reshape(-1, f.pq_M) for c in f.list_codes]) if f.ntotal else \
+                np.zeros((0, f.pq_M), np.uint8)
+            self.load_pq(f.pq_M, f.pq_nbits, f.pq_centroids, codes)
+        return info
 
     def index_info(self) -> dict:
         o = PfIndexInfo()
@@ -265,6 +271,34 @@ class Engine:
         labels = np.zeros(max(total.value, 1), dtype=np.int64)
         self._ck(self.lib.pf_search_lists_plain(self.h, nq, _ptr(x, F32P), _ptr(idx, I64P), nprobe, _ptr(dist, F32P),
                                                 _ptr(labels, I64P), total.value, _ptr(sizes, U64P), C.byref(total)))
+        return dist[:total.value], labels[:total.value], sizes.astype(np.int64)
+
+    def load_pq(self, pq_M: int, pq_nbits: int, pq_centroids, codes):
+        """product quantizer of the loaded index (ref: the IndexIVFPQ built at src/server/server_lib.cpp:34-36): the
+        `pq_M`, `pq_nbits`, `pq_centroids` of a .faiss file (faiss_io.IVFPQFile) and its list codes back to back"""
+        pqc = np.ascontiguousarray(pq_centroids, dtype=np.float32).reshape(-1)
+        cd = np.ascontiguousarray(codes, dtype=np.uint8)
+        if pqc.size != 256 * self.dim or cd.ndim != 2 or cd.shape[1] != pq_M:
+            raise PfError(_capi.PF_ERR_INVALID, "pq_centroids must hold 256 * dim floats and codes must be [ntotal][pq_M]")
+        self._ck(self.lib.pf_load_pq(self.h, pq_M, pq_nbits, _ptr(pqc, F32P), cd.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def coarseSearchPQ(self, precise_query, nearest_centroid_idx):
+        """Server::coarseSearch with the distance the reference's FAISS fork computes today (PQ-ADC over every code
+        of the given lists; ref: src/server/server_lib.cpp:111-138, the search_encrypted call at :126-130): same
+        packing as coarseSearch."""
+        x = np.ascontiguousarray(precise_query, dtype=np.float32)
+        idx = np.ascontiguousarray(nearest_centroid_idx, dtype=np.int64)
+        nq, nprobe = idx.shape
+        sizes = np.zeros(nq, dtype=np.uint64)
+        total = C.c_uint64()
+        rc = self.lib.pf_search_lists_pq(self.h, nq, _ptr(x, F32P), _ptr(idx, I64P), nprobe, None, None, 0,
+                                         _ptr(sizes, U64P), C.byref(total))
+        if rc not in (_capi.PF_OK, _capi.PF_ERR_CAPACITY):
+            self._ck(rc)
+        dist = np.zeros(max(total.value, 1), dtype=np.float32)
+        labels = np.zeros(max(total.value, 1), dtype=np.int64)
+        self._ck(self.lib.pf_search_lists_pq(self.h, nq, _ptr(x, F32P), _ptr(idx, I64P), nprobe, _ptr(dist, F32P),
+                                             _ptr(labels, I64P), total.value, _ptr(sizes, U64P), C.byref(total)))
         return dist[:total.value], labels[:total.value], sizes.astype(np.int64)
 
     def preciseSearch(self, precise_query, nearest_coarse_vector_idx) -> np.ndarray:

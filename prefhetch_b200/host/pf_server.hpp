@@ -110,6 +110,30 @@ class Server {
         list_sizes_per_query.assign(sizes.begin(), sizes.end());
     }
 
+    // The product quantizer of the loaded index (the IndexIVFPQ of ref: src/server/server_lib.cpp:34-36; from the
+    // .faiss file: host/pf_faiss_io.hpp) and Server::coarseSearch with the distance the reference's FAISS fork
+    // computes TODAY — PQ-ADC over every code of the given lists (the search_encrypted call at
+    // ref: src/server/server_lib.cpp:126-130); outputs as coarseSearch
+    void loadProductQuantizer(uint32_t sub_quantizers, uint32_t sub_quantizer_bits, std::span<const float> pq_centroids,
+                              std::span<const uint8_t> codes) {
+        check(pf_load_pq(m_Engine.get(), sub_quantizers, sub_quantizer_bits, pq_centroids.data(), codes.data()));
+    }
+    void coarseSearchPQ(std::span<const float> precise_query, std::span<const idx_t> nearest_centroid_idx, uint32_t nprobe,
+                        std::vector<float> &coarse_distance_scores, std::vector<idx_t> &coarse_distance_indexes,
+                        std::vector<size_t> &list_sizes_per_query) const {
+        const uint64_t nq = precise_query.size() / m_Dim;
+        std::vector<uint64_t> sizes(nq);
+        uint64_t total = 0;
+        int rc = pf_search_lists_pq(m_Engine.get(), nq, precise_query.data(), nearest_centroid_idx.data(), nprobe, nullptr,
+                                    nullptr, 0, sizes.data(), &total);
+        if (rc != PF_OK && rc != PF_ERR_CAPACITY) check(rc);
+        coarse_distance_scores.resize(total);
+        coarse_distance_indexes.resize(total);
+        check(pf_search_lists_pq(m_Engine.get(), nq, precise_query.data(), nearest_centroid_idx.data(), nprobe,
+                                 coarse_distance_scores.data(), coarse_distance_indexes.data(), total, sizes.data(), &total));
+        list_sizes_per_query.assign(sizes.begin(), sizes.end());
+    }
+
     // ref: Server::preciseSearch (src/server/server_lib.cpp:140-167)
     void preciseSearch(std::span<const float> precise_query, std::span<const idx_t> nearest_coarse_vector_idx,
                        uint32_t coarse_probe, std::vector<float> &precise_distance_scores) const {

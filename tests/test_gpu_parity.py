@@ -1030,3 +1030,76 @@ def test_cpp_roundtrip_example():
     assert exe.exists(), "run __graft_entry__.build() first"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "pf_roundtrip_example ok" in r.stdout, r.stdout + r.stderr
+
+
+def _pq_case(oracle, seed, nb, d, nlist, nq, M):
+    """IVF data set + a product quantizer on the residuals (sub-centroids sampled from the residuals themselves: what
+    k-means would start from; the arithmetic under test does not care how the codebook was trained)"""
+    rng = np.random.default_rng(seed)
+    base, query, cent = sift_like(rng, nb, d, nlist, nq)
+    cent = (cent + rng.uniform(-0.5, 0.5, size=cent.shape)).astype(np.float32)
+    offsets, ids, vecs = build_ivf(base, cent)
+    list_of = np.repeat(np.arange(nlist), np.diff(offsets))
+    resid = vecs - cent[list_of]
+    dsub = d // M
+    pick = rng.integers(0, len(vecs), size=(M, 256))
+    pqc = np.stack([resid[pick[m], m * dsub:(m + 1) * dsub] for m in range(M)]).astype(np.float32)      # [M][256][dsub]
+    pqc += rng.normal(0, 0.25, size=pqc.shape).astype(np.float32)
+    codes = oracle.pq_encode_residuals(vecs, offsets, cent, M, pqc)
+    return query, cent, offsets, ids, vecs, pqc, codes
+
+
+@pytest.mark.parametrize("d,M,nlist", [(128, 32, 24), (64, 8, 9), (128, 16, 5)])
+def test_pq_adc_matches_oracle(pf, oracle, tmp_path, d, M, nlist):
+    """the distance the reference's FAISS fork computes today (PQ-ADC over every code of the
+    given lists) through pf_search_lists_pq == the oracle's restatement, float bit patterns and labels, with the
+    quantizer read from a .faiss IndexIVFPQ file (128-d / 32 x 8 bits is the reference's shape: SUB_QUANTIZERS,
+    SUB_QUANTIZER_SIZE); ragged lists, an empty list, M not a multiple of 16."""
+    from prefhetch_b200 import faiss_io
+    query, cent, offsets, ids, vecs, pqc, codes = _pq_case(oracle, 100 + M, 2500, d, nlist, 5, M)
+    # empty the last list (its vectors go nowhere: a list FAISS never added to)
+    keep = int(offsets[-2])
+    offsets = offsets.copy()
+    offsets[-1] = keep
+    ids, vecs, codes = ids[:keep], vecs[:keep], codes[:keep]
+    lists = [ids[offsets[l]:offsets[l + 1]] for l in range(nlist)]
+    f = faiss_io.IVFPQFile(d, len(ids), nlist, 20, cent, lists, [codes[offsets[l]:offsets[l + 1]] for l in range(nlist)],
+                           code_size=M, pq_M=M, pq_nbits=8, pq_centroids=pqc.reshape(-1))
+    faiss_io.write_ivfpq(str(tmp_path / "pq.faiss"), f)
+    base = np.zeros((int(ids.max()) + 1, d), dtype=np.float32)
+    base[ids] = vecs
+    eng = pf.Engine(d, 2048, *_params(2048)[:1], _params(2048)[1], 1, 16)
+    with pytest.raises(pf.PfError) as ei:
+        eng.coarseSearchPQ(query, np.zeros((len(query), 1), np.int64))
+    assert ei.value.code == 4          # PF_ERR_STATE: no index
+    eng.load_index(cent, offsets, ids, vecs)
+    with pytest.raises(pf.PfError) as ei:
+        eng.coarseSearchPQ(query, np.zeros((len(query), 1), np.int64))
+    assert ei.value.code == 4 and "pf_load_pq" in str(ei.value)
+    with pytest.raises(pf.PfError):
+        eng.load_pq(7, 8, pqc, np.zeros((len(ids), 7), np.uint8))          # 7 does not divide d
+    eng.load_index_from_faiss(str(tmp_path / "pq.faiss"), base)            # loads the quantizer with the index
+    nprobe = min(6, nlist)
+    idx = eng.coarse_quantize(query, nprobe)
+    idx[0, 0] = nlist - 1                                                  # the empty list is probed too
+    dist, labels, sizes = eng.coarseSearchPQ(query, idx)
+    odist, olabels, osizes = oracle.search_lists_pq(query, idx, cent, offsets, ids, M, pqc, codes)
+    assert np.array_equal(sizes, osizes) and np.array_equal(labels, olabels)
+    assert np.array_equal(dist.view(np.uint32), odist.view(np.uint32))
+    # ADC is the exact squared L2 to the DECODED vector: float64 evaluation agrees to float rounding
+    list_of = np.repeat(np.arange(nlist), np.diff(offsets))
+    dsub = d // M
+    dec = cent[list_of].astype(np.float64) + np.concatenate([pqc[m, codes[:, m]] for m in range(M)], axis=1).astype(np.float64)
+    pos = {int(i): k for k, i in enumerate(ids)}
+    o = 0
+    for qi in range(len(query)):
+        n = int(sizes[qi])
+        rows = np.array([pos[int(i)] for i in labels[o:o + n]], dtype=np.int64)
+        want = ((dec[rows] - query[qi].astype(np.float64)) ** 2).sum(1) if n else np.zeros(0)
+        assert np.allclose(dist[o:o + n], want, rtol=2e-5, atol=1e-2)
+        o += n
+    # a new index drops the quantizer of the old one
+    eng.load_index(cent, offsets, ids, vecs)
+    with pytest.raises(pf.PfError):
+        eng.coarseSearchPQ(query, idx)
+    eng.close()
