@@ -166,6 +166,17 @@ constexpr size_t kStack = 96 * 1024;
 constexpr int kMaxThreads = 1024;
 constexpr size_t kMaxDynSmem = 232 * 1024;
 
+// Fresh device memory and the dynamic shared memory of a block hold garbage on a GPU; here they hold 0xCD bytes
+// (PF_EMUL_POISON=0 turns it off), so that code which relies on zeroes it never wrote fails the parity tests.
+inline bool poison_enabled() {
+    static const bool on = !(getenv("PF_EMUL_POISON") && atoi(getenv("PF_EMUL_POISON")) == 0);
+    return on;
+}
+inline void *poison(void *p, size_t bytes) {
+    if (p && bytes && poison_enabled()) memset(p, 0xCD, bytes);
+    return p;
+}
+
 struct Barrier {
     int arrived = 0;
     unsigned gen = 0;
@@ -271,6 +282,7 @@ inline void run_block(const std::function<void()> &body, dim3 grid, dim3 block, 
 #endif
     Block &b = w.blk;
     const int T = (int)(block.x * block.y * block.z);
+    poison(w.dyn, smem);
     b.body = &body;
     b.nthreads = b.live = T;
     b.bar = Barrier();
@@ -519,16 +531,16 @@ struct AllocHdr {
 };
 #if defined(PF_EMUL_ASAN)
 inline void *dev_alloc(size_t bytes) {
-    if (ipc_enabled() && bytes <= ipc_max_bytes()) return shm_alloc(bytes ? bytes : 1);
+    if (ipc_enabled() && bytes <= ipc_max_bytes()) return poison(shm_alloc(bytes ? bytes : 1), bytes);
     void *p = nullptr;
-    return posix_memalign(&p, 256, bytes ? bytes : 1) ? nullptr : p;
+    return posix_memalign(&p, 256, bytes ? bytes : 1) ? nullptr : poison(p, bytes);
 }
 inline void dev_free(void *p) {
     if (p && !shm_release(p)) free(p);
 }
 #else
 inline void *dev_alloc(size_t bytes) {
-    if (ipc_enabled() && bytes <= ipc_max_bytes()) return shm_alloc(bytes ? bytes : 1);
+    if (ipc_enabled() && bytes <= ipc_max_bytes()) return poison(shm_alloc(bytes ? bytes : 1), bytes);
     char *raw = nullptr;
     const size_t total = kRed + bytes + kRed;
     if (posix_memalign((void **)&raw, 256, total ? total : 256)) return nullptr;
@@ -536,7 +548,7 @@ inline void *dev_alloc(size_t bytes) {
     memset(raw + kRed + bytes, 0xA5, kRed);
     AllocHdr h{bytes, 0x50464D454D554C21ull};
     memcpy(raw, &h, sizeof h);
-    return raw + kRed;
+    return poison(raw + kRed, bytes);
 }
 inline void dev_free(void *p) {
     if (!p || shm_release(p)) return;
