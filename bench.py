@@ -1073,6 +1073,13 @@ def run_workload(args, cfg_name, cfg, comm, weak, grid, steps, warmup, want_e2e=
         rec["e2e"] = optional("e2e", 300, _e2e)
         if on_progress is not None:
             on_progress(rec)
+        # the same pass with the request a symmetric-key SEAL client sends (seeded streams: half the upload, c1 drawn on
+        # the device).  One rank, main workload only; an extra record beside the headline e2e, never instead of it.
+        if world == 1 and want_parity and rec["e2e"].get("value"):
+            rec["e2e_seeded_requests"] = optional("e2e (seeded requests)", 300, lambda: run_e2e(
+                args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag, guard, seeded=True))
+            if on_progress is not None:
+                on_progress(rec)
 
     # ---- parity self-check on real encryptions (untimed; the oracle is the checker) -------------
     if want_parity and world == 1:
@@ -1221,7 +1228,24 @@ def shm_has_room(nbytes):
         return False
 
 
-def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag, guard=None):
+def seeded_stream_parts(full_header, half_bytes, seed):
+    """(113-byte header, 81-byte PRNG info) of a SEAL seeded ciphertext stream (Serializable<Ciphertext>: c0 + the seed
+    of c1) made from the header of the full stream: total size, DynArray size and word count describe ONE polynomial,
+    and a nested {SEALHeader, prng_type blake2xb = 1, 64-byte seed} follows the data (layout: DESIGN.md §7 f-3)."""
+    import struct
+    hdr = np.array(full_header, dtype=np.uint8, copy=True)
+    hdr[8:16] = np.frombuffer(struct.pack("<Q", 113 + half_bytes + 81), dtype=np.uint8)
+    hdr[97:105] = np.frombuffer(struct.pack("<Q", 16 + 8 + half_bytes), dtype=np.uint8)
+    hdr[105:113] = np.frombuffer(struct.pack("<Q", half_bytes // 8), dtype=np.uint8)
+    info = np.zeros(81, dtype=np.uint8)
+    info[:16] = hdr[:16]
+    info[8:16] = np.frombuffer(struct.pack("<Q", 81), dtype=np.uint8)
+    info[16] = 1
+    info[17:] = np.frombuffer(seed, dtype=np.uint8)
+    return hdr, info
+
+
+def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, steps, nsteps_total, tag, guard=None, seeded=False):
     """End to end through pf_search_submit / pf_search_collect with HOST buffers.  One response buffer for the
     whole node: at N > 1 it is a POSIX shared-memory segment page-locked by every rank (pf_host_register); the
     query blob of a step is read from it and every rank's GPU writes its share of the response into it over
@@ -1238,6 +1262,12 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
     nq_loc = q_hi - q_lo
     L, ctw, ctb = eng.L, eng.ctw, eng.ct_bytes
     hdr = np.frombuffer(eng.ct_serialize(np.zeros((2, L, n), dtype=np.uint64)), dtype=np.uint8)[:ctb - ctw * 8]
+    # seeded=True: the request a symmetric-key SEAL client sends — c0 and the 64-byte seed of c1 (half the bytes); the
+    # engine draws c1 on the device.  c0 = the pool's residues, seeds arbitrary: timing does not depend on the values.
+    info = None
+    if seeded:
+        hdr, info = seeded_stream_parts(hdr, ctw * 4, bytes((7 * i + 1) & 255 for i in range(64)))
+        ctb = len(hdr) + ctw * 4 + len(info)
     qbytes = nq * m * ctb
     seg = max_res * eng.slot_bytes
     nr = open_node_response(comm, qbytes, seg, pinned_alloc=lambda nbytes: torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
@@ -1256,7 +1286,12 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
         for c in range(nq_loc * m):
             o = (q_lo * m + c) * ctb
             qnp[o: o + len(hdr)] = hdr
-            qnp[o + len(hdr): o + ctb] = mine[c].view(np.uint8)
+            if seeded:
+                qnp[o + len(hdr): o + len(hdr) + ctw * 4] = mine[c].view(np.uint8)[:ctw * 4]
+                info[17 + (c & 63)] = (c * 13 + 5) & 255          # a different seed per ciphertext
+                qnp[o + ctb - len(info): o + ctb] = info
+            else:
+                qnp[o + len(hdr): o + ctb] = mine[c].view(np.uint8)
     registered = world > 1 and nr.shared_data
     if world > 1:
         comm.barrier()
@@ -1339,7 +1374,7 @@ def run_e2e(args, eng, comm, cfg, grid, data, qsets, ct_pool, nprobe, max_res, s
     return {"value": float(eu[0].item()) / float(et.item()), "unit": "distances/s",
             "h2d_bytes_per_step": int(eu[1].item()) // e_steps, "d2h_bytes_per_step": int(eu[2].item()) // e_steps,
             "ms_per_step": float(et.item()) / e_steps * 1e3, "steps": e_steps, "pipeline_depth": DEPTH,
-            "lone_request_ms": lat,
+            "lone_request_ms": lat, "request": ("seeded ciphertext streams (c0 + PRNG seed), c1 expanded on the device" if seeded else "full ciphertext streams"),
             "response": ("one host buffer per node" + (" (POSIX shm page-locked by every rank; each GPU writes its share over its own PCIe link)" if world > 1 else " (pinned)"))
             if (shared_note or world == 1) else "per-rank pinned buffers, completion flags shared (/dev/shm too small for one node buffer)"}
 
@@ -1429,7 +1464,7 @@ def build_line(args, cfg_name, cfg, world, weak, grid, rec, clocks, placement, s
         "clocks": clocks, "roofline": rec["roofline"], "rotate_roofline": dict(rec["rotate_roofline"]),
         "phases_ms_per_step": rec["phases_ms_per_step"],
         "db_gib_per_rank": rec["db_gib_per_rank"],
-        "e2e": rec.get("e2e"), "cpu_baseline": rec.get("cpu_baseline"),
+        "e2e": rec.get("e2e"), "e2e_seeded_requests": rec.get("e2e_seeded_requests"), "cpu_baseline": rec.get("cpu_baseline"),
         "parity_checked": (rec.get("parity") or {}).get("parity_checked"), "parity": rec.get("parity"),
         "gather_verified": rec.get("gather_verified"), "placement": placement,
     }

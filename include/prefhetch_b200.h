@@ -263,6 +263,12 @@ int pf_seal_stream_inflate(const uint8_t *in, size_t len, uint8_t *out, size_t c
  * PF_ERR_CAPACITY with *written = bytes needed.  Needs no engine and no GPU. */
 int pf_seal_ct_expand(const uint8_t *in, size_t len, uint64_t poly_degree, const uint64_t *data_primes, uint32_t nprimes,
                       uint8_t *out, size_t cap, size_t *written, size_t *consumed);
+/* The same expansion ON THE DEVICE, as the search calls do it when every query stream of a request is an
+ * uncompressed blake2xb-seeded one (half the upload of a symmetric-key SEAL client): `in` is one such stream of
+ * this engine's top level, ct_words receives [2][L][N] (c0 as sent, c1 = sample_poly_uniform of the seeded
+ * Blake2xb PRNG: one CTA per 4096-byte PRNG refill, rejected words re-drawn in stream order).  Bit-identical to
+ * pf_seal_ct_expand.  PF_SEEDED_HOST=1 makes the search calls expand on the host instead. */
+int pf_seal_ct_expand_device(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct_words, size_t cap_words);
 /* pf_seal_ct_expand for a whole request: the ncts streams in[offsets[c], offsets[c+1]) -> their full compr_mode none
  * forms back to back in out (out_offsets[ncts + 1]; PF_ERR_CAPACITY with out_offsets filled when out is too small).
  * This is the slow path pf_search_submit runs on compressed / seeded queries: the streams are independent and are

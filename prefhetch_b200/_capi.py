@@ -28,7 +28,7 @@ EXPORTS = [
     "pf_ct_from_ntt", "pf_rotate_rows", "pf_rotate_query_set", "pf_batch_encode", "pf_encode_block",
     "pf_ct_serialized_size", "pf_result_slot_size", "pf_result_serialized_size", "pf_set_result_parms_id", "pf_parms_id", "pf_seal_stream_inflate",
     "pf_ct_serialize", "pf_ct_deserialize", "pf_search_submit", "pf_search_collect", "pf_search_set_groups",
-    "pf_host_register", "pf_host_unregister", "pf_device_checksum", "pf_seal_ct_expand", "pf_seal_galois_keys_expand", "pf_seal_ct_expand_batch",
+    "pf_host_register", "pf_host_unregister", "pf_device_checksum", "pf_seal_ct_expand", "pf_seal_ct_expand_device", "pf_seal_galois_keys_expand", "pf_seal_ct_expand_batch",
 ]
 
 
@@ -123,6 +123,7 @@ def load() -> C.CDLL:
         "pf_seal_stream_inflate": ([vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)], C.c_int),
         "pf_seal_ct_expand": ([vp, C.c_size_t, C.c_uint64, u64p, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t),
                                C.POINTER(C.c_size_t)], C.c_int),
+        "pf_seal_ct_expand_device": ([vp, vp, C.c_size_t, u64p, C.c_size_t], C.c_int),
         "pf_seal_ct_expand_batch": ([vp, C.c_size_t, u64p, C.c_uint64, C.c_uint64, u64p, C.c_uint32, vp, C.c_size_t, u64p, C.c_uint32], C.c_int),
         "pf_seal_galois_keys_expand": ([vp, C.c_size_t, C.c_uint64, u64p, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)], C.c_int),
         "pf_ct_serialize": ([vp, u64p, C.c_int, u8p, C.c_size_t, szp], C.c_int),

@@ -31,6 +31,7 @@
 #include "pf_ntt.cuh"
 #include "pf_ntt_fp.cuh"
 #include "pf_plain.cuh"
+#include "pf_seeded.cuh"
 
 #ifndef PF_MAC_DEFAULT_VARIANT
 #define PF_MAC_DEFAULT_VARIANT 0
@@ -125,6 +126,7 @@ struct pf_engine {
     uint64_t result_pid[4] = {0, 0, 0, 0};
     bool result_pid_set = false;
     DevBuf d_mstab, s_full, s_cksum, s_ctoff;
+    DevBuf s_seed; // device-side seeded expansion: SEED_SCRATCH_WORDS per ciphertext (pf_seeded.cuh)
     u32 d = 0, d_pad = 0, m = 0, g = 0, dc = 0, R = 0, K = 0, C = 0;
     u64 t = 0;
     std::mutex mu;
@@ -268,6 +270,9 @@ int check_device_error(pf_engine *e) {
     if (!e->h_err_word) return PF_OK;
     const unsigned long long w = *(volatile unsigned long long *)e->h_err_word;
     if (!w) return PF_OK;
+    if (!(w >> 63) && ((w >> 62) & 1))
+        return e->fail(PF_ERR_CUDA, "device-side expansion of a seeded ciphertext gave up: %u rejected PRNG words in one ciphertext (set PF_SEEDED_HOST=1)",
+                       (unsigned)(w & 0xffffffffu));
     return e->fail(PF_ERR_CUDA, "peer flag wait timed out after %.1f s (flag value %u, waiting for %u): a peer rank is dead or out of protocol order",
                    (double)e->flag_timeout_ns * 1e-9, (unsigned)((w >> 32) & 0x7fffffffu), (unsigned)(w & 0xffffffffu));
 }
@@ -1480,6 +1485,42 @@ int expand_seeded_stream(const uint8_t *p, size_t len, uint64_t N, const uint64_
     return 0;
 }
 
+// An uncompressed seeded stream of exactly the shape expand_seeded_stream expands, drawn with blake2xb: what the
+// device-side expansion takes (anything else — compressed, shake256, malformed — stays on the host path, which
+// names the problem).
+bool is_seeded_raw_stream(const uint8_t *p, size_t len, uint64_t N, uint32_t L) {
+    const size_t half = (size_t)N * L * 8;
+    if (len != SEAL_CT_HEADER + half + SEAL_PRNG_INFO_BYTES) return false;
+    if (p[0] != 0x5E || p[1] != 0xA1 || p[2] != 0x10 || p[3] != 4 || p[5] != 0) return false;
+    uint64_t total, size, n, cms, words, info_total;
+    memcpy(&total, p + 8, 8);
+    memcpy(&size, p + 49, 8);
+    memcpy(&n, p + 57, 8);
+    memcpy(&cms, p + 65, 8);
+    const uint8_t *in = p + 89;
+    if (in[0] != 0x5E || in[1] != 0xA1 || in[5] != 0) return false;
+    memcpy(&words, in + 16, 8);
+    if (total != len || size != 2 || n != N || cms != (uint64_t)L || words != n * cms) return false;
+    const uint8_t *info = p + SEAL_CT_HEADER + half;
+    memcpy(&info_total, info + 8, 8);
+    return info[0] == 0x5E && info[1] == 0xA1 && info[5] == 0 && info_total == SEAL_PRNG_INFO_BYTES && info[16] == 1;
+}
+
+// c0 from the uploaded bytes + c1 from the seed, for `nc` ciphertexts whose data offsets sit in d_off: three launches
+// on the engine stream (pf_seeded.cuh).  scratch: nc * SEED_SCRATCH_WORDS words, zeroed here.
+int expand_seeded_on_device(pf_engine *e, const uint8_t *d_raw, const u64 *d_off, u64 *d_dst, u64 *d_scratch, size_t nc) {
+    if (!nc) return PF_OK;
+    const size_t half = (size_t)e->L * e->N;
+    CK(cudaMemsetAsync(d_scratch, 0, nc * SEED_SCRATCH_WORDS * 8, e->stream));
+    strip_seeded_kernel<<<dim3((unsigned)((half + 255) / 256), (unsigned)nc), 256, 0, e->stream>>>(d_raw, d_off, d_dst, half);
+    SeededParams sp{d_raw, d_off, d_dst, d_scratch, e->d_mods.as<DevModulus>(), e->L, e->N};
+    seeded_expand_kernel<<<dim3((unsigned)(half / 512 + 1), (unsigned)nc), 64, 0, e->stream>>>(sp);
+    seeded_fixup_kernel<<<(unsigned)((nc + 63) / 64), 64, 0, e->stream>>>(sp, (int)nc, e->d_err_word);
+    e->launches += 3;
+    CK(cudaGetLastError());
+    return PF_OK;
+}
+
 // The request's slow path, for a whole batch: ciphertext c needs host work when its stream is compressed (zlib /
 // zstd) or seeded; out[c] receives its full compr_mode none form and stays EMPTY for streams that are already
 // that (the fast path uploads those straight from the caller's blob).  `out` is left empty altogether when no
@@ -2599,7 +2640,21 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
     uint64_t parms_id[4] = {0, 0, 0, 0};
     std::vector<const uint8_t *> ct_src(ncts);
     std::vector<std::vector<uint8_t>> inflated; // full form of compressed / seeded queries (slow path, host threads); empty = none
-    {
+    // Seeded requests (what a symmetric-key SEAL client sends: half the bytes) are expanded ON THE DEVICE when every
+    // stream of the call is an uncompressed blake2xb-seeded one; PF_SEEDED_HOST=1 keeps the host expansion (A/B, tests)
+    bool seeded_dev = ncts > 0 && e->d_err_word && (size_t)L * N % 512 == 0 && !getenv("PF_SEEDED_HOST");
+    for (size_t c = 0; c < ncts && seeded_dev; c++)
+        seeded_dev = is_seeded_raw_stream(query_cts + ct_offsets[c], (size_t)(ct_offsets[c + 1] - ct_offsets[c]), (uint64_t)N, (uint32_t)L);
+    if (seeded_dev) {
+        for (size_t c = 0; c < ncts; c++) {
+            const uint8_t *src = query_cts + ct_offsets[c];
+            ct_src[c] = src;
+            if (src[48]) return e->fail(PF_ERR_FORMAT, "query ciphertext %zu is in NTT form; BFV ciphertexts must be in coefficient form", c);
+            memcpy(parms_id, src + 16, 32);
+            if ((parms_id[0] | parms_id[1] | parms_id[2] | parms_id[3]) && memcmp(parms_id, e->level_pid[L], 32) != 0)
+                return e->fail(PF_ERR_FORMAT, "query ciphertext %zu was made for other encryption parameters (parms_id differs from this engine's top data level)", c);
+        }
+    } else {
         HostTick ht("parse_queries");
         size_t bad = 0;
         int bad_mode = 0;
@@ -2669,6 +2724,7 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
         const uint64_t lo = ct_offsets[0], hi = ct_offsets[ncts];
         CK(fl.qraw.ensure_grow((size_t)(hi - lo) + 64));
         CK(e->s_ctoff.ensure_grow(ncts * 8));
+        if (seeded_dev) CK(e->s_seed.ensure_grow(ncts * SEED_SCRATCH_WORDS * 8));
         for (size_t c = 0; c < ncts; c++) rel_off[c] = ct_offsets[c] - lo + SEAL_CT_HEADER;
         CK(upload_async(e, e->s_ctoff.p, rel_off.data(), ncts * 8)); // engine stream, ahead of the strip kernels
     }
@@ -2711,7 +2767,12 @@ static int submit_search(pf_engine *e, uint64_t nq, const uint8_t *query_cts, ui
     for (uint64_t gi = 0; gi < ngroups; gi++) {
         const uint64_t q_hi = q_end[gi + 1];
         CK(cudaStreamWaitEvent(e->stream, fl.ev_up[gi], 0));
-        if (raw_path && q_hi > q_lo) {
+        if (raw_path && seeded_dev && q_hi > q_lo) {
+            const size_t c_lo = q_lo * e->m, nc = (q_hi - q_lo) * e->m;
+            rc = expand_seeded_on_device(e, fl.qraw.as<uint8_t>(), e->s_ctoff.as<u64>() + c_lo, fl.qcts.as<u64>() + c_lo * ctw,
+                                         e->s_seed.as<u64>() + c_lo * SEED_SCRATCH_WORDS, nc);
+            if (rc) return rc;
+        } else if (raw_path && q_hi > q_lo) {
             const size_t c_lo = q_lo * e->m, nc = (q_hi - q_lo) * e->m;
             strip_headers_kernel<<<dim3((unsigned)((ctw + 255) / 256), (unsigned)nc), 256, 0, e->stream>>>(
                 fl.qraw.as<uint8_t>(), e->s_ctoff.as<u64>() + c_lo, fl.qcts.as<u64>() + c_lo * ctw, ctw);
@@ -3062,6 +3123,32 @@ int pf_ct_serialize(pf_engine *e, const uint64_t *ct, int is_ntt, uint8_t *out, 
     write_ct_prefix(e, out, is_ntt, pid, e->L);
     memcpy(out + SEAL_CT_HEADER, ct, need - SEAL_CT_HEADER);
     return PF_OK;
+}
+
+int pf_seal_ct_expand_device(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct_words, size_t cap_words) {
+    if (!e || !in || !ct_words) return e ? e->fail(PF_ERR_INVALID, "null argument") : PF_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    int rc = check_device_error(e);
+    if (rc) return rc;
+    const size_t ctw = (size_t)2 * e->L * e->N;
+    if (cap_words < ctw) return e->fail(PF_ERR_CAPACITY, "need %zu words", ctw);
+    if ((size_t)e->L * e->N % 512 || !e->d_err_word) return e->fail(PF_ERR_STATE, "device-side expansion unavailable for these parameters");
+    if (!is_seeded_raw_stream(in, len, (uint64_t)e->N, (uint32_t)e->L))
+        return e->fail(PF_ERR_FORMAT, "not an uncompressed blake2xb-seeded ciphertext stream of this engine's top level");
+    CK(cudaSetDevice(e->prm.device));
+    DevBuf raw, out, off, scratch;
+    CK(raw.ensure(len + 64));
+    CK(out.ensure(ctw * 8));
+    CK(off.ensure(8));
+    CK(scratch.ensure(SEED_SCRATCH_WORDS * 8));
+    const u64 data_off = SEAL_CT_HEADER;
+    CK(cudaMemcpyAsync(raw.p, in, len, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(off.p, &data_off, 8, cudaMemcpyHostToDevice, e->stream));
+    rc = expand_seeded_on_device(e, raw.as<uint8_t>(), off.as<u64>(), out.as<u64>(), scratch.as<u64>(), 1);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ct_words, out.p, ctw * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return check_device_error(e);
 }
 
 int pf_ct_deserialize(pf_engine *e, const uint8_t *in, size_t len, uint64_t *ct, size_t cap_words, int *limbs,

@@ -301,6 +301,14 @@ class Engine:
                                              _ptr(labels, I64P), total.value, _ptr(sizes, U64P), C.byref(total)))
         return dist[:total.value], labels[:total.value], sizes.astype(np.int64)
 
+    def ct_expand_seeded_device(self, stream) -> np.ndarray:
+        """pf_seal_ct_expand_device: an uncompressed blake2xb-seeded ciphertext stream -> words [2][L][n], c1 drawn on
+        the device (what the search calls do for all-seeded requests)"""
+        b = np.frombuffer(bytes(stream), dtype=np.uint8)
+        out = np.zeros((2, self.L, self.n), dtype=np.uint64)
+        self._ck(self.lib.pf_seal_ct_expand_device(self.h, b.ctypes.data_as(C.c_void_p), b.size, _ptr(out, U64P), out.size))
+        return out
+
     def preciseSearch(self, precise_query, nearest_coarse_vector_idx) -> np.ndarray:
         """ref: Server::preciseSearch (src/server/server_lib.cpp:140-167)"""
         x = np.ascontiguousarray(precise_query, dtype=np.float32)

@@ -99,6 +99,9 @@ def test_bench_on_the_emulated_device(emul):
     assert line["gpu_launches"] > 0 and line["value"] > 0 and line["roofline"]["achieved"] > 0
     e2e = line["e2e"]
     assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 4 * (113 + 2 * 4 * 8192 * 8) and e2e["d2h_bytes_per_step"] >= 32 * 2 * 8192 * 8
+    es = line["e2e_seeded_requests"]     # the request of a symmetric-key SEAL client: half the upload, c1 drawn on the device
+    assert es["value"] > 0 and es["d2h_bytes_per_step"] == e2e["d2h_bytes_per_step"]
+    assert es["h2d_bytes_per_step"] < 0.51 * e2e["h2d_bytes_per_step"] + 4096 and "seeded" in es["request"]
     assert line["cpu_baseline"]["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["recall_at_10"] is not None and line["config"]["queries_per_step"] == 4
     assert set(line["phases_ms_per_step"]) == {"coarse", "to_ntt", "rotate", "mac", "intt"}

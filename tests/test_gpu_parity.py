@@ -820,7 +820,7 @@ def test_cpp_encrypted_search_matches_python(pf, oracle, tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "labels.i64", dtype=np.int64), labels)
 
 
-def test_seeded_query_ciphertexts(pf, oracle):
+def test_seeded_query_ciphertexts(pf, oracle, monkeypatch):
     """f-3: seeded query streams (Serializable<Ciphertext>: c0 + the PRNG seed of c1), plain and zlib, give the result
     bytes of the same ciphertexts sent in full; pf_ct_deserialize expands them too; a shake256 seed is refused"""
     from tests.util import zlib_stream
@@ -851,6 +851,17 @@ def test_seeded_query_ciphertexts(pf, oracle):
     for parts in (seeded, [zlib_stream(x) for x in seeded], [seeded[0], full[1], zlib_stream(seeded[2])]):
         got = eng.coarseSearchEncrypted(*blob_of(parts), idx)
         assert [got.result(r) for r in range(got.stats["nresults"])] == want
+    # an all-seeded uncompressed request is expanded ON THE DEVICE (3 more launches per query group than the host
+    # expansion needs for its header strip: memset aside, strip + expand + fix-up instead of strip); PF_SEEDED_HOST=1
+    # keeps it on the host; same bytes either way
+    l0 = eng.launch_count()
+    eng.coarseSearchEncrypted(*blob_of(seeded), idx)
+    l1 = eng.launch_count()
+    monkeypatch.setenv("PF_SEEDED_HOST", "1")
+    got = eng.coarseSearchEncrypted(*blob_of(seeded), idx)
+    l2 = eng.launch_count()
+    monkeypatch.delenv("PF_SEEDED_HOST")
+    assert [got.result(r) for r in range(got.stats["nresults"])] == want and (l1 - l0) > (l2 - l1)
     # decrypted distances of the first result are exact (the seeded encryption is a valid one)
     l = idx[0, 0]
     xs = vecs[offsets[l]: offsets[l] + min(cl.lay.C, int(offsets[l + 1] - offsets[l]))].astype(np.int32)
@@ -1102,4 +1113,55 @@ def test_pq_adc_matches_oracle(pf, oracle, tmp_path, d, M, nlist):
     eng.load_index(cent, offsets, ids, vecs)
     with pytest.raises(pf.PfError):
         eng.coarseSearchPQ(query, idx)
+    eng.close()
+
+
+@pytest.mark.parametrize("n,bits", [(2048, 40), (8192, None), (1024, 57)])
+def test_seeded_expansion_on_the_device(pf, oracle, n, bits):
+    """f-3: the device-side expansion of a seeded ciphertext (Blake2xb leaves in parallel, rejected words re-drawn in
+    stream order) == the host expansion == the oracle's, word for word.  57-bit primes make a draw exceed the largest
+    multiple of q below 2^64 with probability ~ 2^-7, so the re-draw path runs (dozens of times per ciphertext,
+    including re-draws of re-draws); BFVDefault primes almost never take it."""
+    from tests.util import ntt_primes
+    if bits is None:
+        primes, t = _params(n)
+    else:
+        primes, t = ntt_primes(n, bits, 3) + ntt_primes(n, bits + 1, 1), ntt_primes(n, 20, 1)[0]
+        if bits == 57:   # far from a power of two: 2^64 mod q is a large fraction of q
+            from tests.util import is_prime
+            primes, c = [], (3 << 55) // (2 * n) * (2 * n) + 1
+            while len(primes) < 4:
+                if is_prime(c):
+                    primes.append(c)
+                c -= 2 * n
+    L = len(primes) - 1
+    ctx = oracle.Context(n, primes, t)
+    sk = ctx.keygen(77)
+    rng = np.random.default_rng(n + (bits or 0))
+    eng = pf.Engine(128, n, primes, t, 1, 16 if n <= 2048 else 8)
+    rejected_total = 0
+    for trial in range(3):
+        seed = rng.bytes(64)
+        pt = ctx.encode(rng.integers(0, t, size=n))
+        ct = ctx.encrypt_seeded(sk, pt, 500 + trial, seed)
+        stream = ctx.ct_save_seeded(ct, seed)
+        got = eng.ct_expand_seeded_device(stream)
+        assert np.array_equal(got, ct), f"trial {trial}: device expansion differs from the oracle's ciphertext"
+        back, is_ntt = eng.ct_deserialize(stream)          # the host expansion (pf_seal_prng.h)
+        assert np.array_equal(back, got) and not is_ntt
+        # how many words of the first L*n stream words were rejected (test bookkeeping, from the oracle's PRNG)
+        stream_bytes = b"".join(oracle.blake2xb(4096, c.to_bytes(8, "little"), seed) for c in range(L * n * 8 // 4096))
+        words = np.frombuffer(stream_bytes, dtype=np.uint64).reshape(L, n)
+        for j in range(L):
+            mm = (2**64 - 1) - ((2**64 - 1) % primes[j]) - 1
+            rejected_total += int((words[j] >= np.uint64(mm)).sum())
+    if bits == 57:
+        assert 10 < rejected_total <= 3 * 96, rejected_total       # the re-draw path ran, within the list's capacity
+    # refusals: a full stream, a shake256 seed, a truncated stream
+    with pytest.raises(pf.PfError):
+        eng.ct_expand_seeded_device(ctx.ct_save(ct))
+    with pytest.raises(pf.PfError):
+        eng.ct_expand_seeded_device(ctx.ct_save_seeded(ct, seed, prng_type=2))
+    with pytest.raises(pf.PfError):
+        eng.ct_expand_seeded_device(stream[:-1])
     eng.close()
