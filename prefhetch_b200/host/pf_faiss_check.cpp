@@ -15,11 +15,13 @@ int main(int argc, char **argv) {
     if (argc != 2) return 2;
     try {
         const prefhetch::IvfFile f = prefhetch::read_ivfpq_file(argv[1]);
-        std::printf("%u %llu %llu %llu %llu %016llx %016llx %016llx\n", f.d, (unsigned long long)f.ntotal,
+        std::printf("%u %llu %llu %llu %llu %016llx %016llx %016llx %llu %llu %016llx %016llx\n", f.d, (unsigned long long)f.ntotal,
                     (unsigned long long)f.nlist, (unsigned long long)f.nprobe, (unsigned long long)f.code_size,
                     (unsigned long long)fnv(f.centroids.data(), f.centroids.size() * 4),
                     (unsigned long long)fnv(f.list_offsets.data(), f.list_offsets.size() * 8),
-                    (unsigned long long)fnv(f.ids.data(), f.ids.size() * 8));
+                    (unsigned long long)fnv(f.ids.data(), f.ids.size() * 8), (unsigned long long)f.pq_M,
+                    (unsigned long long)f.pq_nbits, (unsigned long long)fnv(f.pq_centroids.data(), f.pq_centroids.size() * 4),
+                    (unsigned long long)fnv(f.codes.data(), f.codes.size()));
     } catch (const std::exception &ex) {
         std::fprintf(stderr, "%s\n", ex.what());
         return 1;

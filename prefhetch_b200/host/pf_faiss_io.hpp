@@ -1,7 +1,8 @@
 // pf_faiss_io.hpp — reader for the FAISS IndexIVFPQ file the reference server caches on disk
 // (ref: src/server/server_lib.cpp:38-42 builds the file name, :82 writes it, :91-95 reads it and
-// rejects anything that is not an IndexIVFPQ).  Only what the GPU engine consumes is kept: the
-// coarse centroids and the ids of every inverted list; PQ codebooks and codes are skipped.
+// rejects anything that is not an IndexIVFPQ).  What the GPU engine consumes is kept: the coarse
+// centroids, the ids of every inverted list, and the product quantizer with the lists' codes (for the
+// PQ-ADC distance of today's search_encrypted: pf_load_pq).
 // [EXT, UNVERIFIED] layout restated from the published faiss/impl/index_read.cpp (SURVEY.md
 // App. B.3); FAISS itself is not available here, so it is only checked against the writer in
 // prefhetch_b200/faiss_io.py.
@@ -21,6 +22,9 @@ struct IvfFile {
     std::vector<float> centroids;      // [nlist][d]
     std::vector<int64_t> list_offsets; // [nlist+1]
     std::vector<int64_t> ids;          // list order
+    uint64_t pq_M = 0, pq_nbits = 0;   // ProductQuantizer: M sub-quantizers of nbits bits
+    std::vector<float> pq_centroids;   // [M][2^nbits][d/M]
+    std::vector<uint8_t> codes;        // [ntotal][code_size], list order
 };
 
 namespace detail {
@@ -49,6 +53,7 @@ class Cursor {
         skip(static_cast<size_t>(count * item_bytes));
     }
     bool at_end() const { return m_Pos == m_Buf.size(); }
+    size_t remaining() const { return m_Buf.size() - m_Pos; }
 
   private:
     std::vector<uint8_t> m_Buf;
@@ -99,8 +104,14 @@ inline IvfFile read_ivfpq_file(const std::string &path) {
     if (dm == 2) c.skip_items(c.get<uint64_t>(), 16);
     c.skip(1); // by_residual
     out.code_size = c.get<uint64_t>();
-    c.skip(24); // pq.d, pq.M, pq.nbits
-    c.skip_items(c.get<uint64_t>(), sizeof(float));
+    const uint64_t pq_d = c.get<uint64_t>();
+    out.pq_M = c.get<uint64_t>();
+    out.pq_nbits = c.get<uint64_t>();
+    const uint64_t npq = c.get<uint64_t>();
+    if (pq_d != out.d) throw std::runtime_error("product quantizer dimension does not match the index");
+    if (npq > c.remaining() / sizeof(float)) throw std::runtime_error("truncated index file"); // before allocating
+    out.pq_centroids.resize(npq);
+    c.copy(out.pq_centroids.data(), npq * sizeof(float));
     const uint32_t il = c.get<uint32_t>();
     if (il == fourcc("il00")) throw std::runtime_error("index file holds no inverted lists (il00)");
     if (il != fourcc("ilar")) throw std::runtime_error("unsupported inverted-list container (only in-memory ArrayInvertedLists, 'ilar')");
@@ -129,9 +140,12 @@ inline IvfFile read_ivfpq_file(const std::string &path) {
     }
     if (static_cast<uint64_t>(out.list_offsets[out.nlist]) != out.ntotal)
         throw std::runtime_error("ntotal does not match the inverted lists");
+    // the codes and ids must be in the file before anything is allocated for them
+    if (out.code_size > (1u << 20) || out.ntotal > c.remaining() / (out.code_size + 8)) throw std::runtime_error("truncated index file");
     out.ids.resize(out.ntotal);
+    out.codes.resize(out.ntotal * out.code_size);
     for (uint64_t l = 0; l < out.nlist; l++) {
-        c.skip_items(sizes[l], out.code_size);
+        c.copy(out.codes.data() + static_cast<uint64_t>(out.list_offsets[l]) * out.code_size, sizes[l] * out.code_size);
         c.copy(out.ids.data() + out.list_offsets[l], sizes[l] * 8);
     }
     if (top == fourcc("IwPQ") && !c.at_end()) throw std::runtime_error("trailing bytes after the inverted lists");

@@ -77,6 +77,9 @@ class Server {
             std::copy_n(dataset_base.data() + row * m_Dim, m_Dim, vectors.data() + i * m_Dim);
         }
         init_index(f.nlist, f.centroids.data(), f.list_offsets.data(), f.ids.data(), vectors.data());
+        // the file's product quantizer (8-bit sub-quantizers, one code byte each: what the reference builds) serves coarseSearchPQ
+        if (f.pq_nbits == 8 && f.pq_M && f.code_size == f.pq_M && f.pq_centroids.size() == size_t(256) * m_Dim)
+            loadProductQuantizer(static_cast<uint32_t>(f.pq_M), 8, f.pq_centroids, f.codes);
     }
 
     // ref: Server::retrieve_centroids (src/server/server_lib.cpp:101-109)

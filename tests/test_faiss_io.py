@@ -72,6 +72,10 @@ def test_cpp_reader_matches_python(tmp_path, sparse):
     assert [int(x) for x in out[:5]] == [f.d, f.ntotal, f.nlist, f.nprobe, f.code_size]
     assert int(out[5], 16) == _fnv(np.ascontiguousarray(f.centroids, np.float32).tobytes())
     assert int(out[6], 16) == _fnv(offsets.tobytes()) and int(out[7], 16) == _fnv(ids.tobytes())
+    # the product quantizer and the codes (list order) for pf_load_pq
+    assert [int(out[8]), int(out[9])] == [f.pq_M, f.pq_nbits]
+    assert int(out[10], 16) == _fnv(np.ascontiguousarray(f.pq_centroids, np.float32).tobytes())
+    assert int(out[11], 16) == _fnv(np.concatenate([np.asarray(c, np.uint8).reshape(-1) for c in f.list_codes]).tobytes())
     bad = tmp_path / "bad.faiss"
     bad.write_bytes(b"IxF2" + p.read_bytes()[4:])
     r = subprocess.run([str(exe), str(bad)], capture_output=True, text=True)
