@@ -820,62 +820,6 @@ def test_cpp_encrypted_search_matches_python(pf, oracle, tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "labels.i64", dtype=np.int64), labels)
 
 
-def test_seeded_query_ciphertexts(pf, oracle, monkeypatch):
-    """f-3: seeded query streams (Serializable<Ciphertext>: c0 + the PRNG seed of c1), plain and zlib, give the result
-    bytes of the same ciphertexts sent in full; pf_ct_deserialize expands them too; a shake256 seed is refused"""
-    from tests.util import zlib_stream
-    n, g, d, nprobe = 2048, 16, 128, 3
-    base, query, cent, offsets, ids, vecs = _dataset(51, nb=3000, nlist=12, nq=3)
-    primes, t = _params(n)
-    cl = OracleClient(oracle, n, primes, t, d, 1, g)
-    rng = np.random.default_rng(8)
-    seeds = [rng.bytes(64) for _ in query]
-    cts = [cl.ctx.encrypt_seeded(cl.sk, cl.ctx.encode(cl.lay.query_slots(t, q.astype(np.int64), 0)), 900 + i, seeds[i])
-           for i, q in enumerate(query)]
-    full = [cl.ctx.ct_save(ct) for ct in cts]
-    seeded = [cl.ctx.ct_save_seeded(ct, s) for ct, s in zip(cts, seeds)]
-    assert all(len(a) < 0.51 * len(b) + 200 for a, b in zip(seeded, full))
-
-    def blob_of(parts):
-        return (np.frombuffer(b"".join(parts), dtype=np.uint8).copy(),
-                np.concatenate([[0], np.cumsum([len(x) for x in parts])]).astype(np.uint64))
-    eng, _, _ = _engine(pf, n, g=g)
-    eng.load_index(cent, offsets, ids, vecs)
-    eng.set_list_sizes(offsets)
-    for i, key in enumerate(cl.step_keys()):
-        eng.set_galois_key(eng.galois_elt(i + 1), key)
-    idx = eng.coarse_quantize(query, nprobe)
-    ref = eng.coarseSearchEncrypted(*blob_of(full), idx)
-    want = [ref.result(r) for r in range(ref.stats["nresults"])]
-    assert want
-    for parts in (seeded, [zlib_stream(x) for x in seeded], [seeded[0], full[1], zlib_stream(seeded[2])]):
-        got = eng.coarseSearchEncrypted(*blob_of(parts), idx)
-        assert [got.result(r) for r in range(got.stats["nresults"])] == want
-    # an all-seeded uncompressed request is expanded ON THE DEVICE (3 more launches per query group than the host
-    # expansion needs for its header strip: memset aside, strip + expand + fix-up instead of strip); PF_SEEDED_HOST=1
-    # keeps it on the host; same bytes either way
-    l0 = eng.launch_count()
-    eng.coarseSearchEncrypted(*blob_of(seeded), idx)
-    l1 = eng.launch_count()
-    monkeypatch.setenv("PF_SEEDED_HOST", "1")
-    got = eng.coarseSearchEncrypted(*blob_of(seeded), idx)
-    l2 = eng.launch_count()
-    monkeypatch.delenv("PF_SEEDED_HOST")
-    assert [got.result(r) for r in range(got.stats["nresults"])] == want and (l1 - l0) > (l2 - l1)
-    # decrypted distances of the first result are exact (the seeded encryption is a valid one)
-    l = idx[0, 0]
-    xs = vecs[offsets[l]: offsets[l] + min(cl.lay.C, int(offsets[l + 1] - offsets[l]))].astype(np.int32)
-    ct0, _ = eng.ct_deserialize(want[0])
-    dist, budget = cl.distances(ct0, query[0], len(xs))
-    assert np.array_equal(dist, ((xs.astype(np.int64) - query[0].astype(np.int64)) ** 2).sum(1)) and budget > 0
-    back, is_ntt = eng.ct_deserialize(seeded[1])
-    assert np.array_equal(back, cts[1]) and not is_ntt
-    with pytest.raises(pf.PfError) as ei:
-        eng.coarseSearchEncrypted(*blob_of([cl.ctx.ct_save_seeded(cts[0], seeds[0], prng_type=2), full[1], full[2]]), idx)
-    assert ei.value.code == 5
-    eng.close()
-
-
 def test_cpp_handlers_end_to_end(pf, oracle, tmp_path):
     """the handler bodies of host/pf_query_handlers.hpp (ref: src/server/controllers/Query.cc:10-98 + the additive
     encrypted endpoint): JSON request bodies in the reference's shape in, JSON out, equal to direct calls on the
@@ -1058,6 +1002,65 @@ def _pq_case(oracle, seed, nb, d, nlist, nq, M):
     pqc += rng.normal(0, 0.25, size=pqc.shape).astype(np.float32)
     codes = oracle.pq_encode_residuals(vecs, offsets, cent, M, pqc)
     return query, cent, offsets, ids, vecs, pqc, codes
+
+
+# The tests from here on are about kernels written after the round's GPU budget ended (seeded expansion on the device,
+# PQ-ADC): they run last so that, under -x, a failure in them hides as little as possible of what is above
+# (test_cpp_client_round_trip also sends seeded requests, from the C++ client).
+def test_seeded_query_ciphertexts(pf, oracle, monkeypatch):
+    """f-3: seeded query streams (Serializable<Ciphertext>: c0 + the PRNG seed of c1), plain and zlib, give the result
+    bytes of the same ciphertexts sent in full; pf_ct_deserialize expands them too; a shake256 seed is refused"""
+    from tests.util import zlib_stream
+    n, g, d, nprobe = 2048, 16, 128, 3
+    base, query, cent, offsets, ids, vecs = _dataset(51, nb=3000, nlist=12, nq=3)
+    primes, t = _params(n)
+    cl = OracleClient(oracle, n, primes, t, d, 1, g)
+    rng = np.random.default_rng(8)
+    seeds = [rng.bytes(64) for _ in query]
+    cts = [cl.ctx.encrypt_seeded(cl.sk, cl.ctx.encode(cl.lay.query_slots(t, q.astype(np.int64), 0)), 900 + i, seeds[i])
+           for i, q in enumerate(query)]
+    full = [cl.ctx.ct_save(ct) for ct in cts]
+    seeded = [cl.ctx.ct_save_seeded(ct, s) for ct, s in zip(cts, seeds)]
+    assert all(len(a) < 0.51 * len(b) + 200 for a, b in zip(seeded, full))
+
+    def blob_of(parts):
+        return (np.frombuffer(b"".join(parts), dtype=np.uint8).copy(),
+                np.concatenate([[0], np.cumsum([len(x) for x in parts])]).astype(np.uint64))
+    eng, _, _ = _engine(pf, n, g=g)
+    eng.load_index(cent, offsets, ids, vecs)
+    eng.set_list_sizes(offsets)
+    for i, key in enumerate(cl.step_keys()):
+        eng.set_galois_key(eng.galois_elt(i + 1), key)
+    idx = eng.coarse_quantize(query, nprobe)
+    ref = eng.coarseSearchEncrypted(*blob_of(full), idx)
+    want = [ref.result(r) for r in range(ref.stats["nresults"])]
+    assert want
+    for parts in (seeded, [zlib_stream(x) for x in seeded], [seeded[0], full[1], zlib_stream(seeded[2])]):
+        got = eng.coarseSearchEncrypted(*blob_of(parts), idx)
+        assert [got.result(r) for r in range(got.stats["nresults"])] == want
+    # an all-seeded uncompressed request is expanded ON THE DEVICE (3 more launches per query group than the host
+    # expansion needs for its header strip: memset aside, strip + expand + fix-up instead of strip); PF_SEEDED_HOST=1
+    # keeps it on the host; same bytes either way
+    l0 = eng.launch_count()
+    eng.coarseSearchEncrypted(*blob_of(seeded), idx)
+    l1 = eng.launch_count()
+    monkeypatch.setenv("PF_SEEDED_HOST", "1")
+    got = eng.coarseSearchEncrypted(*blob_of(seeded), idx)
+    l2 = eng.launch_count()
+    monkeypatch.delenv("PF_SEEDED_HOST")
+    assert [got.result(r) for r in range(got.stats["nresults"])] == want and (l1 - l0) > (l2 - l1)
+    # decrypted distances of the first result are exact (the seeded encryption is a valid one)
+    l = idx[0, 0]
+    xs = vecs[offsets[l]: offsets[l] + min(cl.lay.C, int(offsets[l + 1] - offsets[l]))].astype(np.int32)
+    ct0, _ = eng.ct_deserialize(want[0])
+    dist, budget = cl.distances(ct0, query[0], len(xs))
+    assert np.array_equal(dist, ((xs.astype(np.int64) - query[0].astype(np.int64)) ** 2).sum(1)) and budget > 0
+    back, is_ntt = eng.ct_deserialize(seeded[1])
+    assert np.array_equal(back, cts[1]) and not is_ntt
+    with pytest.raises(pf.PfError) as ei:
+        eng.coarseSearchEncrypted(*blob_of([cl.ctx.ct_save_seeded(cts[0], seeds[0], prng_type=2), full[1], full[2]]), idx)
+    assert ei.value.code == 5
+    eng.close()
 
 
 @pytest.mark.parametrize("d,M,nlist", [(128, 32, 24), (64, 8, 9), (128, 16, 5)])
